@@ -1,0 +1,453 @@
+// dcn_api.cu -- the C ABI (include/deacon_cuda.h) over the sm_100a kernels.
+//
+// There is deliberately no CPU path in this file: every entry point either runs CUDA kernels or
+// returns an error.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/deacon_cuda.h"
+#include "dcn_kernels.cuh"
+
+using namespace dcn;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Slot {  // one stage of the host-pointer pipeline
+    DevBuf bases, off, keep, hits, total, plan;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
+    bool busy = false;
+    uint32_t u0 = 0, u1 = 0;
+};
+
+}  // namespace
+
+struct dcn_ctx {
+    int device = 0;
+    int sm_count = 148;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    // resident index
+    DevBuf table;
+    uint64_t n_buckets = 0, n_keys = 0;
+    int has_empty = 0;
+    uint8_t k = 0, w = 0;
+    double load = 0.5;
+    // scratch
+    DevBuf plan;       // BatchStats + tile_first + tile_end (one memset clears all three)
+    DevBuf counters;   // 6 x u64 ProcessingStats + 2 x u64 table-build counters
+    DevBuf keys_stage;
+    Slot slot[2];
+    uint64_t launches = 0;
+    float t_h2d = 0, t_kernel = 0, t_d2h = 0;
+
+    int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+        err = what;
+        if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
+        return code;
+    }
+};
+
+#define CK(call)                                                            \
+    do {                                                                    \
+        cudaError_t e_ = (call);                                            \
+        if (e_ != cudaSuccess) return ctx->fail(DCN_ERR_CUDA, #call, e_);   \
+    } while (0)
+
+using G31 = Geo<31, 15>;
+
+static size_t plan_bytes(uint64_t n_rel_bases) {
+    // smallest stride the planner can choose -> most tiles
+    uint64_t s_min = (uint64_t)G31::BCAP - 14u - DCN_MAX_SHORT;
+    uint64_t n_tiles = n_rel_bases / s_min + 2;
+    return 64 + (size_t)n_tiles * 2 * sizeof(uint32_t);
+}
+
+// Enqueue the whole filter pipeline for one device-resident batch on `st`.
+static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, const uint8_t *d_bases, uint64_t base0, uint64_t n_bases_abs,
+                          const uint64_t *d_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
+                          double rel_thr, int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total,
+                          cudaStream_t st) {
+    if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
+    if (ctx->k != 31 || ctx->w != 15)
+        return ctx->fail(DCN_ERR_UNSUPPORTED, "only k=31, w=15 indexes are implemented by the CUDA path");
+    const uint32_t rpu = paired ? 2u : 1u;
+    if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
+    const uint32_t n_units = n_rec / rpu;
+    if (n_units == 0) return DCN_OK;
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) || (base0 & 15u))
+        return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
+
+    const uint64_t n_rel = n_bases_abs - base0;
+    const size_t pbytes = plan_bytes(n_rel);
+    CK(plan.ensure(pbytes));
+    const uint64_t n_tiles_max = (pbytes - 64) / (2 * sizeof(uint32_t));
+    BatchStats *d_stats = plan.as<BatchStats>();
+    uint32_t *tile_first = reinterpret_cast<uint32_t *>(plan.as<uint8_t>() + 64);
+    uint32_t *tile_end = tile_first + n_tiles_max;
+    CK(cudaMemsetAsync(plan.p, 0, pbytes, st));
+
+    const int pb = 256;
+    const int pg = (int)std::min<uint64_t>((n_units + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
+    prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_stats);
+    prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, rpu, n_units, base0, d_stats, tile_first, tile_end);
+
+    FilterParams P;
+    P.bases = d_bases; P.base0 = base0; P.n_bases = n_bases_abs;
+    P.rec_off = d_off; P.n_rec = n_rec; P.rpu = rpu; P.n_units = n_units;
+    P.prefix_len = prefix_len; P.abs_thr = abs_thr; P.rel_thr = rel_thr; P.deplete = deplete;
+    P.table.slots = ctx->table.as<uint64_t>(); P.table.n_buckets = ctx->n_buckets; P.table.has_empty_key = ctx->has_empty;
+    P.keep = d_keep; P.hits = d_hits; P.total = d_total;
+
+    const size_t smem = sizeof(TileSmem<G31>);
+    const uint64_t tiles_lb = n_rel / G31::BCAP + 1;
+    const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * 2);
+    filter_fused_kernel<G31><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end);
+    stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_keep, ctx->counters.as<unsigned long long>());
+    ctx->launches += 4;
+    CK(cudaGetLastError());
+    return DCN_OK;
+}
+
+extern "C" {
+
+int dcn_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+dcn_ctx *dcn_ctx_create(int device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        g_create_error = std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device index out of range"; return nullptr; }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return nullptr; }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return nullptr; }
+    if (prop.major < 10) {
+        g_create_error = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
+        return nullptr;
+    }
+    dcn_ctx *ctx = new dcn_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 2; i++) {
+        Slot &s = ctx->slot[i];
+        ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_h2d) == cudaSuccess;
+        ok = ok && cudaEventCreate(&s.ev_kernel) == cudaSuccess && cudaEventCreate(&s.ev_done) == cudaSuccess;
+    }
+    ok = ok && ctx->counters.ensure(8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->counters.p, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(TileSmem<G31>)) == cudaSuccess;
+    if (!ok) {
+        g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
+        dcn_ctx_destroy(ctx);
+        return nullptr;
+    }
+    return ctx;
+}
+
+void dcn_ctx_destroy(dcn_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    ctx->table.release(); ctx->plan.release(); ctx->counters.release(); ctx->keys_stage.release();
+    for (int i = 0; i < 2; i++) {
+        Slot &s = ctx->slot[i];
+        s.bases.release(); s.off.release(); s.keep.release(); s.hits.release(); s.total.release(); s.plan.release();
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.ev_start) cudaEventDestroy(s.ev_start);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *dcn_last_error(dcn_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void *dcn_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void dcn_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------- index residency
+int dcn_index_set_load_factor(dcn_ctx *ctx, double load) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!(load >= 0.05 && load <= 0.9)) return ctx->fail(DCN_ERR_ARG, "load factor must be in [0.05, 0.9]");
+    ctx->load = load;
+    return DCN_OK;
+}
+
+static int table_begin(dcn_ctx *ctx, uint64_t n_keys, uint8_t k, uint8_t w, cudaStream_t st) {
+    CK(cudaSetDevice(ctx->device));
+    ctx->n_buckets = table_buckets_for(n_keys, ctx->load);
+    ctx->n_keys = 0; ctx->has_empty = 0; ctx->k = k; ctx->w = w;
+    CK(ctx->table.ensure(ctx->n_buckets * 4 * sizeof(uint64_t)));
+    table_fill_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->table.as<uint64_t>(), ctx->n_buckets * 4);
+    CK(cudaMemsetAsync(ctx->counters.as<unsigned long long>() + 6, 0, 2 * sizeof(unsigned long long), st));
+    ctx->launches += 1;
+    return DCN_OK;
+}
+static int table_insert(dcn_ctx *ctx, const uint64_t *d_keys, uint64_t n, cudaStream_t st) {
+    if (!n) return DCN_OK;
+    int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 16);
+    table_insert_kernel<<<grid, 256, 0, st>>>(ctx->table.as<uint64_t>(), ctx->n_buckets, d_keys, n,
+                                              ctx->counters.as<unsigned long long>() + 6);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return DCN_OK;
+}
+static int table_end(dcn_ctx *ctx, cudaStream_t st) {
+    unsigned long long c[2] = {0, 0};
+    CK(cudaMemcpyAsync(c, ctx->counters.as<unsigned long long>() + 6, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->has_empty = c[1] != 0;
+    ctx->n_keys = c[0] + (c[1] ? 1 : 0);
+    return DCN_OK;
+}
+
+int dcn_index_upload_device(dcn_ctx *ctx, const uint64_t *d_keys, uint64_t n_keys, uint8_t k, uint8_t w, void *stream) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!d_keys && n_keys) return ctx->fail(DCN_ERR_ARG, "null key pointer");
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    int rc = table_begin(ctx, n_keys, k, w, st);
+    if (rc) return rc;
+    if ((rc = table_insert(ctx, d_keys, n_keys, st))) return rc;
+    return table_end(ctx, st);
+}
+
+int dcn_index_upload(dcn_ctx *ctx, const uint64_t *keys, uint64_t n_keys, uint8_t k, uint8_t w) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!keys && n_keys) return ctx->fail(DCN_ERR_ARG, "null key pointer");
+    cudaStream_t st = ctx->stream;
+    int rc = table_begin(ctx, n_keys, k, w, st);
+    if (rc) return rc;
+    const uint64_t CH = 32ull << 20;  // keys per staging chunk (256 MB)
+    CK(ctx->keys_stage.ensure(std::min(CH, std::max<uint64_t>(n_keys, 1)) * sizeof(uint64_t)));
+    for (uint64_t i = 0; i < n_keys; i += CH) {
+        uint64_t n = std::min(CH, n_keys - i);
+        CK(cudaMemcpyAsync(ctx->keys_stage.p, keys + i, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        if ((rc = table_insert(ctx, ctx->keys_stage.as<uint64_t>(), n, st))) return rc;
+        CK(cudaStreamSynchronize(st));  // staging buffer is reused
+    }
+    return table_end(ctx, st);
+}
+
+int dcn_index_info(dcn_ctx *ctx, uint64_t *n_keys, uint8_t *k, uint8_t *w, uint64_t *table_bytes) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident");
+    if (n_keys) *n_keys = ctx->n_keys;
+    if (k) *k = ctx->k;
+    if (w) *w = ctx->w;
+    if (table_bytes) *table_bytes = ctx->n_buckets * 4 * sizeof(uint64_t);
+    return DCN_OK;
+}
+
+// ---------------------------------------------------------------------------- B1 filter
+int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                            uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
+                            int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream) {
+    if (!ctx) return DCN_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    return enqueue_filter(ctx, ctx->plan, d_bases, 0, n_bases, d_rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr,
+                          deplete, d_keep, d_hits, d_total, st);
+}
+
+// Host-pointer form: unit-aligned chunks, double-buffered over two streams so that the H2D copy
+// of chunk c+1 overlaps the kernels of chunk c (SURVEY.md 8f.1 "pinned double-buffered streams").
+int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, int paired,
+                     uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
+                     uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!rec_off || (!bases && n_rec && rec_off[n_rec] > rec_off[0])) return ctx->fail(DCN_ERR_ARG, "null input pointer");
+    if (!keep || !hits || !total) return ctx->fail(DCN_ERR_ARG, "null output pointer");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t rpu = paired ? 2u : 1u;
+    if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
+    const uint32_t n_units = n_rec / rpu;
+    if (n_units == 0) return DCN_OK;
+
+    static const uint64_t chunk_bases = []() {
+        const char *e = getenv("DCN_CHUNK_MB");
+        uint64_t mb = e ? strtoull(e, nullptr, 10) : 32;
+        if (mb < 1) mb = 1;
+        return mb << 20;
+    }();
+
+    ctx->t_h2d = ctx->t_kernel = ctx->t_d2h = 0;
+    auto retire = [&](Slot &s) -> int {  // copy a finished chunk's results out
+        if (!s.busy) return DCN_OK;
+        uint32_t nu = s.u1 - s.u0;
+        CK(cudaMemcpyAsync(keep + s.u0, s.keep.p, nu * sizeof(uint8_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(hits + s.u0, s.hits.p, nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaMemcpyAsync(total + s.u0, s.total.p, nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
+        BatchStats bs;
+        CK(cudaMemcpyAsync(&bs, s.plan.p, sizeof(bs), cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaEventRecord(s.ev_done, s.stream));
+        CK(cudaEventSynchronize(s.ev_done));
+        if (bs.n_long) { s.busy = false; return ctx->fail(DCN_ERR_UNSUPPORTED, "units longer than 1024 bases: long path not implemented yet"); }
+        float a = 0, b = 0, c = 0;
+        cudaEventElapsedTime(&a, s.ev_start, s.ev_h2d);
+        cudaEventElapsedTime(&b, s.ev_h2d, s.ev_kernel);
+        cudaEventElapsedTime(&c, s.ev_kernel, s.ev_done);
+        ctx->t_h2d += a; ctx->t_kernel += b; ctx->t_d2h += c;
+        s.busy = false;
+        return DCN_OK;
+    };
+
+    uint32_t u0 = 0;
+    int which = 0;
+    int rc = DCN_OK;
+    while (u0 < n_units) {
+        // largest u1 with rec_off[u1*rpu] - rec_off[u0*rpu] <= chunk_bases (at least one unit)
+        const uint64_t b0 = rec_off[(uint64_t)u0 * rpu];
+        uint32_t lo = u0 + 1, hi = n_units;
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo + 1) / 2;
+            if (rec_off[(uint64_t)mid * rpu] - b0 <= chunk_bases) lo = mid; else hi = mid - 1;
+        }
+        const uint32_t u1 = lo;
+        const uint64_t b1 = rec_off[(uint64_t)u1 * rpu];
+        const uint64_t a0 = b0 & ~15ull;
+        const uint32_t nr = (u1 - u0) * rpu, nu = u1 - u0;
+
+        Slot &s = ctx->slot[which];
+        if ((rc = retire(s))) break;  // the slot's previous chunk (two chunks ago)
+        if (s.bases.ensure((size_t)(b1 - a0) + 64) != cudaSuccess || s.off.ensure((size_t)(nr + 1) * 8) != cudaSuccess ||
+            s.keep.ensure(nu) != cudaSuccess || s.hits.ensure((size_t)nu * 4) != cudaSuccess ||
+            s.total.ensure((size_t)nu * 4) != cudaSuccess) {
+            rc = ctx->fail(DCN_ERR_NOMEM, "device allocation failed", cudaGetLastError());
+            break;
+        }
+        CK(cudaEventRecord(s.ev_start, s.stream));
+        if (b1 > a0) CK(cudaMemcpyAsync(s.bases.p, bases + a0, (size_t)(b1 - a0), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.off.p, rec_off + (uint64_t)u0 * rpu, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        CK(cudaEventRecord(s.ev_h2d, s.stream));
+        rc = enqueue_filter(ctx, s.plan, s.bases.as<uint8_t>(), a0, b1, s.off.as<uint64_t>(), nr, paired, prefix_len,
+                            abs_thr, rel_thr, deplete, s.keep.as<uint8_t>(), s.hits.as<uint32_t>(),
+                            s.total.as<uint32_t>(), s.stream);
+        if (rc) break;
+        CK(cudaEventRecord(s.ev_kernel, s.stream));
+        s.busy = true; s.u0 = u0; s.u1 = u1;
+        // the other slot's chunk was enqueued before this one: drain it while this one runs
+        if ((rc = retire(ctx->slot[which ^ 1]))) break;
+        which ^= 1;
+        u0 = u1;
+    }
+    for (int i = 0; i < 2; i++) {
+        int r2 = retire(ctx->slot[i]);
+        if (!rc) rc = r2;
+    }
+    if (rc) { cudaDeviceSynchronize(); ctx->slot[0].busy = ctx->slot[1].busy = false; }
+    return rc;
+}
+
+// ---------------------------------------------------------------------------- not yet built (round 1)
+int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *, const uint64_t *, uint32_t, uint32_t, double, int, uint8_t *,
+                     uint32_t *, uint32_t *) {
+    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_lookup_batch: not implemented yet") : DCN_ERR_ARG;
+}
+int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *, const uint64_t *, uint32_t, uint32_t, double, int,
+                            uint8_t *, uint32_t *, uint32_t *, void *) {
+    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_lookup_batch_device: not implemented yet") : DCN_ERR_ARG;
+}
+int dcn_extract(dcn_ctx *ctx, int, const uint8_t *, const uint64_t *, uint32_t, uint8_t, uint8_t, uint32_t, float,
+                uint64_t *, uint32_t *, uint64_t *, uint64_t) {
+    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_extract: not implemented yet") : DCN_ERR_ARG;
+}
+int dcn_index_build(dcn_ctx *ctx, const uint8_t *, const uint64_t *, uint32_t, uint8_t, uint8_t, float, int, uint64_t *) {
+    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_index_build: not implemented yet") : DCN_ERR_ARG;
+}
+int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *, const uint64_t *, uint32_t, uint64_t, uint8_t, uint8_t, float,
+                           int, uint64_t *, void *) {
+    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_index_build_device: not implemented yet") : DCN_ERR_ARG;
+}
+int dcn_index_build_keys(dcn_ctx *ctx, uint64_t *, uint64_t) {
+    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_index_build_keys: not implemented yet") : DCN_ERR_ARG;
+}
+const uint64_t *dcn_index_build_keys_device(dcn_ctx *) { return nullptr; }
+
+// ---------------------------------------------------------------------------- counters
+int dcn_stats_get(dcn_ctx *ctx, uint64_t counters[6]) {
+    if (!ctx || !counters) return DCN_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(counters, ctx->counters.p, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DCN_OK;
+}
+int dcn_stats_reset(dcn_ctx *ctx) {
+    if (!ctx) return DCN_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(ctx->counters.p, 0, 6 * sizeof(uint64_t)));
+    return DCN_OK;
+}
+
+// ---------------------------------------------------------------------------- measurement
+int dcn_last_timing(dcn_ctx *ctx, float *h2d_ms, float *kernel_ms, float *d2h_ms) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (h2d_ms) *h2d_ms = ctx->t_h2d;
+    if (kernel_ms) *kernel_ms = ctx->t_kernel;
+    if (d2h_ms) *d2h_ms = ctx->t_d2h;
+    return DCN_OK;
+}
+
+int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms) {
+    if (!ctx || !ms || !n_probes) return DCN_ERR_ARG;
+    if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident");
+    CK(cudaSetDevice(ctx->device));
+    const int threads = 256, grid = ctx->sm_count * 8;
+    uint64_t per_thread = *n_probes / ((uint64_t)threads * grid);
+    per_thread = std::max<uint64_t>(4, (per_thread + 3) / 4 * 4);
+    *n_probes = per_thread * threads * grid;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    CK(cudaEventRecord(a, ctx->stream));
+    random_access_kernel<<<grid, threads, 0, ctx->stream>>>(ctx->table.as<uint64_t>(), ctx->n_buckets, (uint32_t)per_thread,
+                                                            ctx->counters.as<unsigned long long>() + 7);
+    CK(cudaEventRecord(b, ctx->stream));
+    CK(cudaEventSynchronize(b));
+    CK(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    ctx->launches += 1;
+    return DCN_OK;
+}
+
+uint64_t dcn_launch_count(dcn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// dcn_kernels.cuh -- device execution policy and the __global__ kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "dcn_tile.cuh"
+
+namespace dcn {
+
+// Execution policy for the device: one phase = every thread runs it, then a CTA barrier.
+template <class G>
+struct DevExec {
+    TilePriv<G> pv;
+    uint32_t *wsum;
+
+    template <class F>
+    __device__ __forceinline__ void par(F f) {
+        f((int)threadIdx.x, pv);
+        __syncthreads();
+    }
+    // block-wide exclusive sum of a u32 (two packed 16-bit counters in our use)
+    template <class Get, class Put>
+    __device__ __forceinline__ void scan(Get get, Put put) {
+        const int t = (int)threadIdx.x, lane = t & 31, warp = t >> 5;
+        const uint32_t v = get(t, pv);
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        uint32_t base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < G::NT / 32; w++) {
+            uint32_t sv = wsum[w];
+            total += sv;
+            if (w < warp) base += sv;
+        }
+        put(t, pv, base + x - v, total);
+        __syncthreads();
+    }
+    __device__ __forceinline__ void ballot2(int t, uint32_t idx, bool valid, bool hit, uint32_t *vm, uint32_t *hm) {
+        uint32_t a = __ballot_sync(0xFFFFFFFFu, valid), b = __ballot_sync(0xFFFFFFFFu, hit);
+        if ((t & 31) == 0 && idx < (uint32_t)G::PKCAP) { vm[idx >> 5] = a; hm[idx >> 5] = b; }
+    }
+};
+
+// device-side batch statistics, written by the prep kernels
+struct BatchStats {
+    uint32_t max_short;   // longest short unit
+    uint32_t n_long;      // units longer than DCN_MAX_SHORT
+    uint32_t n_chunks;    // chunk descriptors of the long path
+    uint32_t overflow;    // an internal table overflowed
+};
+
+// ------------------------------------------------------------------ prep: unit statistics
+__global__ void prep_stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,
+                                  BatchStats *st) {  // lengths only: independent of base0
+    uint32_t mx = 0, nl = 0;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x)
+        plan_unit_stats(rec_off, rpu, u, mx, nl);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
+        nl += __shfl_xor_sync(0xFFFFFFFFu, nl, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mx) atomicMax(&st->max_short, mx);
+        if (nl) atomicAdd(&st->n_long, nl);
+    }
+}
+
+// ------------------------------------------------------------------ prep: tile ownership
+template <class G>
+__global__ void prep_tiles_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,
+                                  uint64_t base0, const BatchStats *st, uint32_t *tile_first, uint32_t *tile_end) {
+    const PlanCfg cfg = plan_make_cfg<G>(st->max_short);
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x)
+        plan_unit_tiles(rec_off, base0, rpu, n_units, u, cfg, tile_first, tile_end);
+}
+
+// ------------------------------------------------------------------ the fused filter kernel
+// Persistent CTAs; tile i -> CTA (i mod grid).  2 CTAs per SM (register- and smem-limited).
+template <class G>
+__global__ void __launch_bounds__(G::NT, 2)
+filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ tile_first,
+                    const uint32_t *__restrict__ tile_end) {
+    extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
+    TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);
+    DevExec<G> ex;
+    ex.wsum = s.wsum;
+    init_tables<G>((int)threadIdx.x, s);
+    __syncthreads();
+    const PlanCfg cfg = plan_make_cfg<G>(st->max_short);
+    const uint32_t n_tiles = plan_num_tiles(P.n_bases - P.base0, cfg);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        uint32_t a = tile_first[tile], b = tile_end[tile];
+        if (a < b) filter_tile<G>(ex, s, P, cfg, a, b);
+    }
+}
+
+// ------------------------------------------------------------------ summary counters (a13)
+// src/local_filter.rs:347-371 (single) / 488-525 (pair): seqs and bp in / kept / filtered.
+__global__ void stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,
+                             const uint8_t *__restrict__ keep, unsigned long long *counters) {
+    unsigned long long bp_all = 0, bp_kept = 0, n_all = 0, n_kept = 0;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        unsigned long long len = rec_off[(uint64_t)(u + 1) * rpu] - rec_off[(uint64_t)u * rpu];
+        bp_all += len; n_all += rpu;
+        if (keep[u]) { bp_kept += len; n_kept += rpu; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        bp_all += __shfl_xor_sync(0xFFFFFFFFu, bp_all, d);
+        bp_kept += __shfl_xor_sync(0xFFFFFFFFu, bp_kept, d);
+        n_all += __shfl_xor_sync(0xFFFFFFFFu, n_all, d);
+        n_kept += __shfl_xor_sync(0xFFFFFFFFu, n_kept, d);
+    }
+    if ((threadIdx.x & 31) == 0 && n_all) {
+        atomicAdd(&counters[0], n_all);                  // total_seqs
+        atomicAdd(&counters[1], n_all - n_kept);         // filtered_seqs
+        atomicAdd(&counters[2], bp_all);                 // total_bp
+        atomicAdd(&counters[3], bp_kept);                // output_bp
+        atomicAdd(&counters[4], bp_all - bp_kept);       // filtered_bp
+        atomicAdd(&counters[5], n_kept);                 // output_seq_counter
+    }
+}
+
+// ------------------------------------------------------------------ table build (K4)
+__global__ void table_fill_kernel(uint64_t *slots, uint64_t n_slots) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_slots; i += (uint64_t)gridDim.x * blockDim.x)
+        slots[i] = DCN_EMPTY;
+}
+
+// Insert keys (duplicates allowed).  counts[0] += newly inserted keys, counts[1] = DCN_EMPTY seen.
+__global__ void table_insert_kernel(uint64_t *slots, uint64_t n_buckets, const uint64_t *__restrict__ keys,
+                                    uint64_t n_keys, unsigned long long *counts) {
+    unsigned long long added = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_keys; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t h = keys[i];
+        if (h == DCN_EMPTY) { counts[1] = 1; continue; }
+        uint64_t b = table_bucket(h, n_buckets);
+        bool done = false;
+        while (!done) {
+            unsigned long long *bp = reinterpret_cast<unsigned long long *>(slots + 4 * b);
+#pragma unroll
+            for (int sI = 0; sI < 4 && !done; sI++) {
+                unsigned long long cur = bp[sI];
+                if (cur == h) { done = true; break; }
+                if (cur == DCN_EMPTY) {
+                    unsigned long long old = atomicCAS(&bp[sI], (unsigned long long)DCN_EMPTY, (unsigned long long)h);
+                    if (old == DCN_EMPTY) { added++; done = true; }
+                    else if (old == h) done = true;
+                }
+            }
+            if (!done && ++b == n_buckets) b = 0;
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) added += __shfl_xor_sync(0xFFFFFFFFu, added, d);
+    if ((threadIdx.x & 31) == 0 && added) atomicAdd(&counts[0], added);
+}
+
+// ------------------------------------------------------------------ random-access ceiling probe
+// Every thread issues `per_thread` independent 32-byte loads at pseudo-random buckets.
+__global__ void random_access_kernel(const uint64_t *__restrict__ slots, uint64_t n_buckets, uint32_t per_thread,
+                                     unsigned long long *sink) {
+    uint64_t x = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
+    unsigned long long acc = 0;
+    for (uint32_t i = 0; i < per_thread; i += 4) {
+        Bucket bk[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            x = xxh3_u64(x + i + j);
+            bk[j] = load_bucket(slots, table_bucket(x, n_buckets));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc += bk[j].k0 ^ bk[j].k1 ^ bk[j].k2 ^ bk[j].k3;
+    }
+    if (acc == 0x0123456789ABCDEFULL) *sink = acc;
+}
+
+}  // namespace dcn

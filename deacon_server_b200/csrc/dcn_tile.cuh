@@ -1,0 +1,620 @@
+// dcn_tile.cuh -- the tile pipeline of the fused extract -> lookup -> classify kernel.
+//
+// One CTA (256 threads) owns a tile: a 16-byte-aligned span of the concatenated base stream that
+// holds up to 4080 window starts.  Thread t owns the 16 bases [16t, 16t+16) of the span: it
+// converts them (2-bit codes + non-ACGT mask), hashes the 16 k-mers that start there (rolling
+// canonical ntHash, seeded from per-thread aggregates so no thread re-reads 31 bases), and picks
+// the minimizer of the 16 windows that start there (van Herk / Gil-Werman min over w = 15 with
+// R = w + 1 = 16 outputs per thread).  Picks are compacted into a shared-memory list and then
+// processed one pick per thread: ACGT filter, canonical 2-bit k-mer, xxh3, one 32-byte probe
+// of the HBM table, per-unit distinct-hit count, threshold test.
+//
+// Every phase is a function of (thread id, shared state, per-thread private state) so the same
+// code runs on the device (phases separated by __syncthreads) and, for tests only, on the host
+// (phases run as loops over t).  Reference semantics: SURVEY.md Appendix A.
+#pragma once
+#include "dcn_core.cuh"
+#include "dcn_plan.cuh"
+
+namespace dcn {
+
+enum Flavour { FLAVOUR_FILTER = 0, FLAVOUR_INDEX = 1 };
+
+template <int K_, int W_>
+struct Geo {
+    static_assert(W_ == 15, "fast path is specialised for w = 15 (R = w + 1 = 16 windows per thread)");
+    static_assert(K_ >= 17 && K_ <= 31, "fast path needs 17 <= k <= 31 (k-mer spans exactly 3 threads' words)");
+    static constexpr int K = K_, W = W_, L = K_ + W_ - 1;
+    static constexpr int NT = 256;              // threads per CTA
+    static constexpr int NV = NT + 2;           // 16-byte vectors loaded per tile
+    static constexpr int WCAP = NT * 16 - 16;   // window starts per tile (thread 255 only hashes)
+    static constexpr int BCAP = WCAP + L - 1;   // bases a tile may reference
+    static constexpr int NBW = 132;             // 32-bit words of the per-position bit arrays
+    static constexpr int MAXR = 512;            // records per sub-batch
+    static constexpr int PKCAP = NT * 16;       // worst case: every window emits a pick
+    static constexpr int HP = 20;               // hrow pitch in words (16 data + 4 pad: conflict-free LDS.128)
+};
+
+struct u32x2 { uint32_t x, y; };
+struct u32x4 { uint32_t x, y, z, w; };
+
+template <class G>
+struct alignas(16) TileSmem {
+    u32x4 ag[G::NV + 6];              // per vector: E_fw, E_rc (own role), N_fw, N_rc (right-neighbour role)
+    uint32_t hrow[G::NT * G::HP];     // ntHash of the 16 k-mers of each thread
+    uint64_t pk_hash[G::PKCAP];       // xxh3 of each pick
+    uint32_t pk_pos[G::PKCAP];        // local position | start-rank << 16 | valid << 31
+    u32x2 tb0[256];                   // 4-base aggregate table (fw, rc)
+    u32x2 tin[4], tout[4], tsb[4];    // rolling-step tables: incoming / outgoing base, single base
+    uint32_t codes[G::NV + 6];        // 16 bases x 2 bit per word
+    uint32_t inv[(G::NV + 6 + 1) / 2 + 2];  // non-ACGT bits, 32 positions per word
+    uint32_t brk[G::NBW + 2];         // position is a record start or lies outside every effective sequence
+    uint32_t dead[G::NBW + 2];        // no window may start here
+    uint32_t ustart[G::NBW + 2];      // a unit (record or pair) starts here
+    uint32_t lastpick[G::NT];
+    uint32_t poff[G::NT];             // exclusive pick offset | exclusive start-rank << 16
+    uint32_t emk[G::NT];              // emit mask | ustart bits << 16
+    uint32_t vmask[G::PKCAP / 32], hmask[G::PKCAP / 32];
+    uint32_t roff[G::MAXR + 1];       // record offsets relative to the tile origin
+    uint32_t ufirst[G::MAXR + 2];     // first pick index of each unit
+    uint32_t rkfirst[G::MAXR + 2];    // first pick index by start-rank
+    uint16_t ustartpos[G::MAXR + 2];
+    uint32_t wsum[16];
+    uint32_t npicks;
+};
+
+template <class G>
+struct TilePriv {
+    uint32_t c0;           // own 16 codes
+    uint32_t efw, erc;     // own aggregates
+    uint32_t h[16];        // ntHash of own 16 k-mers
+    uint32_t rel4[4];      // pick position relative to 16t, 8 bits per window
+    uint32_t emask;        // windows that emit a pick
+    uint32_t ust16;        // unit-start bits of own 16 positions
+    uint32_t valid16;
+    uint32_t pickoff, rankoff;
+};
+
+// ------------------------------------------------------------------ tables
+template <class G>
+DCN_HD void init_tables(int t, TileSmem<G> &s) {
+    // tb0[b]: bases c0..c3 of byte b at group 0: fw = XOR rotl(F[c_m], 30-m), rc = XOR rotl(F[c_m^2], m)
+    uint32_t fw = 0, rc = 0;
+    for (int m = 0; m < 4; m++) {
+        uint32_t c = ((uint32_t)t >> (2 * m)) & 3u;
+        fw ^= rotl32(nt_f(c), (uint32_t)(30 - m));
+        rc ^= rotl32(nt_f(c ^ 2u), (uint32_t)m);
+    }
+    s.tb0[t].x = fw; s.tb0[t].y = rc;
+    if (t < 4) {
+        uint32_t c = (uint32_t)t;
+        s.tin[t].x = nt_f(c);                          s.tin[t].y = rotl32(nt_f(c ^ 2u), G::K);
+        s.tout[t].x = rotl32(nt_f(c), G::K);           s.tout[t].y = nt_f(c ^ 2u);
+        s.tsb[t].x = rotl32(nt_f(c), 15);              s.tsb[t].y = rotl32(nt_f(c ^ 2u), 15);
+    }
+}
+
+// ------------------------------------------------------------------ phase 1: load + convert
+// FILTER flavour: packed-seq lossy code (b >> 1) & 3, src/filter_common.rs:238.
+// INDEX flavour: IUPAC map first (src/minimizers.rs:24-43), then the same packing.
+DCN_HD uint32_t code_index_flavour(uint32_t b) {
+    // letters only differ from the lossy code when non-ACGT: R,S,K,D,V,G -> G(3); A,W -> A(0); T -> T(2); else C(1)
+    uint32_t idx = b & 0x1fu;
+    bool letter = (b & 0xC0u) == 0x40u && idx >= 1 && idx <= 26;
+    const uint32_t MG = (1u << 18) | (1u << 19) | (1u << 11) | (1u << 4) | (1u << 22) | (1u << 7);
+    const uint32_t MA = (1u << 1) | (1u << 23);
+    const uint32_t MT = (1u << 20);
+    if (!letter) return 1u;
+    if ((MG >> idx) & 1u) return 3u;
+    if ((MA >> idx) & 1u) return 0u;
+    if ((MT >> idx) & 1u) return 2u;
+    return 1u;
+}
+
+template <class G, int FLAV>
+DCN_HD void convert_vector(int v, TileSmem<G> &s, const uint8_t *bases, uint64_t n_bases, uint64_t origin,
+                           uint32_t &codes_out, uint32_t &efw_out, uint32_t &erc_out) {
+    // `bases`, `n_bases` and `origin` are relative to base0 here (the caller rebased them)
+    uint64_t g = origin + 16ull * (uint64_t)v;
+    uint32_t w[4];
+    if (g + 16 <= n_bases) {
+#ifdef __CUDA_ARCH__
+        uint4 q = __ldg(reinterpret_cast<const uint4 *>(bases + g));
+#else
+        u32x4 q = *reinterpret_cast<const u32x4 *>(bases + g);
+#endif
+        w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
+    } else {
+        for (int i = 0; i < 4; i++) {
+            uint32_t x = 0;
+            for (int b = 0; b < 4; b++) {
+                uint64_t a = g + (uint64_t)(4 * i + b);
+                uint32_t byte = a < n_bases ? bases[a] : 0u;
+                x |= byte << (8 * b);
+            }
+            w[i] = x;
+        }
+    }
+    uint32_t codes = 0, inv16 = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t x = w[i];
+        uint32_t c = (x >> 1) & 0x03030303u;
+        // exact ACGT/acgt test: (byte & 0xDF) must equal the letter its own code stands for
+        uint32_t c0b = c & 0x01010101u, c1b = (c >> 1) & 0x01010101u;
+        uint32_t e = 0x41414141u + c0b * 2u + c1b * 0x13u - (c0b & c1b) * 0xFu;
+        uint32_t d = (x & 0xDFDFDFDFu) ^ e;
+        uint32_t nz = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+        uint32_t inv4 = (nz * 0x00204081u) >> 28;
+        if (FLAV == FLAVOUR_INDEX) {
+            uint32_t cc = 0;
+            for (int b = 0; b < 4; b++) cc |= code_index_flavour((x >> (8 * b)) & 0xffu) << (8 * b);
+            c = cc;
+        }
+        uint32_t packed8 = (c * 0x01041040u) >> 24;
+        codes |= packed8 << (8 * i);
+        inv16 |= inv4 << (4 * i);
+    }
+    // aggregates over the 16 bases: E_fw = XOR rotl(F[c_i], 30-i), E_rc = XOR rotl(F[c_i^2], i)
+    uint32_t efw = 0, erc = 0;
+#pragma unroll
+    for (int gI = 0; gI < 4; gI++) {
+        u32x2 e = s.tb0[(codes >> (8 * gI)) & 0xffu];
+        efw ^= rotr32(e.x, 4 * gI);
+        erc ^= rotl32(e.y, 4 * gI);
+    }
+    u32x2 last = s.tsb[codes >> 30];
+    u32x4 a;
+    a.x = efw; a.y = erc;
+    a.z = rot16(efw ^ last.x);   // role "bases 16..30 of the k-mer that starts one thread to the left"
+    a.w = rot16(erc ^ last.y);
+    s.ag[v] = a;
+    s.codes[v] = codes;
+    reinterpret_cast<uint16_t *>(s.inv)[v] = (uint16_t)inv16;
+    codes_out = codes; efw_out = efw; erc_out = erc;
+}
+
+template <class G, int FLAV>
+DCN_HD void phase_convert(int t, TileSmem<G> &s, TilePriv<G> &pv, const uint8_t *bases, uint64_t n_bases,
+                          uint64_t origin) {
+    convert_vector<G, FLAV>(t, s, bases, n_bases, origin, pv.c0, pv.efw, pv.erc);
+    if (t < G::NV - G::NT) {
+        uint32_t a, b, c;
+        convert_vector<G, FLAV>(G::NT + t, s, bases, n_bases, origin, a, b, c);
+    }
+    if (t < 6) {  // zero pad words read by the last threads
+        s.codes[G::NV + t] = 0;
+        if (t < 2) s.inv[(G::NV + 1) / 2 + t] = 0;
+    }
+}
+
+// ------------------------------------------------------------------ phase 2: rolling ntHash
+template <class G>
+DCN_HD void phase_hash(int t, TileSmem<G> &s, TilePriv<G> &pv) {
+    const uint32_t c0 = pv.c0, c1 = s.codes[t + 1], c2 = s.codes[t + 2];
+    u32x4 nb = s.ag[t + 1];
+    // k-mer at 16t covers own bases 0..15 and the neighbour's bases 0..K-17.  The aggregates are
+    // built for K = 31 (neighbour contributes 15 bases); for K < 31 peel the surplus bases off.
+    uint32_t fw = pv.efw ^ nb.z, rc = pv.erc ^ nb.w;
+    if (G::K < 31) {
+        // aggregates carry rotation (30 - i) for fw; a K-mer needs (K-1-i): rotate right by 31-K.
+        // Remove neighbour bases K-16 .. 14 (indices 16+j in k-mer coordinates).
+        for (int j = G::K - 16; j < 15; j++) {
+            uint32_t c = (c1 >> (2 * j)) & 3u;
+            fw ^= rotl32(nt_f(c), (uint32_t)((30 - 16 - j) & 31));
+            rc ^= rotl32(nt_f(c ^ 2u), (uint32_t)(16 + j));
+        }
+        fw = rotr32(fw, 31 - G::K);
+    }
+    pv.h[0] = fw + rc;
+#pragma unroll
+    for (int i = 1; i < 16; i++) {
+        uint32_t oc = (c0 >> (2 * (i - 1))) & 3u;
+        int in_idx = G::K - 1 + i;  // base index relative to 16t, in [K, K+14]
+        uint32_t ic = in_idx < 32 ? (c1 >> (2 * (in_idx - 16))) & 3u : (c2 >> (2 * (in_idx - 32))) & 3u;
+        u32x2 o = s.tout[oc], n = s.tin[ic];
+        fw = rotl32(fw, 1) ^ o.x ^ n.x;
+        rc = rotr32(rc ^ o.y ^ n.y, 1);
+        pv.h[i] = fw + rc;
+    }
+    uint32_t *row = &s.hrow[t * G::HP];
+#pragma unroll
+    for (int i = 0; i < 16; i++) row[i] = pv.h[i];
+}
+
+// ------------------------------------------------------------------ phase 3: window minima
+DCN_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+DCN_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// 64-bit window of a bit array starting at bit 16*t
+DCN_HD uint64_t bits64_at(const uint32_t *arr, int t) {
+    int w0 = t >> 1;
+    uint32_t sh = (uint32_t)(t & 1) * 16u;
+    uint32_t a = arr[w0], b = arr[w0 + 1], c = arr[w0 + 2];
+    uint32_t lo = fshr(a, b, sh), hi = fshr(b, c, sh);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+template <class G>
+DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
+    pv.emask = 0; pv.valid16 = 0; pv.ust16 = 0;
+    pv.rel4[0] = pv.rel4[1] = pv.rel4[2] = pv.rel4[3] = 0;
+    if (t >= G::NT - 1) { s.lastpick[t] = 0xFFFFFFFFu; return; }
+
+    uint32_t hv[30];
+#pragma unroll
+    for (int i = 0; i < 16; i++) hv[i] = pv.h[i];
+    const uint32_t *nrow = &s.hrow[(t + 1) * G::HP];
+#pragma unroll
+    for (int i = 0; i < 14; i++) hv[16 + i] = nrow[i];
+
+    // left keys: (h >> 16) << 16 | i  -> min = smallest hash, leftmost;  SURVEY A.3 steps 1-2
+    uint32_t key[30], oL[16], oR[16];
+#pragma unroll
+    for (int i = 0; i < 30; i++) key[i] = (hv[i] & 0xFFFF0000u) | (uint32_t)i;
+    {
+#pragma unroll
+        for (int i = 13; i >= 0; i--) key[i] = umin32(key[i], key[i + 1]);      // suffix min of block A
+#pragma unroll
+        for (int i = 16; i < 30; i++) key[i] = umin32(key[i], key[i - 1]);      // prefix min of block B
+        oL[0] = key[0];
+#pragma unroll
+        for (int i = 1; i < 15; i++) oL[i] = umin32(key[i], key[14 + i]);
+        oL[15] = key[29];
+    }
+    // right keys: ~(h >> 16) << 16 | i -> max = smallest hash, rightmost;  A.3 step 3
+#pragma unroll
+    for (int i = 0; i < 30; i++) key[i] = (~hv[i] & 0xFFFF0000u) | (uint32_t)i;
+    {
+#pragma unroll
+        for (int i = 13; i >= 0; i--) key[i] = umax32(key[i], key[i + 1]);
+#pragma unroll
+        for (int i = 16; i < 30; i++) key[i] = umax32(key[i], key[i - 1]);
+        oR[0] = key[0];
+#pragma unroll
+        for (int i = 1; i < 15; i++) oR[i] = umax32(key[i], key[14 + i]);
+        oR[15] = key[29];
+    }
+
+    // canonical strand: #(T|G) > #(A|C) over the L bases of the window (A.3 step 4).
+    // T/G <=> bit 1 of the 2-bit code.
+    const uint32_t c0 = pv.c0, c1 = s.codes[t + 1], c2 = s.codes[t + 2], c3 = s.codes[t + 3];
+    auto tgbit = [&](int b) -> uint32_t {  // TG bit of base b (0..63) relative to 16t
+        uint32_t w = b < 16 ? c0 : b < 32 ? c1 : b < 48 ? c2 : c3;
+        return (w >> (2 * (b & 15) + 1)) & 1u;
+    };
+    uint32_t cnt = 0;
+    {
+        // bases 0 .. L-1
+        cnt = popc32(c0 & 0xAAAAAAAAu) + popc32(c1 & 0xAAAAAAAAu);
+        constexpr int rem = G::L - 32;  // bases 32 .. L-1 live in c2 (and c3 if L > 48)
+        if (rem >= 16) {
+            cnt += popc32(c2 & 0xAAAAAAAAu);
+            constexpr int rem3 = rem - 16;
+            if (rem3 > 0) cnt += popc32(c3 & (rem3 >= 16 ? 0xAAAAAAAAu : (0xAAAAAAAAu & ((1u << (2 * (rem3 & 15))) - 1u))));
+        } else if (rem > 0) {
+            cnt += popc32(c2 & (0xAAAAAAAAu & ((1u << (2 * (rem & 15))) - 1u)));
+        }
+    }
+    uint32_t rel[16];
+    uint32_t neq = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        if (i > 0) cnt += tgbit(i - 1 + G::L) - tgbit(i - 1);
+        bool canonical = 2 * cnt > (uint32_t)G::L;
+        rel[i] = (canonical ? oL[i] : oR[i]) & 0xFFFFu;
+        if (i > 0 && rel[i] != rel[i - 1]) neq |= 1u << i;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; i++) pv.rel4[i >> 2] |= rel[i] << (8 * (i & 3));
+
+    // window validity from the record structure: window j is valid iff j is not dead and no
+    // break bit lies in (j, j + L - 1].
+    uint64_t bw = bits64_at(s.brk, t);
+    uint32_t dead16 = (uint32_t)bits64_at(s.dead, t) & 0xFFFFu;
+    uint64_t m = bw >> 1;
+    // smear right by L-2: bit j of x = OR of m[j .. j+L-2]
+    uint64_t x = m;
+    {
+        int have = 0;  // current smear reach
+        // doubling while reach*2+1 <= L-2
+        int target = G::L - 2;
+        int sh = 1;
+        while (have + sh <= target) { x |= x >> sh; have += sh; sh <<= 1; }
+        if (have < target) { x |= x >> (target - have); }
+    }
+    uint32_t invalid16 = ((uint32_t)x | dead16) & 0xFFFFu;
+    uint32_t valid16 = ~invalid16 & 0xFFFFu;
+    uint32_t first16 = (uint32_t)bw & ~dead16 & 0xFFFFu;      // first window of a record: always emits
+    pv.valid16 = valid16;
+    pv.ust16 = (uint32_t)bits64_at(s.ustart, t) & 0xFFFFu;
+    // emit(j) = valid(j) && (first(j) || (valid(j-1) && pick(j) != pick(j-1)));  A.3 step 5
+    pv.emask = valid16 & (first16 | ((valid16 << 1) & neq));  // bit 0 completed in phase_emit_fix
+    s.lastpick[t] = (valid16 & 0x8000u) ? (uint32_t)(16 * t) + rel[15] : 0xFFFFFFFFu;
+}
+
+// bit 0 of the emit mask needs the last pick of the thread to the left
+template <class G>
+DCN_HD uint32_t phase_emit_fix(int t, TileSmem<G> &s, TilePriv<G> &pv) {
+    if (t < G::NT - 1 && (pv.valid16 & 1u) && !(pv.emask & 1u)) {
+        uint32_t lp = t > 0 ? s.lastpick[t - 1] : 0xFFFFFFFFu;
+        uint32_t mine = (uint32_t)(16 * t) + (pv.rel4[0] & 0xFFu);
+        if (lp != 0xFFFFFFFFu && lp != mine) pv.emask |= 1u;
+    }
+    return popc32(pv.emask) | (popc32(pv.ust16) << 16);
+}
+
+// ------------------------------------------------------------------ phase 4: compact picks
+template <class G>
+DCN_HD void phase_emit(int t, TileSmem<G> &s, TilePriv<G> &pv, uint32_t excl, uint32_t total) {
+    pv.pickoff = excl & 0xFFFFu;
+    pv.rankoff = excl >> 16;
+    s.poff[t] = excl;
+    s.emk[t] = pv.emask | (pv.ust16 << 16);
+    if (t == 0) s.npicks = total & 0xFFFFu;
+    const uint32_t em = pv.emask;
+    uint32_t idx = pv.pickoff;
+#pragma unroll
+    for (int i = 0; i < 16; i++) {   // static indexing keeps pv in registers
+        if (em & (1u << i)) {
+            uint32_t rel = (pv.rel4[i >> 2] >> (8 * (i & 3))) & 0xFFu;
+            uint32_t rank = pv.rankoff + popc32(pv.ust16 & ((2u << i) - 1u)) - 1u;
+            s.pk_pos[idx++] = ((uint32_t)(16 * t) + rel) | ((rank & 0x7FFFu) << 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ pick -> canonical k-mer -> xxh3
+template <class G>
+DCN_HD bool pick_kmer_valid(const TileSmem<G> &s, uint32_t p) {
+    // non-ACGT bits of [p, p+K): src/filter_common.rs:275-286 / src/minimizers.rs:157-160
+    uint32_t w0 = p >> 5, sh = p & 31u;
+    uint32_t a = s.inv[w0], b = s.inv[w0 + 1];
+    uint32_t bits = fshr(a, b, sh);
+    return (bits & ((G::K >= 32) ? 0xFFFFFFFFu : ((1u << (G::K & 31)) - 1u))) == 0;
+}
+
+template <class G>
+DCN_HD uint64_t pick_kmer_fw(const TileSmem<G> &s, uint32_t p) {
+    uint32_t w0 = p >> 4, sh = 2u * (p & 15u);
+    uint32_t a = s.codes[w0], b = s.codes[w0 + 1], c = s.codes[w0 + 2];
+    uint32_t lo = fshr(a, b, sh), hi = fshr(b, c, sh);
+    uint64_t v = ((uint64_t)hi << 32) | lo;
+    return G::K >= 32 ? v : v & ((1ULL << (2 * (G::K & 31))) - 1ULL);
+}
+
+template <class G>
+DCN_HD uint64_t pick_hash(const TileSmem<G> &s, uint32_t p) {
+    uint64_t fw = pick_kmer_fw<G>(s, p);
+    uint64_t rc = revcomp_2bit(fw, G::K);
+    return xxh3_u64(fw < rc ? fw : rc);
+}
+
+// ------------------------------------------------------------------ table probe
+struct Bucket { uint64_t k0, k1, k2, k3; };
+
+DCN_HD Bucket load_bucket(const uint64_t *slots, uint64_t b) {
+    Bucket r;
+    const uint64_t *p = slots + 4 * b;
+#ifdef __CUDA_ARCH__
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.k0), "=l"(r.k1), "=l"(r.k2), "=l"(r.k3) : "l"(p));
+#else
+    r.k0 = p[0]; r.k1 = p[1]; r.k2 = p[2]; r.k3 = p[3];
+#endif
+    return r;
+}
+DCN_HD void prefetch_bucket(const uint64_t *slots, uint64_t b) {
+#ifdef __CUDA_ARCH__
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(slots + 4 * b));
+#else
+    (void)slots; (void)b;
+#endif
+}
+// continue a probe whose first bucket has been loaded
+DCN_HD bool table_contains_from(const TableView &tv, uint64_t h, uint64_t b, Bucket k) {
+    if (h == DCN_EMPTY) return tv.has_empty_key != 0;
+    for (;;) {
+        if (k.k0 == h || k.k1 == h || k.k2 == h || k.k3 == h) return true;
+        if (k.k0 == DCN_EMPTY || k.k1 == DCN_EMPTY || k.k2 == DCN_EMPTY || k.k3 == DCN_EMPTY) return false;
+        if (++b == tv.n_buckets) b = 0;
+        k = load_bucket(tv.slots, b);
+    }
+}
+DCN_HD bool table_contains(const TableView &tv, uint64_t h) {
+    uint64_t b = table_bucket(h, tv.n_buckets);
+    return table_contains_from(tv, h, b, load_bucket(tv.slots, b));
+}
+
+// popcount of bits [a, b) of a bit array
+DCN_HD uint32_t popc_range(const uint32_t *m, uint32_t a, uint32_t b) {
+    uint32_t n = 0;
+    while (a < b) {
+        uint32_t w = a >> 5, lo = a & 31u;
+        uint32_t end = (w + 1) << 5;
+        if (end > b) end = b;
+        uint32_t width = end - a;
+        uint32_t mask = width == 32 ? 0xFFFFFFFFu : (((1u << width) - 1u) << lo);
+        n += popc32(m[w] & mask);
+        a = end;
+    }
+    return n;
+}
+
+// set bits [a, b) of a 32-bit-word bit array (shared memory on device)
+DCN_HD void set_bits(uint32_t *arr, uint32_t a, uint32_t b) {
+    while (a < b) {
+        uint32_t w = a >> 5, lo = a & 31u;
+        uint32_t end = (w + 1) << 5;
+        if (end > b) end = b;
+        uint32_t width = end - a;
+        uint32_t mask = width == 32 ? 0xFFFFFFFFu : (((1u << width) - 1u) << lo);
+#ifdef __CUDA_ARCH__
+        atomicOr(&arr[w], mask);
+#else
+        arr[w] |= mask;
+#endif
+        a = end;
+    }
+}
+
+// ------------------------------------------------------------------ filter parameters
+struct FilterParams {
+    const uint8_t *bases;     // concatenated ASCII records (device), 16-byte aligned
+    uint64_t base0;           // absolute offset of bases[0] (multiple of 16); rec_off is absolute
+    uint64_t n_bases;         // absolute end offset: bases[x - base0] is readable for base0 <= x < n_bases
+    const uint64_t *rec_off;  // n_rec + 1 offsets (device)
+    uint32_t n_rec;
+    uint32_t rpu;             // records per unit: 1 (single) or 2 (pair: records 2i, 2i+1)
+    uint32_t n_units;
+    uint32_t prefix_len;      // src/filter_common.rs:222-226
+    uint32_t abs_thr;
+    double rel_thr;
+    int deplete;
+    TableView table;
+    uint8_t *keep;            // per unit
+    uint32_t *hits;
+    uint32_t *total;
+};
+
+// effective end of a record (src/filter_common.rs:217-229): raw-length guard, prefix, one '\n'
+template <class G, int FLAV>
+DCN_HD uint32_t effective_len(const uint8_t *bases, uint64_t gstart, uint32_t len, uint32_t prefix_len) {
+    if (len < (uint32_t)G::K) return 0;
+    if (FLAV == FLAVOUR_INDEX) return len;
+    uint32_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;
+    if (n > 0 && bases[gstart + n - 1] == (uint8_t)'\n') n--;
+    return n;
+}
+
+// ------------------------------------------------------------------ short-unit tile driver
+// Units [u_begin, u_end) are whole (record or pair) and fit the tile: every base of every unit
+// lies in [origin, origin + BCAP).  Ex provides par(f) = run f for every thread then barrier,
+// and scan(get, put) = block-wide exclusive sum.
+template <class G, class Ex>
+DCN_HD void filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
+    using Priv = TilePriv<G>;
+    const uint32_t rpu = P.rpu;
+    const uint32_t r_begin = u_begin * rpu;
+    const uint32_t n_rec_t = (u_end - u_begin) * rpu;
+    const uint32_t n_units_t = u_end - u_begin;
+    const uint64_t first_start = P.rec_off[r_begin] - P.base0;
+    const uint64_t origin = first_start & ~15ull;   // relative to base0, like every offset below
+    const uint64_t n_rel = P.n_bases - P.base0;
+
+    ex.par([&](int t, Priv &) {
+        for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
+        for (int i = t; i < G::PKCAP / 32; i += G::NT) { s.vmask[i] = 0; s.hmask[i] = 0; }
+    });
+    ex.par([&](int t, Priv &) {
+        for (uint32_t i = (uint32_t)t; i < n_rec_t; i += G::NT) {
+            uint64_t gs = P.rec_off[r_begin + i] - P.base0, ge = P.rec_off[r_begin + i + 1] - P.base0;
+            uint32_t sL = (uint32_t)(gs - origin), eL = (uint32_t)(ge - origin);
+            uint32_t eff = sL + effective_len<G, FLAVOUR_FILTER>(P.bases, gs, eL - sL, P.prefix_len);
+            s.roff[i] = sL;
+            set_bits(s.brk, sL, sL + 1);
+            if (i % rpu == 0) { set_bits(s.ustart, sL, sL + 1); s.ustartpos[i / rpu] = (uint16_t)sL; }
+            if (eff < eL) { set_bits(s.dead, eff, eL); set_bits(s.brk, eff, eL); }
+            if (i == 0 && sL > 0) { set_bits(s.dead, 0, sL); set_bits(s.brk, 0, sL); }
+            if (i == n_rec_t - 1) {
+                s.roff[n_rec_t] = eL;
+                set_bits(s.dead, eL, G::NBW * 32); set_bits(s.brk, eL, G::NBW * 32);
+            }
+        }
+    });
+    ex.par([&](int t, Priv &pv) { phase_convert<G, FLAVOUR_FILTER>(t, s, pv, P.bases, n_rel, origin); });
+    ex.par([&](int t, Priv &pv) { phase_hash<G>(t, s, pv); });
+    ex.par([&](int t, Priv &pv) { phase_slide<G>(t, s, pv); });
+    ex.scan([&](int t, Priv &pv) { return phase_emit_fix<G>(t, s, pv); },
+            [&](int t, Priv &pv, uint32_t excl, uint32_t total) { phase_emit<G>(t, s, pv, excl, total); });
+    const uint32_t npicks = s.npicks;
+
+    // first pick index of every unit, and of every distinct unit-start position (rank)
+    ex.par([&](int t, Priv &) {
+        for (uint32_t u = (uint32_t)t; u < n_units_t; u += G::NT) {
+            uint32_t pos = s.ustartpos[u];
+            uint32_t tt = pos >> 4, ii = pos & 15u;
+            // a unit that starts in the last 16-position chunk or beyond has no window in this tile
+            bool tail = tt >= (uint32_t)(G::NT - 1);
+            uint32_t po = tail ? 0u : s.poff[tt], em = tail ? 0u : s.emk[tt];
+            uint32_t uf = tail ? npicks : (po & 0xFFFFu) + popc32(em & 0xFFFFu & ((1u << ii) - 1u));
+            s.ufirst[u] = uf;
+            bool last_at_pos = (u + 1 == n_units_t) || (s.ustartpos[u + 1] != pos);
+            if (last_at_pos && !tail) {
+                uint32_t rank = (po >> 16) + popc32((em >> 16) & ((1u << ii) - 1u));
+                s.rkfirst[rank] = uf;
+            }
+            if (u == 0) s.ufirst[n_units_t] = npicks;
+        }
+    });
+
+    // hash every pick; start the table access early
+    ex.par([&](int t, Priv &) {
+        for (uint32_t idx = (uint32_t)t; idx < npicks; idx += G::NT) {
+            uint32_t pp = s.pk_pos[idx];
+            uint32_t p = pp & 0xFFFFu;
+            if (pick_kmer_valid<G>(s, p)) {
+                uint64_t h = pick_hash<G>(s, p);
+                s.pk_hash[idx] = h;
+                s.pk_pos[idx] = pp | 0x80000000u;
+                prefetch_bucket(P.table.slots, table_bucket(h, P.table.n_buckets));
+            }
+        }
+    });
+    // probe + distinct-hit test (src/filter_common.rs:143-145: contains && seen.insert)
+    ex.par([&](int t, Priv &) {
+        const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
+        for (uint32_t r = 0; r < rounds; r++) {
+            uint32_t idx = r * G::NT + (uint32_t)t;
+            bool valid = false, hit = false;
+            if (idx < npicks) {
+                uint32_t pp = s.pk_pos[idx];
+                valid = (pp & 0x80000000u) != 0;
+                if (valid) {
+                    uint64_t h = s.pk_hash[idx];
+                    uint64_t b = table_bucket(h, P.table.n_buckets);
+                    Bucket bk = load_bucket(P.table.slots, b);
+                    uint32_t first = s.rkfirst[(pp >> 16) & 0x7FFFu];
+                    bool dup = false;
+                    for (uint32_t j = first; j < idx; j++)
+                        dup |= (s.pk_hash[j] == h) && (s.pk_pos[j] & 0x80000000u);
+                    hit = !dup && table_contains_from(P.table, h, b, bk);
+                }
+            }
+            ex.ballot2(t, idx, valid, hit, s.vmask, s.hmask);
+        }
+    });
+    // per-unit totals and the threshold test
+    ex.par([&](int t, Priv &) {
+        for (uint32_t u = (uint32_t)t; u < n_units_t; u += G::NT) {
+            uint32_t a = s.ufirst[u], b = s.ufirst[u + 1];
+            uint32_t total = popc_range(s.vmask, a, b);
+            uint32_t hits = popc_range(s.hmask, a, b);
+            uint32_t gu = u_begin + u;
+            P.total[gu] = total;
+            P.hits[gu] = hits;
+            P.keep[gu] = meets_criteria(hits, total, P.abs_thr, P.rel_thr, P.deplete) ? 1 : 0;
+        }
+    });
+}
+
+// All units whose first base lies in one tile: runs of short units go through
+// filter_short_tile; long units are skipped here (they are cut into chunks by the long path).
+template <class G, class Ex>
+DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const PlanCfg &cfg, uint32_t u_first,
+                        uint32_t u_end) {
+    const uint64_t rpu = P.rpu;
+    uint32_t u = u_first;
+    while (u < u_end) {
+        uint64_t len = P.rec_off[(uint64_t)(u + 1) * rpu] - P.rec_off[(uint64_t)u * rpu];
+        if (len > cfg.max_short) { u++; continue; }
+        uint32_t v = u + 1;
+        while (v < u_end && (uint64_t)(v - u + 1) * rpu <= (uint64_t)G::MAXR &&
+               P.rec_off[(uint64_t)(v + 1) * rpu] - P.rec_off[(uint64_t)v * rpu] <= cfg.max_short)
+            v++;
+        filter_short_tile<G>(ex, s, P, u, v);
+        u = v;
+    }
+}
+
+}  // namespace dcn

@@ -1,0 +1,134 @@
+/*
+ * deacon_cuda.h -- C ABI of the B200-native filter hot path of Deacon (deacon-server fork).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no CUDA/torch types.  Every entry point
+ * cites the reference interface (file:line under /root/reference) it replaces; INTEGRATION.md shows
+ * the Rust `extern "C"` block and the call sites a maintainer would change.
+ *
+ * Conventions
+ *   - Return value: 0 = ok, negative = error (DCN_ERR_*); dcn_last_error(ctx) gives the text.
+ *     Nothing here aborts; there is NO CPU fallback -- without a CUDA device dcn_ctx_create fails.
+ *   - The caller owns every host buffer (inputs and pre-sized outputs); the library owns device
+ *     memory inside dcn_ctx.  A dcn_ctx is bound to one GPU; calls on one ctx are serialised by the
+ *     caller (the reference's server holds a mutex for a whole request, src/server.rs:121,145);
+ *     different ctxs are independent and may be driven from different host threads.
+ *   - Records are passed the way the reference's batch engine holds them (src/remote_filter.rs:727-755):
+ *     one concatenated byte buffer `bases` + `rec_off[n_rec + 1]` byte offsets.  With `paired != 0`
+ *     records 2i and 2i+1 are the mates of pair i and per-unit outputs have n_rec / 2 entries.
+ *   - `*_device` variants take device pointers (inputs already in HBM, outputs left in HBM) and a
+ *     cudaStream_t passed as void* (NULL = the ctx stream); they are asynchronous on that stream.
+ */
+#ifndef DEACON_CUDA_H
+#define DEACON_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dcn_ctx dcn_ctx;
+
+enum {
+    DCN_OK = 0,
+    DCN_ERR_CUDA = -1,        /* a CUDA runtime call failed (text in dcn_last_error) */
+    DCN_ERR_ARG = -2,         /* invalid argument */
+    DCN_ERR_NO_INDEX = -3,    /* no index resident in this ctx */
+    DCN_ERR_UNSUPPORTED = -4, /* (k, w) outside what the kernels implement */
+    DCN_ERR_NOMEM = -5,
+    DCN_ERR_OVERFLOW = -6     /* an internal table overflowed even after retries */
+};
+
+enum { DCN_FLAVOUR_FILTER = 0, DCN_FLAVOUR_INDEX = 1 };
+
+/* ---- context ------------------------------------------------------------------------------- */
+int dcn_device_count(void);
+/* Replaces nothing in the reference (it has no device); one ctx per GPU. */
+dcn_ctx *dcn_ctx_create(int device);
+void dcn_ctx_destroy(dcn_ctx *ctx);
+/* ctx may be NULL: returns the error text of the last failed dcn_ctx_create on this thread. */
+const char *dcn_last_error(dcn_ctx *ctx);
+/* Pinned host memory for callers that want full PCIe rate on the *_batch entry points. */
+void *dcn_host_alloc(size_t bytes);
+void dcn_host_free(void *p);
+
+/* ---- B4: index residency --------------------------------------------------------------------
+ * Replaces load_minimizer_hashes' insert loop (src/index.rs:98-105), the Arc<FxHashSet<u64>> held by
+ * FilterProcessor (src/local_filter.rs:156,631) and the server's static INDEX (src/server.rs:17,68-86).
+ * `keys` need not be sorted or unique.  k, w are the IndexHeader fields (src/index.rs:17-22). */
+int dcn_index_upload(dcn_ctx *ctx, const uint64_t *keys, uint64_t n_keys, uint8_t k, uint8_t w);
+int dcn_index_upload_device(dcn_ctx *ctx, const uint64_t *d_keys, uint64_t n_keys, uint8_t k, uint8_t w,
+                            void *stream);
+/* n_keys = distinct keys resident (what `deacon index info` prints, src/index.rs:311-340). */
+int dcn_index_info(dcn_ctx *ctx, uint64_t *n_keys, uint8_t *k, uint8_t *w, uint64_t *table_bytes);
+/* Table load factor used by the next upload (default 0.5; 4 keys per 32-byte bucket). */
+int dcn_index_set_load_factor(dcn_ctx *ctx, double load);
+
+/* ---- B1: batch classify on raw sequences ------------------------------------------------------
+ * Replaces FilterProcessor::should_keep_sequence / should_keep_pair (src/local_filter.rs:221-285) and
+ * the par_iter extraction + check pair of the batch engine (src/remote_filter.rs:762-790, 963-986,
+ * 1219-1241): per unit (keep, hit_count, total_minimizers).  k, w come from the resident index.
+ * abs_thr / rel_thr / deplete / prefix_len: src/filter_common.rs:84-112, 222-226. */
+int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, int paired,
+                     uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
+                     uint8_t *keep, uint32_t *hits, uint32_t *total);
+/* d_bases must be 16-byte aligned; n_bases = rec_off[n_rec] (known to the caller, saves a sync). */
+int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                            uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
+                            int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream);
+
+/* ---- B2: batch classify on pre-hashed records --------------------------------------------------
+ * Replaces unpaired_should_keep / paired_should_keep (src/remote_filter.rs:230-301), i.e. the body of
+ * the server's POST handlers (src/server.rs:120-164).  A paired request carries one pooled hash list
+ * per pair (src/filter_common.rs:312-348), so both forms are "one hash list per record" here. */
+int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_off, uint32_t n_rec,
+                     uint32_t abs_thr, double rel_thr, int deplete,
+                     uint8_t *keep, uint32_t *hits, uint32_t *total);
+int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t *d_rec_off, uint32_t n_rec,
+                            uint32_t abs_thr, double rel_thr, int deplete,
+                            uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream);
+
+/* ---- B3: extraction only ------------------------------------------------------------------------
+ * Replaces get_minimizer_hashes_and_positions (src/filter_common.rs:211, flavour FILTER) and
+ * compute_minimizer_hashes / fill_minimizer_hashes (src/minimizers.rs:53,125, flavour INDEX).
+ * Output is CSR: out_off[n_rec + 1] offsets into out_hashes / out_pos (positions relative to the
+ * record's effective sequence; out_pos may be NULL).  Returns DCN_ERR_OVERFLOW if out_cap is too small;
+ * out_off[n_rec] then still holds the required capacity. */
+int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec,
+                uint8_t k, uint8_t w, uint32_t prefix_len, float entropy_thr,
+                uint64_t *out_hashes, uint32_t *out_pos, uint64_t *out_off, uint64_t out_cap);
+
+/* ---- index build (config 4) ---------------------------------------------------------------------
+ * Replaces index::build's extraction + FxHashSet::extend (src/index.rs:225-284): index-flavour
+ * extraction of every record, radix sort + unique on the GPU.  The sorted unique key set stays in the
+ * ctx; fetch it with dcn_index_build_keys (for write_minimizers, src/index.rs:130-164) and/or make it
+ * the resident index with make_resident != 0. */
+int dcn_index_build(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec,
+                    uint8_t k, uint8_t w, float entropy_thr, int make_resident, uint64_t *n_keys_out);
+int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                           uint64_t n_bases, uint8_t k, uint8_t w, float entropy_thr, int make_resident,
+                           uint64_t *n_keys_out, void *stream);
+int dcn_index_build_keys(dcn_ctx *ctx, uint64_t *out_keys, uint64_t cap);
+/* device pointer to the sorted unique keys of the last build (valid until the next build) */
+const uint64_t *dcn_index_build_keys_device(dcn_ctx *ctx);
+
+/* ---- a13: the six summary counters (ProcessingStats, src/local_filter.rs:179-187) ----------------
+ * counters[6] = {total_seqs, filtered_seqs, total_bp, output_bp, filtered_bp, output_seq_counter},
+ * accumulated over every dcn_filter_batch call since the last reset.  These are the values the
+ * multi-GPU driver all-reduces over NCCL. */
+int dcn_stats_get(dcn_ctx *ctx, uint64_t counters[6]);
+int dcn_stats_reset(dcn_ctx *ctx);
+
+/* ---- measurement helpers ------------------------------------------------------------------------
+ * Milliseconds of the last host-pointer call: H2D copies, kernels, D2H copies (CUDA events). */
+int dcn_last_timing(dcn_ctx *ctx, float *h2d_ms, float *kernel_ms, float *d2h_ms);
+/* Random 32-byte-sector read ceiling over the resident table: about *n_probes independent loads;
+ * on return *n_probes is the exact number issued and *ms the kernel time. */
+int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms);
+/* Number of kernel launches issued by this ctx so far. */
+uint64_t dcn_launch_count(dcn_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

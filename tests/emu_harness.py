@@ -1,0 +1,51 @@
+"""Loads the TEST-ONLY host emulation of the CUDA tile pipeline (tests/emu/dcn_emu.cpp)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
+_SO = os.path.join(_HERE, "libdcn_emu.so")
+_CSRC = os.path.join(os.path.dirname(_HERE), "..", "deacon_server_b200", "csrc")
+u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+
+
+def build():
+    srcs = [os.path.join(_HERE, "dcn_emu.cpp")] + [os.path.join(_CSRC, f) for f in ("dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh")]
+    if os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs):
+        return _SO
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+    return _lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+def filter_batch(keys, bases, off, paired=False, prefix=0, abs_thr=2, rel=0.01, deplete=False, load=0.5):
+    L = lib()
+    keys = np.ascontiguousarray(keys, np.uint64)
+    slots, nb, he = u64p(), C.c_uint64(), C.c_int()
+    kk = keys if len(keys) else np.zeros(1, np.uint64)
+    L.emu_table_build(_p(kk, u64p), C.c_uint64(len(keys)), C.c_double(load), C.byref(slots), C.byref(nb), C.byref(he))
+    n_rec = len(off) - 1
+    nu = n_rec // 2 if paired else n_rec
+    keep = np.zeros(max(nu, 1), np.uint8)
+    hits = np.zeros(max(nu, 1), np.uint32)
+    tot = np.zeros(max(nu, 1), np.uint32)
+    b = bases if len(bases) else np.zeros(1, np.uint8)
+    rc = L.emu_filter_batch(slots, nb, he, _p(b, u8p), _p(off, u64p), C.c_uint32(n_rec), int(paired), C.c_uint32(prefix),
+                            C.c_uint32(abs_thr), C.c_double(rel), int(deplete), _p(keep, u8p), _p(hits, u32p), _p(tot, u32p))
+    L.emu_free(slots)
+    return rc, keep[:nu], hits[:nu], tot[:nu]

@@ -1,0 +1,72 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/deacon_cuda.h
+declares (no compute calls: there is no GPU here), and the host-side mirror logic (.idx codec,
+classification rule) agrees with the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import deacon_server_b200 as D
+from deacon_server_b200 import _lib, api
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "deacon_cuda.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcn_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = D.load()
+    names = _declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libdeacon_cuda.so does not export {n}"
+    assert sorted(_lib.SIGNATURES) == names, "python binding table out of sync with the header"
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    with pytest.raises(D.DeaconCudaError, match="no CUDA device|no CPU fallback|device"):
+        D.DeaconGpu(0)
+
+
+def test_product_does_not_import_oracle():
+    for root, _, files in os.walk(os.path.join(ROOT, "deacon_server_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(root, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
+
+
+def test_idx_codec_matches_oracle_codec(tmp_path):
+    rng = np.random.default_rng(5)
+    keys = np.unique(rng.integers(0, 2**63, 3000, dtype=np.uint64) * np.uint64(2) + np.uint64(1))
+    hdr = api.IndexHeader(2, 31, 15)
+    assert api.encode_index(keys, hdr) == O.idx_encode(keys, 31, 15)
+    mixed = np.array([0, 5, 250, 251, 70000, 2**32, 2**64 - 1], np.uint64)
+    assert api.encode_index(mixed, hdr) == O.idx_encode(mixed, 31, 15)
+    got, h2 = api.decode_index(O.idx_encode(mixed, 21, 11))
+    assert np.array_equal(got, mixed) and (h2.kmer_length, h2.window_size) == (21, 11)
+    p = tmp_path / "x.idx"
+    api.write_minimizers(keys[::-1], hdr, p)
+    got, h3 = api.load_minimizer_hashes(p)
+    assert np.array_equal(got, keys) and h3.format_version == 2
+    with pytest.raises(ValueError, match="Unsupported index format version"):
+        api.decode_index(bytes([1, 31, 15, 0]))
+
+
+def test_host_classification_matches_oracle():
+    for total in list(range(0, 300)) + [10**6, 2**31]:
+        for rel in (0.0, 0.01, 0.015, 0.25, 0.5, 1.0):
+            for abs_ in (0, 1, 2, 7):
+                assert api.calculate_required_hits(abs_, rel, total) == O.required_hits(abs_, rel, total)
+    assert api.meets_filtering_criteria(1, 48, 2, 0.01, True) is True    # tests/filter_tests.rs:943-1015
+    assert api.meets_filtering_criteria(0, 0, 2, 0.01, False) is False

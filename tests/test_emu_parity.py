@@ -1,0 +1,41 @@
+"""CPU tests: the CUDA tile pipeline, compiled for the host and run phase by phase, must agree
+bit-for-bit with the oracle.  This checks the kernel's LOGIC without a GPU; the GPU tests
+(test_gpu_parity.py) then check the same cases through the C ABI on a B200."""
+import numpy as np
+import pytest
+
+import cases as CASES
+import emu_harness as E
+import helpers as H
+from oracle import oracle as O
+
+
+def _index_for(case):
+    idx = O.index_build([np.asarray(r, np.uint8) for r in case["index_records"]], 31, 15)
+    if case.get("extra_keys") is not None:
+        idx.insert(case["extra_keys"])
+    return idx
+
+
+@pytest.mark.parametrize("case", CASES.make_cases(), ids=lambda c: c["name"])
+def test_short_path_matches_oracle(case):
+    idx = _index_for(case)
+    bases, off = H.concat(case["records"])
+    rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"])
+    assert rc == 0
+    ok, oh, ot = O.filter_batch(idx, bases, off, paired=case["paired"], prefix_len=case["prefix"], abs_thr=case["abs"],
+                                rel_thr=case["rel"], deplete=case["deplete"])
+    assert np.array_equal(t, ot), "total minimizers differ"
+    assert np.array_equal(h, oh), "distinct hit counts differ"
+    assert np.array_equal(k, ok), "keep decisions differ"
+
+
+def test_high_load_factor_table_probing():
+    g = H.random_genome(60_000, 3)
+    idx = O.index_build([g], 31, 15)
+    reads = H.sample_reads(g, 500, 150, 4)
+    bases, off = H.concat(reads)
+    ok, oh, ot = O.filter_batch(idx, bases, off)
+    for load in (0.05, 0.5, 0.9):
+        rc, k, h, t = E.filter_batch(idx.keys(), bases, off, load=load)
+        assert rc == 0 and np.array_equal(h, oh) and np.array_equal(t, ot) and np.array_equal(k, ok)
