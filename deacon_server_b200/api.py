@@ -321,5 +321,24 @@ class DeaconGpu:
         self._check(self._lib.dcn_measure_random_access(self._ctx, C.byref(n), C.byref(ms)))
         return n.value, ms.value
 
+    def fused_time_take(self):
+        """(total ms, launches) of the fused kernel since the last call (CUDA events, launching stream)."""
+        ms, n = C.c_float(), C.c_uint32()
+        self._check(self._lib.dcn_fused_time_take(self._ctx, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def index_build_device(self, d_bases, d_rec_off, n_rec, n_bases, k=31, w=15, entropy_threshold=0.0,
+                           make_resident=True, stream: int = 0) -> int:
+        """GPU index build from device-resident sequences -> number of distinct keys."""
+        n = C.c_uint64()
+        self._check(self._lib.dcn_index_build_device(self._ctx, d_bases.data_ptr(), d_rec_off.data_ptr(), n_rec, n_bases,
+                                                     k, w, entropy_threshold, int(make_resident), C.byref(n), stream))
+        if make_resident:
+            self.header = IndexHeader(2, k, w)
+        return n.value
+
+    def index_build_keys_ptr(self) -> int:
+        return int(self._lib.dcn_index_build_keys_device(self._ctx) or 0)
+
     def launch_count(self) -> int:
         return int(self._lib.dcn_launch_count(self._ctx))

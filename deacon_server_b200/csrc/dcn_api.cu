@@ -11,6 +11,10 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <math.h>
+
 #include "../../include/deacon_cuda.h"
 #include "dcn_kernels.cuh"
 
@@ -36,7 +40,7 @@ struct DevBuf {
 };
 
 struct Slot {  // one stage of the host-pointer pipeline
-    DevBuf bases, off, keep, hits, total, plan;
+    DevBuf bases, off, keep, hits, total, plan, longs, dedup;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
     bool busy = false;
@@ -60,9 +64,17 @@ struct dcn_ctx {
     DevBuf plan;       // BatchStats + tile_first + tile_end (one memset clears all three)
     DevBuf counters;   // 6 x u64 ProcessingStats + 2 x u64 table-build counters
     DevBuf keys_stage;
+    DevBuf longs, dedup;   // long-path scratch of the device-pointer API
+    // index build
+    DevBuf ib_bases, ib_off, ib_desc, ib_keys, ib_alt, ib_tmp, ib_entropy, ib_stats;
+    uint64_t ib_n = 0;     // sorted unique keys of the last build (in ib_keys)
     Slot slot[2];
     uint64_t launches = 0;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
+    // CUDA-event pairs around every launch of the fused kernel (ring), for dcn_fused_time_take
+    static const int KEV = 256;
+    cudaEvent_t kev0[KEV], kev1[KEV];
+    uint32_t kev_head = 0, kev_count = 0;
 
     int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
         err = what;
@@ -86,11 +98,14 @@ static size_t plan_bytes(uint64_t n_rel_bases) {
     return 64 + (size_t)n_tiles * 2 * sizeof(uint32_t);
 }
 
+static uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
+
 // Enqueue the whole filter pipeline for one device-resident batch on `st`.
-static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, const uint8_t *d_bases, uint64_t base0, uint64_t n_bases_abs,
-                          const uint64_t *d_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
-                          double rel_thr, int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total,
-                          cudaStream_t st) {
+// `longs` / `dedup` are scratch for the long path (units > DCN_MAX_SHORT bases).
+static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &dedup, const uint8_t *d_bases,
+                          uint64_t base0, uint64_t n_bases_abs, const uint64_t *d_off, uint32_t n_rec, int paired,
+                          uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep,
+                          uint32_t *d_hits, uint32_t *d_total, cudaStream_t st) {
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
     if (ctx->k != 31 || ctx->w != 15)
         return ctx->fail(DCN_ERR_UNSUPPORTED, "only k=31, w=15 indexes are implemented by the CUDA path");
@@ -108,12 +123,6 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, const uint8_t *d_bases, ui
     BatchStats *d_stats = plan.as<BatchStats>();
     uint32_t *tile_first = reinterpret_cast<uint32_t *>(plan.as<uint8_t>() + 64);
     uint32_t *tile_end = tile_first + n_tiles_max;
-    CK(cudaMemsetAsync(plan.p, 0, pbytes, st));
-
-    const int pb = 256;
-    const int pg = (int)std::min<uint64_t>((n_units + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
-    prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_stats);
-    prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, rpu, n_units, base0, d_stats, tile_first, tile_end);
 
     FilterParams P;
     P.bases = d_bases; P.base0 = base0; P.n_bases = n_bases_abs;
@@ -122,12 +131,68 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, const uint8_t *d_bases, ui
     P.table.slots = ctx->table.as<uint64_t>(); P.table.n_buckets = ctx->n_buckets; P.table.has_empty_key = ctx->has_empty;
     P.keep = d_keep; P.hits = d_hits; P.total = d_total;
 
+    const int pb = 256;
+    const int pg = (int)std::min<uint64_t>((n_units + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
     const size_t smem = sizeof(TileSmem<G31>);
     const uint64_t tiles_lb = n_rel / G31::BCAP + 1;
-    const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * 2);
-    filter_fused_kernel<G31><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end);
+    const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * 4);
+
+    // A batch can only contain a long unit if it holds more than DCN_MAX_SHORT bases; otherwise the
+    // stats readback (one small sync) is skipped.
+    uint64_t dedup_cap = 0;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CK(cudaMemsetAsync(plan.p, 0, pbytes, st));
+        prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_stats);
+        prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, rpu, n_units, base0, d_stats, tile_first, tile_end);
+        ctx->launches += 2;
+        BatchStats hs;
+        memset(&hs, 0, sizeof(hs));
+        if (n_rel > DCN_MAX_SHORT) {
+            CK(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        DedupView dd;
+        dd.slots = nullptr; dd.mask = 0; dd.overflow = &d_stats->overflow;
+        uint32_t *long_units = nullptr;
+        ChunkDesc *desc = nullptr;
+        if (hs.n_long) {
+            // distinct hits of long units go through a global (hash, unit) set: expected picks are
+            // ~0.13 per base; start at 0.5 entries per base and grow on overflow (exactness is kept
+            // by retrying, never by dropping)
+            if (!dedup_cap) dedup_cap = next_pow2(std::max<uint64_t>(4096, hs.long_bases / 2));
+            const uint32_t desc_cap = (uint32_t)(hs.long_bases / ChunkGeo<G31>::CSTRIDE + (uint64_t)hs.n_long * rpu + 16);
+            CK(dedup.ensure(dedup_cap * 16));
+            CK(longs.ensure((size_t)hs.n_long * 4 + 64 + (size_t)desc_cap * sizeof(ChunkDesc)));
+            CK(cudaMemsetAsync(dedup.p, 0, dedup_cap * 16, st));
+            dd.slots = dedup.as<unsigned __int128>(); dd.mask = dedup_cap - 1;
+            long_units = longs.as<uint32_t>();
+            desc = reinterpret_cast<ChunkDesc *>(longs.as<uint8_t>() + (((size_t)hs.n_long * 4 + 63) & ~(size_t)63));
+            prep_long_kernel<G31><<<pg, pb, 0, st>>>(P, d_stats, long_units, desc, desc_cap);
+            ctx->launches += 1;
+        }
+        const uint32_t ke = ctx->kev_head % dcn_ctx::KEV;
+        CK(cudaEventRecord(ctx->kev0[ke], st));
+        filter_fused_kernel<G31><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
+        CK(cudaEventRecord(ctx->kev1[ke], st));
+        ctx->kev_head++;
+        if (ctx->kev_count < dcn_ctx::KEV) ctx->kev_count++;
+        ctx->launches += 1;
+        if (hs.n_long) {
+            finalize_long_kernel<<<std::max(1, (int)std::min<uint32_t>((hs.n_long + 255) / 256, 1024)), 256, 0, st>>>(P, d_stats, long_units);
+            ctx->launches += 1;
+            BatchStats after;
+            CK(cudaMemcpyAsync(&after, d_stats, sizeof(after), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (after.overflow) {
+                if (attempt == 3) return ctx->fail(DCN_ERR_OVERFLOW, "distinct-hit set overflowed after 4 attempts");
+                dedup_cap *= 4;
+                continue;
+            }
+        }
+        break;
+    }
     stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_keep, ctx->counters.as<unsigned long long>());
-    ctx->launches += 4;
+    ctx->launches += 1;
     CK(cudaGetLastError());
     return DCN_OK;
 }
@@ -156,6 +221,8 @@ dcn_ctx *dcn_ctx_create(int device) {
         return nullptr;
     }
     dcn_ctx *ctx = new dcn_ctx();
+    memset(ctx->kev0, 0, sizeof(ctx->kev0));
+    memset(ctx->kev1, 0, sizeof(ctx->kev1));
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -165,9 +232,13 @@ dcn_ctx *dcn_ctx_create(int device) {
         ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_h2d) == cudaSuccess;
         ok = ok && cudaEventCreate(&s.ev_kernel) == cudaSuccess && cudaEventCreate(&s.ev_done) == cudaSuccess;
     }
+    for (int i = 0; ok && i < dcn_ctx::KEV; i++)
+        ok = ok && cudaEventCreate(&ctx->kev0[i]) == cudaSuccess && cudaEventCreate(&ctx->kev1[i]) == cudaSuccess;
     ok = ok && ctx->counters.ensure(8 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->counters.p, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(TileSmem<G31>)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(extract_index_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     if (!ok) {
         g_create_error = std::string("context setup failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -182,14 +253,22 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     ctx->table.release(); ctx->plan.release(); ctx->counters.release(); ctx->keys_stage.release();
+    ctx->longs.release(); ctx->dedup.release();
+    ctx->ib_bases.release(); ctx->ib_off.release(); ctx->ib_desc.release(); ctx->ib_keys.release();
+    ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->ib_entropy.release(); ctx->ib_stats.release();
     for (int i = 0; i < 2; i++) {
         Slot &s = ctx->slot[i];
         s.bases.release(); s.off.release(); s.keep.release(); s.hits.release(); s.total.release(); s.plan.release();
+        s.longs.release(); s.dedup.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.ev_start) cudaEventDestroy(s.ev_start);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    for (int i = 0; i < dcn_ctx::KEV; i++) {
+        if (ctx->kev0[i]) cudaEventDestroy(ctx->kev0[i]);
+        if (ctx->kev1[i]) cudaEventDestroy(ctx->kev1[i]);
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -243,7 +322,7 @@ static int table_end(dcn_ctx *ctx, cudaStream_t st) {
 int dcn_index_upload_device(dcn_ctx *ctx, const uint64_t *d_keys, uint64_t n_keys, uint8_t k, uint8_t w, void *stream) {
     if (!ctx) return DCN_ERR_ARG;
     if (!d_keys && n_keys) return ctx->fail(DCN_ERR_ARG, "null key pointer");
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     int rc = table_begin(ctx, n_keys, k, w, st);
     if (rc) return rc;
     if ((rc = table_insert(ctx, d_keys, n_keys, st))) return rc;
@@ -283,9 +362,9 @@ int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t
                             int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream) {
     if (!ctx) return DCN_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-    return enqueue_filter(ctx, ctx->plan, d_bases, 0, n_bases, d_rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr,
-                          deplete, d_keep, d_hits, d_total, st);
+    cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, like any CUDA API
+    return enqueue_filter(ctx, ctx->plan, ctx->longs, ctx->dedup, d_bases, 0, n_bases, d_rec_off, n_rec, paired,
+                          prefix_len, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, st);
 }
 
 // Host-pointer form: unit-aligned chunks, double-buffered over two streams so that the H2D copy
@@ -316,11 +395,8 @@ int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off
         CK(cudaMemcpyAsync(keep + s.u0, s.keep.p, nu * sizeof(uint8_t), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaMemcpyAsync(hits + s.u0, s.hits.p, nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaMemcpyAsync(total + s.u0, s.total.p, nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-        BatchStats bs;
-        CK(cudaMemcpyAsync(&bs, s.plan.p, sizeof(bs), cudaMemcpyDeviceToHost, s.stream));
         CK(cudaEventRecord(s.ev_done, s.stream));
         CK(cudaEventSynchronize(s.ev_done));
-        if (bs.n_long) { s.busy = false; return ctx->fail(DCN_ERR_UNSUPPORTED, "units longer than 1024 bases: long path not implemented yet"); }
         float a = 0, b = 0, c = 0;
         cudaEventElapsedTime(&a, s.ev_start, s.ev_h2d);
         cudaEventElapsedTime(&b, s.ev_h2d, s.ev_kernel);
@@ -358,7 +434,7 @@ int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off
         if (b1 > a0) CK(cudaMemcpyAsync(s.bases.p, bases + a0, (size_t)(b1 - a0), cudaMemcpyHostToDevice, s.stream));
         CK(cudaMemcpyAsync(s.off.p, rec_off + (uint64_t)u0 * rpu, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, s.stream));
         CK(cudaEventRecord(s.ev_h2d, s.stream));
-        rc = enqueue_filter(ctx, s.plan, s.bases.as<uint8_t>(), a0, b1, s.off.as<uint64_t>(), nr, paired, prefix_len,
+        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, s.bases.as<uint8_t>(), a0, b1, s.off.as<uint64_t>(), nr, paired, prefix_len,
                             abs_thr, rel_thr, deplete, s.keep.as<uint8_t>(), s.hits.as<uint32_t>(),
                             s.total.as<uint32_t>(), s.stream);
         if (rc) break;
@@ -390,17 +466,130 @@ int dcn_extract(dcn_ctx *ctx, int, const uint8_t *, const uint64_t *, uint32_t, 
                 uint64_t *, uint32_t *, uint64_t *, uint64_t) {
     return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_extract: not implemented yet") : DCN_ERR_ARG;
 }
-int dcn_index_build(dcn_ctx *ctx, const uint8_t *, const uint64_t *, uint32_t, uint8_t, uint8_t, float, int, uint64_t *) {
-    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_index_build: not implemented yet") : DCN_ERR_ARG;
+// src/minimizers.rs:73-121 evaluated on the host for every base-count triple: the same f32
+// operations in the same order (p = count / total; entropy -= p * log2f(p); entropy / 2 >= thr).
+static void build_entropy_bitmap(int k, float thr, std::vector<uint32_t> &bits) {
+    bits.assign(32 * 32 * 32 / 32, 0);
+    for (int a = 0; a <= k; a++)
+        for (int c = 0; a + c <= k; c++)
+            for (int g = 0; a + c + g <= k; g++) {
+                int counts[4] = {a, c, g, k - a - c - g};   // A, C, G, T order of the reference
+                volatile float entropy = 0.0f;
+                float total_f = (float)k;
+                if (k >= 10) {
+                    for (int i = 0; i < 4; i++)
+                        if (counts[i] > 0) {
+                            volatile float p = (float)counts[i] / total_f;
+                            volatile float term = p * log2f(p);
+                            entropy = entropy - term;
+                        }
+                }
+                float scaled = k < 10 ? 1.0f : entropy / 2.0f;
+                if (scaled >= thr) {
+                    uint32_t idx = ((uint32_t)a * 32u + (uint32_t)c) * 32u + (uint32_t)g;
+                    bits[idx >> 5] |= 1u << (idx & 31);
+                }
+            }
 }
-int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *, const uint64_t *, uint32_t, uint64_t, uint8_t, uint8_t, float,
-                           int, uint64_t *, void *) {
-    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_index_build_device: not implemented yet") : DCN_ERR_ARG;
+
+int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                           uint64_t n_bases, uint8_t k, uint8_t w, float entropy_thr, int make_resident,
+                           uint64_t *n_keys_out, void *stream) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (k != 31 || w != 15) return ctx->fail(DCN_ERR_UNSUPPORTED, "only k=31, w=15 is implemented by the CUDA path");
+    if (reinterpret_cast<uintptr_t>(d_bases) & 15u) return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->ib_n = 0;
+    if (n_keys_out) *n_keys_out = 0;
+
+    const uint32_t *d_entropy = nullptr;
+    if (entropy_thr != 0.0f) {
+        std::vector<uint32_t> bits;
+        build_entropy_bitmap(k, entropy_thr, bits);
+        CK(ctx->ib_entropy.ensure(bits.size() * 4));
+        CK(cudaMemcpyAsync(ctx->ib_entropy.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));
+        d_entropy = ctx->ib_entropy.as<uint32_t>();
+    }
+    const uint32_t desc_cap = (uint32_t)(n_bases / ChunkGeo<G31>::CSTRIDE + n_rec + 16);
+    CK(ctx->ib_desc.ensure((size_t)desc_cap * sizeof(ChunkDesc)));
+    CK(ctx->ib_stats.ensure(64 + 16));
+    BatchStats *d_stats = ctx->ib_stats.as<BatchStats>();
+    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(ctx->ib_stats.as<uint8_t>() + 64);
+
+    // typical density is 0.1255 picks per base; low-complexity sequence can reach 1 per window
+    uint64_t cap = (uint64_t)((double)n_bases * 0.16) + 4096;
+    unsigned long long n_picks = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(ctx->ib_alt.ensure(cap * sizeof(uint64_t)));
+        CK(cudaMemsetAsync(ctx->ib_stats.p, 0, 64 + 16, st));
+        const int pb = 256;
+        const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_rec + pb - 1) / pb, (uint64_t)ctx->sm_count * 8));
+        prep_index_chunks_kernel<G31><<<pg, pb, 0, st>>>(d_rec_off, n_rec, d_stats, reinterpret_cast<ChunkDesc *>(ctx->ib_desc.p), desc_cap);
+        IndexParams P;
+        P.bases = d_bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = d_rec_off; P.n_rec = n_rec;
+        P.entropy_pass = d_entropy; P.out = ctx->ib_alt.as<uint64_t>(); P.out_cap = cap; P.out_count = d_count;
+        extract_index_kernel<G31><<<ctx->sm_count * 4, G31::NT, sizeof(TileSmem<G31>), st>>>(P, d_stats, reinterpret_cast<ChunkDesc *>(ctx->ib_desc.p));
+        ctx->launches += 2;
+        CK(cudaMemcpyAsync(&n_picks, d_count, sizeof(n_picks), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (n_picks <= cap) break;
+        if (attempt == 1) return ctx->fail(DCN_ERR_OVERFLOW, "minimizer buffer overflowed twice");
+        cap = n_picks + 1024;
+    }
+    if (n_picks == 0) {
+        if (make_resident) return dcn_index_upload_device(ctx, nullptr, 0, k, w, st);
+        return DCN_OK;
+    }
+    // FxHashSet::extend (src/index.rs:267-284) == radix sort + unique
+    CK(ctx->ib_keys.ensure(n_picks * sizeof(uint64_t)));
+    size_t tmp_sort = 0, tmp_sel = 0;
+    cub::DoubleBuffer<uint64_t> db(ctx->ib_alt.as<uint64_t>(), ctx->ib_keys.as<uint64_t>());
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
+    CK(cub::DeviceSelect::Unique(nullptr, tmp_sel, (const uint64_t *)nullptr, (uint64_t *)nullptr, (unsigned long long *)nullptr, (int64_t)n_picks, st));
+    CK(ctx->ib_tmp.ensure(std::max(tmp_sort, tmp_sel)));
+    CK(cub::DeviceRadixSort::SortKeys(ctx->ib_tmp.p, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
+    uint64_t *sorted = db.Current();
+    uint64_t *uniq = db.Alternate();
+    CK(cub::DeviceSelect::Unique(ctx->ib_tmp.p, tmp_sel, sorted, uniq, d_count, (int64_t)n_picks, st));
+    ctx->launches += 8;
+    unsigned long long n_unique = 0;
+    CK(cudaMemcpyAsync(&n_unique, d_count, sizeof(n_unique), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (uniq != ctx->ib_keys.as<uint64_t>()) {  // keep the result in ib_keys
+        std::swap(ctx->ib_keys, ctx->ib_alt);
+    }
+    ctx->ib_n = n_unique;
+    if (n_keys_out) *n_keys_out = n_unique;
+    if (make_resident) return dcn_index_upload_device(ctx, ctx->ib_keys.as<uint64_t>(), n_unique, k, w, st);
+    return DCN_OK;
 }
-int dcn_index_build_keys(dcn_ctx *ctx, uint64_t *, uint64_t) {
-    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_index_build_keys: not implemented yet") : DCN_ERR_ARG;
+
+int dcn_index_build(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint8_t w,
+                    float entropy_thr, int make_resident, uint64_t *n_keys_out) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!rec_off || (!bases && n_rec && rec_off[n_rec] > 0)) return ctx->fail(DCN_ERR_ARG, "null input pointer");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n_bases = n_rec ? rec_off[n_rec] : 0;
+    if (n_rec && rec_off[0] != 0) return ctx->fail(DCN_ERR_ARG, "rec_off[0] must be 0");
+    CK(ctx->ib_bases.ensure(n_bases + 64));
+    CK(ctx->ib_off.ensure((size_t)(n_rec + 1) * 8));
+    if (n_bases) CK(cudaMemcpyAsync(ctx->ib_bases.p, bases, n_bases, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->ib_off.p, rec_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    return dcn_index_build_device(ctx, ctx->ib_bases.as<uint8_t>(), ctx->ib_off.as<uint64_t>(), n_rec, n_bases, k, w,
+                                  entropy_thr, make_resident, n_keys_out, ctx->stream);
 }
-const uint64_t *dcn_index_build_keys_device(dcn_ctx *) { return nullptr; }
+
+int dcn_index_build_keys(dcn_ctx *ctx, uint64_t *out_keys, uint64_t cap) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (cap < ctx->ib_n) return ctx->fail(DCN_ERR_ARG, "output buffer smaller than the key count");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->ib_n) CK(cudaMemcpy(out_keys, ctx->ib_keys.p, ctx->ib_n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    return DCN_OK;
+}
+const uint64_t *dcn_index_build_keys_device(dcn_ctx *ctx) { return ctx && ctx->ib_n ? ctx->ib_keys.as<uint64_t>() : nullptr; }
 
 // ---------------------------------------------------------------------------- counters
 int dcn_stats_get(dcn_ctx *ctx, uint64_t counters[6]) {
@@ -449,5 +638,22 @@ int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms) {
 }
 
 uint64_t dcn_launch_count(dcn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int dcn_fused_time_take(dcn_ctx *ctx, float *total_ms, uint32_t *n_launches) {
+    if (!ctx || !total_ms || !n_launches) return DCN_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    float sum = 0;
+    for (uint32_t i = 0; i < ctx->kev_count; i++) {
+        uint32_t e = (ctx->kev_head - 1 - i) % dcn_ctx::KEV;
+        CK(cudaEventSynchronize(ctx->kev1[e]));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->kev0[e], ctx->kev1[e]));
+        sum += ms;
+    }
+    *total_ms = sum;
+    *n_launches = ctx->kev_count;
+    ctx->kev_count = 0;
+    return DCN_OK;
+}
 
 }  // extern "C"

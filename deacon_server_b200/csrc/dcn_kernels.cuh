@@ -17,6 +17,35 @@ struct DevExec {
         f((int)threadIdx.x, pv);
         __syncthreads();
     }
+    template <class F>
+    __device__ __forceinline__ void par_nosync(F f) { f((int)threadIdx.x, pv); }
+    __device__ __forceinline__ void barrier() { __syncthreads(); }
+    __device__ __forceinline__ uint32_t ballot(int, bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+    // lanes of this warp holding the same 64-bit value
+    __device__ __forceinline__ uint32_t match64(int, uint64_t v, bool) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
+    // add the number of lanes with a / b set to two shared-memory counters
+    __device__ __forceinline__ void tally2(int t, bool a, bool b, uint32_t *ca, uint32_t *cb) {
+        uint32_t ma = __ballot_sync(0xFFFFFFFFu, a), mb = __ballot_sync(0xFFFFFFFFu, b);
+        if ((t & 31) == 0) {
+            if (ma) atomicAdd(ca, (uint32_t)__popc(ma));
+            if (mb) atomicAdd(cb, (uint32_t)__popc(mb));
+        }
+    }
+    __device__ __forceinline__ void global_add(uint32_t *p, uint32_t v) { if (v) atomicAdd(p, v); }
+    // warp-aggregated append to a global array
+    __device__ __forceinline__ void append64(int t, bool valid, uint64_t v, uint64_t *out, uint64_t cap,
+                                             unsigned long long *count) {
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+        if (!m) return;
+        const int lane = t & 31;
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (valid) {
+            unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << lane) - 1u));
+            if (pos < cap) out[pos] = v;
+        }
+    }
     // block-wide exclusive sum of a u32 (two packed 16-bit counters in our use)
     template <class Get, class Put>
     __device__ __forceinline__ void scan(Get get, Put put) {
@@ -48,27 +77,95 @@ struct DevExec {
 
 // device-side batch statistics, written by the prep kernels
 struct BatchStats {
-    uint32_t max_short;   // longest short unit
-    uint32_t n_long;      // units longer than DCN_MAX_SHORT
-    uint32_t n_chunks;    // chunk descriptors of the long path
-    uint32_t overflow;    // an internal table overflowed
+    uint32_t max_short;      // longest short unit
+    uint32_t n_long;         // units longer than DCN_MAX_SHORT
+    uint32_t n_chunks;       // chunk descriptors written
+    uint32_t overflow;       // an internal table overflowed
+    uint32_t n_long_listed;  // entries of the long-unit list
+    uint32_t pad;
+    unsigned long long long_bases;  // bases in long units
 };
 
 // ------------------------------------------------------------------ prep: unit statistics
 __global__ void prep_stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,
                                   BatchStats *st) {  // lengths only: independent of base0
     uint32_t mx = 0, nl = 0;
-    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x)
+    unsigned long long lb = 0;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        uint32_t before = nl;
         plan_unit_stats(rec_off, rpu, u, mx, nl);
+        if (nl != before) lb += rec_off[(uint64_t)(u + 1) * rpu] - rec_off[(uint64_t)u * rpu];
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, d));
         nl += __shfl_xor_sync(0xFFFFFFFFu, nl, d);
+        lb += __shfl_xor_sync(0xFFFFFFFFu, lb, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (mx) atomicMax(&st->max_short, mx);
-        if (nl) atomicAdd(&st->n_long, nl);
+        if (nl) { atomicAdd(&st->n_long, nl); atomicAdd(&st->long_bases, lb); }
     }
+}
+
+// ------------------------------------------------------------------ prep: chunk descriptors
+// Filter long path: one thread per unit; long units are listed, their outputs zeroed, and every
+// record of theirs is cut into chunks.
+template <class G>
+__global__ void prep_long_kernel(FilterParams P, BatchStats *st, uint32_t *long_units, ChunkDesc *desc,
+                                 uint32_t desc_cap) {
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < P.n_units; u += gridDim.x * blockDim.x) {
+        uint64_t len = P.rec_off[(uint64_t)(u + 1) * P.rpu] - P.rec_off[(uint64_t)u * P.rpu];
+        if (len <= DCN_MAX_SHORT) continue;
+        long_units[atomicAdd(&st->n_long_listed, 1u)] = u;
+        P.hits[u] = 0; P.total[u] = 0;
+        for (uint32_t r = u * P.rpu; r < (u + 1) * P.rpu; r++) {
+            uint64_t gs = P.rec_off[r] - P.base0, rl = P.rec_off[r + 1] - P.base0 - gs;
+            uint32_t nc = chunks_of<G>(effective_len64<G, FLAVOUR_FILTER>(P.bases, gs, rl, P.prefix_len));
+            if (!nc) continue;
+            uint32_t at = atomicAdd(&st->n_chunks, nc);
+            for (uint32_t c = 0; c < nc; c++)
+                if (at + c < desc_cap) desc[at + c] = ChunkDesc{r, c};
+                else st->overflow = 1;
+        }
+    }
+}
+
+// Index build: every record is cut into chunks.
+template <class G>
+__global__ void prep_index_chunks_kernel(const uint64_t *__restrict__ rec_off, uint32_t n_rec, BatchStats *st,
+                                         ChunkDesc *desc, uint32_t desc_cap) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+        uint64_t rl = rec_off[r + 1] - rec_off[r];
+        uint32_t nc = chunks_of<G>(rl < (uint64_t)G::K ? 0 : rl);
+        if (!nc) continue;
+        uint32_t at = atomicAdd(&st->n_chunks, nc);
+        for (uint32_t c = 0; c < nc; c++)
+            if (at + c < desc_cap) desc[at + c] = ChunkDesc{r, c};
+            else st->overflow = 1;
+    }
+}
+
+// keep flag of the long units once every chunk has added its counts
+__global__ void finalize_long_kernel(FilterParams P, const BatchStats *st, const uint32_t *long_units) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < st->n_long_listed; i += gridDim.x * blockDim.x) {
+        uint32_t u = long_units[i];
+        P.keep[u] = meets_criteria(P.hits[u], P.total[u], P.abs_thr, P.rel_thr, P.deplete) ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------ index-flavour extraction kernel
+template <class G>
+__global__ void __launch_bounds__(G::NT, 4)
+extract_index_kernel(IndexParams P, const BatchStats *st, const ChunkDesc *__restrict__ desc) {
+    extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
+    TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);
+    DevExec<G> ex;
+    ex.wsum = s.wsum;
+    init_tables<G>((int)threadIdx.x, s);
+    __syncthreads();
+    const uint32_t n_chunks = st->n_chunks;
+    for (uint32_t w = blockIdx.x; w < n_chunks; w += gridDim.x) index_chunk<G>(ex, s, P, desc[w]);
 }
 
 // ------------------------------------------------------------------ prep: tile ownership
@@ -81,11 +178,11 @@ __global__ void prep_tiles_kernel(const uint64_t *__restrict__ rec_off, uint32_t
 }
 
 // ------------------------------------------------------------------ the fused filter kernel
-// Persistent CTAs; tile i -> CTA (i mod grid).  2 CTAs per SM (register- and smem-limited).
+// Persistent CTAs; tile i -> CTA (i mod grid).  4 CTAs per SM (64 registers, ~53 KB shared memory each).
 template <class G>
-__global__ void __launch_bounds__(G::NT, 2)
+__global__ void __launch_bounds__(G::NT, 4)
 filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ tile_first,
-                    const uint32_t *__restrict__ tile_end) {
+                    const uint32_t *__restrict__ tile_end, DedupView dd, const ChunkDesc *__restrict__ desc) {
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
     TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);
     DevExec<G> ex;
@@ -94,9 +191,16 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     __syncthreads();
     const PlanCfg cfg = plan_make_cfg<G>(st->max_short);
     const uint32_t n_tiles = plan_num_tiles(P.n_bases - P.base0, cfg);
+    const uint32_t n_long = st->n_long;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t a = tile_first[tile], b = tile_end[tile];
-        if (a < b) filter_tile<G>(ex, s, P, cfg, a, b);
+        if (a < b) filter_tile<G>(ex, s, P, cfg, n_long, a, b);
+    }
+    if (n_long) {  // long units: chunks, spread over the CTAs in reverse so short and long work interleave
+        __syncthreads();
+        const uint32_t n_chunks = st->n_chunks;
+        for (uint32_t w = gridDim.x - 1 - blockIdx.x; w < n_chunks; w += gridDim.x)
+            filter_long_chunk<G>(ex, s, P, dd, desc[w]);
     }
 }
 

@@ -31,7 +31,7 @@ struct Geo {
     static constexpr int BCAP = WCAP + L - 1;   // bases a tile may reference
     static constexpr int NBW = 132;             // 32-bit words of the per-position bit arrays
     static constexpr int MAXR = 512;            // records per sub-batch
-    static constexpr int PKCAP = NT * 16;       // worst case: every window emits a pick
+    static constexpr int PKCAP = 2048;          // picks per pass; a denser run of units is split (see filter_tile)
     static constexpr int HP = 20;               // hrow pitch in words (16 data + 4 pad: conflict-free LDS.128)
 };
 
@@ -41,9 +41,11 @@ struct u32x4 { uint32_t x, y, z, w; };
 template <class G>
 struct alignas(16) TileSmem {
     u32x4 ag[G::NV + 6];              // per vector: E_fw, E_rc (own role), N_fw, N_rc (right-neighbour role)
-    uint32_t hrow[G::NT * G::HP];     // ntHash of the 16 k-mers of each thread
+    union {                           // hrow is dead once the window minima are taken; picks reuse it
+        uint32_t hrow[G::NT * G::HP]; // ntHash of the 16 k-mers of each thread
+        uint32_t pk_pos[G::PKCAP];    // local position | start-rank << 16 | valid << 31
+    };
     uint64_t pk_hash[G::PKCAP];       // xxh3 of each pick
-    uint32_t pk_pos[G::PKCAP];        // local position | start-rank << 16 | valid << 31
     u32x2 tb0[256];                   // 4-base aggregate table (fw, rc)
     u32x2 tin[4], tout[4], tsb[4];    // rolling-step tables: incoming / outgoing base, single base
     uint32_t codes[G::NV + 6];        // 16 bases x 2 bit per word
@@ -55,13 +57,13 @@ struct alignas(16) TileSmem {
     uint32_t poff[G::NT];             // exclusive pick offset | exclusive start-rank << 16
     uint32_t emk[G::NT];              // emit mask | ustart bits << 16
     uint32_t vmask[G::PKCAP / 32], hmask[G::PKCAP / 32];
-    uint32_t roff[G::MAXR + 1];       // record offsets relative to the tile origin
-    uint32_t ufirst[G::MAXR + 2];     // first pick index of each unit
-    uint32_t rkfirst[G::MAXR + 2];    // first pick index by start-rank
+    uint16_t ufirst[G::MAXR + 2];     // first pick index of each unit
+    uint16_t rkfirst[G::MAXR + 2];    // first pick index by start-rank
     uint16_t ustartpos[G::MAXR + 2];
     uint32_t wsum[16];
     uint32_t npicks;
 };
+static_assert(Geo<31, 15>::NT * Geo<31, 15>::HP >= Geo<31, 15>::PKCAP, "pk_pos must fit inside hrow");
 
 template <class G>
 struct TilePriv {
@@ -346,12 +348,14 @@ DCN_HD uint32_t phase_emit_fix(int t, TileSmem<G> &s, TilePriv<G> &pv) {
 
 // ------------------------------------------------------------------ phase 4: compact picks
 template <class G>
-DCN_HD void phase_emit(int t, TileSmem<G> &s, TilePriv<G> &pv, uint32_t excl, uint32_t total) {
+DCN_HD void phase_emit(int t, TileSmem<G> &s, TilePriv<G> &pv, uint32_t excl, uint32_t total,
+                       uint32_t cap = (uint32_t)G::PKCAP) {
     pv.pickoff = excl & 0xFFFFu;
     pv.rankoff = excl >> 16;
     s.poff[t] = excl;
     s.emk[t] = pv.emask | (pv.ust16 << 16);
     if (t == 0) s.npicks = total & 0xFFFFu;
+    if ((total & 0xFFFFu) > cap) return;   // the caller splits the run and retries
     const uint32_t em = pv.emask;
     uint32_t idx = pv.pickoff;
 #pragma unroll
@@ -490,66 +494,74 @@ DCN_HD uint32_t effective_len(const uint8_t *bases, uint64_t gstart, uint32_t le
 // ------------------------------------------------------------------ short-unit tile driver
 // Units [u_begin, u_end) are whole (record or pair) and fit the tile: every base of every unit
 // lies in [origin, origin + BCAP).  Ex provides par(f) = run f for every thread then barrier,
-// and scan(get, put) = block-wide exclusive sum.
-template <class G, class Ex>
-DCN_HD void filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
-    using Priv = TilePriv<G>;
+// scan(get, put) = block-wide exclusive sum, match64 / ballot = warp votes.
+// Barriers per tile: 7.  The last phase has no trailing barrier: the first phase of the next
+// tile touches none of the arrays it reads.
+template <class G>
+DCN_HD void phase_structure(int t, TileSmem<G> &s, const FilterParams &P, uint32_t r_begin, uint32_t n_rec_t,
+                            uint64_t origin) {
     const uint32_t rpu = P.rpu;
-    const uint32_t r_begin = u_begin * rpu;
-    const uint32_t n_rec_t = (u_end - u_begin) * rpu;
+    for (uint32_t i = (uint32_t)t; i < n_rec_t; i += G::NT) {
+        uint64_t gs = P.rec_off[r_begin + i] - P.base0, ge = P.rec_off[r_begin + i + 1] - P.base0;
+        uint32_t sL = (uint32_t)(gs - origin), eL = (uint32_t)(ge - origin);
+        uint32_t eff = sL + effective_len<G, FLAVOUR_FILTER>(P.bases, gs, eL - sL, P.prefix_len);
+        set_bits(s.brk, sL, sL + 1);
+        if (i % rpu == 0) { set_bits(s.ustart, sL, sL + 1); s.ustartpos[i / rpu] = (uint16_t)sL; }
+        if (eff < eL) { set_bits(s.dead, eff, eL); set_bits(s.brk, eff, eL); }
+        if (i == 0 && sL > 0) { set_bits(s.dead, 0, sL); set_bits(s.brk, 0, sL); }
+        if (i == n_rec_t - 1) { set_bits(s.dead, eL, G::NBW * 32); set_bits(s.brk, eL, G::NBW * 32); }
+    }
+}
+
+// first pick index of every unit, and of every distinct unit-start position (rank)
+template <class G>
+DCN_HD void phase_unit_first(int t, TileSmem<G> &s, uint32_t n_units_t, uint32_t npicks) {
+    for (uint32_t u = (uint32_t)t; u < n_units_t; u += G::NT) {
+        uint32_t pos = s.ustartpos[u];
+        uint32_t tt = pos >> 4, ii = pos & 15u;
+        // a unit that starts in the last 16-position chunk or beyond has no window in this tile
+        bool tail = tt >= (uint32_t)(G::NT - 1);
+        uint32_t po = tail ? 0u : s.poff[tt], em = tail ? 0u : s.emk[tt];
+        uint32_t uf = tail ? npicks : (po & 0xFFFFu) + popc32(em & 0xFFFFu & ((1u << ii) - 1u));
+        s.ufirst[u] = (uint16_t)uf;
+        bool last_at_pos = (u + 1 == n_units_t) || (s.ustartpos[u + 1] != pos);
+        if (last_at_pos && !tail) {
+            uint32_t rank = (po >> 16) + popc32((em >> 16) & ((1u << ii) - 1u));
+            s.rkfirst[rank] = (uint16_t)uf;
+        }
+        if (u == 0) s.ufirst[n_units_t] = (uint16_t)npicks;
+    }
+}
+
+// Returns false (after one barrier-consistent decision, nothing written) when the run emits more
+// than PKCAP picks: the caller then splits the run.  A single short unit (<= 1024 bases) never does.
+template <class G, class Ex>
+DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
+    using Priv = TilePriv<G>;
+    const uint32_t r_begin = u_begin * P.rpu;
+    const uint32_t n_rec_t = (u_end - u_begin) * P.rpu;
     const uint32_t n_units_t = u_end - u_begin;
     const uint64_t first_start = P.rec_off[r_begin] - P.base0;
     const uint64_t origin = first_start & ~15ull;   // relative to base0, like every offset below
     const uint64_t n_rel = P.n_bases - P.base0;
 
-    ex.par([&](int t, Priv &) {
+    ex.par([&](int t, Priv &pv) {
         for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
-        for (int i = t; i < G::PKCAP / 32; i += G::NT) { s.vmask[i] = 0; s.hmask[i] = 0; }
+        phase_convert<G, FLAVOUR_FILTER>(t, s, pv, P.bases, n_rel, origin);
     });
-    ex.par([&](int t, Priv &) {
-        for (uint32_t i = (uint32_t)t; i < n_rec_t; i += G::NT) {
-            uint64_t gs = P.rec_off[r_begin + i] - P.base0, ge = P.rec_off[r_begin + i + 1] - P.base0;
-            uint32_t sL = (uint32_t)(gs - origin), eL = (uint32_t)(ge - origin);
-            uint32_t eff = sL + effective_len<G, FLAVOUR_FILTER>(P.bases, gs, eL - sL, P.prefix_len);
-            s.roff[i] = sL;
-            set_bits(s.brk, sL, sL + 1);
-            if (i % rpu == 0) { set_bits(s.ustart, sL, sL + 1); s.ustartpos[i / rpu] = (uint16_t)sL; }
-            if (eff < eL) { set_bits(s.dead, eff, eL); set_bits(s.brk, eff, eL); }
-            if (i == 0 && sL > 0) { set_bits(s.dead, 0, sL); set_bits(s.brk, 0, sL); }
-            if (i == n_rec_t - 1) {
-                s.roff[n_rec_t] = eL;
-                set_bits(s.dead, eL, G::NBW * 32); set_bits(s.brk, eL, G::NBW * 32);
-            }
-        }
+    ex.par([&](int t, Priv &pv) {
+        phase_structure<G>(t, s, P, r_begin, n_rec_t, origin);
+        phase_hash<G>(t, s, pv);
     });
-    ex.par([&](int t, Priv &pv) { phase_convert<G, FLAVOUR_FILTER>(t, s, pv, P.bases, n_rel, origin); });
-    ex.par([&](int t, Priv &pv) { phase_hash<G>(t, s, pv); });
     ex.par([&](int t, Priv &pv) { phase_slide<G>(t, s, pv); });
     ex.scan([&](int t, Priv &pv) { return phase_emit_fix<G>(t, s, pv); },
             [&](int t, Priv &pv, uint32_t excl, uint32_t total) { phase_emit<G>(t, s, pv, excl, total); });
     const uint32_t npicks = s.npicks;
+    if (npicks > (uint32_t)G::PKCAP) { ex.barrier(); return false; }
 
-    // first pick index of every unit, and of every distinct unit-start position (rank)
+    // hash every pick and start its table access early; unit -> pick-range tables on the side
     ex.par([&](int t, Priv &) {
-        for (uint32_t u = (uint32_t)t; u < n_units_t; u += G::NT) {
-            uint32_t pos = s.ustartpos[u];
-            uint32_t tt = pos >> 4, ii = pos & 15u;
-            // a unit that starts in the last 16-position chunk or beyond has no window in this tile
-            bool tail = tt >= (uint32_t)(G::NT - 1);
-            uint32_t po = tail ? 0u : s.poff[tt], em = tail ? 0u : s.emk[tt];
-            uint32_t uf = tail ? npicks : (po & 0xFFFFu) + popc32(em & 0xFFFFu & ((1u << ii) - 1u));
-            s.ufirst[u] = uf;
-            bool last_at_pos = (u + 1 == n_units_t) || (s.ustartpos[u + 1] != pos);
-            if (last_at_pos && !tail) {
-                uint32_t rank = (po >> 16) + popc32((em >> 16) & ((1u << ii) - 1u));
-                s.rkfirst[rank] = uf;
-            }
-            if (u == 0) s.ufirst[n_units_t] = npicks;
-        }
-    });
-
-    // hash every pick; start the table access early
-    ex.par([&](int t, Priv &) {
+        phase_unit_first<G>(t, s, n_units_t, npicks);
         for (uint32_t idx = (uint32_t)t; idx < npicks; idx += G::NT) {
             uint32_t pp = s.pk_pos[idx];
             uint32_t p = pp & 0xFFFFu;
@@ -561,31 +573,49 @@ DCN_HD void filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
             }
         }
     });
-    // probe + distinct-hit test (src/filter_common.rs:143-145: contains && seen.insert)
+    // probe + distinct-hit test (src/filter_common.rs:143-145: contains && seen.insert).
+    // A pick is a duplicate iff an EARLIER valid pick of the same unit has the same hash: lanes of
+    // the same warp are compared with a warp match, the part of the unit that lies before this
+    // warp's 32 picks is scanned in shared memory (32-bit compare first).
     ex.par([&](int t, Priv &) {
         const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
+        const uint32_t lane = (uint32_t)t & 31u;
         for (uint32_t r = 0; r < rounds; r++) {
-            uint32_t idx = r * G::NT + (uint32_t)t;
+            const uint32_t idx = r * G::NT + (uint32_t)t;
+            const uint32_t wbase = idx - lane;
             bool valid = false, hit = false;
+            uint64_t h = 0, b = 0;
+            uint32_t first = 0;
+            Bucket bk;
+            bk.k0 = bk.k1 = bk.k2 = bk.k3 = 0;
             if (idx < npicks) {
                 uint32_t pp = s.pk_pos[idx];
                 valid = (pp & 0x80000000u) != 0;
                 if (valid) {
-                    uint64_t h = s.pk_hash[idx];
-                    uint64_t b = table_bucket(h, P.table.n_buckets);
-                    Bucket bk = load_bucket(P.table.slots, b);
-                    uint32_t first = s.rkfirst[(pp >> 16) & 0x7FFFu];
-                    bool dup = false;
-                    for (uint32_t j = first; j < idx; j++)
-                        dup |= (s.pk_hash[j] == h) && (s.pk_pos[j] & 0x80000000u);
-                    hit = !dup && table_contains_from(P.table, h, b, bk);
+                    h = s.pk_hash[idx];
+                    b = table_bucket(h, P.table.n_buckets);
+                    bk = load_bucket(P.table.slots, b);
+                    first = s.rkfirst[(pp >> 16) & 0x7FFFu];
                 }
+            }
+            const uint32_t vmask = ex.ballot(t, valid);
+            uint32_t same = ex.match64(t, valid ? h : (0x8000000000000000ULL | idx) ^ 0x5bd1e9955bd1e995ULL, valid);
+            bool dup = false;
+            if (valid) {
+                uint32_t unit_lanes = first <= wbase ? 0xFFFFFFFFu : (first - wbase >= 32 ? 0u : 0xFFFFFFFFu << (first - wbase));
+                uint32_t lt = (1u << lane) - 1u;
+                dup = (same & vmask & unit_lanes & lt) != 0;
+                const uint32_t hlo = (uint32_t)h;
+                const uint32_t *h32 = reinterpret_cast<const uint32_t *>(s.pk_hash);
+                for (uint32_t j = first; j < wbase && !dup; j++)
+                    if (h32[2 * j] == hlo) dup = (s.pk_hash[j] == h) && (s.pk_pos[j] & 0x80000000u);
+                hit = !dup && table_contains_from(P.table, h, b, bk);
             }
             ex.ballot2(t, idx, valid, hit, s.vmask, s.hmask);
         }
     });
-    // per-unit totals and the threshold test
-    ex.par([&](int t, Priv &) {
+    // per-unit totals and the threshold test (no trailing barrier, see above)
+    ex.par_nosync([&](int t, Priv &) {
         for (uint32_t u = (uint32_t)t; u < n_units_t; u += G::NT) {
             uint32_t a = s.ufirst[u], b = s.ufirst[u + 1];
             uint32_t total = popc_range(s.vmask, a, b);
@@ -596,14 +626,36 @@ DCN_HD void filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
             P.keep[gu] = meets_criteria(hits, total, P.abs_thr, P.rel_thr, P.deplete) ? 1 : 0;
         }
     });
+    return true;
+}
+
+// a run of short units, split in halves while it emits more picks than one pass can hold
+template <class G, class Ex>
+DCN_HD void filter_short_run(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
+    uint32_t lo = u_begin;
+    uint32_t span = u_end - u_begin;
+    while (lo < u_end) {
+        uint32_t hi = lo + span < u_end ? lo + span : u_end;
+        if (filter_short_tile<G>(ex, s, P, lo, hi)) {
+            if (hi < u_end) ex.barrier();  // the next pass rewrites tables the last phase still reads
+            lo = hi;
+        } else {
+            span = (hi - lo + 1) / 2;      // hi - lo >= 2 here: one short unit always fits
+        }
+    }
 }
 
 // All units whose first base lies in one tile: runs of short units go through
 // filter_short_tile; long units are skipped here (they are cut into chunks by the long path).
 template <class G, class Ex>
-DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const PlanCfg &cfg, uint32_t u_first,
-                        uint32_t u_end) {
+DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const PlanCfg &cfg, uint32_t n_long,
+                        uint32_t u_first, uint32_t u_end) {
     const uint64_t rpu = P.rpu;
+    // common case: the batch has no long unit and the tile's records fit one pass
+    if (n_long == 0 && (uint64_t)(u_end - u_first) * rpu <= (uint64_t)G::MAXR) {
+        filter_short_run<G>(ex, s, P, u_first, u_end);
+        return;
+    }
     uint32_t u = u_first;
     while (u < u_end) {
         uint64_t len = P.rec_off[(uint64_t)(u + 1) * rpu] - P.rec_off[(uint64_t)u * rpu];
@@ -612,9 +664,201 @@ DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const Pla
         while (v < u_end && (uint64_t)(v - u + 1) * rpu <= (uint64_t)G::MAXR &&
                P.rec_off[(uint64_t)(v + 1) * rpu] - P.rec_off[(uint64_t)v * rpu] <= cfg.max_short)
             v++;
-        filter_short_tile<G>(ex, s, P, u, v);
+        filter_short_run<G>(ex, s, P, u, v);
+        ex.barrier();  // a following pass rewrites the tables the last phase still reads
         u = v;
     }
+}
+
+// =====================================================================================
+// Chunked path: one record cut into chunks of CSTRIDE window starts.  Used for units longer than
+// DCN_MAX_SHORT in the filter ("long path", any chunk on any CTA; distinct hits are established
+// through a global (hash, unit) set) and for every record of an index build.
+// =====================================================================================
+struct ChunkDesc { uint32_t rec, chunk; };
+
+template <class G>
+struct ChunkGeo {
+    // a chunk loads from a 16-byte aligned origin (<= 15 bases of slack) and computes one extra
+    // "carry" window before its first own window, so that the consecutive-duplicate rule
+    //  sees its predecessor
+    static constexpr uint32_t CSTRIDE = (uint32_t)G::WCAP - 16u;
+    static constexpr uint32_t PICKCAP = (uint32_t)(G::NT * G::HP);   // pk_pos capacity when it owns all of hrow
+    static_assert(PICKCAP >= CSTRIDE + 1, "every window of a chunk may emit");
+};
+
+// number of chunks of a record with `eff_len` effective bases
+template <class G>
+DCN_HD uint32_t chunks_of(uint64_t eff_len) {
+    if (eff_len < (uint64_t)G::L) return 0;
+    uint64_t nwin = eff_len - (uint64_t)G::L + 1;
+    return (uint32_t)((nwin + ChunkGeo<G>::CSTRIDE - 1) / ChunkGeo<G>::CSTRIDE);
+}
+
+// effective length for long records (64-bit length)
+template <class G, int FLAV>
+DCN_HD uint64_t effective_len64(const uint8_t *bases, uint64_t gstart, uint64_t len, uint32_t prefix_len) {
+    if (len < (uint64_t)G::K) return 0;
+    if (FLAV == FLAVOUR_INDEX) return len;
+    uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;
+    if (n > 0 && bases[gstart + n - 1] == (uint8_t)'\n') n--;
+    return n;
+}
+
+// Runs the per-position phases for chunk `c` of the record whose effective sequence is
+// [gs, gs + eff_len) (offsets relative to base0).  On return pk_pos[0 .. npicks) holds the picks'
+// local positions and *origin_out the offset of local position 0.  Returns npicks.
+template <class G, int FLAV, class Ex>
+DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const uint8_t *bases, uint64_t n_rel, uint64_t gs,
+                            uint64_t eff_len, uint32_t c, uint64_t *origin_out) {
+    using Priv = TilePriv<G>;
+    const uint64_t nwin = eff_len - (uint64_t)G::L + 1;
+    const uint64_t w0 = (uint64_t)c * ChunkGeo<G>::CSTRIDE;
+    const uint32_t nw = (uint32_t)(nwin - w0 < ChunkGeo<G>::CSTRIDE ? nwin - w0 : ChunkGeo<G>::CSTRIDE);
+    const uint32_t carry = c > 0 ? 1u : 0u;
+    const uint64_t a = gs + w0 - carry;          // first window computed by this chunk
+    const uint64_t origin = a & ~15ull;
+    const uint32_t la = (uint32_t)(a - origin);
+    const uint64_t eff_end = gs + eff_len;
+    *origin_out = origin;
+
+    ex.par([&](int t, Priv &pv) {
+        for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
+        phase_convert<G, FLAV>(t, s, pv, bases, n_rel, origin);
+    });
+    ex.par([&](int t, Priv &pv) {
+        if (t == 0) {
+            s.wsum[8] = 0; s.wsum[9] = 0;                            // per-chunk tallies of the consumer phase
+            if (la > 0) { set_bits(s.dead, 0, la); set_bits(s.brk, 0, la); }
+            if (!carry) set_bits(s.brk, la, la + 1);                 // record start: first window always emits
+            set_bits(s.ustart, la, la + 1);                          // one "unit": every pick gets rank 0
+            set_bits(s.dead, la + carry + nw, G::NBW * 32);          // windows of later chunks
+            uint64_t e = eff_end - origin;                           // bases beyond the effective sequence
+            if (e < (uint64_t)(G::NBW * 32)) set_bits(s.brk, (uint32_t)e, G::NBW * 32);
+        }
+        phase_hash<G>(t, s, pv);
+    });
+    ex.par([&](int t, Priv &pv) { phase_slide<G>(t, s, pv); });
+    ex.scan([&](int t, Priv &pv) { return phase_emit_fix<G>(t, s, pv); },
+            [&](int t, Priv &pv, uint32_t excl, uint32_t total) { phase_emit<G>(t, s, pv, excl, total, ChunkGeo<G>::PICKCAP); });
+    return s.npicks;
+}
+
+// ------------------------------------------------------------------ global (hash, unit) set
+// 16-byte entries {hash, unit + 1}; all-zero = empty.  Exact: the full key is stored.
+struct DedupView {
+    unsigned __int128 *slots;
+    uint64_t mask;        // capacity - 1 (power of two)
+    uint32_t *overflow;   // set when an insert gives up
+};
+
+DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
+    const unsigned __int128 val = ((unsigned __int128)((uint64_t)unit + 1) << 64) | h;
+    uint64_t slot = (h ^ ((uint64_t)unit * 0x9E3779B97F4A7C15ULL)) & d.mask;
+    for (uint32_t probes = 0; probes < 4096; probes++) {
+#ifdef __CUDA_ARCH__
+        unsigned __int128 old = atomicCAS(&d.slots[slot], (unsigned __int128)0, val);
+#else
+        unsigned __int128 old = d.slots[slot];
+        if (old == 0) d.slots[slot] = val;
+#endif
+        if (old == 0) return true;
+        if (old == val) return false;
+        slot = (slot + 1) & d.mask;
+    }
+    *d.overflow = 1;
+    return false;
+}
+
+// ------------------------------------------------------------------ long path of the filter
+template <class G, class Ex>
+DCN_HD void filter_long_chunk(Ex &ex, TileSmem<G> &s, const FilterParams &P, const DedupView &dd, ChunkDesc cd) {
+    using Priv = TilePriv<G>;
+    const uint64_t gs = P.rec_off[cd.rec] - P.base0;
+    const uint64_t len = P.rec_off[cd.rec + 1] - P.base0 - gs;
+    const uint64_t eff_len = effective_len64<G, FLAVOUR_FILTER>(P.bases, gs, len, P.prefix_len);
+    const uint32_t unit = cd.rec / P.rpu;
+    uint64_t origin;
+    const uint32_t npicks = chunk_picks<G, FLAVOUR_FILTER>(ex, s, P.bases, P.n_bases - P.base0, gs, eff_len, cd.chunk, &origin);
+    ex.par([&](int t, Priv &) {
+        const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
+        for (uint32_t r = 0; r < rounds; r++) {
+            const uint32_t idx = r * G::NT + (uint32_t)t;
+            bool valid = false, fresh = false;
+            if (idx < npicks) {
+                uint32_t p = s.pk_pos[idx] & 0xFFFFu;
+                valid = pick_kmer_valid<G>(s, p);
+                if (valid) {
+                    uint64_t h = pick_hash<G>(s, p);
+                    if (table_contains(P.table, h)) fresh = dedup_insert(dd, h, unit);
+                }
+            }
+            ex.tally2(t, valid, fresh, &s.wsum[8], &s.wsum[9]);
+        }
+    });
+    ex.par([&](int t, Priv &) {
+        if (t == 0) {
+            ex.global_add(&P.total[unit], s.wsum[8]);
+            ex.global_add(&P.hits[unit], s.wsum[9]);
+        }
+    });
+}
+
+// ------------------------------------------------------------------ index-flavour extraction
+struct IndexParams {
+    const uint8_t *bases;
+    uint64_t base0, n_bases;
+    const uint64_t *rec_off;
+    uint32_t n_rec;
+    const uint32_t *entropy_pass;  // bitmap over (cA, cC, cG) or nullptr when the threshold is 0
+    uint64_t *out;                 // hashes, unordered (duplicates are removed by the sort/unique that follows)
+    uint64_t out_cap;
+    unsigned long long *out_count; // cursor; may exceed out_cap (overflow is detected by the host)
+};
+
+// src/minimizers.rs:73-121 reduced to a table: the scaled entropy of an all-ACGT k-mer depends
+// only on its base counts.  v = forward 2-bit k-mer (A=0 C=1 T=2 G=3).
+template <class G>
+DCN_HD bool entropy_ok(const uint32_t *pass, uint64_t v) {
+    if (!pass) return true;
+    const uint64_t M = 0x5555555555555555ULL;
+    uint64_t lo = v & M, hi = (v >> 1) & M;
+    uint32_t nC = popc32((uint32_t)(lo & ~hi)) + popc32((uint32_t)((lo & ~hi) >> 32));
+    uint32_t nG = popc32((uint32_t)(lo & hi)) + popc32((uint32_t)((lo & hi) >> 32));
+    uint32_t nT = popc32((uint32_t)(~lo & hi)) + popc32((uint32_t)((~lo & hi) >> 32));
+    uint32_t nA = (uint32_t)G::K - nC - nG - nT;
+    uint32_t idx = (nA * 32u + nC) * 32u + nG;   // counts <= K <= 31
+    return (pass[idx >> 5] >> (idx & 31u)) & 1u;
+}
+
+template <class G, class Ex>
+DCN_HD void index_chunk(Ex &ex, TileSmem<G> &s, const IndexParams &P, ChunkDesc cd) {
+    using Priv = TilePriv<G>;
+    const uint64_t gs = P.rec_off[cd.rec] - P.base0;
+    const uint64_t len = P.rec_off[cd.rec + 1] - P.base0 - gs;
+    const uint64_t eff_len = effective_len64<G, FLAVOUR_INDEX>(P.bases, gs, len, 0);
+    uint64_t origin;
+    const uint32_t npicks = chunk_picks<G, FLAVOUR_INDEX>(ex, s, P.bases, P.n_bases - P.base0, gs, eff_len, cd.chunk, &origin);
+    ex.par([&](int t, Priv &) {
+        const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
+        for (uint32_t r = 0; r < rounds; r++) {
+            const uint32_t idx = r * G::NT + (uint32_t)t;
+            bool valid = false;
+            uint64_t h = 0;
+            if (idx < npicks) {
+                uint32_t p = s.pk_pos[idx] & 0xFFFFu;
+                if (pick_kmer_valid<G>(s, p)) {
+                    uint64_t fw = pick_kmer_fw<G>(s, p);
+                    if (entropy_ok<G>(P.entropy_pass, fw)) {
+                        uint64_t rc = revcomp_2bit(fw, G::K);
+                        h = xxh3_u64(fw < rc ? fw : rc);
+                        valid = true;
+                    }
+                }
+            }
+            ex.append64(t, valid, h, P.out, P.out_cap, P.out_count);
+        }
+    });
 }
 
 }  // namespace dcn

@@ -16,7 +16,8 @@
  *     one concatenated byte buffer `bases` + `rec_off[n_rec + 1]` byte offsets.  With `paired != 0`
  *     records 2i and 2i+1 are the mates of pair i and per-unit outputs have n_rec / 2 entries.
  *   - `*_device` variants take device pointers (inputs already in HBM, outputs left in HBM) and a
- *     cudaStream_t passed as void* (NULL = the ctx stream); they are asynchronous on that stream.
+ *     cudaStream_t passed as void* (NULL = the legacy default stream); work is enqueued on that
+ *     stream.  A batch that may contain a unit longer than 1024 bases costs one small stream sync.
  */
 #ifndef DEACON_CUDA_H
 #define DEACON_CUDA_H
@@ -127,6 +128,9 @@ int dcn_last_timing(dcn_ctx *ctx, float *h2d_ms, float *kernel_ms, float *d2h_ms
 int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms);
 /* Number of kernel launches issued by this ctx so far. */
 uint64_t dcn_launch_count(dcn_ctx *ctx);
+/* Sum of the CUDA-event durations of the fused filter kernel's launches since the last take (at most
+ * the last 256), measured on the stream they were launched on; waits for them to finish. */
+int dcn_fused_time_take(dcn_ctx *ctx, float *total_ms, uint32_t *n_launches);
 
 #ifdef __cplusplus
 }

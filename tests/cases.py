@@ -59,6 +59,11 @@ def make_cases():
         mates.append(H.revcomp(g[p + ins - 150:p + ins]))
     add("overlapping_mates", mates, paired=True, deplete=True)
     add("overlapping_mates_search", mates, paired=True)
+    # every window emits a pick (poly-A: non-canonical windows take the rightmost minimum): a tile
+    # with more picks than one pass holds must be split
+    add("dense_picks_polyA", [_b("A" * 150)] * 200 + r150[:30] + [_b("A" * 1000)] * 8, index_records=[_b("A" * 200), g[:3000]])
+    add("dense_picks_polyA_paired", [_b("A" * 150)] * 200 + [_b("T" * 151)] * 100, paired=True, deplete=True,
+        index_records=[_b("A" * 200), g[:3000]])
     # all-N and mixed garbage bytes
     junk = [_b("N" * 150), _b("ACGT" * 20 + "N" + "ACGT" * 20), np.arange(256, dtype=np.uint8), _b("acgtn" * 40)]
     add("non_acgt_bytes", junk * 10 + r150[:100])

@@ -21,8 +21,28 @@ struct HostExec {
     HostExec() : pv(G::NT) {}
     template <class F>
     void par(F f) {
+        // two passes so that warp votes can be answered (see ballot/match64); phases are
+        // idempotent apart from the votes' consumers, which only act in pass 1
+        calls.assign(G::NT, 0);
+        pass = 0;
+        std::vector<TilePriv<G>> saved = pv;
+        snapshot_begin();
+        for (int t = 0; t < G::NT; t++) f(t, pv[t]);
+        bool used_votes = false;
+        for (auto c : calls) used_votes |= c != 0;
+        if (!used_votes) { pass = 1; return; }
+        pv = saved;
+        snapshot_restore();
+        calls.assign(G::NT, 0);
+        pass = 1;
         for (int t = 0; t < G::NT; t++) f(t, pv[t]);
     }
+    // shared-memory snapshot so that pass 0 of a vote-using phase has no side effects
+    void *smem_ptr = nullptr;
+    size_t smem_bytes = 0;
+    std::vector<uint8_t> smem_copy;
+    void snapshot_begin() { if (smem_ptr) { smem_copy.assign((uint8_t *)smem_ptr, (uint8_t *)smem_ptr + smem_bytes); } }
+    void snapshot_restore() { if (smem_ptr) memcpy(smem_ptr, smem_copy.data(), smem_bytes); }
     template <class Get, class Put>
     void scan(Get get, Put put) {
         std::vector<uint32_t> v(G::NT);
@@ -32,14 +52,60 @@ struct HostExec {
         for (int t = 0; t < G::NT; t++) { ex[t] = total; total += v[t]; }
         for (int t = 0; t < G::NT; t++) put(t, pv[t], ex[t], total);
     }
-    void ballot2(int, uint32_t idx, bool valid, bool hit, uint32_t *vm, uint32_t *hm) {
-        if (idx >= (uint32_t)G::PKCAP) return;
+    template <class F>
+    void par_nosync(F f) { par(f); }
+    void barrier() {}
+    // Warp votes: a phase runs thread after thread here, so a vote is emulated in two passes --
+    // pass 0 records every lane's operand, pass 1 (the phase re-run) answers from the record.
+    // par() runs vote-using phases twice when `two_pass` is set by the phase itself.
+    std::vector<uint8_t> vote_p;
+    std::vector<uint64_t> vote_v;
+    int pass = 0;
+    uint32_t ballot(int t, bool p) {
+        size_t slot = vote_slot(t);
+        if (pass == 0) { vote_p[slot] = p; return 0; }
+        uint32_t m = 0;
+        size_t w = slot - (size_t)(t & 31);
+        for (int l = 0; l < 32; l++) m |= (uint32_t)vote_p[w + l] << l;
+        return m;
+    }
+    uint32_t match64(int t, uint64_t v, bool) {
+        size_t slot = vote_slot(t);
+        if (pass == 0) { vote_v[slot] = v; return 0; }
+        uint32_t m = 0;
+        size_t w = slot - (size_t)(t & 31);
+        for (int l = 0; l < 32; l++) m |= (uint32_t)(vote_v[w + l] == v) << l;
+        return m;
+    }
+    // one slot per (vote call number of this thread, thread)
+    std::vector<uint32_t> calls;
+    size_t vote_slot(int t) {
+        if (calls.empty()) calls.assign(G::NT, 0);
+        size_t c = calls[t]++;
+        size_t slot = c * G::NT + (size_t)t;
+        if (vote_p.size() <= slot + 32) { vote_p.resize(slot + 64 * G::NT, 0); vote_v.resize(slot + 64 * G::NT, 0); }
+        return slot;
+    }
+    void tally2(int, bool a, bool b, uint32_t *ca, uint32_t *cb) { *ca += a; *cb += b; }
+    void global_add(uint32_t *p, uint32_t v) { *p += v; }
+    void append64(int, bool valid, uint64_t v, uint64_t *out, uint64_t cap, unsigned long long *count) {
+        if (!valid) return;
+        unsigned long long pos = (*count)++;
+        if (pos < cap) out[pos] = v;
+    }
+    void ballot2(int t, uint32_t idx, bool valid, bool hit, uint32_t *vm, uint32_t *hm) {
+        if (pass == 0 || idx >= (uint32_t)G::PKCAP) return;
+        if ((t & 31) == 0) { vm[idx >> 5] = 0; hm[idx >> 5] = 0; }
         if (valid) vm[idx >> 5] |= 1u << (idx & 31);
         if (hit) hm[idx >> 5] |= 1u << (idx & 31);
     }
 };
 
+static uint64_t dedup_cap_override = 0;
+
 extern "C" {
+
+void emu_set_dedup_cap(uint64_t cap) { dedup_cap_override = cap; }
 
 // bucketed table, same layout as the device table (dcn_core.cuh)
 int emu_table_build(const uint64_t *keys, uint64_t n, double load, uint64_t **slots_out, uint64_t *nb_out,
@@ -95,14 +161,68 @@ int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const ui
     auto *s = new TileSmem<G>();
     memset(s, 0xA5, sizeof(*s));  // shared memory starts out as garbage on the device
     HostExec<G> ex;
+    ex.smem_ptr = s; ex.smem_bytes = sizeof(*s);
     ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); });
-    int rc = 0;
     for (uint32_t tile = 0; tile < n_tiles; tile++)
-        filter_tile<G>(ex, *s, P, cfg, tile_first[tile], tile_end[tile]);
-    if (n_long) rc = -100;  // long units are handled by a different kernel (not emulated here)
+        if (tile_first[tile] < tile_end[tile])
+            filter_tile<G>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
+    int rc = 0;
+    if (n_long) {  // mirrors prep_long_kernel + the chunk loop of filter_fused_kernel + finalize_long_kernel
+        std::vector<uint32_t> long_units;
+        std::vector<ChunkDesc> desc;
+        uint64_t long_bases = 0;
+        for (uint32_t u = 0; u < P.n_units; u++) {
+            uint64_t len = rec_off[(uint64_t)(u + 1) * P.rpu] - rec_off[(uint64_t)u * P.rpu];
+            if (len <= DCN_MAX_SHORT) continue;
+            long_units.push_back(u);
+            long_bases += len;
+            hits[u] = 0; total[u] = 0;
+            for (uint32_t r = u * P.rpu; r < (u + 1) * P.rpu; r++) {
+                uint64_t gs = rec_off[r], rl = rec_off[r + 1] - gs;
+                uint32_t nc = chunks_of<G>(effective_len64<G, FLAVOUR_FILTER>(bases, gs, rl, prefix_len));
+                for (uint32_t c = 0; c < nc; c++) desc.push_back(ChunkDesc{r, c});
+            }
+        }
+        uint64_t cap = 4096;
+        while (cap < long_bases / 2) cap <<= 1;
+        if (dedup_cap_override) cap = dedup_cap_override;
+        std::vector<unsigned __int128> slots(cap, 0);
+        uint32_t overflow = 0;
+        DedupView dd{slots.data(), cap - 1, &overflow};
+        for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G>(ex, *s, P, dd, desc[i]);
+        for (uint32_t u : long_units)
+            keep[u] = meets_criteria(hits[u], total[u], abs_thr, rel_thr, deplete) ? 1 : 0;
+        if (overflow) rc = -6;
+    }
     delete s;
     free(bases);
     return rc;
+}
+
+// mirrors dcn_index_build_device's extraction (k=31, w=15): unordered hashes, duplicates included
+long long emu_index_extract(const uint8_t *bases_in, const uint64_t *rec_off, uint32_t n_rec, const uint32_t *entropy_pass,
+                            uint64_t *out, uint64_t out_cap) {
+    using G = Geo<31, 15>;
+    uint64_t n_bases = rec_off[n_rec];
+    uint8_t *bases = (uint8_t *)aligned_alloc(16, ((n_bases + 15) / 16 + 1) * 16);
+    memcpy(bases, bases_in, n_bases);
+    unsigned long long count = 0;
+    IndexParams P;
+    P.bases = bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = rec_off; P.n_rec = n_rec;
+    P.entropy_pass = entropy_pass; P.out = out; P.out_cap = out_cap; P.out_count = &count;
+    auto *s = new TileSmem<G>();
+    memset(s, 0xA5, sizeof(*s));
+    HostExec<G> ex;
+    ex.smem_ptr = s; ex.smem_bytes = sizeof(*s);
+    ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); });
+    for (uint32_t r = 0; r < n_rec; r++) {
+        uint64_t rl = rec_off[r + 1] - rec_off[r];
+        uint32_t nc = chunks_of<G>(rl < (uint64_t)G::K ? 0 : rl);
+        for (uint32_t c = 0; c < nc; c++) index_chunk<G>(ex, *s, P, ChunkDesc{r, c});
+    }
+    delete s;
+    free(bases);
+    return (long long)count;
 }
 
 }  // extern "C"

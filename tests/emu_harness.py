@@ -49,3 +49,21 @@ def filter_batch(keys, bases, off, paired=False, prefix=0, abs_thr=2, rel=0.01, 
                             C.c_uint32(abs_thr), C.c_double(rel), int(deplete), _p(keep, u8p), _p(hits, u32p), _p(tot, u32p))
     L.emu_free(slots)
     return rc, keep[:nu], hits[:nu], tot[:nu]
+
+
+def index_extract(bases, off, entropy_bitmap=None):
+    """-> unordered hashes (with duplicates) of every record, index flavour."""
+    L = lib()
+    L.emu_index_extract.restype = C.c_longlong
+    n_rec = len(off) - 1
+    cap = max(16, len(bases))
+    out = np.zeros(cap, np.uint64)
+    b = bases if len(bases) else np.zeros(1, np.uint8)
+    eb = None if entropy_bitmap is None else _p(np.ascontiguousarray(entropy_bitmap, np.uint32), u32p)
+    n = L.emu_index_extract(_p(b, u8p), _p(off, u64p), C.c_uint32(n_rec), eb, _p(out, u64p), C.c_uint64(cap))
+    assert 0 <= n <= cap
+    return out[:n]
+
+
+def set_dedup_cap(cap):
+    lib().emu_set_dedup_cap(C.c_uint64(cap))

@@ -39,3 +39,39 @@ def test_high_load_factor_table_probing():
     for load in (0.05, 0.5, 0.9):
         rc, k, h, t = E.filter_batch(idx.keys(), bases, off, load=load)
         assert rc == 0 and np.array_equal(h, oh) and np.array_equal(t, ot) and np.array_equal(k, ok)
+
+
+@pytest.mark.parametrize("case", CASES.make_long_cases(), ids=lambda c: c["name"])
+def test_long_path_matches_oracle(case):
+    idx = _index_for(case)
+    bases, off = H.concat(case["records"])
+    rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"])
+    assert rc == 0
+    ok, oh, ot = O.filter_batch(idx, bases, off, paired=case["paired"], prefix_len=case["prefix"], abs_thr=case["abs"],
+                                rel_thr=case["rel"], deplete=case["deplete"])
+    assert np.array_equal(t, ot), "total minimizers differ"
+    assert np.array_equal(h, oh), "distinct hit counts differ"
+    assert np.array_equal(k, ok), "keep decisions differ"
+
+
+def test_long_path_reports_dedup_overflow():
+    case = CASES.make_long_cases()[0]
+    idx = _index_for(case)
+    bases, off = H.concat(case["records"])
+    E.set_dedup_cap(64)
+    try:
+        rc, *_ = E.filter_batch(idx.keys(), bases, off)
+        assert rc == -6      # DCN_ERR_OVERFLOW: the API retries with a larger set, never drops hits
+    finally:
+        E.set_dedup_cap(0)
+
+
+def test_index_extraction_matches_oracle_set():
+    g = H.random_genome(50_000, 41)
+    recs = [g[:20_000].copy(), g[20_000:20_040].copy(), np.zeros(0, np.uint8), g[20_040:].copy(),
+            np.frombuffer(b"ACGTNNNNRYKMacgtnryk" * 300, np.uint8).copy(), np.frombuffer(b"A" * 9000, np.uint8).copy()]
+    recs[0][[100, 5000, 5001, 19_999]] = [ord("N"), ord("R"), ord("y"), ord("-")]
+    bases, off = H.concat(recs)
+    got = np.unique(E.index_extract(bases, off))
+    want = O.index_build((bases, off), 31, 15).keys()
+    assert np.array_equal(got, want)

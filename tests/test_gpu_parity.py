@@ -134,3 +134,93 @@ def test_device_pointer_api_matches_host_api(gpu):
     assert np.array_equal(d_k.cpu().numpy(), k)
     assert np.array_equal(d_h.cpu().numpy().view(np.uint32), h)
     assert np.array_equal(d_t.cpu().numpy().view(np.uint32), t)
+
+
+@pytest.mark.parametrize("case", CASES.make_long_cases(), ids=lambda c: c["name"])
+def test_long_path_matches_oracle(gpu, case):
+    """Units longer than 1024 bases: chunked kernel + global (hash, unit) distinct-hit set."""
+    _check(gpu, _index_for(case), case)
+
+
+def test_ont_like_reads_config3_shape(gpu):
+    """BASELINE config 3 shape, scaled: gamma(2) lengths, mean 10 kbp, 5 % substitutions, search mode."""
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(2_000_000, 51)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    rng = np.random.default_rng(52)
+    lens = np.clip(rng.gamma(2.0, 5000.0, 600), 200, 200_000).astype(int)
+    reads = []
+    for i, ln in enumerate(lens):
+        if i % 2 == 0:
+            p = int(rng.integers(0, len(g) - ln))
+            r = g[p:p + ln].copy()
+            m = rng.random(ln) < 0.05
+            r[m] = H.ACGT[rng.integers(0, 4, int(m.sum()))]
+        else:
+            r = H.ACGT[rng.integers(0, 4, ln)]
+        reads.append(r)
+    bases, off = H.concat(reads)
+    k, h, t = gpu.filter_batch(bases, off)
+    ok, oh, ot = O.filter_batch(idx, bases, off, threads=8)
+    assert np.array_equal(t, ot) and np.array_equal(h, oh) and np.array_equal(k, ok)
+    assert int(oh.max()) > 500   # long host-derived reads carry hundreds of distinct hits
+
+
+def test_index_build_matches_oracle_key_set(gpu):
+    """Config 4 shape, scaled: GPU extraction + radix sort + unique == the oracle's key set; the
+    resident table then answers like the oracle's set."""
+    g = H.random_genome(3_000_000, 61)
+    recs = [g[:1_000_000].copy(), g[1_000_000:1_000_030].copy(), np.zeros(0, np.uint8), g[1_000_030:].copy(),
+            np.frombuffer(b"ACGTNNNNRYKMacgtnryk" * 500, np.uint8).copy(), np.frombuffer(b"A" * 20_000, np.uint8).copy()]
+    recs[0][[100, 5000, 5001, 999_999]] = [ord("N"), ord("R"), ord("y"), ord("-")]
+    bases, off = H.concat(recs)
+    keys = gpu.index_build(bases, off, 31, 15, 0.0, make_resident=True)
+    want = O.index_build((bases, off), 31, 15, threads=8).keys()
+    assert np.array_equal(keys, want)
+    assert gpu.index_info()["n_keys"] == len(want)
+    reads = H.sample_reads(g, 5000, 150, 62)
+    rb, ro = H.concat(reads)
+    k, h, t = gpu.filter_batch(rb, ro, paired=True, deplete=True)
+    ok, oh, ot = O.filter_batch(O.IndexSet(want), rb, ro, paired=True, deplete=True, threads=8)
+    assert np.array_equal(t, ot) and np.array_equal(h, oh) and np.array_equal(k, ok)
+
+
+def test_index_build_entropy_filter(gpu):
+    """-e 0.5 (src/minimizers.rs:163-168) on a reference with low-complexity inserts."""
+    g = H.random_genome(400_000, 71)
+    rng = np.random.default_rng(72)
+    for _ in range(80):   # homopolymer / dinucleotide / low-entropy runs
+        p = int(rng.integers(0, len(g) - 400))
+        unit = [b"A", b"T", b"AC", b"GT", b"AAC", b"AAAAAAAG"][int(rng.integers(0, 6))]
+        run = np.frombuffer((unit * 400)[:int(rng.integers(60, 400))], np.uint8)
+        g[p:p + len(run)] = run
+    bases, off = H.concat([g])
+    for thr in (0.5, 0.25, 0.9):
+        keys = gpu.index_build(bases, off, 31, 15, thr, make_resident=False)
+        want = O.index_build((bases, off), 31, 15, entropy=thr, threads=8).keys()
+        assert np.array_equal(keys, want), f"entropy threshold {thr}"
+    full = gpu.index_build(bases, off, 31, 15, 0.0, make_resident=False)
+    assert len(full) > len(gpu.index_build(bases, off, 31, 15, 0.5, make_resident=False))
+
+
+def test_idx_file_roundtrip_through_gpu(gpu, tmp_path):
+    """write_minimizers -> load_minimizer_hashes -> resident table (src/index.rs:80-164)."""
+    from deacon_server_b200 import IndexHeader, load_minimizer_hashes, write_minimizers
+    g = H.random_genome(300_000, 81)
+    bases, off = H.concat([g])
+    keys = gpu.index_build(bases, off, 31, 15, 0.0, make_resident=False)
+    p = tmp_path / "ref.idx"
+    write_minimizers(keys, IndexHeader(2, 31, 15), p)
+    ver, k, w, okeys = O.idx_decode(open(p, "rb").read())       # the oracle's codec reads what we wrote
+    assert (ver, k, w) == (2, 31, 15) and np.array_equal(okeys, keys)
+    got, hdr = load_minimizer_hashes(p)
+    hdr2 = gpu.load_index(p)
+    assert hdr2.kmer_length == 31 and gpu.index_info()["n_keys"] == len(keys) and np.array_equal(got, keys)
+
+
+def test_unsupported_kw_fails_loudly(gpu):
+    from deacon_server_b200 import DeaconCudaError, IndexHeader
+    gpu.index_upload(np.array([1, 2, 3], np.uint64), IndexHeader(2, 21, 11))
+    with pytest.raises(DeaconCudaError, match="k=31"):
+        gpu.filter_batch(np.frombuffer(b"ACGT" * 40, np.uint8), np.array([0, 160], np.uint64))
