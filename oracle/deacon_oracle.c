@@ -498,7 +498,8 @@ void dcno_filter_batch(const dcno_set *idx, const uint8_t *bases, const uint64_t
  * whose start lies in its range, and only the SET of hashes matters for an index. */
 #define DCNO_CHUNK (1u << 20)
 typedef struct {
-    dcno_set *dst; const uint8_t *seq; size_t len; int k, w; float thr; pthread_mutex_t mu;
+    const uint8_t *seq; size_t len; int k, w; float thr;
+    uint64_t **chunk_h; size_t *chunk_n;   /* per-chunk results, merged after the parallel phase */
 } build_ctx;
 static void build_body(void *c_, uint64_t b, uint64_t e, int tid) {
     (void)tid;
@@ -509,9 +510,9 @@ static void build_body(void *c_, uint64_t b, uint64_t e, int tid) {
         size_t s = (size_t)ch * DCNO_CHUNK, en = s + DCNO_CHUNK + l - 1;
         if (en > c->len) en = c->len;
         size_t n = dcno_extract_index(c->seq + s, en - s, c->k, c->w, c->thr, hb);
-        pthread_mutex_lock(&c->mu);
-        dcno_set_insert_many(c->dst, hb, n, 1);
-        pthread_mutex_unlock(&c->mu);
+        c->chunk_h[ch] = (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+        memcpy(c->chunk_h[ch], hb, n * sizeof(uint64_t));
+        c->chunk_n[ch] = n;
     }
     free(hb);
 }
@@ -520,8 +521,21 @@ void dcno_index_build(dcno_set *dst, const uint8_t *bases, const uint64_t *rec_o
     for (uint32_t r = 0; r < n_rec; r++) {
         size_t len = (size_t)(rec_off[r + 1] - rec_off[r]);
         if (len < (size_t)k) continue;                               /* src/minimizers.rs:135-137 */
-        build_ctx c = {dst, bases + rec_off[r], len, k, w, entropy_thr, PTHREAD_MUTEX_INITIALIZER};
-        parallel_for((len + DCNO_CHUNK - 1) / DCNO_CHUNK, 1, threads, build_body, &c);
+        size_t nchunk = (len + DCNO_CHUNK - 1) / DCNO_CHUNK;
+        build_ctx c = {bases + rec_off[r], len, k, w, entropy_thr,
+                       (uint64_t **)calloc(nchunk, sizeof(uint64_t *)), (size_t *)calloc(nchunk, sizeof(size_t))};
+        parallel_for(nchunk, 1, threads, build_body, &c);
+        size_t total = 0;
+        for (size_t i = 0; i < nchunk; i++) total += c.chunk_n[i];
+        uint64_t *all = (uint64_t *)malloc((total ? total : 1) * sizeof(uint64_t));
+        size_t at = 0;
+        for (size_t i = 0; i < nchunk; i++) {
+            memcpy(all + at, c.chunk_h[i], c.chunk_n[i] * sizeof(uint64_t));
+            at += c.chunk_n[i];
+            free(c.chunk_h[i]);
+        }
+        dcno_set_insert_many(dst, all, total, threads);               /* src/index.rs:267-284 extend */
+        free(all); free(c.chunk_h); free(c.chunk_n);
     }
 }
 

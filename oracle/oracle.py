@@ -158,8 +158,8 @@ def meets_criteria(hits: int, total: int, abs_thr: int, rel_thr: float, deplete:
 class IndexSet:
     """FxHashSet<u64> stand-in."""
 
-    def __init__(self, keys=None, threads: int = 1):
-        self._h = lib().dcno_set_new(0 if keys is None else len(keys))
+    def __init__(self, keys=None, threads: int = 1, expected: int = 0):
+        self._h = lib().dcno_set_new(max(expected, 0 if keys is None else len(keys)))
         if keys is not None and len(keys):
             self.insert(keys, threads)
 
@@ -199,7 +199,7 @@ def concat_records(records):
 
 def index_build(records, k=31, w=15, entropy=0.0, threads=1) -> IndexSet:
     bases, off = records if isinstance(records, tuple) else concat_records(records)
-    s = IndexSet()
+    s = IndexSet(expected=int(0.14 * len(bases)) + 64)   # pre-sized: ~0.126 minimizers per base
     if len(bases) == 0:
         bases = np.zeros(1, np.uint8)
     lib().dcno_index_build(s._h, _p(bases, _u8p), _p(off, _u64p), len(off) - 1, k, w, entropy, threads)
