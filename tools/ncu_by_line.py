@@ -76,3 +76,28 @@ for key, e in sorted(agg.items(), key=lambda kv: -kv[1][2])[:top]:
     st = sorted(e[3].items(), key=lambda kv: -kv[1])[:3]
     sts = " ".join(f"{h[6:]}={v}" for h, v in st if v)
     print(f"{key[0] + ':' + str(key[1]):28s} {100*e[0]/tot_inst:6.2f} {100*e[2]/max(tot_samp,1):6.2f}  [{sts}] {src(*key)}")
+
+# ---- per-phase roll-up (line ranges of dcn_tile.cuh)
+if os.environ.get("NCU_PHASES", "1") == "1":
+    import bisect
+    tile = os.path.join(root, "deacon_server_b200", "csrc", "dcn_tile.cuh")
+    marks = []
+    for i, ln in enumerate(open(tile).read().splitlines(), 1):
+        m = re.match(r"DCN_HD\s+\S+\s+\*?(\w+)\(", ln)
+        if m:
+            marks.append((i, m.group(1)))
+    starts = [m[0] for m in marks]
+    ph = defaultdict(lambda: [0, 0, defaultdict(int)])
+    for key, e in agg.items():
+        if key[0] == "dcn_tile.cuh":
+            j = bisect.bisect_right(starts, key[1]) - 1
+            name = marks[j][1] if j >= 0 else "?"
+        else:
+            name = key[0]
+        ph[name][0] += e[0]; ph[name][1] += e[2]
+        for h, v in e[3].items():
+            ph[name][2][h] += v
+    print("\nper function: inst%  samp%  top stalls")
+    for name, e in sorted(ph.items(), key=lambda kv: -kv[1][0]):
+        st = sorted(e[2].items(), key=lambda kv: -kv[1])[:3]
+        print(f"{name:28s} {100*e[0]/tot_inst:6.2f} {100*e[1]/max(tot_samp,1):6.2f}  " + " ".join(f"{h[6:]}={100*v/max(tot_samp,1):.1f}%" for h, v in st if v))
