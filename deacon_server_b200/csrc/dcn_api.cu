@@ -453,19 +453,82 @@ int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off
     return rc;
 }
 
+// ---------------------------------------------------------------------------- B2 lookup
+int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t *d_rec_off, uint32_t n_rec,
+                            uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep, uint32_t *d_hits,
+                            uint32_t *d_total, void *stream) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
+    if (n_rec == 0) return DCN_OK;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    TableView tv;
+    tv.slots = ctx->table.as<uint64_t>(); tv.n_buckets = ctx->n_buckets; tv.has_empty_key = ctx->has_empty;
+    CK(ctx->plan.ensure(256));
+    BatchStats *d_stats = ctx->plan.as<BatchStats>();
+    const int pb = 256;
+    const int pg = (int)std::min<uint64_t>(((uint64_t)n_rec + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
+    uint64_t dedup_cap = 0;
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CK(cudaMemsetAsync(d_stats, 0, sizeof(BatchStats), st));
+        prep_stats_kernel<<<pg, pb, 0, st>>>(d_rec_off, 1, n_rec, d_stats);   // records with > 1024 hashes
+        BatchStats hs;
+        CK(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        DedupView dd;
+        dd.slots = nullptr; dd.mask = 0; dd.overflow = &d_stats->overflow;
+        if (hs.n_long) {
+            if (!dedup_cap) dedup_cap = next_pow2(std::max<uint64_t>(4096, hs.long_bases * 2));
+            CK(ctx->dedup.ensure(dedup_cap * 16));
+            CK(cudaMemsetAsync(ctx->dedup.p, 0, dedup_cap * 16, st));
+            dd.slots = ctx->dedup.as<unsigned __int128>(); dd.mask = dedup_cap - 1;
+        }
+        const int grid = (int)std::min<uint64_t>(((uint64_t)n_rec * 32 + 255) / 256, (uint64_t)ctx->sm_count * 8);
+        lookup_kernel<<<grid, 256, 0, st>>>(d_hashes, d_rec_off, n_rec, tv, dd, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        if (!hs.n_long) break;
+        BatchStats after;
+        CK(cudaMemcpyAsync(&after, d_stats, sizeof(after), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (!after.overflow) break;
+        if (attempt == 3) return ctx->fail(DCN_ERR_OVERFLOW, "distinct-hit set overflowed after 4 attempts");
+        dedup_cap *= 4;
+    }
+    return DCN_OK;
+}
+
+int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_off, uint32_t n_rec, uint32_t abs_thr,
+                     double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!rec_off || !keep || !hits || !total) return ctx->fail(DCN_ERR_ARG, "null pointer");
+    if (n_rec == 0) return DCN_OK;
+    if (rec_off[0] != 0) return ctx->fail(DCN_ERR_ARG, "rec_off[0] must be 0");
+    const uint64_t n_hash = rec_off[n_rec];
+    if (n_hash && !hashes) return ctx->fail(DCN_ERR_ARG, "null hash pointer");
+    CK(cudaSetDevice(ctx->device));
+    Slot &s = ctx->slot[0];
+    cudaStream_t st = s.stream;
+    CK(s.bases.ensure(n_hash * 8 + 64)); CK(s.off.ensure((size_t)(n_rec + 1) * 8));
+    CK(s.keep.ensure(n_rec)); CK(s.hits.ensure((size_t)n_rec * 4)); CK(s.total.ensure((size_t)n_rec * 4));
+    if (n_hash) CK(cudaMemcpyAsync(s.bases.p, hashes, n_hash * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s.off.p, rec_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = dcn_lookup_batch_device(ctx, s.bases.as<uint64_t>(), s.off.as<uint64_t>(), n_rec, abs_thr, rel_thr, deplete,
+                                     s.keep.as<uint8_t>(), s.hits.as<uint32_t>(), s.total.as<uint32_t>(), st);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(keep, s.keep.p, n_rec, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hits, s.hits.p, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(total, s.total.p, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return DCN_OK;
+}
+
 // ---------------------------------------------------------------------------- not yet built (round 1)
-int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *, const uint64_t *, uint32_t, uint32_t, double, int, uint8_t *,
-                     uint32_t *, uint32_t *) {
-    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_lookup_batch: not implemented yet") : DCN_ERR_ARG;
-}
-int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *, const uint64_t *, uint32_t, uint32_t, double, int,
-                            uint8_t *, uint32_t *, uint32_t *, void *) {
-    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_lookup_batch_device: not implemented yet") : DCN_ERR_ARG;
-}
 int dcn_extract(dcn_ctx *ctx, int, const uint8_t *, const uint64_t *, uint32_t, uint8_t, uint8_t, uint32_t, float,
                 uint64_t *, uint32_t *, uint64_t *, uint64_t) {
     return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_extract: not implemented yet") : DCN_ERR_ARG;
 }
+
 // src/minimizers.rs:73-121 evaluated on the host for every base-count triple: the same f32
 // operations in the same order (p = count / total; entropy -= p * log2f(p); entropy / 2 >= thr).
 static void build_entropy_bitmap(int k, float thr, std::vector<uint32_t> &bits) {

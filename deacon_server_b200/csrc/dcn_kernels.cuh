@@ -21,6 +21,7 @@ struct DevExec {
     __device__ __forceinline__ void par_nosync(F f) { f((int)threadIdx.x, pv); }
     __device__ __forceinline__ void barrier() { __syncthreads(); }
     __device__ __forceinline__ uint32_t ballot(int, bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ __forceinline__ uint32_t bcast0(int, uint32_t v) { return __shfl_sync(0xFFFFFFFFu, v, 0); }
     // lanes of this warp holding the same 64-bit value
     __device__ __forceinline__ uint32_t match64(int, uint64_t v, bool) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
     // add the number of lanes with a / b set to two shared-memory counters
@@ -201,6 +202,59 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
         const uint32_t n_chunks = st->n_chunks;
         for (uint32_t w = gridDim.x - 1 - blockIdx.x; w < n_chunks; w += gridDim.x)
             filter_long_chunk<G>(ex, s, P, dd, desc[w]);
+    }
+}
+
+// ------------------------------------------------------------------ B2: lookup on pre-hashed records
+// unpaired_should_keep / paired_should_keep (src/remote_filter.rs:230-301): one hash list per
+// record.  One warp per record: lanes take 32 consecutive hashes (coalesced 8-byte loads), each
+// lane probes one 32-byte bucket, distinct hits by warp match within the 32 and a scan of the
+// record's earlier hashes for records of up to DCN_MAX_SHORT hashes; longer records go through
+// the global (hash, record) set.  No shared memory, so 64 warps per SM keep ~2000 probes in flight.
+__global__ void __launch_bounds__(256)
+lookup_kernel(const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ rec_off, uint32_t n_rec,
+              TableView table, DedupView dd, uint32_t abs_thr, double rel_thr, int deplete,
+              uint8_t *__restrict__ keep, uint32_t *__restrict__ hits_out, uint32_t *__restrict__ total_out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rec; r += warps) {
+        const uint64_t a = rec_off[r], b = rec_off[r + 1];
+        const bool big = b - a > DCN_MAX_SHORT;
+        uint32_t hits = 0;
+        for (uint64_t base = a; base < b; base += 32) {
+            const uint64_t i = base + lane;
+            const bool in = i < b;
+            uint64_t h = 0;
+            bool found = false;
+            if (in) {
+                h = hashes[i];
+                found = table_contains(table, h);
+            }
+            bool fresh;
+            if (big) {
+                fresh = found && dedup_insert(dd, h, r);
+            } else {
+                const uint32_t inmask = __ballot_sync(0xFFFFFFFFu, in);
+                const uint32_t same = __match_any_sync(0xFFFFFFFFu, (unsigned long long)h);
+                bool dup = (same & inmask & lt) != 0;
+                if (found && !dup) {
+                    const uint32_t hlo = (uint32_t)h;
+                    for (uint64_t j = a; j < base && !dup; j++) {
+                        uint64_t e = hashes[j];
+                        if ((uint32_t)e == hlo) dup = e == h;
+                    }
+                }
+                fresh = found && !dup;
+            }
+            hits += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, fresh));
+        }
+        if (lane == 0) {
+            const uint64_t total = b - a;
+            hits_out[r] = hits;
+            total_out[r] = (uint32_t)total;
+            keep[r] = meets_criteria(hits, total, abs_thr, rel_thr, deplete) ? 1 : 0;
+        }
     }
 }
 

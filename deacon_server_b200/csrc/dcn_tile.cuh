@@ -43,7 +43,7 @@ struct alignas(16) TileSmem {
     u32x4 ag[G::NV + 6];              // per vector: E_fw, E_rc (own role), N_fw, N_rc (right-neighbour role)
     union {                           // hrow is dead once the window minima are taken; picks reuse it
         uint32_t hrow[G::NT * G::HP]; // ntHash of the 16 k-mers of each thread
-        uint32_t pk_pos[G::PKCAP];    // local position | start-rank << 16 | valid << 31
+        uint32_t pk_pos[G::PKCAP];    // local position | start-rank << 16 | in-index << 30 | valid << 31
     };
     uint64_t pk_hash[G::PKCAP];       // xxh3 of each pick
     u32x2 tb0[256];                   // 4-base aggregate table (fw, rc)
@@ -60,6 +60,8 @@ struct alignas(16) TileSmem {
     uint16_t ufirst[G::MAXR + 2];     // first pick index of each unit
     uint16_t rkfirst[G::MAXR + 2];    // first pick index by start-rank
     uint16_t ustartpos[G::MAXR + 2];
+    uint32_t rec_se[G::MAXR];         // record start | end << 16 (tile-local), loaded one phase early
+    uint16_t rec_eff[G::MAXR];        // end of the record's effective sequence (tile-local)
     uint32_t wsum[16];
     uint32_t npicks;
 };
@@ -356,15 +358,19 @@ DCN_HD void phase_emit(int t, TileSmem<G> &s, TilePriv<G> &pv, uint32_t excl, ui
     s.emk[t] = pv.emask | (pv.ust16 << 16);
     if (t == 0) s.npicks = total & 0xFFFFu;
     if ((total & 0xFFFFu) > cap) return;   // the caller splits the run and retries
-    const uint32_t em = pv.emask;
+    uint32_t em = pv.emask;
     uint32_t idx = pv.pickoff;
-#pragma unroll
-    for (int i = 0; i < 16; i++) {   // static indexing keeps pv in registers
-        if (em & (1u << i)) {
-            uint32_t rel = (pv.rel4[i >> 2] >> (8 * (i & 3))) & 0xFFu;
-            uint32_t rank = pv.rankoff + popc32(pv.ust16 & ((2u << i) - 1u)) - 1u;
-            s.pk_pos[idx++] = ((uint32_t)(16 * t) + rel) | ((rank & 0x7FFFu) << 16);
-        }
+    const uint64_t relA = pv.rel4[0] | ((uint64_t)pv.rel4[1] << 32), relB = pv.rel4[2] | ((uint64_t)pv.rel4[3] << 32);
+    while (em) {   // one iteration per emitted pick (no dynamic register indexing: pv stays in registers)
+#ifdef __CUDA_ARCH__
+        const int i = __ffs((int)em) - 1;
+#else
+        const int i = __builtin_ctz(em);
+#endif
+        em &= em - 1;
+        const uint32_t rel = (uint32_t)(((i & 8) ? relB : relA) >> (8 * (i & 7))) & 0xFFu;
+        const uint32_t rank = pv.rankoff + popc32(pv.ust16 & ((2u << i) - 1u)) - 1u;
+        s.pk_pos[idx++] = ((uint32_t)(16 * t) + rel) | ((rank & 0x3FFFu) << 16);
     }
 }
 
@@ -497,14 +503,25 @@ DCN_HD uint32_t effective_len(const uint8_t *bases, uint64_t gstart, uint32_t le
 // scan(get, put) = block-wide exclusive sum, match64 / ballot = warp votes.
 // Barriers per tile: 7.  The last phase has no trailing barrier: the first phase of the next
 // tile touches none of the arrays it reads.
+// Record boundaries of the tile: loaded in the same phase as the base vectors (so the dependent
+// rec_off -> last-byte loads overlap the tile's own DRAM latency) ...
 template <class G>
-DCN_HD void phase_structure(int t, TileSmem<G> &s, const FilterParams &P, uint32_t r_begin, uint32_t n_rec_t,
-                            uint64_t origin) {
-    const uint32_t rpu = P.rpu;
+DCN_HD void phase_structure_load(int t, TileSmem<G> &s, const FilterParams &P, uint32_t r_begin, uint32_t n_rec_t,
+                                 uint64_t origin) {
     for (uint32_t i = (uint32_t)t; i < n_rec_t; i += G::NT) {
         uint64_t gs = P.rec_off[r_begin + i] - P.base0, ge = P.rec_off[r_begin + i + 1] - P.base0;
         uint32_t sL = (uint32_t)(gs - origin), eL = (uint32_t)(ge - origin);
         uint32_t eff = sL + effective_len<G, FLAVOUR_FILTER>(P.bases, gs, eL - sL, P.prefix_len);
+        s.rec_se[i] = sL | (eL << 16);
+        s.rec_eff[i] = (uint16_t)eff;
+    }
+}
+// ... and turned into the per-position bit arrays one phase later.
+template <class G>
+DCN_HD void phase_structure(int t, TileSmem<G> &s, uint32_t rpu, uint32_t n_rec_t) {
+    for (uint32_t i = (uint32_t)t; i < n_rec_t; i += G::NT) {
+        const uint32_t se = s.rec_se[i];
+        const uint32_t sL = se & 0xFFFFu, eL = se >> 16, eff = s.rec_eff[i];
         set_bits(s.brk, sL, sL + 1);
         if (i % rpu == 0) { set_bits(s.ustart, sL, sL + 1); s.ustartpos[i / rpu] = (uint16_t)sL; }
         if (eff < eL) { set_bits(s.dead, eff, eL); set_bits(s.brk, eff, eL); }
@@ -547,10 +564,11 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
 
     ex.par([&](int t, Priv &pv) {
         for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
+        phase_structure_load<G>(t, s, P, r_begin, n_rec_t, origin);
         phase_convert<G, FLAVOUR_FILTER>(t, s, pv, P.bases, n_rel, origin);
     });
     ex.par([&](int t, Priv &pv) {
-        phase_structure<G>(t, s, P, r_begin, n_rec_t, origin);
+        phase_structure<G>(t, s, P.rpu, n_rec_t);
         phase_hash<G>(t, s, pv);
     });
     ex.par([&](int t, Priv &pv) { phase_slide<G>(t, s, pv); });
@@ -559,58 +577,92 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
     const uint32_t npicks = s.npicks;
     if (npicks > (uint32_t)G::PKCAP) { ex.barrier(); return false; }
 
-    // hash every pick and start its table access early; unit -> pick-range tables on the side
+    // hash every pick and probe the table: two picks per thread are in flight at a time (hash A,
+    // request A, hash B, request B, then test A and B), the answer is kept as bit 30 of the pick;
+    // unit -> pick-range tables on the side
     ex.par([&](int t, Priv &) {
         phase_unit_first<G>(t, s, n_units_t, npicks);
-        for (uint32_t idx = (uint32_t)t; idx < npicks; idx += G::NT) {
-            uint32_t pp = s.pk_pos[idx];
-            uint32_t p = pp & 0xFFFFu;
-            if (pick_kmer_valid<G>(s, p)) {
-                uint64_t h = pick_hash<G>(s, p);
-                s.pk_hash[idx] = h;
-                s.pk_pos[idx] = pp | 0x80000000u;
-                prefetch_bucket(P.table.slots, table_bucket(h, P.table.n_buckets));
+        for (uint32_t idx = (uint32_t)t; idx < npicks; idx += 2 * G::NT) {
+            const uint32_t idxB = idx + G::NT;
+            uint32_t ppA = s.pk_pos[idx], ppB = idxB < npicks ? s.pk_pos[idxB] : 0u;
+            const bool vA = pick_kmer_valid<G>(s, ppA & 0xFFFFu);
+            const bool vB = idxB < npicks && pick_kmer_valid<G>(s, ppB & 0xFFFFu);
+            uint64_t hA = 0, hB = 0, bA = 0, bB = 0;
+            Bucket kA, kB;
+            kA.k0 = kA.k1 = kA.k2 = kA.k3 = 0; kB = kA;
+            if (vA) {
+                hA = pick_hash<G>(s, ppA & 0xFFFFu);
+                bA = table_bucket(hA, P.table.n_buckets);
+                kA = load_bucket(P.table.slots, bA);
+            }
+            if (vB) {
+                hB = pick_hash<G>(s, ppB & 0xFFFFu);
+                bB = table_bucket(hB, P.table.n_buckets);
+                kB = load_bucket(P.table.slots, bB);
+            }
+            if (vA) {
+                s.pk_hash[idx] = hA;
+                s.pk_pos[idx] = ppA | 0x80000000u | (table_contains_from(P.table, hA, bA, kA) ? 0x40000000u : 0u);
+            }
+            if (vB) {
+                s.pk_hash[idxB] = hB;
+                s.pk_pos[idxB] = ppB | 0x80000000u | (table_contains_from(P.table, hB, bB, kB) ? 0x40000000u : 0u);
             }
         }
     });
     // probe + distinct-hit test (src/filter_common.rs:143-145: contains && seen.insert).
-    // A pick is a duplicate iff an EARLIER valid pick of the same unit has the same hash: lanes of
-    // the same warp are compared with a warp match, the part of the unit that lies before this
-    // warp's 32 picks is scanned in shared memory (32-bit compare first).
+    // A pick is a duplicate iff an EARLIER valid pick of the same unit has the same hash.  Picks of
+    // one warp-round (32 consecutive list entries) are compared with a warp match; the earlier
+    // picks of the unit that straddles into this round are brought in by a second match when they
+    // fit the lanes that do not belong to that unit, else scanned in shared memory.
     ex.par([&](int t, Priv &) {
         const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
         const uint32_t lane = (uint32_t)t & 31u;
+        const uint32_t lt = (1u << lane) - 1u;
         for (uint32_t r = 0; r < rounds; r++) {
             const uint32_t idx = r * G::NT + (uint32_t)t;
             const uint32_t wbase = idx - lane;
-            bool valid = false, hit = false;
-            uint64_t h = 0, b = 0;
-            uint32_t first = 0;
-            Bucket bk;
-            bk.k0 = bk.k1 = bk.k2 = bk.k3 = 0;
-            if (idx < npicks) {
+            bool valid = false, found = false, hit = false, inlist = idx < npicks;
+            uint64_t h = 0;
+            uint32_t first = 0xFFFFFFFFu;
+            if (inlist) {
                 uint32_t pp = s.pk_pos[idx];
                 valid = (pp & 0x80000000u) != 0;
-                if (valid) {
-                    h = s.pk_hash[idx];
-                    b = table_bucket(h, P.table.n_buckets);
-                    bk = load_bucket(P.table.slots, b);
-                    first = s.rkfirst[(pp >> 16) & 0x7FFFu];
-                }
+                found = (pp & 0x40000000u) != 0;
+                first = s.rkfirst[(pp >> 16) & 0x3FFFu];
+                if (valid) h = s.pk_hash[idx];
             }
             const uint32_t vmask = ex.ballot(t, valid);
-            uint32_t same = ex.match64(t, valid ? h : (0x8000000000000000ULL | idx) ^ 0x5bd1e9955bd1e995ULL, valid);
+            const uint32_t same = ex.match64(t, h, valid);
             bool dup = false;
             if (valid) {
                 uint32_t unit_lanes = first <= wbase ? 0xFFFFFFFFu : (first - wbase >= 32 ? 0u : 0xFFFFFFFFu << (first - wbase));
-                uint32_t lt = (1u << lane) - 1u;
                 dup = (same & vmask & unit_lanes & lt) != 0;
-                const uint32_t hlo = (uint32_t)h;
-                const uint32_t *h32 = reinterpret_cast<const uint32_t *>(s.pk_hash);
-                for (uint32_t j = first; j < wbase && !dup; j++)
-                    if (h32[2 * j] == hlo) dup = (s.pk_hash[j] == h) && (s.pk_pos[j] & 0x80000000u);
-                hit = !dup && table_contains_from(P.table, h, b, bk);
             }
+            // the unit of lane 0 may have started in an earlier warp-round
+            const uint32_t first0 = ex.bcast0(t, first);
+            const uint32_t in0 = ex.ballot(t, inlist && first == first0);       // lanes of that unit (a prefix)
+            const uint32_t m = (first0 != 0xFFFFFFFFu && first0 < wbase) ? wbase - first0 : 0u;   // its earlier picks
+            if (m) {
+                const uint32_t c = popc32(in0);
+                if (m + c <= 32u) {
+                    // lanes [32 - m, 32) present the earlier picks, lanes [0, c) their own pick
+                    const bool is_e = lane >= 32u - m;
+                    const uint32_t j = first0 + (lane - (32u - m));
+                    bool e_valid = false;
+                    uint64_t v = h;
+                    if (is_e) { e_valid = (s.pk_pos[j] & 0x80000000u) != 0; v = s.pk_hash[j]; }
+                    const uint32_t emask = ex.ballot(t, e_valid);
+                    const uint32_t same2 = ex.match64(t, v, true);
+                    if (valid && lane < c && (same2 & emask)) dup = true;
+                } else if (valid && first == first0 && !dup) {
+                    const uint32_t hlo = (uint32_t)h;
+                    const uint32_t *h32 = reinterpret_cast<const uint32_t *>(s.pk_hash);
+                    for (uint32_t j = first0; j < wbase && !dup; j++)
+                        if (h32[2 * j] == hlo) dup = (s.pk_hash[j] == h) && (s.pk_pos[j] & 0x80000000u);
+                }
+            }
+            hit = valid && found && !dup;
             ex.ballot2(t, idx, valid, hit, s.vmask, s.hmask);
         }
     });

@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../deacon_server_b200/csrc/dcn_plan.cuh"
@@ -19,30 +20,70 @@ template <class G>
 struct HostExec {
     std::vector<TilePriv<G>> pv;
     HostExec() : pv(G::NT) {}
-    template <class F>
-    void par(F f) {
-        // two passes so that warp votes can be answered (see ballot/match64); phases are
-        // idempotent apart from the votes' consumers, which only act in pass 1
-        calls.assign(G::NT, 0);
-        pass = 0;
-        std::vector<TilePriv<G>> saved = pv;
-        snapshot_begin();
-        for (int t = 0; t < G::NT; t++) f(t, pv[t]);
-        bool used_votes = false;
-        for (auto c : calls) used_votes |= c != 0;
-        if (!used_votes) { pass = 1; return; }
-        pv = saved;
-        snapshot_restore();
-        calls.assign(G::NT, 0);
-        pass = 1;
-        for (int t = 0; t < G::NT; t++) f(t, pv[t]);
+
+    // ---- warp votes.  A phase runs thread after thread here, so a vote cannot see the other
+    // lanes' operands of the same pass.  The phase is therefore re-run from a snapshot until the
+    // recorded operands stop changing: pass n answers vote k from the operands recorded in pass
+    // n-1, which are final for every vote whose inputs depend on fewer than n earlier votes.
+    std::vector<uint64_t> cur_v, prev_v;
+    std::vector<uint32_t> calls;
+    size_t vote_slot(int t) {
+        size_t c = calls[t]++;
+        size_t slot = c * G::NT + (size_t)t;
+        if (cur_v.size() <= slot) cur_v.resize(slot + 16 * G::NT, 0);
+        return slot;
     }
-    // shared-memory snapshot so that pass 0 of a vote-using phase has no side effects
+    uint64_t prev_at(size_t slot) const { return slot < prev_v.size() ? prev_v[slot] : 0; }
+    uint32_t ballot(int t, bool p) {
+        size_t slot = vote_slot(t);
+        cur_v[slot] = p;
+        uint32_t m = 0;
+        size_t w = slot - (size_t)(t & 31);
+        for (int l = 0; l < 32; l++) m |= (uint32_t)(prev_at(w + l) & 1) << l;
+        return m;
+    }
+    uint32_t bcast0(int t, uint32_t v) {
+        size_t slot = vote_slot(t);
+        cur_v[slot] = v;
+        return (uint32_t)prev_at(slot - (size_t)(t & 31));
+    }
+    uint32_t match64(int t, uint64_t v, bool) {
+        size_t slot = vote_slot(t);
+        cur_v[slot] = v;
+        uint32_t m = 0;
+        size_t w = slot - (size_t)(t & 31);
+        for (int l = 0; l < 32; l++) m |= (uint32_t)(prev_at(w + l) == prev_at(slot)) << l;
+        return m;
+    }
+
     void *smem_ptr = nullptr;
     size_t smem_bytes = 0;
-    std::vector<uint8_t> smem_copy;
-    void snapshot_begin() { if (smem_ptr) { smem_copy.assign((uint8_t *)smem_ptr, (uint8_t *)smem_ptr + smem_bytes); } }
-    void snapshot_restore() { if (smem_ptr) memcpy(smem_ptr, smem_copy.data(), smem_bytes); }
+
+    template <class F>
+    void par(F f) {
+        std::vector<TilePriv<G>> saved_pv = pv;
+        std::vector<uint8_t> saved_smem;
+        if (smem_ptr) saved_smem.assign((uint8_t *)smem_ptr, (uint8_t *)smem_ptr + smem_bytes);
+        prev_v.clear();
+        for (int pass = 0; pass < 64; pass++) {
+            cur_v.clear();
+            calls.assign(G::NT, 0);
+            for (int t = 0; t < G::NT; t++) f(t, pv[t]);
+            bool used = false;
+            for (auto c : calls) used |= c != 0;
+            if (!used) return;                       // no votes: one pass is the phase
+            cur_v.resize(std::max(cur_v.size(), prev_v.size()), 0);
+            prev_v.resize(cur_v.size(), 0);
+            if (pass > 0 && cur_v == prev_v) return;  // fixpoint: this pass saw final operands everywhere
+            prev_v = cur_v;
+            pv = saved_pv;
+            if (smem_ptr) memcpy(smem_ptr, saved_smem.data(), smem_bytes);
+        }
+        abort();  // votes did not converge: a bug in the phase or in this emulation
+    }
+    template <class F>
+    void par_nosync(F f) { par(f); }
+    void barrier() {}
     template <class Get, class Put>
     void scan(Get get, Put put) {
         std::vector<uint32_t> v(G::NT);
@@ -52,40 +93,6 @@ struct HostExec {
         for (int t = 0; t < G::NT; t++) { ex[t] = total; total += v[t]; }
         for (int t = 0; t < G::NT; t++) put(t, pv[t], ex[t], total);
     }
-    template <class F>
-    void par_nosync(F f) { par(f); }
-    void barrier() {}
-    // Warp votes: a phase runs thread after thread here, so a vote is emulated in two passes --
-    // pass 0 records every lane's operand, pass 1 (the phase re-run) answers from the record.
-    // par() runs vote-using phases twice when `two_pass` is set by the phase itself.
-    std::vector<uint8_t> vote_p;
-    std::vector<uint64_t> vote_v;
-    int pass = 0;
-    uint32_t ballot(int t, bool p) {
-        size_t slot = vote_slot(t);
-        if (pass == 0) { vote_p[slot] = p; return 0; }
-        uint32_t m = 0;
-        size_t w = slot - (size_t)(t & 31);
-        for (int l = 0; l < 32; l++) m |= (uint32_t)vote_p[w + l] << l;
-        return m;
-    }
-    uint32_t match64(int t, uint64_t v, bool) {
-        size_t slot = vote_slot(t);
-        if (pass == 0) { vote_v[slot] = v; return 0; }
-        uint32_t m = 0;
-        size_t w = slot - (size_t)(t & 31);
-        for (int l = 0; l < 32; l++) m |= (uint32_t)(vote_v[w + l] == v) << l;
-        return m;
-    }
-    // one slot per (vote call number of this thread, thread)
-    std::vector<uint32_t> calls;
-    size_t vote_slot(int t) {
-        if (calls.empty()) calls.assign(G::NT, 0);
-        size_t c = calls[t]++;
-        size_t slot = c * G::NT + (size_t)t;
-        if (vote_p.size() <= slot + 32) { vote_p.resize(slot + 64 * G::NT, 0); vote_v.resize(slot + 64 * G::NT, 0); }
-        return slot;
-    }
     void tally2(int, bool a, bool b, uint32_t *ca, uint32_t *cb) { *ca += a; *cb += b; }
     void global_add(uint32_t *p, uint32_t v) { *p += v; }
     void append64(int, bool valid, uint64_t v, uint64_t *out, uint64_t cap, unsigned long long *count) {
@@ -94,7 +101,7 @@ struct HostExec {
         if (pos < cap) out[pos] = v;
     }
     void ballot2(int t, uint32_t idx, bool valid, bool hit, uint32_t *vm, uint32_t *hm) {
-        if (pass == 0 || idx >= (uint32_t)G::PKCAP) return;
+        if (idx >= (uint32_t)G::PKCAP) return;
         if ((t & 31) == 0) { vm[idx >> 5] = 0; hm[idx >> 5] = 0; }
         if (valid) vm[idx >> 5] |= 1u << (idx & 31);
         if (hit) hm[idx >> 5] |= 1u << (idx & 31);

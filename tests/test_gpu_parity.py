@@ -224,3 +224,63 @@ def test_unsupported_kw_fails_loudly(gpu):
     gpu.index_upload(np.array([1, 2, 3], np.uint64), IndexHeader(2, 21, 11))
     with pytest.raises(DeaconCudaError, match="k=31"):
         gpu.filter_batch(np.frombuffer(b"ACGT" * 40, np.uint8), np.array([0, 160], np.uint64))
+
+
+# --------------------------------------------------------------------------- B2: pre-hashed records
+def _hash_lists(idx, g, seed, n_rec, paired):
+    """Per-record hash lists as the reference client builds them (src/remote_filter.rs:762-774,
+    963-975): oracle extraction of simulated reads, mates pooled for pairs."""
+    rng = np.random.default_rng(seed)
+    reads = H.sample_reads(g, n_rec * (2 if paired else 1), (0, 400), seed)
+    lists = []
+    for i in range(n_rec):
+        if paired:
+            h = np.concatenate([O.extract_filter(reads[2 * i])[0], O.extract_filter(reads[2 * i + 1])[0]])
+        else:
+            h = O.extract_filter(reads[i])[0]
+        if i % 7 == 0 and len(h):          # repeated hashes must count once (src/filter_common.rs:143-145)
+            h = np.concatenate([h, h[::-1], h[:3]])
+        if i % 11 == 0:                    # a few values that are not in the index
+            h = np.concatenate([h, rng.integers(0, 2**63, 5).astype(np.uint64)])
+        lists.append(np.ascontiguousarray(h, np.uint64))
+    return lists
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_lookup_batch_matches_oracle(gpu, paired):
+    """dcn_lookup_batch == unpaired_should_keep / paired_should_keep (src/remote_filter.rs:230-301)."""
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(300_000, 91)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    lists = _hash_lists(idx, g, 92 + int(paired), 3000, paired)
+    lists[5] = np.zeros(0, np.uint64)                                   # empty record
+    keys = idx.keys()
+    lists[6] = np.tile(keys[:40], 3)                                   # 120 hashes, 40 distinct hits
+    lists[7] = np.concatenate([keys[:33], keys[:33]])                  # duplicates straddle a warp round
+    big = np.concatenate([keys[:3000], keys[1000:2500], np.arange(1, 2000, dtype=np.uint64)])
+    lists[8] = big                                                     # > 1024 hashes: global (hash, record) set
+    lists[9] = np.tile(keys[100:1500], 2)
+    off = np.zeros(len(lists) + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in lists], dtype=np.uint64)
+    hashes = np.concatenate(lists)
+    for (a, r, dep) in ((2, 0.01, False), (2, 0.01, True), (1, 0.0, False), (3, 0.5, True)):
+        k, h, t = gpu.lookup_batch(hashes, off, a, r, dep)
+        ok, oh, ot = O.lookup_batch(idx, hashes, off, a, r, dep, threads=8)
+        assert np.array_equal(t, ot) and np.array_equal(h, oh) and np.array_equal(k, ok), (a, r, dep)
+    assert int(h[6]) == 40 and int(h[7]) == 33 and int(h[8]) == 3000
+
+
+def test_lookup_equals_filter_on_same_reads(gpu):
+    """B1 (raw sequences) and B2 (pre-hashed, oracle-extracted) must give the same decisions."""
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(200_000, 95)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    reads = H.sample_reads(g, 4000, 150, 96)
+    bases, off = H.concat(reads)
+    k1, h1, t1 = gpu.filter_batch(bases, off, paired=True, deplete=True)
+    lists = [np.concatenate([O.extract_filter(reads[2 * i])[0], O.extract_filter(reads[2 * i + 1])[0]]) for i in range(2000)]
+    res = gpu.paired_should_keep([(x, [], []) for x in lists], 31, 2, 0.01, True)
+    assert [r[0] for r in res] == [bool(x) for x in k1]
+    assert [r[1] for r in res] == [int(x) for x in h1] and [r[2] for r in res] == [int(x) for x in t1]
