@@ -12,11 +12,13 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <math.h>
 
 #include "../../include/deacon_cuda.h"
 #include "dcn_kernels.cuh"
+#include "dcn_generic.cuh"
 
 using namespace dcn;
 
@@ -68,6 +70,8 @@ struct dcn_ctx {
     // index build
     DevBuf ib_bases, ib_off, ib_desc, ib_keys, ib_alt, ib_tmp, ib_entropy, ib_stats;
     uint64_t ib_n = 0;     // sorted unique keys of the last build (in ib_keys)
+    // generic (k, w) path and B3 extraction: staging, chunk plan, CSR outputs
+    DevBuf gx_bases, gx_off, gx_rc, gx_cc, gx_tmp, gx_h, gx_p, gx_oo, gx_entropy;
     Slot slot[2];
     uint64_t launches = 0;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
@@ -100,6 +104,164 @@ static size_t plan_bytes(uint64_t n_rel_bases) {
 
 static uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
 
+// src/minimizers.rs:73-121 evaluated on the host for every base-count triple: the same f32
+// operations in the same order (p = count / total; entropy -= p * log2f(p); entropy / 2 >= thr).
+// `stride` values per axis: 32 for the k = 31 tile kernel, 64 for the generic path (k <= 57).
+static void build_entropy_bitmap(int k, float thr, uint32_t stride, std::vector<uint32_t> &bits) {
+    bits.assign((size_t)stride * stride * stride / 32, 0);
+    for (int a = 0; a <= k; a++)
+        for (int c = 0; a + c <= k; c++)
+            for (int g = 0; a + c + g <= k; g++) {
+                int counts[4] = {a, c, g, k - a - c - g};   // A, C, G, T order of the reference
+                volatile float entropy = 0.0f;
+                float total_f = (float)k;
+                if (k >= 10) {
+                    for (int i = 0; i < 4; i++)
+                        if (counts[i] > 0) {
+                            volatile float p = (float)counts[i] / total_f;
+                            volatile float term = p * log2f(p);
+                            entropy = entropy - term;
+                        }
+                }
+                float scaled = k < 10 ? 1.0f : entropy / 2.0f;
+                if (scaled >= thr) {
+                    uint32_t idx = ((uint32_t)a * stride + (uint32_t)c) * stride + (uint32_t)g;
+                    bits[idx >> 5] |= 1u << (idx & 31);
+                }
+            }
+}
+
+// (k, w) accepted by the reference: k + w - 1 odd (src/index.rs:186-194 and the upstream assert),
+// k <= 56 when filtering (src/filter_common.rs:269-272), k <= 57 at index time (src/main.rs:166).
+static int check_kw(dcn_ctx *ctx, int k, int w, int flavour) {
+    const int kmax = flavour == DCN_FLAVOUR_INDEX ? 57 : 56;
+    if (k < 1 || k > kmax) return ctx->fail(DCN_ERR_UNSUPPORTED, flavour == DCN_FLAVOUR_INDEX ? "k must be in 1..=57" : "k must be in 1..=56 for filtering");
+    if (w < 1 || w > DCN_MAX_W) return ctx->fail(DCN_ERR_UNSUPPORTED, "w must be in 1..=255");
+    if (((k + w - 1) & 1) == 0) return ctx->fail(DCN_ERR_ARG, "k + w - 1 must be odd");
+    return DCN_OK;
+}
+
+// chunk plan of the generic path: per-record chunk counts -> exclusive scan (in place); one sync
+static int generic_plan(dcn_ctx *ctx, GenericBatch &B, int flavour, uint64_t *rc, DevBuf &tmp, cudaStream_t st, uint64_t *n_chunks) {
+    const int pb = 256;
+    const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)B.n_rec + 1 + pb - 1) / pb, (uint64_t)ctx->sm_count * 8));
+    if (flavour == DCN_FLAVOUR_INDEX) generic_rec_chunks_kernel<FLAVOUR_INDEX><<<pg, pb, 0, st>>>(B, rc);
+    else generic_rec_chunks_kernel<FLAVOUR_FILTER><<<pg, pb, 0, st>>>(B, rc);
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, rc, rc, (int64_t)B.n_rec + 1, st));
+    CK(tmp.ensure(tb));
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, rc, rc, (int64_t)B.n_rec + 1, st));
+    ctx->launches += 3;
+    CK(cudaMemcpyAsync(n_chunks, rc + B.n_rec, sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    B.rec_chunk_off = rc;
+    return DCN_OK;
+}
+
+static int grid_for(dcn_ctx *ctx, uint64_t n, int block) {
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>((n + block - 1) / block, (uint64_t)ctx->sm_count * 16));
+}
+
+// Generic extraction into device CSR buffers (ctx->gx_h / gx_p / gx_oo).  *n_out = minimizers.
+// If `cap_limit` is non-zero and exceeded, only the offsets are produced (the caller reports overflow).
+static int generic_extract_device(dcn_ctx *ctx, int flavour, const uint8_t *d_bases, const uint64_t *d_off, uint32_t n_rec,
+                                  int k, int w, uint32_t prefix_len, float entropy_thr, bool want_pos, uint64_t cap_limit,
+                                  cudaStream_t st, uint64_t *n_out, bool *written) {
+    *n_out = 0; *written = false;
+    GenericBatch B;
+    B.bases = d_bases; B.base0 = 0; B.rec_off = d_off; B.n_rec = n_rec; B.prefix_len = prefix_len;
+    B.k = k; B.w = w; B.cstride = DCN_GENERIC_CSTRIDE; B.entropy_pass = nullptr; B.rec_chunk_off = nullptr;
+    if (flavour == DCN_FLAVOUR_INDEX && entropy_thr != 0.0f) {
+        std::vector<uint32_t> bits;
+        build_entropy_bitmap(k, entropy_thr, 64, bits);
+        CK(ctx->gx_entropy.ensure(bits.size() * 4));
+        CK(cudaMemcpyAsync(ctx->gx_entropy.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaStreamSynchronize(st));   // `bits` dies with this scope
+        B.entropy_pass = ctx->gx_entropy.as<uint32_t>();
+    }
+    CK(ctx->gx_rc.ensure(((size_t)n_rec + 1) * 8));
+    CK(ctx->gx_oo.ensure(((size_t)n_rec + 1) * 8));
+    uint64_t n_chunks = 0;
+    int rc = generic_plan(ctx, B, flavour, ctx->gx_rc.as<uint64_t>(), ctx->gx_tmp, st, &n_chunks);
+    if (rc) return rc;
+    CK(ctx->gx_cc.ensure((n_chunks + 1) * 8));
+    uint64_t *cc = ctx->gx_cc.as<uint64_t>();
+    const int g1 = grid_for(ctx, n_chunks + 1, 128);
+    if (flavour == DCN_FLAVOUR_INDEX) generic_count_kernel<FLAVOUR_INDEX><<<g1, 128, 0, st>>>(B, n_chunks, cc);
+    else generic_count_kernel<FLAVOUR_FILTER><<<g1, 128, 0, st>>>(B, n_chunks, cc);
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, cc, cc, (int64_t)n_chunks + 1, st));
+    CK(ctx->gx_tmp.ensure(tb));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->gx_tmp.p, tb, cc, cc, (int64_t)n_chunks + 1, st));
+    generic_rec_off_kernel<<<grid_for(ctx, (uint64_t)n_rec + 1, 256), 256, 0, st>>>(ctx->gx_rc.as<uint64_t>(), cc, n_rec, ctx->gx_oo.as<uint64_t>());
+    ctx->launches += 4;
+    uint64_t m = 0;
+    CK(cudaMemcpyAsync(&m, cc + n_chunks, sizeof(m), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    *n_out = m;
+    if (cap_limit && m > cap_limit) return DCN_OK;
+    CK(ctx->gx_h.ensure(std::max<uint64_t>(m, 1) * 8));
+    if (want_pos) CK(ctx->gx_p.ensure(std::max<uint64_t>(m, 1) * 4));
+    if (n_chunks) {
+        const int g2 = grid_for(ctx, n_chunks, 128);
+        uint32_t *pp = want_pos ? ctx->gx_p.as<uint32_t>() : nullptr;
+        if (flavour == DCN_FLAVOUR_INDEX) generic_write_kernel<FLAVOUR_INDEX><<<g2, 128, 0, st>>>(B, n_chunks, cc, ctx->gx_h.as<uint64_t>(), pp);
+        else generic_write_kernel<FLAVOUR_FILTER><<<g2, 128, 0, st>>>(B, n_chunks, cc, ctx->gx_h.as<uint64_t>(), pp);
+        ctx->launches += 1;
+        CK(cudaGetLastError());
+    }
+    *written = true;
+    return DCN_OK;
+}
+
+// B1 for indexes whose (k, w) is not the specialised (31, 15)
+static int enqueue_filter_generic(dcn_ctx *ctx, DevBuf &plan, DevBuf &tmp, DevBuf &dedup, const uint8_t *d_bases, uint64_t base0,
+                                  uint64_t n_bases_abs, const uint64_t *d_off, uint32_t n_rec, uint32_t rpu, uint32_t n_units,
+                                  uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep,
+                                  uint32_t *d_hits, uint32_t *d_total, cudaStream_t st) {
+    int rc = check_kw(ctx, ctx->k, ctx->w, DCN_FLAVOUR_FILTER);
+    if (rc) return rc;
+    GenericBatch B;
+    B.bases = d_bases; B.base0 = base0; B.rec_off = d_off; B.n_rec = n_rec; B.prefix_len = prefix_len;
+    B.k = ctx->k; B.w = ctx->w; B.cstride = DCN_GENERIC_CSTRIDE; B.entropy_pass = nullptr; B.rec_chunk_off = nullptr;
+    CK(plan.ensure(64 + ((size_t)n_rec + 1) * 8));
+    BatchStats *d_stats = plan.as<BatchStats>();
+    uint64_t *rcoff = reinterpret_cast<uint64_t *>(plan.as<uint8_t>() + 64);
+    uint64_t n_chunks = 0;
+    if ((rc = generic_plan(ctx, B, DCN_FLAVOUR_FILTER, rcoff, tmp, st, &n_chunks))) return rc;
+    TableView tv;
+    tv.slots = ctx->table.as<uint64_t>(); tv.n_buckets = ctx->n_buckets; tv.has_empty_key = ctx->has_empty;
+    const uint64_t n_rel = n_bases_abs - base0;
+    // expected picks ~ 2 / (w + 1) per base; twice that many slots, grown x4 on overflow
+    uint64_t dedup_cap = next_pow2(std::max<uint64_t>(4096, 4 * n_rel / ((uint64_t)ctx->w + 1)));
+    for (int attempt = 0; attempt < 4; attempt++) {
+        CK(cudaMemsetAsync(d_stats, 0, sizeof(BatchStats), st));
+        CK(cudaMemsetAsync(d_hits, 0, (size_t)n_units * 4, st));
+        CK(cudaMemsetAsync(d_total, 0, (size_t)n_units * 4, st));
+        CK(dedup.ensure(dedup_cap * 16));
+        CK(cudaMemsetAsync(dedup.p, 0, dedup_cap * 16, st));
+        DedupView dd;
+        dd.slots = dedup.as<unsigned __int128>(); dd.mask = dedup_cap - 1; dd.overflow = &d_stats->overflow;
+        if (n_chunks) {
+            generic_filter_kernel<<<grid_for(ctx, n_chunks, 128), 128, 0, st>>>(B, n_chunks, rpu, tv, dd, d_hits, d_total);
+            ctx->launches += 1;
+        }
+        BatchStats after;
+        CK(cudaMemcpyAsync(&after, d_stats, sizeof(after), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (!after.overflow) break;
+        if (attempt == 3) return ctx->fail(DCN_ERR_OVERFLOW, "distinct-hit set overflowed after 4 attempts");
+        dedup_cap *= 4;
+    }
+    generic_finalize_kernel<<<grid_for(ctx, n_units, 256), 256, 0, st>>>(n_units, d_hits, d_total, abs_thr, rel_thr, deplete, d_keep);
+    stats_kernel<<<grid_for(ctx, n_units, 256), 256, 0, st>>>(d_off, rpu, n_units, d_keep, ctx->counters.as<unsigned long long>());
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return DCN_OK;
+}
+
 // Enqueue the whole filter pipeline for one device-resident batch on `st`.
 // `longs` / `dedup` are scratch for the long path (units > DCN_MAX_SHORT bases).
 static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &dedup, const uint8_t *d_bases,
@@ -107,12 +269,13 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
                           uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep,
                           uint32_t *d_hits, uint32_t *d_total, cudaStream_t st) {
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
-    if (ctx->k != 31 || ctx->w != 15)
-        return ctx->fail(DCN_ERR_UNSUPPORTED, "only k=31, w=15 indexes are implemented by the CUDA path");
     const uint32_t rpu = paired ? 2u : 1u;
     if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
     const uint32_t n_units = n_rec / rpu;
     if (n_units == 0) return DCN_OK;
+    if (ctx->k != 31 || ctx->w != 15)   // the tile kernel is specialised for the default parameters
+        return enqueue_filter_generic(ctx, plan, longs, dedup, d_bases, base0, n_bases_abs, d_off, n_rec, rpu, n_units,
+                                      prefix_len, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, st);
     if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) || (base0 & 15u))
         return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
 
@@ -256,6 +419,8 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     ctx->longs.release(); ctx->dedup.release();
     ctx->ib_bases.release(); ctx->ib_off.release(); ctx->ib_desc.release(); ctx->ib_keys.release();
     ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->ib_entropy.release(); ctx->ib_stats.release();
+    ctx->gx_bases.release(); ctx->gx_off.release(); ctx->gx_rc.release(); ctx->gx_cc.release(); ctx->gx_tmp.release();
+    ctx->gx_h.release(); ctx->gx_p.release(); ctx->gx_oo.release(); ctx->gx_entropy.release();
     for (int i = 0; i < 2; i++) {
         Slot &s = ctx->slot[i];
         s.bases.release(); s.off.release(); s.keep.release(); s.hits.release(); s.total.release(); s.plan.release();
@@ -523,53 +688,100 @@ int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_o
     return DCN_OK;
 }
 
-// ---------------------------------------------------------------------------- not yet built (round 1)
-int dcn_extract(dcn_ctx *ctx, int, const uint8_t *, const uint64_t *, uint32_t, uint8_t, uint8_t, uint32_t, float,
-                uint64_t *, uint32_t *, uint64_t *, uint64_t) {
-    return ctx ? ctx->fail(DCN_ERR_UNSUPPORTED, "dcn_extract: not implemented yet") : DCN_ERR_ARG;
+// ---------------------------------------------------------------------------- B3 extraction
+int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k,
+                uint8_t w, uint32_t prefix_len, float entropy_thr, uint64_t *out_hashes, uint32_t *out_pos,
+                uint64_t *out_off, uint64_t out_cap) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (flavour != DCN_FLAVOUR_FILTER && flavour != DCN_FLAVOUR_INDEX) return ctx->fail(DCN_ERR_ARG, "unknown flavour");
+    if (!rec_off || !out_off || (!out_hashes && out_cap)) return ctx->fail(DCN_ERR_ARG, "null pointer");
+    int rc = check_kw(ctx, k, w, flavour);
+    if (rc) return rc;
+    if (n_rec && rec_off[0] != 0) return ctx->fail(DCN_ERR_ARG, "rec_off[0] must be 0");
+    const uint64_t n_bases = n_rec ? rec_off[n_rec] : 0;
+    if (n_bases && !bases) return ctx->fail(DCN_ERR_ARG, "null input pointer");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CK(ctx->gx_bases.ensure(n_bases + 64));
+    CK(ctx->gx_off.ensure(((size_t)n_rec + 1) * 8));
+    if (n_bases) CK(cudaMemcpyAsync(ctx->gx_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+    if (n_rec) CK(cudaMemcpyAsync(ctx->gx_off.p, rec_off, ((size_t)n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    else CK(cudaMemsetAsync(ctx->gx_off.p, 0, 8, st));
+    uint64_t m = 0;
+    bool written = false;
+    rc = generic_extract_device(ctx, flavour, ctx->gx_bases.as<uint8_t>(), ctx->gx_off.as<uint64_t>(), n_rec, k, w,
+                                flavour == DCN_FLAVOUR_FILTER ? prefix_len : 0, entropy_thr, out_pos != nullptr, out_cap ? out_cap : 1,
+                                st, &m, &written);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_off, ctx->gx_oo.p, ((size_t)n_rec + 1) * 8, cudaMemcpyDeviceToHost, st));
+    if (written && m) {
+        CK(cudaMemcpyAsync(out_hashes, ctx->gx_h.p, m * 8, cudaMemcpyDeviceToHost, st));
+        if (out_pos) CK(cudaMemcpyAsync(out_pos, ctx->gx_p.p, m * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    if (m > out_cap) return ctx->fail(DCN_ERR_OVERFLOW, "out_cap too small: out_off[n_rec] holds the required capacity");
+    return DCN_OK;
 }
 
-// src/minimizers.rs:73-121 evaluated on the host for every base-count triple: the same f32
-// operations in the same order (p = count / total; entropy -= p * log2f(p); entropy / 2 >= thr).
-static void build_entropy_bitmap(int k, float thr, std::vector<uint32_t> &bits) {
-    bits.assign(32 * 32 * 32 / 32, 0);
-    for (int a = 0; a <= k; a++)
-        for (int c = 0; a + c <= k; c++)
-            for (int g = 0; a + c + g <= k; g++) {
-                int counts[4] = {a, c, g, k - a - c - g};   // A, C, G, T order of the reference
-                volatile float entropy = 0.0f;
-                float total_f = (float)k;
-                if (k >= 10) {
-                    for (int i = 0; i < 4; i++)
-                        if (counts[i] > 0) {
-                            volatile float p = (float)counts[i] / total_f;
-                            volatile float term = p * log2f(p);
-                            entropy = entropy - term;
-                        }
-                }
-                float scaled = k < 10 ? 1.0f : entropy / 2.0f;
-                if (scaled >= thr) {
-                    uint32_t idx = ((uint32_t)a * 32u + (uint32_t)c) * 32u + (uint32_t)g;
-                    bits[idx >> 5] |= 1u << (idx & 31);
-                }
-            }
+// FxHashSet::extend (src/index.rs:267-284) == radix sort + unique of the n_picks hashes in ib_alt
+static int index_sort_unique(dcn_ctx *ctx, uint64_t n_picks, uint8_t k, uint8_t w, int make_resident, uint64_t *n_keys_out,
+                             cudaStream_t st) {
+    if (n_picks == 0) {
+        if (make_resident) return dcn_index_upload_device(ctx, nullptr, 0, k, w, st);
+        return DCN_OK;
+    }
+    unsigned long long *d_count = reinterpret_cast<unsigned long long *>(ctx->ib_stats.as<uint8_t>() + 64);
+    CK(ctx->ib_keys.ensure(n_picks * sizeof(uint64_t)));
+    size_t tmp_sort = 0, tmp_sel = 0;
+    cub::DoubleBuffer<uint64_t> db(ctx->ib_alt.as<uint64_t>(), ctx->ib_keys.as<uint64_t>());
+    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
+    CK(cub::DeviceSelect::Unique(nullptr, tmp_sel, (const uint64_t *)nullptr, (uint64_t *)nullptr, (unsigned long long *)nullptr, (int64_t)n_picks, st));
+    CK(ctx->ib_tmp.ensure(std::max(tmp_sort, tmp_sel)));
+    CK(cub::DeviceRadixSort::SortKeys(ctx->ib_tmp.p, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
+    uint64_t *sorted = db.Current();
+    uint64_t *uniq = db.Alternate();
+    CK(cub::DeviceSelect::Unique(ctx->ib_tmp.p, tmp_sel, sorted, uniq, d_count, (int64_t)n_picks, st));
+    ctx->launches += 8;
+    unsigned long long n_unique = 0;
+    CK(cudaMemcpyAsync(&n_unique, d_count, sizeof(n_unique), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (uniq != ctx->ib_keys.as<uint64_t>()) {  // keep the result in ib_keys
+        std::swap(ctx->ib_keys, ctx->ib_alt);
+    }
+    ctx->ib_n = n_unique;
+    if (n_keys_out) *n_keys_out = n_unique;
+    if (make_resident) return dcn_index_upload_device(ctx, ctx->ib_keys.as<uint64_t>(), n_unique, k, w, st);
+    return DCN_OK;
 }
 
 int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
                            uint64_t n_bases, uint8_t k, uint8_t w, float entropy_thr, int make_resident,
                            uint64_t *n_keys_out, void *stream) {
     if (!ctx) return DCN_ERR_ARG;
-    if (k != 31 || w != 15) return ctx->fail(DCN_ERR_UNSUPPORTED, "only k=31, w=15 is implemented by the CUDA path");
-    if (reinterpret_cast<uintptr_t>(d_bases) & 15u) return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
+    int rc0 = check_kw(ctx, k, w, DCN_FLAVOUR_INDEX);
+    if (rc0) return rc0;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     ctx->ib_n = 0;
     if (n_keys_out) *n_keys_out = 0;
+    CK(ctx->ib_stats.ensure(64 + 16));
+    if (k != 31 || w != 15) {   // generic extraction (ordered CSR, offsets unused), then the same sort + unique
+        uint64_t m = 0;
+        bool written = false;
+        rc0 = generic_extract_device(ctx, DCN_FLAVOUR_INDEX, d_bases, d_rec_off, n_rec, k, w, 0, entropy_thr, false, 0, st, &m, &written);
+        if (rc0) return rc0;
+        if (m) {
+            CK(ctx->ib_alt.ensure(m * sizeof(uint64_t)));
+            CK(cudaMemcpyAsync(ctx->ib_alt.p, ctx->gx_h.p, m * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
+        }
+        return index_sort_unique(ctx, m, k, w, make_resident, n_keys_out, st);
+    }
+    if (reinterpret_cast<uintptr_t>(d_bases) & 15u) return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
 
     const uint32_t *d_entropy = nullptr;
     if (entropy_thr != 0.0f) {
         std::vector<uint32_t> bits;
-        build_entropy_bitmap(k, entropy_thr, bits);
+        build_entropy_bitmap(k, entropy_thr, 32, bits);
         CK(ctx->ib_entropy.ensure(bits.size() * 4));
         CK(cudaMemcpyAsync(ctx->ib_entropy.p, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice, st));
         CK(cudaStreamSynchronize(st));
@@ -602,32 +814,7 @@ int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t 
         if (attempt == 1) return ctx->fail(DCN_ERR_OVERFLOW, "minimizer buffer overflowed twice");
         cap = n_picks + 1024;
     }
-    if (n_picks == 0) {
-        if (make_resident) return dcn_index_upload_device(ctx, nullptr, 0, k, w, st);
-        return DCN_OK;
-    }
-    // FxHashSet::extend (src/index.rs:267-284) == radix sort + unique
-    CK(ctx->ib_keys.ensure(n_picks * sizeof(uint64_t)));
-    size_t tmp_sort = 0, tmp_sel = 0;
-    cub::DoubleBuffer<uint64_t> db(ctx->ib_alt.as<uint64_t>(), ctx->ib_keys.as<uint64_t>());
-    CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
-    CK(cub::DeviceSelect::Unique(nullptr, tmp_sel, (const uint64_t *)nullptr, (uint64_t *)nullptr, (unsigned long long *)nullptr, (int64_t)n_picks, st));
-    CK(ctx->ib_tmp.ensure(std::max(tmp_sort, tmp_sel)));
-    CK(cub::DeviceRadixSort::SortKeys(ctx->ib_tmp.p, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
-    uint64_t *sorted = db.Current();
-    uint64_t *uniq = db.Alternate();
-    CK(cub::DeviceSelect::Unique(ctx->ib_tmp.p, tmp_sel, sorted, uniq, d_count, (int64_t)n_picks, st));
-    ctx->launches += 8;
-    unsigned long long n_unique = 0;
-    CK(cudaMemcpyAsync(&n_unique, d_count, sizeof(n_unique), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    if (uniq != ctx->ib_keys.as<uint64_t>()) {  // keep the result in ib_keys
-        std::swap(ctx->ib_keys, ctx->ib_alt);
-    }
-    ctx->ib_n = n_unique;
-    if (n_keys_out) *n_keys_out = n_unique;
-    if (make_resident) return dcn_index_upload_device(ctx, ctx->ib_keys.as<uint64_t>(), n_unique, k, w, st);
-    return DCN_OK;
+    return index_sort_unique(ctx, n_picks, k, w, make_resident, n_keys_out, st);
 }
 
 int dcn_index_build(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint8_t w,

@@ -13,6 +13,7 @@
 
 #include "../../deacon_server_b200/csrc/dcn_plan.cuh"
 #include "../../deacon_server_b200/csrc/dcn_tile.cuh"
+#include "../../deacon_server_b200/csrc/dcn_generic.cuh"
 
 using namespace dcn;
 
@@ -233,3 +234,77 @@ long long emu_index_extract(const uint8_t *bases_in, const uint64_t *rec_off, ui
 }
 
 }  // extern "C"
+
+// ---- generic (k, w) path: mirrors generic_rec_chunks_kernel + scan + generic_count/write/filter kernels
+template <int FLAV>
+static std::vector<uint64_t> emu_rec_chunk_off(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint32_t prefix,
+                                               int k, int w, uint32_t cstride) {
+    std::vector<uint64_t> off(n_rec + 1, 0);
+    for (uint32_t r = 0; r < n_rec; r++) {
+        uint64_t gs = rec_off[r], len = rec_off[r + 1] - gs;
+        off[r + 1] = off[r] + generic_chunks_of(generic_eff_len<FLAV>(bases, gs, len, prefix, k), k, w, cstride);
+    }
+    return off;
+}
+
+template <int FLAV>
+static long long emu_generic_extract_t(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, int k, int w,
+                                       uint32_t prefix, const uint32_t *entropy_pass, uint32_t cstride, uint64_t *out_h,
+                                       uint32_t *out_p, uint64_t *out_off, uint64_t cap) {
+    std::vector<uint64_t> rco = emu_rec_chunk_off<FLAV>(bases, rec_off, n_rec, prefix, k, w, cstride);
+    GenericBatch B;
+    B.bases = bases; B.base0 = 0; B.rec_off = rec_off; B.n_rec = n_rec; B.prefix_len = prefix; B.k = k; B.w = w;
+    B.cstride = cstride; B.entropy_pass = entropy_pass; B.rec_chunk_off = rco.data();
+    const uint64_t n_chunks = rco[n_rec];
+    std::vector<uint64_t> coff(n_chunks + 1, 0);
+    for (uint64_t g = 0; g < n_chunks; g++) {   // pass 1
+        uint64_t n = 0;
+        uint32_t r;
+        generic_chunk<FLAV>(B, g, r, [&](uint64_t, uint64_t) { n++; });
+        coff[g + 1] = coff[g] + n;
+    }
+    for (uint32_t r = 0; r <= n_rec; r++) out_off[r] = coff[rco[r]];
+    if (coff[n_chunks] > cap) return -6;
+    for (uint64_t g = n_chunks; g-- > 0;) {     // pass 2, any order
+        uint64_t at = coff[g];
+        uint32_t r;
+        generic_chunk<FLAV>(B, g, r, [&](uint64_t pos, uint64_t h) { out_h[at] = h; out_p[at] = (uint32_t)pos; at++; });
+        if (at != coff[g + 1]) return -100;
+    }
+    return (long long)coff[n_chunks];
+}
+
+extern "C" long long emu_generic_extract(int flavour, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, int k, int w,
+                                         uint32_t prefix, const uint32_t *entropy_pass, uint32_t cstride, uint64_t *out_h,
+                                         uint32_t *out_p, uint64_t *out_off, uint64_t cap) {
+    if (flavour == 1) return emu_generic_extract_t<FLAVOUR_INDEX>(bases, rec_off, n_rec, k, w, 0, entropy_pass, cstride, out_h, out_p, out_off, cap);
+    return emu_generic_extract_t<FLAVOUR_FILTER>(bases, rec_off, n_rec, k, w, prefix, nullptr, cstride, out_h, out_p, out_off, cap);
+}
+
+extern "C" int emu_generic_filter(const uint64_t *slots, uint64_t nb, int has_empty, const uint8_t *bases, const uint64_t *rec_off,
+                                  uint32_t n_rec, int paired, uint32_t prefix, int k, int w, uint32_t cstride, uint32_t abs_thr,
+                                  double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    const uint32_t rpu = paired ? 2 : 1, n_units = n_rec / rpu;
+    std::vector<uint64_t> rco = emu_rec_chunk_off<FLAVOUR_FILTER>(bases, rec_off, n_rec, prefix, k, w, cstride);
+    GenericBatch B;
+    B.bases = bases; B.base0 = 0; B.rec_off = rec_off; B.n_rec = n_rec; B.prefix_len = prefix; B.k = k; B.w = w;
+    B.cstride = cstride; B.entropy_pass = nullptr; B.rec_chunk_off = rco.data();
+    TableView tv{slots, nb, has_empty};
+    uint64_t cap = 4096;
+    while (cap < 4 * rec_off[n_rec] / ((uint64_t)w + 1)) cap <<= 1;
+    std::vector<unsigned __int128> set(cap, 0);
+    uint32_t overflow = 0;
+    DedupView dd{set.data(), cap - 1, &overflow};
+    for (uint32_t u = 0; u < n_units; u++) hits[u] = total[u] = 0;
+    for (uint64_t g = rco[n_rec]; g-- > 0;) {
+        uint32_t r = 0, nt = 0, nh = 0;
+        const uint32_t unit = generic_find_record(rco.data(), n_rec, g) / rpu;
+        generic_chunk<FLAVOUR_FILTER>(B, g, r, [&](uint64_t, uint64_t h) {
+            nt++;
+            if (table_contains(tv, h) && dedup_insert(dd, h, unit)) nh++;
+        });
+        total[unit] += nt; hits[unit] += nh;
+    }
+    for (uint32_t u = 0; u < n_units; u++) keep[u] = meets_criteria(hits[u], total[u], abs_thr, rel_thr, deplete) ? 1 : 0;
+    return overflow ? -6 : 0;
+}

@@ -12,7 +12,7 @@ u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uin
 
 
 def build():
-    srcs = [os.path.join(_HERE, "dcn_emu.cpp")] + [os.path.join(_CSRC, f) for f in ("dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh")]
+    srcs = [os.path.join(_HERE, "dcn_emu.cpp")] + [os.path.join(_CSRC, f) for f in ("dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh", "dcn_generic.cuh")]
     if os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
@@ -67,3 +67,36 @@ def index_extract(bases, off, entropy_bitmap=None):
 
 def set_dedup_cap(cap):
     lib().emu_set_dedup_cap(C.c_uint64(cap))
+
+
+def generic_extract(bases, off, flavour=0, k=31, w=15, prefix=0, entropy_bitmap=None, cstride=256, cap=None):
+    """-> (hashes, positions, out_off): the generic (k, w) extraction (B3), CSR per record."""
+    L = lib()
+    L.emu_generic_extract.restype = C.c_longlong
+    n_rec = len(off) - 1
+    cap = max(16, len(bases)) if cap is None else cap
+    oh, op, oo = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(n_rec + 1, np.uint64)
+    b = bases if len(bases) else np.zeros(1, np.uint8)
+    eb = None if entropy_bitmap is None else _p(np.ascontiguousarray(entropy_bitmap, np.uint32), u32p)
+    n = L.emu_generic_extract(int(flavour), _p(b, u8p), _p(off, u64p), C.c_uint32(n_rec), int(k), int(w), C.c_uint32(prefix), eb,
+                              C.c_uint32(cstride), _p(oh, u64p), _p(op, u32p), _p(oo, u64p), C.c_uint64(cap))
+    if n < 0:
+        return int(n), None, oo
+    return oh[:n], op[:n], oo
+
+
+def generic_filter(keys, bases, off, k, w, paired=False, prefix=0, abs_thr=2, rel=0.01, deplete=False, cstride=256):
+    L = lib()
+    keys = np.ascontiguousarray(keys, np.uint64)
+    slots, nb, he = u64p(), C.c_uint64(), C.c_int()
+    kk = keys if len(keys) else np.zeros(1, np.uint64)
+    L.emu_table_build(_p(kk, u64p), C.c_uint64(len(keys)), C.c_double(0.5), C.byref(slots), C.byref(nb), C.byref(he))
+    n_rec = len(off) - 1
+    nu = n_rec // 2 if paired else n_rec
+    keep, hits, tot = np.zeros(max(nu, 1), np.uint8), np.zeros(max(nu, 1), np.uint32), np.zeros(max(nu, 1), np.uint32)
+    b = bases if len(bases) else np.zeros(1, np.uint8)
+    rc = L.emu_generic_filter(slots, nb, he, _p(b, u8p), _p(off, u64p), C.c_uint32(n_rec), int(paired), C.c_uint32(prefix), int(k),
+                              int(w), C.c_uint32(cstride), C.c_uint32(abs_thr), C.c_double(rel), int(deplete), _p(keep, u8p),
+                              _p(hits, u32p), _p(tot, u32p))
+    L.emu_free(slots)
+    return rc, keep[:nu], hits[:nu], tot[:nu]

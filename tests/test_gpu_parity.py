@@ -220,10 +220,114 @@ def test_idx_file_roundtrip_through_gpu(gpu, tmp_path):
 
 
 def test_unsupported_kw_fails_loudly(gpu):
+    """Parameters the reference itself rejects: even k + w - 1 (src/index.rs:186-194), k > 56 when
+    filtering (src/filter_common.rs:269-272).  Errors, never a silent CPU path."""
     from deacon_server_b200 import DeaconCudaError, IndexHeader
-    gpu.index_upload(np.array([1, 2, 3], np.uint64), IndexHeader(2, 21, 11))
-    with pytest.raises(DeaconCudaError, match="k=31"):
-        gpu.filter_batch(np.frombuffer(b"ACGT" * 40, np.uint8), np.array([0, 160], np.uint64))
+    reads = (np.frombuffer(b"ACGT" * 40, np.uint8), np.array([0, 160], np.uint64))
+    gpu.index_upload(np.array([1, 2, 3], np.uint64), IndexHeader(2, 21, 10))
+    with pytest.raises(DeaconCudaError, match="odd"):
+        gpu.filter_batch(*reads)
+    gpu.index_upload(np.array([1, 2, 3], np.uint64), IndexHeader(2, 57, 1))
+    with pytest.raises(DeaconCudaError, match="56"):
+        gpu.filter_batch(*reads)
+    with pytest.raises(DeaconCudaError, match="odd"):
+        gpu.index_build(*reads, 31, 16)
+
+
+# --------------------------------------------------------------------------- any (k, w) + B3 extraction
+GENERIC_KW = [(31, 1), (5, 5), (41, 15), (21, 11), (56, 2), (32, 2), (33, 1)]
+
+
+def _generic_records(seed):
+    g = H.random_genome(60_000, seed)
+    recs = H.sample_reads(g, 1500, (0, 700), seed + 1, n_rate=0.05, lower_rate=0.1)
+    recs += [g[:20_000].copy(), np.frombuffer(b"ACGTNNNNRYKMacgtnryk" * 40, np.uint8).copy(), np.frombuffer(b"A" * 900, np.uint8).copy(),
+             np.zeros(0, np.uint8), np.arange(256, dtype=np.uint8), np.concatenate([g[100:400], np.frombuffer(b"\n", np.uint8)])]
+    return g, recs
+
+
+@pytest.mark.parametrize("k,w", GENERIC_KW)
+def test_generic_kw_filter_matches_oracle(gpu, k, w):
+    """Indexes with non-default parameters (generic kernel; u128 k-mers above k = 32)."""
+    from deacon_server_b200 import IndexHeader
+    g, recs = _generic_records(400 + k)
+    idx = O.index_build([g[:40_000]], k, w, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, k, w))
+    bases, off = H.concat(recs[: len(recs) // 2 * 2])
+    for paired in (False, True):
+        for (a, r, dep, prefix) in ((2, 0.01, False, 0), (1, 0.0, True, 0), (2, 0.2, True, 100)):
+            kk, hh, tt = gpu.filter_batch(bases, off, paired=paired, prefix_length=prefix, abs_threshold=a, rel_threshold=r, deplete=dep)
+            ok, oh, ot = O.filter_batch(idx, bases, off, paired=paired, prefix_len=prefix, k=k, w=w, abs_thr=a, rel_thr=r,
+                                        deplete=dep, threads=8)
+            assert np.array_equal(tt, ot) and np.array_equal(hh, oh) and np.array_equal(kk, ok), (k, w, paired, a, r, dep)
+
+
+def test_reference_behavioural_known_answers_all_kw(gpu):
+    """tests/filter_tests.rs scenarios with non-default parameters: k=31 w=1 (:1133-1187), k=5 w=5
+    (:1190-1251), k=41 (:1254-1296), through the C ABI."""
+    from deacon_server_b200 import IndexHeader
+    with open(os.path.join(GOLD, "reference_kats.json")) as f:
+        kats = json.load(f)["cases"]
+    ran = 0
+    for c in kats:
+        k, w = c["k"], c["w"]
+        if (k, w) == (31, 15):
+            continue
+        bases, off = O.concat_records([r.encode() for r in c["ref"]])
+        keys = gpu.index_build(bases, off, k, w, 0.0, make_resident=True)         # the index is built on the GPU too
+        assert np.array_equal(keys, O.index_build((bases, off), k, w).keys()), c["name"]
+        recs = [r.encode() for r in c["reads"]]
+        rb, ro = O.concat_records(recs)
+        kk, hh, tt = gpu.filter_batch(rb, ro, abs_threshold=c["abs"], rel_threshold=c["rel"], deplete=c["deplete"])
+        assert list(map(int, kk)) == c["expect_keep"], c["name"]
+        ran += 1
+    assert ran == 3
+
+
+@pytest.mark.parametrize("k,w", [(31, 15)] + GENERIC_KW)
+def test_extract_matches_oracle(gpu, k, w):
+    """dcn_extract (B3): get_minimizer_hashes_and_positions (src/filter_common.rs:211-310) and
+    fill_minimizer_hashes (src/minimizers.rs:125-191) per record, hashes AND positions, in order."""
+    _, recs = _generic_records(500 + k)
+    bases, off = H.concat(recs)
+    for prefix in (0, 90):
+        h, p, oo = gpu.extract(bases, off, 0, k, w, prefix)
+        for i, r in enumerate(recs):
+            wh, wp = O.extract_filter(r, k, w, prefix)
+            a, b = int(oo[i]), int(oo[i + 1])
+            assert np.array_equal(h[a:b], wh) and np.array_equal(p[a:b], wp), (k, w, prefix, i)
+    for thr in (0.0, 0.5):
+        h, _, oo = gpu.extract(bases, off, 1, k, w, 0, thr)
+        for i, r in enumerate(recs):
+            assert np.array_equal(h[int(oo[i]):int(oo[i + 1])], O.extract_index(r, k, w, thr)), (k, w, thr, i)
+
+
+def test_extract_single_record_api_and_overflow(gpu):
+    from deacon_server_b200 import DeaconCudaError
+    g = H.random_genome(5000, 77)
+    h, p = gpu.get_minimizer_hashes_and_positions(g, 0, 31, 15)
+    wh, wp = O.extract_filter(g, 31, 15, 0)
+    assert np.array_equal(h, wh) and np.array_equal(p, wp)
+    assert np.array_equal(gpu.compute_minimizer_hashes(g, 31, 15, 0.0), O.extract_index(g, 31, 15, 0.0))
+    bases, off = H.concat([g])
+    with pytest.raises(DeaconCudaError, match="out_cap"):
+        gpu.extract(bases, off, 0, 31, 15, cap=10)
+
+
+@pytest.mark.parametrize("k,w,thr", [(21, 11, 0.0), (41, 15, 0.5), (57, 1, 0.0), (15, 5, 0.7)])
+def test_index_build_generic_kw(gpu, k, w, thr):
+    """`deacon index build -k K -w W [-e E]` for non-default parameters == the oracle's key set."""
+    g = H.random_genome(400_000, 600 + k)
+    g[1000:1300] = ord("A")
+    g[5000:5400] = np.frombuffer(b"AC" * 200, np.uint8)
+    recs = [g[:250_000].copy(), g[250_000:250_020].copy(), np.zeros(0, np.uint8), g[250_020:].copy(),
+            np.frombuffer(b"ACGTNNNNRYKMacgtnryk" * 500, np.uint8).copy()]
+    bases, off = H.concat(recs)
+    keys = gpu.index_build(bases, off, k, w, thr, make_resident=True)
+    want = O.index_build((bases, off), k, w, entropy=thr, threads=8).keys()
+    assert np.array_equal(keys, want)
+    info = gpu.index_info()
+    assert info["n_keys"] == len(want) and info["kmer_length"] == k and info["window_size"] == w
 
 
 # --------------------------------------------------------------------------- B2: pre-hashed records
