@@ -33,6 +33,13 @@ SIGNATURES = {
     "dcn_filter_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "dcn_filter_batch_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
+                                          C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcn_newline_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint32, C.c_void_p]),
+    "dcn_host_pack_threads": (C.c_int, [C.c_void_p, C.c_int]),
+    "dcn_host_pack_fraction": (C.c_int, [C.c_void_p, C.c_double]),
+    "dcn_pack_ascii": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "dcn_last_pack_ms": (C.c_int, [C.c_void_p, f32p]),
     "dcn_lookup_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_lookup_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double,

@@ -222,6 +222,33 @@ class DeaconGpu:
             abs_threshold, rel_threshold, int(deplete), d_keep.data_ptr(), d_hits.data_ptr(), d_total.data_ptr(),
             stream))
 
+    def filter_batch_packed(self, codes, inv, nl_bits, rec_off, paired=False, prefix_length=0, abs_threshold=2,
+                            rel_threshold=0.01, deplete=False):
+        """filter_batch for a batch already in the packed form (pack_ascii / newline_bits)."""
+        rec_off = np.ascontiguousarray(rec_off, np.uint64)
+        n_rec = len(rec_off) - 1
+        nu = n_rec // 2 if paired else n_rec
+        keep, hits, total = np.zeros(max(nu, 1), np.uint8), np.zeros(max(nu, 1), np.uint32), np.zeros(max(nu, 1), np.uint32)
+        self._check(self._lib.dcn_filter_batch_packed(
+            self._ctx, codes.ctypes.data, inv.ctypes.data, nl_bits.ctypes.data if nl_bits is not None else None,
+            rec_off.ctypes.data, n_rec, int(paired), prefix_length, abs_threshold, rel_threshold, int(deplete),
+            keep.ctypes.data, hits.ctypes.data, total.ctypes.data))
+        return keep[:nu], hits[:nu], total[:nu]
+
+    def filter_batch_packed_ptr(self, codes_ptr, inv_ptr, nl_ptr, off_ptr, n_rec, paired, prefix_length, abs_threshold,
+                                rel_threshold, deplete, keep_ptr, hits_ptr, total_ptr):
+        self._check(self._lib.dcn_filter_batch_packed(self._ctx, codes_ptr, inv_ptr, nl_ptr, off_ptr, n_rec, int(paired),
+                                                      prefix_length, abs_threshold, rel_threshold, int(deplete), keep_ptr,
+                                                      hits_ptr, total_ptr))
+
+    def host_pack_threads(self, n: int):
+        """Host threads that pack chunks for filter_batch (0 = ship ASCII over PCIe)."""
+        self._check(self._lib.dcn_host_pack_threads(self._ctx, int(n)))
+
+    def host_pack_fraction(self, fraction: float):
+        """Share of chunks packed on the host (negative = automatic balance with the PCIe copy engine)."""
+        self._check(self._lib.dcn_host_pack_fraction(self._ctx, float(fraction)))
+
     def should_keep_sequence(self, seq, **kw):
         """FilterProcessor::should_keep_sequence (src/local_filter.rs:221-252) -> (keep, hits, total)."""
         bases, off = _concat([seq])
@@ -316,6 +343,11 @@ class DeaconGpu:
         self._check(self._lib.dcn_last_timing(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
         return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}
 
+    def last_pack_ms(self) -> float:
+        a = C.c_float()
+        self._check(self._lib.dcn_last_pack_ms(self._ctx, C.byref(a)))
+        return a.value
+
     def measure_random_access(self, n_probes: int):
         n, ms = C.c_uint64(n_probes), C.c_float()
         self._check(self._lib.dcn_measure_random_access(self._ctx, C.byref(n), C.byref(ms)))
@@ -342,3 +374,30 @@ class DeaconGpu:
 
     def launch_count(self) -> int:
         return int(self._lib.dcn_launch_count(self._ctx))
+
+
+def pack_ascii(bases: np.ndarray):
+    """Host packer of the ingest stage (no GPU): -> (codes u32[], inv u16[]), see dcn_pack_ascii."""
+    bases = np.ascontiguousarray(bases, np.uint8)
+    n = len(bases)
+    nw = 2 * ((n + 31) // 32)
+    codes = np.zeros(max(nw, 1), np.uint32)
+    inv = np.zeros(max(nw, 1), np.uint16)
+    bptr = bases.ctypes.data if n else codes.ctypes.data
+    rc = _lib.load().dcn_pack_ascii(bptr, n, codes.ctypes.data, inv.ctypes.data)
+    if rc:
+        raise DeaconCudaError(rc, "dcn_pack_ascii failed")
+    return codes[:nw], inv[:nw]
+
+
+def newline_bits(bases: np.ndarray, rec_off: np.ndarray, k: int = 31, prefix_length: int = 0) -> np.ndarray:
+    """Per-record flag of the packed ingest form (dcn_newline_bits): the effective prefix ends in a newline."""
+    bases = np.ascontiguousarray(bases, np.uint8)
+    rec_off = np.ascontiguousarray(rec_off, np.uint64)
+    n = len(rec_off) - 1
+    out = np.zeros(max(1, (n + 31) // 32), np.uint32)
+    bptr = bases.ctypes.data if len(bases) else out.ctypes.data
+    rc = _lib.load().dcn_newline_bits(bptr, rec_off.ctypes.data, n, k, prefix_length, out.ctypes.data)
+    if rc:
+        raise DeaconCudaError(rc, "dcn_newline_bits failed")
+    return out

@@ -8,7 +8,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -19,6 +22,7 @@
 #include "../../include/deacon_cuda.h"
 #include "dcn_kernels.cuh"
 #include "dcn_generic.cuh"
+#include "dcn_host_pack.h"
 
 using namespace dcn;
 
@@ -41,12 +45,37 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+struct HostBuf {  // pinned staging
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
 struct Slot {  // one stage of the host-pointer pipeline
-    DevBuf bases, off, keep, hits, total, plan, longs, dedup;
+    DevBuf in, out, plan, longs, dedup;   // in: bases | off (ASCII) or codes | inv | off | nl (packed); out: hits | total | keep
+    HostBuf h_in, h_out;                  // pinned mirrors of `in` (packed mode only) and `out`
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
     bool busy = false;
     uint32_t u0 = 0, u1 = 0;
+};
+
+// what the fused kernel reads: ASCII bytes, or the host-packed form (dcn_host_pack.h)
+struct FilterInput {
+    const uint8_t *bases = nullptr;
+    const uint32_t *codes = nullptr;
+    const uint16_t *inv = nullptr;
+    const uint32_t *nl = nullptr;
+    uint32_t nl_bit0 = 0;
 };
 
 }  // namespace
@@ -72,7 +101,17 @@ struct dcn_ctx {
     uint64_t ib_n = 0;     // sorted unique keys of the last build (in ib_keys)
     // generic (k, w) path and B3 extraction: staging, chunk plan, CSR outputs
     DevBuf gx_bases, gx_off, gx_rc, gx_cc, gx_tmp, gx_h, gx_p, gx_oo, gx_entropy;
-    Slot slot[2];
+    static const int NSLOT = 3;
+    Slot slot[NSLOT];
+    // host ingest (packing) pool; pack_threads = 0 ships ASCII over PCIe instead
+    int pack_threads = -1;   // -1: decide at first use (DCN_PACK_THREADS or min(hardware threads, 16))
+    std::unique_ptr<HostPool> pool;
+    float t_pack = 0;
+    // Ingest: a chunk is either packed by the host pool (CPU reads 1 B/bp, PCIe carries 0.4 B/bp) or shipped
+    // as ASCII (PCIe carries 1 B/bp, no CPU work); `pack_fraction` of the chunks take the first route.
+    double pack_gbps = 0;       // packing rate of the last call that packed (ASCII GB/s), for reporting
+    double pack_fraction = -1;  // < 0: automatic (pinned caller buffers: 0, pageable: 1); DCN_PACK_FRACTION overrides
+    uint64_t n_packed_chunks = 0, n_ascii_chunks = 0;
     uint64_t launches = 0;
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
     // CUDA-event pairs around every launch of the fused kernel (ring), for dcn_fused_time_take
@@ -264,19 +303,22 @@ static int enqueue_filter_generic(dcn_ctx *ctx, DevBuf &plan, DevBuf &tmp, DevBu
 
 // Enqueue the whole filter pipeline for one device-resident batch on `st`.
 // `longs` / `dedup` are scratch for the long path (units > DCN_MAX_SHORT bases).
-static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &dedup, const uint8_t *d_bases,
+static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &dedup, const FilterInput &in,
                           uint64_t base0, uint64_t n_bases_abs, const uint64_t *d_off, uint32_t n_rec, int paired,
                           uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep,
-                          uint32_t *d_hits, uint32_t *d_total, cudaStream_t st) {
+                          uint32_t *d_hits, uint32_t *d_total, cudaStream_t st, const BatchStats *host_stats = nullptr) {
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
     const uint32_t rpu = paired ? 2u : 1u;
     if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
     const uint32_t n_units = n_rec / rpu;
     if (n_units == 0) return DCN_OK;
-    if (ctx->k != 31 || ctx->w != 15)   // the tile kernel is specialised for the default parameters
+    const uint8_t *d_bases = in.bases;
+    if (ctx->k != 31 || ctx->w != 15) {   // the tile kernel is specialised for the default parameters
+        if (!d_bases) return ctx->fail(DCN_ERR_ARG, "packed input is only implemented for k=31, w=15");
         return enqueue_filter_generic(ctx, plan, longs, dedup, d_bases, base0, n_bases_abs, d_off, n_rec, rpu, n_units,
                                       prefix_len, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, st);
-    if ((reinterpret_cast<uintptr_t>(d_bases) & 15u) || (base0 & 15u))
+    }
+    if ((d_bases && (reinterpret_cast<uintptr_t>(d_bases) & 15u)) || (base0 & 15u))
         return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
 
     const uint64_t n_rel = n_bases_abs - base0;
@@ -288,7 +330,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     uint32_t *tile_end = tile_first + n_tiles_max;
 
     FilterParams P;
-    P.bases = d_bases; P.base0 = base0; P.n_bases = n_bases_abs;
+    P.bases = d_bases; P.pk_codes = in.codes; P.pk_inv = in.inv; P.nl_bits = in.nl; P.nl_bit0 = in.nl_bit0; P.base0 = base0; P.n_bases = n_bases_abs;
     P.rec_off = d_off; P.n_rec = n_rec; P.rpu = rpu; P.n_units = n_units;
     P.prefix_len = prefix_len; P.abs_thr = abs_thr; P.rel_thr = rel_thr; P.deplete = deplete;
     P.table.slots = ctx->table.as<uint64_t>(); P.table.n_buckets = ctx->n_buckets; P.table.has_empty_key = ctx->has_empty;
@@ -310,7 +352,9 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         ctx->launches += 2;
         BatchStats hs;
         memset(&hs, 0, sizeof(hs));
-        if (n_rel > DCN_MAX_SHORT) {
+        if (host_stats) {
+            hs = *host_stats;   // the host-pointer pipeline knows the unit lengths: no readback, no sync
+        } else if (n_rel > DCN_MAX_SHORT) {
             CK(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
         }
@@ -335,7 +379,8 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         }
         const uint32_t ke = ctx->kev_head % dcn_ctx::KEV;
         CK(cudaEventRecord(ctx->kev0[ke], st));
-        filter_fused_kernel<G31><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
+        if (in.codes) filter_fused_kernel<G31, true><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
+        else filter_fused_kernel<G31, false><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
         CK(cudaEventRecord(ctx->kev1[ke], st));
         ctx->kev_head++;
         if (ctx->kev_count < dcn_ctx::KEV) ctx->kev_count++;
@@ -389,7 +434,7 @@ dcn_ctx *dcn_ctx_create(int device) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 2; i++) {
+    for (int i = 0; ok && i < dcn_ctx::NSLOT; i++) {
         Slot &s = ctx->slot[i];
         ok = ok && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreate(&s.ev_start) == cudaSuccess && cudaEventCreate(&s.ev_h2d) == cudaSuccess;
@@ -399,7 +444,9 @@ dcn_ctx *dcn_ctx_create(int device) {
         ok = ok && cudaEventCreate(&ctx->kev0[i]) == cudaSuccess && cudaEventCreate(&ctx->kev1[i]) == cudaSuccess;
     ok = ok && ctx->counters.ensure(8 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->counters.p, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(TileSmem<G31>)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(extract_index_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
@@ -421,10 +468,11 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->ib_entropy.release(); ctx->ib_stats.release();
     ctx->gx_bases.release(); ctx->gx_off.release(); ctx->gx_rc.release(); ctx->gx_cc.release(); ctx->gx_tmp.release();
     ctx->gx_h.release(); ctx->gx_p.release(); ctx->gx_oo.release(); ctx->gx_entropy.release();
-    for (int i = 0; i < 2; i++) {
+    ctx->pool.reset();
+    for (int i = 0; i < dcn_ctx::NSLOT; i++) {
         Slot &s = ctx->slot[i];
-        s.bases.release(); s.off.release(); s.keep.release(); s.hits.release(); s.total.release(); s.plan.release();
-        s.longs.release(); s.dedup.release();
+        s.in.release(); s.out.release(); s.plan.release(); s.longs.release(); s.dedup.release();
+        s.h_in.release(); s.h_out.release();
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.ev_start) cudaEventDestroy(s.ev_start);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
@@ -528,18 +576,47 @@ int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t
     if (!ctx) return DCN_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, like any CUDA API
-    return enqueue_filter(ctx, ctx->plan, ctx->longs, ctx->dedup, d_bases, 0, n_bases, d_rec_off, n_rec, paired,
+    FilterInput in;
+    in.bases = d_bases;
+    return enqueue_filter(ctx, ctx->plan, ctx->longs, ctx->dedup, in, 0, n_bases, d_rec_off, n_rec, paired,
                           prefix_len, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, st);
 }
 
-// Host-pointer form: unit-aligned chunks, double-buffered over two streams so that the H2D copy
-// of chunk c+1 overlaps the kernels of chunk c (SURVEY.md 8f.1 "pinned double-buffered streams").
-int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, int paired,
-                     uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
-                     uint8_t *keep, uint32_t *hits, uint32_t *total) {
-    if (!ctx) return DCN_ERR_ARG;
-    if (!rec_off || (!bases && n_rec && rec_off[n_rec] > rec_off[0])) return ctx->fail(DCN_ERR_ARG, "null input pointer");
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int pack_pool(dcn_ctx *ctx) {   // -> threads used for host packing (0 = ship ASCII)
+    if (ctx->pack_threads < 0) {
+        const char *e = getenv("DCN_PACK_THREADS");
+        int n = e ? atoi(e) : (int)std::min<unsigned>(std::thread::hardware_concurrency(), 16u);
+        ctx->pack_threads = std::max(0, std::min(n, 256));
+    }
+    if (ctx->pack_threads > 0 && (!ctx->pool || ctx->pool->size() != ctx->pack_threads))
+        ctx->pool.reset(new HostPool(ctx->pack_threads));
+    return ctx->pack_threads;
+}
+
+// Host-pointer form (SURVEY.md 8f.1 "pinned double-buffered streams"): unit-aligned chunks go
+// through NSLOT pipeline stages, each with its own stream.  For the default index parameters a
+// chunk is first packed by the host pool (2-bit codes + non-ACGT bits, plus its record offsets and
+// newline flags) into ONE pinned staging blob, so 0.375 + ~0.06 B/bp cross PCIe in a single copy
+// while earlier chunks are still in their kernels; other (k, w) ship the ASCII bytes.  Results come
+// back through a pinned blob and are scattered into the caller's arrays when the stage is reused.
+struct HostSrc {   // caller's host buffers: ASCII, or already packed (dcn_filter_batch_packed)
+    const uint8_t *bases = nullptr;
+    const uint32_t *codes = nullptr;
+    const uint16_t *inv = nullptr;
+    const uint32_t *nl = nullptr;
+};
+
+static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec_off, uint32_t n_rec, int paired,
+                           uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
+                           uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    const uint8_t *bases = src.bases;
+    const bool prepacked = src.codes != nullptr;
+    if (!rec_off || (!bases && !prepacked && n_rec && rec_off[n_rec] > rec_off[0])) return ctx->fail(DCN_ERR_ARG, "null input pointer");
     if (!keep || !hits || !total) return ctx->fail(DCN_ERR_ARG, "null output pointer");
+    if (prepacked && (ctx->k != 31 || ctx->w != 15)) return ctx->fail(DCN_ERR_UNSUPPORTED, "packed input is only implemented for k=31, w=15");
+    if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
     CK(cudaSetDevice(ctx->device));
     const uint32_t rpu = paired ? 2u : 1u;
     if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
@@ -552,16 +629,33 @@ int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off
         if (mb < 1) mb = 1;
         return mb << 20;
     }();
+    const bool can_pack = !prepacked && ctx->k == 31 && ctx->w == 15 && pack_pool(ctx) > 0;
+    double frac = 0;   // fraction of chunks the host packs
+    if (can_pack) {
+        cudaPointerAttributes pa;
+        const bool pinned = cudaPointerGetAttributes(&pa, bases) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        static const double env_frac = []() { const char *e = getenv("DCN_PACK_FRACTION"); return e ? atof(e) : -1.0; }();
+        const double forced = ctx->pack_fraction >= 0 ? ctx->pack_fraction : env_frac;
+        if (forced >= 0) frac = std::min(1.0, forced);
+        // Measured on the round-1 box (16 vCPUs, ~60 GB/s of host memory bandwidth, PCIe 5 x16 at 53 GB/s): every
+        // ASCII byte has to leave host memory once, read either by the copy engine or by a packing core, so for
+        // pinned buffers packing buys nothing there (50 Gbp/s either way) and the cores stay free for the caller.
+        // Pageable buffers are different: a direct copy is staged by the driver at ~8 GB/s, the pool reaches ~25.
+        else frac = pinned ? 0.0 : 1.0;
+    }
+    double frac_acc = 0.5;
+    uint64_t packed_bytes = 0;
 
-    ctx->t_h2d = ctx->t_kernel = ctx->t_d2h = 0;
-    auto retire = [&](Slot &s) -> int {  // copy a finished chunk's results out
+    ctx->t_h2d = ctx->t_kernel = ctx->t_d2h = ctx->t_pack = 0;
+    auto retire = [&](Slot &s) -> int {  // wait for a stage and scatter its results
         if (!s.busy) return DCN_OK;
-        uint32_t nu = s.u1 - s.u0;
-        CK(cudaMemcpyAsync(keep + s.u0, s.keep.p, nu * sizeof(uint8_t), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaMemcpyAsync(hits + s.u0, s.hits.p, nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaMemcpyAsync(total + s.u0, s.total.p, nu * sizeof(uint32_t), cudaMemcpyDeviceToHost, s.stream));
-        CK(cudaEventRecord(s.ev_done, s.stream));
         CK(cudaEventSynchronize(s.ev_done));
+        const uint32_t nu = s.u1 - s.u0;
+        const uint8_t *o = s.h_out.as<uint8_t>();
+        memcpy(hits + s.u0, o, (size_t)nu * 4);
+        memcpy(total + s.u0, o + (size_t)nu * 4, (size_t)nu * 4);
+        memcpy(keep + s.u0, o + (size_t)nu * 8, nu);
         float a = 0, b = 0, c = 0;
         cudaEventElapsedTime(&a, s.ev_start, s.ev_h2d);
         cudaEventElapsedTime(&b, s.ev_h2d, s.ev_kernel);
@@ -584,38 +678,195 @@ int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off
         }
         const uint32_t u1 = lo;
         const uint64_t b1 = rec_off[(uint64_t)u1 * rpu];
-        const uint64_t a0 = b0 & ~15ull;
+        const uint64_t a0 = b0 & ~63ull;   // chunk origin: keeps 16-byte loads and 32-base pack blocks aligned
+        const uint64_t nb = b1 - a0;
         const uint32_t nr = (u1 - u0) * rpu, nu = u1 - u0;
+        const uint64_t *off0 = rec_off + (uint64_t)u0 * rpu;
 
+        bool packed = false;
+        if (frac > 0) {   // error diffusion: the packed share of the chunks approaches `frac`
+            frac_acc += frac;
+            if (frac_acc >= 1.0) { packed = true; frac_acc -= 1.0; }
+        }
         Slot &s = ctx->slot[which];
-        if ((rc = retire(s))) break;  // the slot's previous chunk (two chunks ago)
-        if (s.bases.ensure((size_t)(b1 - a0) + 64) != cudaSuccess || s.off.ensure((size_t)(nr + 1) * 8) != cudaSuccess ||
-            s.keep.ensure(nu) != cudaSuccess || s.hits.ensure((size_t)nu * 4) != cudaSuccess ||
-            s.total.ensure((size_t)nu * 4) != cudaSuccess) {
-            rc = ctx->fail(DCN_ERR_NOMEM, "device allocation failed", cudaGetLastError());
+        if ((rc = retire(s))) break;  // the stage's previous chunk (NSLOT chunks ago)
+        // blob layouts
+        const size_t n_words = 2 * ((nb + 31) / 32);
+        const size_t o_inv = n_words * 4, o_off_p = align_up(o_inv + n_words * 2, 8), o_nl = o_off_p + ((size_t)nr + 1) * 8;
+        const size_t in_packed = o_nl + align_up(((size_t)nr + 31) / 32 * 4, 8);
+        const size_t o_off_a = align_up(nb + 16, 16), in_ascii = o_off_a + ((size_t)nr + 1) * 8;
+        const size_t out_bytes = (size_t)nu * 9;
+        if (s.in.ensure((packed || prepacked) ? in_packed + 8 : in_ascii) != cudaSuccess || s.out.ensure(out_bytes) != cudaSuccess ||
+            s.h_out.ensure(out_bytes) != cudaSuccess || (packed && s.h_in.ensure(in_packed) != cudaSuccess)) {
+            rc = ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
             break;
         }
-        CK(cudaEventRecord(s.ev_start, s.stream));
-        if (b1 > a0) CK(cudaMemcpyAsync(s.bases.p, bases + a0, (size_t)(b1 - a0), cudaMemcpyHostToDevice, s.stream));
-        CK(cudaMemcpyAsync(s.off.p, rec_off + (uint64_t)u0 * rpu, (size_t)(nr + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+        uint8_t *din = s.in.as<uint8_t>();
+        FilterInput in;
+        const uint64_t *d_off;
+        // unit-length statistics of the chunk (what prep_stats_kernel computes on the device)
+        const int T = ctx->pool ? ctx->pool->size() * 2 : 1;
+        std::vector<BatchStats> part((size_t)T);
+        memset(part.data(), 0, sizeof(BatchStats) * (size_t)T);
+        const uint32_t upiece = (nu + (uint32_t)T - 1) / (uint32_t)T;
+        auto stats_task = [&](int i) {
+            BatchStats &b = part[(size_t)i];
+            const uint32_t ua = std::min<uint64_t>((uint64_t)i * upiece, nu), ub = std::min<uint64_t>((uint64_t)ua + upiece, nu);
+            for (uint32_t u = ua; u < ub; u++) {
+                const uint64_t len = off0[(uint64_t)(u + 1) * rpu] - off0[(uint64_t)u * rpu];
+                if (len > DCN_MAX_SHORT) { b.n_long++; b.long_bases += len; }
+                else if ((uint32_t)len > b.max_short) b.max_short = (uint32_t)len;
+            }
+        };
+        if (prepacked) {   // slices of the caller's packed arrays, copied as they are
+            for (int i = 0; i < T; i++) stats_task(i);   // on this thread: hidden behind the copies already queued
+            const uint64_t r_first = (uint64_t)u0 * rpu;
+            CK(cudaEventRecord(s.ev_start, s.stream));
+            CK(cudaMemcpyAsync(din, src.codes + a0 / 16, n_words * 4, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(din + o_inv, src.inv + a0 / 16, n_words * 2, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(din + o_off_p, off0, ((size_t)nr + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            if (src.nl) {
+                const uint64_t w0 = r_first / 32, w1 = (r_first + nr + 31) / 32;
+                CK(cudaMemcpyAsync(din + o_nl, src.nl + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s.stream));
+                in.nl = reinterpret_cast<const uint32_t *>(din + o_nl);
+                in.nl_bit0 = (uint32_t)(r_first % 32);
+            }
+            in.codes = reinterpret_cast<const uint32_t *>(din);
+            in.inv = reinterpret_cast<const uint16_t *>(din + o_inv);
+            d_off = reinterpret_cast<const uint64_t *>(din + o_off_p);
+        } else if (packed) {
+            const auto t0 = std::chrono::steady_clock::now();
+            uint8_t *hin = s.h_in.as<uint8_t>();
+            uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
+            uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + o_inv);
+            uint64_t *h_off = reinterpret_cast<uint64_t *>(hin + o_off_p);
+            uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + o_nl);
+            const uint64_t piece = align_up((nb + T - 1) / T, 64);           // bases per task
+            const uint32_t rpiece = (uint32_t)align_up(((size_t)nr + 1 + T - 1) / T, 32);   // records per task
+            const uint8_t *src = bases + a0;
+            ctx->pool->run(T, [&](int i) {
+                stats_task(i);
+                const uint64_t p0 = (uint64_t)i * piece;
+                if (p0 < nb) {
+                    const uint64_t pn = std::min(piece, nb - p0);
+                    pack_ascii(src + p0, pn, h_codes + p0 / 16, h_inv + p0 / 16, 1);
+                }
+                const uint32_t r0 = (uint32_t)i * rpiece;
+                if (r0 <= nr) {
+                    const uint32_t r1 = std::min<uint64_t>((uint64_t)r0 + rpiece, (uint64_t)nr + 1);
+                    memcpy(h_off + r0, off0 + r0, (size_t)(r1 - r0) * 8);
+                    for (uint32_t rw = r0; rw < r1 && rw < nr; rw += 32) {     // newline flags, 32 records per word
+                        uint32_t bits = 0;
+                        for (uint32_t r = rw; r < std::min(rw + 32, std::min(r1, nr)); r++) {
+                            const uint64_t len = off0[r + 1] - off0[r];
+                            if (len < (uint64_t)ctx->k) continue;                              // src/filter_common.rs:217-219
+                            const uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;   // :222-226
+                            if (bases[off0[r] + n - 1] == (uint8_t)'\n') bits |= 1u << (r - rw);      // :229
+                        }
+                        h_nl[rw / 32] = bits;
+                    }
+                }
+            });
+            ctx->t_pack += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            packed_bytes += nb;
+            ctx->n_packed_chunks++;
+            CK(cudaEventRecord(s.ev_start, s.stream));
+            CK(cudaMemcpyAsync(din, hin, in_packed, cudaMemcpyHostToDevice, s.stream));
+            in.codes = reinterpret_cast<const uint32_t *>(din);
+            in.inv = reinterpret_cast<const uint16_t *>(din + o_inv);
+            in.nl = reinterpret_cast<const uint32_t *>(din + o_nl);
+            d_off = reinterpret_cast<const uint64_t *>(din + o_off_p);
+        } else {
+            for (int i = 0; i < T; i++) stats_task(i);
+            ctx->n_ascii_chunks++;
+            CK(cudaEventRecord(s.ev_start, s.stream));
+            if (nb) CK(cudaMemcpyAsync(din, bases + a0, (size_t)nb, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(din + o_off_a, off0, ((size_t)nr + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+            in.bases = din;
+            d_off = reinterpret_cast<const uint64_t *>(din + o_off_a);
+        }
         CK(cudaEventRecord(s.ev_h2d, s.stream));
-        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, s.bases.as<uint8_t>(), a0, b1, s.off.as<uint64_t>(), nr, paired, prefix_len,
-                            abs_thr, rel_thr, deplete, s.keep.as<uint8_t>(), s.hits.as<uint32_t>(),
-                            s.total.as<uint32_t>(), s.stream);
+        BatchStats hstats;
+        memset(&hstats, 0, sizeof(hstats));
+        for (const BatchStats &b : part) {
+            hstats.max_short = std::max(hstats.max_short, b.max_short);
+            hstats.n_long += b.n_long;
+            hstats.long_bases += b.long_bases;
+        }
+        uint8_t *dout = s.out.as<uint8_t>();
+        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, a0, b1, d_off, nr, paired, prefix_len, abs_thr, rel_thr, deplete,
+                            dout + (size_t)nu * 8, reinterpret_cast<uint32_t *>(dout), reinterpret_cast<uint32_t *>(dout + (size_t)nu * 4),
+                            s.stream, &hstats);
         if (rc) break;
         CK(cudaEventRecord(s.ev_kernel, s.stream));
+        CK(cudaMemcpyAsync(s.h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, s.stream));
+        CK(cudaEventRecord(s.ev_done, s.stream));
         s.busy = true; s.u0 = u0; s.u1 = u1;
-        // the other slot's chunk was enqueued before this one: drain it while this one runs
-        if ((rc = retire(ctx->slot[which ^ 1]))) break;
-        which ^= 1;
+        which = (which + 1) % dcn_ctx::NSLOT;
         u0 = u1;
     }
-    for (int i = 0; i < 2; i++) {
-        int r2 = retire(ctx->slot[i]);
+    for (int i = 0; i < dcn_ctx::NSLOT; i++) {   // oldest first
+        int r2 = retire(ctx->slot[(which + i) % dcn_ctx::NSLOT]);
         if (!rc) rc = r2;
     }
-    if (rc) { cudaDeviceSynchronize(); ctx->slot[0].busy = ctx->slot[1].busy = false; }
+    if (rc) { cudaDeviceSynchronize(); for (auto &sl : ctx->slot) sl.busy = false; }
+    if (!rc && packed_bytes && ctx->t_pack > 0) ctx->pack_gbps = (double)packed_bytes / 1e6 / ctx->t_pack;
     return rc;
+}
+
+int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, int paired,
+                     uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
+                     uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    if (!ctx) return DCN_ERR_ARG;
+    HostSrc src;
+    src.bases = bases;
+    return filter_pipeline(ctx, src, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr, deplete, keep, hits, total);
+}
+
+int dcn_filter_batch_packed(dcn_ctx *ctx, const uint32_t *codes, const uint16_t *inv, const uint32_t *nl_bits,
+                            const uint64_t *rec_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
+                            double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!codes || !inv) return ctx->fail(DCN_ERR_ARG, "null input pointer");
+    if (n_rec && rec_off && rec_off[0] != 0) return ctx->fail(DCN_ERR_ARG, "rec_off[0] must be 0");
+    HostSrc src;
+    src.codes = codes; src.inv = inv; src.nl = nl_bits;
+    return filter_pipeline(ctx, src, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr, deplete, keep, hits, total);
+}
+
+int dcn_newline_bits(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
+                     uint32_t *nl_bits) {
+    if (!rec_off || !nl_bits || (!bases && n_rec && rec_off[n_rec] > rec_off[0])) return DCN_ERR_ARG;
+    for (uint32_t w = 0; w < (n_rec + 31) / 32; w++) nl_bits[w] = 0;
+    for (uint32_t r = 0; r < n_rec; r++) {
+        const uint64_t len = rec_off[r + 1] - rec_off[r];
+        if (len < (uint64_t)k) continue;                                                        // src/filter_common.rs:217-219
+        const uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;             // :222-226
+        if (bases[rec_off[r] + n - 1] == (uint8_t)'\n') nl_bits[r >> 5] |= 1u << (r & 31u);    // :229
+    }
+    return DCN_OK;
+}
+
+int dcn_host_pack_fraction(dcn_ctx *ctx, double fraction) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (fraction > 1.0) return ctx->fail(DCN_ERR_ARG, "fraction must be <= 1 (negative = automatic)");
+    ctx->pack_fraction = fraction;
+    return DCN_OK;
+}
+
+int dcn_host_pack_threads(dcn_ctx *ctx, int n_threads) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (n_threads < 0 || n_threads > 256) return ctx->fail(DCN_ERR_ARG, "n_threads must be in 0..=256");
+    ctx->pack_threads = n_threads;
+    ctx->pack_gbps = 0;
+    if (n_threads == 0) ctx->pool.reset();
+    return DCN_OK;
+}
+
+int dcn_pack_ascii(const uint8_t *bases, uint64_t n_bases, uint32_t *codes, uint16_t *inv) {
+    if ((!bases && n_bases) || !codes || !inv) return DCN_ERR_ARG;
+    pack_ascii(bases, n_bases, codes, inv, 1);
+    return DCN_OK;
 }
 
 // ---------------------------------------------------------------------------- B2 lookup
@@ -674,16 +925,19 @@ int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_o
     CK(cudaSetDevice(ctx->device));
     Slot &s = ctx->slot[0];
     cudaStream_t st = s.stream;
-    CK(s.bases.ensure(n_hash * 8 + 64)); CK(s.off.ensure((size_t)(n_rec + 1) * 8));
-    CK(s.keep.ensure(n_rec)); CK(s.hits.ensure((size_t)n_rec * 4)); CK(s.total.ensure((size_t)n_rec * 4));
-    if (n_hash) CK(cudaMemcpyAsync(s.bases.p, hashes, n_hash * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(s.off.p, rec_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
-    int rc = dcn_lookup_batch_device(ctx, s.bases.as<uint64_t>(), s.off.as<uint64_t>(), n_rec, abs_thr, rel_thr, deplete,
-                                     s.keep.as<uint8_t>(), s.hits.as<uint32_t>(), s.total.as<uint32_t>(), st);
+    const size_t o_off = align_up(n_hash * 8, 8), o_tot = (size_t)n_rec * 4, o_keep = (size_t)n_rec * 8;
+    CK(s.in.ensure(o_off + ((size_t)n_rec + 1) * 8));
+    CK(s.out.ensure((size_t)n_rec * 9));
+    uint8_t *din = s.in.as<uint8_t>(), *dout = s.out.as<uint8_t>();
+    if (n_hash) CK(cudaMemcpyAsync(din, hashes, n_hash * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(din + o_off, rec_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = dcn_lookup_batch_device(ctx, reinterpret_cast<uint64_t *>(din), reinterpret_cast<uint64_t *>(din + o_off), n_rec, abs_thr,
+                                     rel_thr, deplete, dout + o_keep, reinterpret_cast<uint32_t *>(dout),
+                                     reinterpret_cast<uint32_t *>(dout + o_tot), st);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(keep, s.keep.p, n_rec, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(hits, s.hits.p, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(total, s.total.p, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(keep, dout + o_keep, n_rec, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hits, dout, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(total, dout + o_tot, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return DCN_OK;
 }
@@ -884,6 +1138,12 @@ int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms) {
     CK(cudaEventElapsedTime(ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     ctx->launches += 1;
+    return DCN_OK;
+}
+
+int dcn_last_pack_ms(dcn_ctx *ctx, float *pack_ms) {
+    if (!ctx || !pack_ms) return DCN_ERR_ARG;
+    *pack_ms = ctx->t_pack;
     return DCN_OK;
 }
 

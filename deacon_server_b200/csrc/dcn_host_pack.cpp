@@ -1,0 +1,186 @@
+// dcn_host_pack.cpp -- see dcn_host_pack.h.
+#include "dcn_host_pack.h"
+
+#include <string.h>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define DCN_X86 1
+#endif
+
+namespace dcn {
+
+static inline bool is_acgt(uint8_t b) {
+    uint8_t u = b & 0xDFu;
+    return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+}
+
+// 32 bases -> 2 code words + 2 mask halves
+static inline void pack32_scalar(const uint8_t *p, uint32_t *codes, uint16_t *inv) {
+    for (int h = 0; h < 2; h++) {
+        uint32_t c = 0, m = 0;
+        for (int j = 0; j < 16; j++) {
+            uint8_t b = p[16 * h + j];
+            c |= (uint32_t)((b >> 1) & 3u) << (2 * j);
+            m |= (uint32_t)(!is_acgt(b)) << j;
+        }
+        codes[h] = c;
+        inv[h] = (uint16_t)m;
+    }
+}
+
+#ifdef DCN_X86
+__attribute__((target("avx2,bmi2"))) static void pack_blocks_avx2(const uint8_t *p, uint64_t n_blocks, uint32_t *codes,
+                                                                  uint16_t *inv) {
+    // letter expected for each low nibble of the byte: 1 -> 'A', 3 -> 'C', 4 -> 'T', 7 -> 'G'
+    const __m256i lut = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,
+                                         -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
+    const __m256i m0f = _mm256_set1_epi8(0x0F), mdf = _mm256_set1_epi8((char)0xDF);
+    const uint64_t M = 0x0606060606060606ULL;
+    for (uint64_t i = 0; i < n_blocks; i++) {
+        const uint8_t *q = p + 32 * i;
+        __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(q));
+        __m256i want = _mm256_shuffle_epi8(lut, _mm256_and_si256(v, m0f));
+        uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(want, _mm256_and_si256(v, mdf)));
+        uint32_t bad = ~ok;
+        memcpy(inv + 2 * i, &bad, 4);
+        uint64_t x0, x1, x2, x3;
+        memcpy(&x0, q, 8); memcpy(&x1, q + 8, 8); memcpy(&x2, q + 16, 8); memcpy(&x3, q + 24, 8);
+        uint64_t c = _pext_u64(x0, M) | (_pext_u64(x1, M) << 16) | (_pext_u64(x2, M) << 32) | (_pext_u64(x3, M) << 48);
+        memcpy(codes + 2 * i, &c, 8);
+    }
+}
+
+// AVX-512 (BW): 64 bases per step.  Codes: (byte >> 1) & 3, then two multiply-adds fold 4 bytes into one
+// (c0 + 4 c1 + 16 c2 + 64 c3) and a narrowing move keeps the low byte of every dword.  Mask: compare
+// (byte & 0xDF) with the letter its low nibble stands for.  `nt` = streaming stores: the output is a
+// pinned staging buffer the GPU's copy engine reads next, so keep it out of the cores' caches.
+__attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_blocks_avx512(const uint8_t *p, uint64_t n_blocks64,
+                                                                                   uint32_t *codes, uint16_t *inv, bool nt) {
+    const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1));
+    const __m512i m0f = _mm512_set1_epi8(0x0F), mdf = _mm512_set1_epi8((char)0xDF), m03 = _mm512_set1_epi8(0x03);
+    const __m512i mul8 = _mm512_set1_epi16(0x0401), mul16 = _mm512_set1_epi32(0x00100001);
+    for (uint64_t i = 0; i < n_blocks64; i++) {
+        _mm_prefetch(reinterpret_cast<const char *>(p + 64 * i + 2048), _MM_HINT_NTA);   // runs ahead across 4 KB pages
+        __m512i v = _mm512_loadu_si512(p + 64 * i);
+        __m512i want = _mm512_shuffle_epi8(lut, _mm512_and_si512(v, m0f));
+        uint64_t bad = ~_mm512_cmpeq_epi8_mask(want, _mm512_and_si512(v, mdf));
+        __m512i c = _mm512_and_si512(_mm512_srli_epi16(v, 1), m03);
+        __m512i c4 = _mm512_maddubs_epi16(c, mul8);          // c0 + 4 c1 per 16-bit lane
+        __m512i c8 = _mm512_madd_epi16(c4, mul16);           // + 16 * (c2 + 4 c3) per 32-bit lane
+        __m128i out = _mm512_cvtepi32_epi8(c8);              // 16 bytes = 64 bases
+        if (nt) {
+            _mm_stream_si128(reinterpret_cast<__m128i *>(codes + 4 * i), out);
+            _mm_stream_si64(reinterpret_cast<long long *>(inv + 4 * i), (long long)bad);
+        } else {
+            _mm_storeu_si128(reinterpret_cast<__m128i *>(codes + 4 * i), out);
+            memcpy(inv + 4 * i, &bad, 8);
+        }
+    }
+    if (nt) _mm_sfence();
+}
+
+static int simd_level() {   // 0 scalar, 1 AVX2 + BMI2, 2 AVX-512 BW
+    static const int lvl = []() {
+        if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512vl")) return 2;
+        if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2")) return 1;
+        return 0;
+    }();
+    return lvl;
+}
+#endif
+
+bool pack_has_simd() {
+#ifdef DCN_X86
+    return simd_level() > 0;
+#else
+    return false;
+#endif
+}
+
+void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd) {
+    const uint64_t full = n / 32;
+    uint64_t done = 0;
+#ifdef DCN_X86
+    // simd: 1 = best available, 2 = force the AVX2 path (tests), 0 = scalar
+    if (simd == 1 && simd_level() == 2) {
+        const bool nt = ((reinterpret_cast<uintptr_t>(codes) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(inv) & 7u) == 0);
+        pack_blocks_avx512(bases, n / 64, codes, inv, nt);
+        done = (n / 64) * 2;
+    } else if (simd && simd_level() >= 1) {
+        pack_blocks_avx2(bases, full, codes, inv);
+        done = full;
+    }
+#else
+    (void)simd;
+#endif
+    for (uint64_t i = done; i < full; i++) pack32_scalar(bases + 32 * i, codes + 2 * i, inv + 2 * i);
+    if (n % 32) {
+        uint8_t tail[32];
+        memset(tail, 0, sizeof(tail));   // byte 0: code 0, not ACGT
+        memcpy(tail, bases + 32 * full, n % 32);
+        pack32_scalar(tail, codes + 2 * full, inv + 2 * full);
+    }
+}
+
+// ------------------------------------------------------------------ thread pool
+HostPool::HostPool(int n_threads) : n_(n_threads < 1 ? 1 : n_threads) {
+    for (int i = 1; i < n_; i++) th_.emplace_back([this] { worker(); });
+}
+
+HostPool::~HostPool() {
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        stop_ = true;
+    }
+    cv_start_.notify_all();
+    for (auto &t : th_) t.join();
+}
+
+void HostPool::drain() {
+    for (;;) {
+        int i = next_.fetch_add(1, std::memory_order_relaxed);
+        if (i >= n_tasks_) return;
+        (*fn_)(i);
+    }
+}
+
+void HostPool::worker() {
+    uint64_t seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            cv_start_.wait(lk, [&] { return stop_ || gen_ != seen; });
+            if (stop_) return;
+            seen = gen_;
+        }
+        drain();
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (--busy_ == 0) cv_done_.notify_one();
+        }
+    }
+}
+
+void HostPool::run(int n_tasks, const std::function<void(int)> &fn) {
+    if (n_tasks <= 0) return;
+    if (th_.empty() || n_tasks == 1) {
+        for (int i = 0; i < n_tasks; i++) fn(i);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        fn_ = &fn;
+        n_tasks_ = n_tasks;
+        next_.store(0, std::memory_order_relaxed);
+        busy_ = (int)th_.size();
+        gen_++;
+    }
+    cv_start_.notify_all();
+    drain();
+    std::unique_lock<std::mutex> lk(m_);
+    cv_done_.wait(lk, [&] { return busy_ == 0; });
+    fn_ = nullptr;
+}
+
+}  // namespace dcn

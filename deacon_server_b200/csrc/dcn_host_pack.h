@@ -1,0 +1,49 @@
+// dcn_host_pack.h -- host-side ingest helpers of the host-pointer pipeline: the
+// 2-bit packing + non-ACGT bitmask the reference computes per record on the CPU
+// (PackedSeqVec::from_ascii and the mask loop, src/filter_common.rs:238-258), done here once per
+// batch by a small thread pool straight into pinned staging buffers, so that 0.375 B/bp instead
+// of 1 B/bp cross PCIe.  Plain C++ (no CUDA): also compiled into the test-only host emulation.
+#pragma once
+#include <stdint.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace dcn {
+
+// Packs bases[0 .. n): codes[i] holds bases [16 i, 16 i + 16) as 2-bit codes (byte >> 1) & 3, base j
+// at bits 2 j (packed-seq order A=0 C=1 T=2 G=3); inv[i] bit j = base 16 i + j is not one of
+// ACGTacgt.  Both arrays must hold 2 * ceil(n / 32) entries; positions >= n are padded with code 0,
+// non-ACGT 1.  simd = 0 forces the scalar loop (tests compare the two).
+void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd);
+bool pack_has_simd();
+
+class HostPool {
+  public:
+    explicit HostPool(int n_threads);   // n_threads - 1 workers; the caller of run() is the last one
+    ~HostPool();
+    HostPool(const HostPool &) = delete;
+    HostPool &operator=(const HostPool &) = delete;
+    int size() const { return n_; }
+    // runs fn(0 .. n_tasks - 1) over the pool and returns when every task is done
+    void run(int n_tasks, const std::function<void(int)> &fn);
+
+  private:
+    void worker();
+    void drain();
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_start_, cv_done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int n_tasks_ = 0, busy_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace dcn

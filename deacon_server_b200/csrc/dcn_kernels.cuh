@@ -122,7 +122,7 @@ __global__ void prep_long_kernel(FilterParams P, BatchStats *st, uint32_t *long_
         P.hits[u] = 0; P.total[u] = 0;
         for (uint32_t r = u * P.rpu; r < (u + 1) * P.rpu; r++) {
             uint64_t gs = P.rec_off[r] - P.base0, rl = P.rec_off[r + 1] - P.base0 - gs;
-            uint32_t nc = chunks_of<G>(effective_len64<G, FLAVOUR_FILTER>(P.bases, gs, rl, P.prefix_len));
+            uint32_t nc = chunks_of<G>(filter_eff_len<G>(P, r, gs, rl));
             if (!nc) continue;
             uint32_t at = atomicAdd(&st->n_chunks, nc);
             for (uint32_t c = 0; c < nc; c++)
@@ -180,7 +180,7 @@ __global__ void prep_tiles_kernel(const uint64_t *__restrict__ rec_off, uint32_t
 
 // ------------------------------------------------------------------ the fused filter kernel
 // Persistent CTAs; tile i -> CTA (i mod grid).  4 CTAs per SM (64 registers, ~53 KB shared memory each).
-template <class G>
+template <class G, bool PACKED>
 __global__ void __launch_bounds__(G::NT, 4)
 filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ tile_first,
                     const uint32_t *__restrict__ tile_end, DedupView dd, const ChunkDesc *__restrict__ desc) {
@@ -195,13 +195,13 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     const uint32_t n_long = st->n_long;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         uint32_t a = tile_first[tile], b = tile_end[tile];
-        if (a < b) filter_tile<G>(ex, s, P, cfg, n_long, a, b);
+        if (a < b) filter_tile<G, PACKED>(ex, s, P, cfg, n_long, a, b);
     }
     if (n_long) {  // long units: chunks, spread over the CTAs in reverse so short and long work interleave
         __syncthreads();
         const uint32_t n_chunks = st->n_chunks;
         for (uint32_t w = gridDim.x - 1 - blockIdx.x; w < n_chunks; w += gridDim.x)
-            filter_long_chunk<G>(ex, s, P, dd, desc[w]);
+            filter_long_chunk<G, PACKED>(ex, s, P, dd, desc[w]);
     }
 }
 

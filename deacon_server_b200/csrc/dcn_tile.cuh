@@ -115,11 +115,29 @@ DCN_HD uint32_t code_index_flavour(uint32_t b) {
     return 1u;
 }
 
-template <class G, int FLAV>
-DCN_HD void convert_vector(int v, TileSmem<G> &s, const uint8_t *bases, uint64_t n_bases, uint64_t origin,
+// Where a tile's bases come from: ASCII bytes (device-resident batches, index builds) or the
+// host-packed form the host-pointer pipeline ships over PCIe (2-bit codes, 16 bases per u32 word
+// in packed-seq order, plus one non-ACGT bit per base: 0.375 B/bp instead of 1 B/bp).  Offsets are
+// relative to base0; word i of `codes` / `inv` covers relative bases [16 i, 16 i + 16).
+struct TileSrc {
+    const uint8_t *bases;
+    const uint32_t *codes;
+    const uint16_t *inv;
+    uint64_t n_bases;   // readable extent (relative)
+};
+
+template <class G, int FLAV, bool PACKED>
+DCN_HD void convert_vector(int v, TileSmem<G> &s, const TileSrc &src, uint64_t origin,
                            uint32_t &codes_out, uint32_t &efw_out, uint32_t &erc_out) {
-    // `bases`, `n_bases` and `origin` are relative to base0 here (the caller rebased them)
     uint64_t g = origin + 16ull * (uint64_t)v;
+    const uint64_t n_bases = src.n_bases;
+    uint32_t codes = 0, inv16 = 0;
+    if (PACKED) {
+        // the packer pads the last word (codes 0, non-ACGT bits 1), like the byte path below
+        if (g < n_bases) { codes = src.codes[g >> 4]; inv16 = src.inv[g >> 4]; }
+        else inv16 = 0xFFFFu;
+    } else {
+    const uint8_t *bases = src.bases;
     uint32_t w[4];
     if (g + 16 <= n_bases) {
 #ifdef __CUDA_ARCH__
@@ -139,7 +157,6 @@ DCN_HD void convert_vector(int v, TileSmem<G> &s, const uint8_t *bases, uint64_t
             w[i] = x;
         }
     }
-    uint32_t codes = 0, inv16 = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         uint32_t x = w[i];
@@ -158,6 +175,7 @@ DCN_HD void convert_vector(int v, TileSmem<G> &s, const uint8_t *bases, uint64_t
         uint32_t packed8 = (c * 0x01041040u) >> 24;
         codes |= packed8 << (8 * i);
         inv16 |= inv4 << (4 * i);
+    }
     }
     // aggregates over the 16 bases: E_fw = XOR rotl(F[c_i], 30-i), E_rc = XOR rotl(F[c_i^2], i)
     uint32_t efw = 0, erc = 0;
@@ -178,13 +196,12 @@ DCN_HD void convert_vector(int v, TileSmem<G> &s, const uint8_t *bases, uint64_t
     codes_out = codes; efw_out = efw; erc_out = erc;
 }
 
-template <class G, int FLAV>
-DCN_HD void phase_convert(int t, TileSmem<G> &s, TilePriv<G> &pv, const uint8_t *bases, uint64_t n_bases,
-                          uint64_t origin) {
-    convert_vector<G, FLAV>(t, s, bases, n_bases, origin, pv.c0, pv.efw, pv.erc);
+template <class G, int FLAV, bool PACKED>
+DCN_HD void phase_convert(int t, TileSmem<G> &s, TilePriv<G> &pv, const TileSrc &src, uint64_t origin) {
+    convert_vector<G, FLAV, PACKED>(t, s, src, origin, pv.c0, pv.efw, pv.erc);
     if (t < G::NV - G::NT) {
         uint32_t a, b, c;
-        convert_vector<G, FLAV>(G::NT + t, s, bases, n_bases, origin, a, b, c);
+        convert_vector<G, FLAV, PACKED>(G::NT + t, s, src, origin, a, b, c);
     }
     if (t < 6) {  // zero pad words read by the last threads
         s.codes[G::NV + t] = 0;
@@ -470,7 +487,11 @@ DCN_HD void set_bits(uint32_t *arr, uint32_t a, uint32_t b) {
 
 // ------------------------------------------------------------------ filter parameters
 struct FilterParams {
-    const uint8_t *bases;     // concatenated ASCII records (device), 16-byte aligned
+    const uint8_t *bases;     // concatenated ASCII records (device), 16-byte aligned; nullptr when packed
+    const uint32_t *pk_codes; // host-packed form (see TileSrc): 2-bit codes ...
+    const uint16_t *pk_inv;   // ... and non-ACGT bits; both cover [base0, n_bases) rounded up to 16
+    const uint32_t *nl_bits;  // packed form only: bit nl_bit0 + r = record r ends its effective prefix in '\n'
+    uint32_t nl_bit0;
     uint64_t base0;           // absolute offset of bases[0] (multiple of 16); rec_off is absolute
     uint64_t n_bases;         // absolute end offset: bases[x - base0] is readable for base0 <= x < n_bases
     const uint64_t *rec_off;  // n_rec + 1 offsets (device)
@@ -487,14 +508,20 @@ struct FilterParams {
     uint32_t *total;
 };
 
-// effective end of a record (src/filter_common.rs:217-229): raw-length guard, prefix, one '\n'
-template <class G, int FLAV>
-DCN_HD uint32_t effective_len(const uint8_t *bases, uint64_t gstart, uint32_t len, uint32_t prefix_len) {
-    if (len < (uint32_t)G::K) return 0;
-    if (FLAV == FLAVOUR_INDEX) return len;
-    uint32_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;
-    if (n > 0 && bases[gstart + n - 1] == (uint8_t)'\n') n--;
-    return n;
+// effective length of a record (src/filter_common.rs:217-229): raw-length guard, prefix, one '\n'.
+// `r` is the record's index in P.rec_off, `gs` its start relative to base0.
+template <class G>
+DCN_HD uint64_t filter_eff_len(const FilterParams &P, uint32_t r, uint64_t gs, uint64_t len) {
+    if (len < (uint64_t)G::K) return 0;
+    uint64_t n = (P.prefix_len > 0 && len > P.prefix_len) ? P.prefix_len : len;
+    const uint32_t nb = P.nl_bit0 + r;
+    const bool nl = P.bases ? P.bases[gs + n - 1] == (uint8_t)'\n' : (P.nl_bits && ((P.nl_bits[nb >> 5] >> (nb & 31u)) & 1u) != 0);
+    return nl ? n - 1 : n;
+}
+DCN_HD TileSrc filter_src(const FilterParams &P) {
+    TileSrc src;
+    src.bases = P.bases; src.codes = P.pk_codes; src.inv = P.pk_inv; src.n_bases = P.n_bases - P.base0;
+    return src;
 }
 
 // ------------------------------------------------------------------ short-unit tile driver
@@ -511,7 +538,7 @@ DCN_HD void phase_structure_load(int t, TileSmem<G> &s, const FilterParams &P, u
     for (uint32_t i = (uint32_t)t; i < n_rec_t; i += G::NT) {
         uint64_t gs = P.rec_off[r_begin + i] - P.base0, ge = P.rec_off[r_begin + i + 1] - P.base0;
         uint32_t sL = (uint32_t)(gs - origin), eL = (uint32_t)(ge - origin);
-        uint32_t eff = sL + effective_len<G, FLAVOUR_FILTER>(P.bases, gs, eL - sL, P.prefix_len);
+        uint32_t eff = sL + (uint32_t)filter_eff_len<G>(P, r_begin + i, gs, eL - sL);
         s.rec_se[i] = sL | (eL << 16);
         s.rec_eff[i] = (uint16_t)eff;
     }
@@ -552,7 +579,7 @@ DCN_HD void phase_unit_first(int t, TileSmem<G> &s, uint32_t n_units_t, uint32_t
 
 // Returns false (after one barrier-consistent decision, nothing written) when the run emits more
 // than PKCAP picks: the caller then splits the run.  A single short unit (<= 1024 bases) never does.
-template <class G, class Ex>
+template <class G, bool PACKED, class Ex>
 DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
     using Priv = TilePriv<G>;
     const uint32_t r_begin = u_begin * P.rpu;
@@ -560,12 +587,12 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
     const uint32_t n_units_t = u_end - u_begin;
     const uint64_t first_start = P.rec_off[r_begin] - P.base0;
     const uint64_t origin = first_start & ~15ull;   // relative to base0, like every offset below
-    const uint64_t n_rel = P.n_bases - P.base0;
+    const TileSrc src = filter_src(P);
 
     ex.par([&](int t, Priv &pv) {
         for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
         phase_structure_load<G>(t, s, P, r_begin, n_rec_t, origin);
-        phase_convert<G, FLAVOUR_FILTER>(t, s, pv, P.bases, n_rel, origin);
+        phase_convert<G, FLAVOUR_FILTER, PACKED>(t, s, pv, src, origin);
     });
     ex.par([&](int t, Priv &pv) {
         phase_structure<G>(t, s, P.rpu, n_rec_t);
@@ -682,13 +709,13 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
 }
 
 // a run of short units, split in halves while it emits more picks than one pass can hold
-template <class G, class Ex>
+template <class G, bool PACKED, class Ex>
 DCN_HD void filter_short_run(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
     uint32_t lo = u_begin;
     uint32_t span = u_end - u_begin;
     while (lo < u_end) {
         uint32_t hi = lo + span < u_end ? lo + span : u_end;
-        if (filter_short_tile<G>(ex, s, P, lo, hi)) {
+        if (filter_short_tile<G, PACKED>(ex, s, P, lo, hi)) {
             if (hi < u_end) ex.barrier();  // the next pass rewrites tables the last phase still reads
             lo = hi;
         } else {
@@ -699,13 +726,13 @@ DCN_HD void filter_short_run(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint
 
 // All units whose first base lies in one tile: runs of short units go through
 // filter_short_tile; long units are skipped here (they are cut into chunks by the long path).
-template <class G, class Ex>
+template <class G, bool PACKED, class Ex>
 DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const PlanCfg &cfg, uint32_t n_long,
                         uint32_t u_first, uint32_t u_end) {
     const uint64_t rpu = P.rpu;
     // common case: the batch has no long unit and the tile's records fit one pass
     if (n_long == 0 && (uint64_t)(u_end - u_first) * rpu <= (uint64_t)G::MAXR) {
-        filter_short_run<G>(ex, s, P, u_first, u_end);
+        filter_short_run<G, PACKED>(ex, s, P, u_first, u_end);
         return;
     }
     uint32_t u = u_first;
@@ -716,7 +743,7 @@ DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const Pla
         while (v < u_end && (uint64_t)(v - u + 1) * rpu <= (uint64_t)G::MAXR &&
                P.rec_off[(uint64_t)(v + 1) * rpu] - P.rec_off[(uint64_t)v * rpu] <= cfg.max_short)
             v++;
-        filter_short_run<G>(ex, s, P, u, v);
+        filter_short_run<G, PACKED>(ex, s, P, u, v);
         ex.barrier();  // a following pass rewrites the tables the last phase still reads
         u = v;
     }
@@ -747,21 +774,11 @@ DCN_HD uint32_t chunks_of(uint64_t eff_len) {
     return (uint32_t)((nwin + ChunkGeo<G>::CSTRIDE - 1) / ChunkGeo<G>::CSTRIDE);
 }
 
-// effective length for long records (64-bit length)
-template <class G, int FLAV>
-DCN_HD uint64_t effective_len64(const uint8_t *bases, uint64_t gstart, uint64_t len, uint32_t prefix_len) {
-    if (len < (uint64_t)G::K) return 0;
-    if (FLAV == FLAVOUR_INDEX) return len;
-    uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;
-    if (n > 0 && bases[gstart + n - 1] == (uint8_t)'\n') n--;
-    return n;
-}
-
 // Runs the per-position phases for chunk `c` of the record whose effective sequence is
 // [gs, gs + eff_len) (offsets relative to base0).  On return pk_pos[0 .. npicks) holds the picks'
 // local positions and *origin_out the offset of local position 0.  Returns npicks.
-template <class G, int FLAV, class Ex>
-DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const uint8_t *bases, uint64_t n_rel, uint64_t gs,
+template <class G, int FLAV, bool PACKED, class Ex>
+DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const TileSrc &src, uint64_t gs,
                             uint64_t eff_len, uint32_t c, uint64_t *origin_out) {
     using Priv = TilePriv<G>;
     const uint64_t nwin = eff_len - (uint64_t)G::L + 1;
@@ -776,7 +793,7 @@ DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const uint8_t *bases, uint64
 
     ex.par([&](int t, Priv &pv) {
         for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
-        phase_convert<G, FLAV>(t, s, pv, bases, n_rel, origin);
+        phase_convert<G, FLAV, PACKED>(t, s, pv, src, origin);
     });
     ex.par([&](int t, Priv &pv) {
         if (t == 0) {
@@ -823,15 +840,15 @@ DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
 }
 
 // ------------------------------------------------------------------ long path of the filter
-template <class G, class Ex>
+template <class G, bool PACKED, class Ex>
 DCN_HD void filter_long_chunk(Ex &ex, TileSmem<G> &s, const FilterParams &P, const DedupView &dd, ChunkDesc cd) {
     using Priv = TilePriv<G>;
     const uint64_t gs = P.rec_off[cd.rec] - P.base0;
     const uint64_t len = P.rec_off[cd.rec + 1] - P.base0 - gs;
-    const uint64_t eff_len = effective_len64<G, FLAVOUR_FILTER>(P.bases, gs, len, P.prefix_len);
+    const uint64_t eff_len = filter_eff_len<G>(P, cd.rec, gs, len);
     const uint32_t unit = cd.rec / P.rpu;
     uint64_t origin;
-    const uint32_t npicks = chunk_picks<G, FLAVOUR_FILTER>(ex, s, P.bases, P.n_bases - P.base0, gs, eff_len, cd.chunk, &origin);
+    const uint32_t npicks = chunk_picks<G, FLAVOUR_FILTER, PACKED>(ex, s, filter_src(P), gs, eff_len, cd.chunk, &origin);
     ex.par([&](int t, Priv &) {
         const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
         for (uint32_t r = 0; r < rounds; r++) {
@@ -888,9 +905,11 @@ DCN_HD void index_chunk(Ex &ex, TileSmem<G> &s, const IndexParams &P, ChunkDesc 
     using Priv = TilePriv<G>;
     const uint64_t gs = P.rec_off[cd.rec] - P.base0;
     const uint64_t len = P.rec_off[cd.rec + 1] - P.base0 - gs;
-    const uint64_t eff_len = effective_len64<G, FLAVOUR_INDEX>(P.bases, gs, len, 0);
+    const uint64_t eff_len = len < (uint64_t)G::K ? 0 : len;   // src/minimizers.rs:135-137
     uint64_t origin;
-    const uint32_t npicks = chunk_picks<G, FLAVOUR_INDEX>(ex, s, P.bases, P.n_bases - P.base0, gs, eff_len, cd.chunk, &origin);
+    TileSrc src;
+    src.bases = P.bases; src.codes = nullptr; src.inv = nullptr; src.n_bases = P.n_bases - P.base0;
+    const uint32_t npicks = chunk_picks<G, FLAVOUR_INDEX, false>(ex, s, src, gs, eff_len, cd.chunk, &origin);
     ex.par([&](int t, Priv &) {
         const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
         for (uint32_t r = 0; r < rounds; r++) {

@@ -78,6 +78,34 @@ int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t
                             uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
                             int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream);
 
+/* Host ingest of dcn_filter_batch.  For k=31, w=15 indexes a chunk of the batch can be
+ * packed on `n_threads` host threads (2-bit codes + non-ACGT bits: what PackedSeqVec::from_ascii and the mask
+ * loop of src/filter_common.rs:238-258 compute per record on the CPU) into pinned staging, so 0.4 B/bp cross
+ * PCIe instead of 1 B/bp; otherwise the ASCII bytes are copied and the GPU converts them.  Results are identical.
+ * Default threads: DCN_PACK_THREADS, else min(hardware threads, 16); 0 = never pack. */
+int dcn_host_pack_threads(dcn_ctx *ctx, int n_threads);
+/* Share of the chunks that take the packing route.  Negative (default) = automatic: 0 for pinned caller
+ * buffers (on the measured box the copy engine alone already runs at the host-memory / PCIe limit), 1 for
+ * pageable buffers (a direct copy would be staged by the driver at a few GB/s). */
+int dcn_host_pack_fraction(dcn_ctx *ctx, double fraction);
+/* The packer itself (no GPU needed): codes[i] = bases [16i, 16i+16) as (byte >> 1) & 3, base j at bits 2j;
+ * inv[i] bit j = base 16i+j is not one of ACGTacgt.  Both arrays hold 2 * ceil(n_bases / 32) entries;
+ * positions past n_bases are padded with code 0 / non-ACGT. */
+int dcn_pack_ascii(const uint8_t *bases, uint64_t n_bases, uint32_t *codes, uint16_t *inv);
+
+/* ---- B1 with host-packed input ("host ingest at rate") --------------------------------
+ * Same as dcn_filter_batch for callers that already hold the batch in the packed form (a FASTQ parser can
+ * emit it while it touches the bytes anyway): `codes` / `inv` as written by dcn_pack_ascii over the whole
+ * concatenated buffer (base 0 of the batch = bit 0 of word 0), `nl_bits` as written by dcn_newline_bits (NULL
+ * = no record ends in a newline), `rec_off` in bases as before.  0.43 B/bp cross PCIe; k=31, w=15 only. */
+int dcn_filter_batch_packed(dcn_ctx *ctx, const uint32_t *codes, const uint16_t *inv, const uint32_t *nl_bits,
+                            const uint64_t *rec_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
+                            double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total);
+/* bit r of nl_bits[(n_rec + 31) / 32] = record r (raw length >= k) ends its effective prefix in '\n'
+ * (the one byte of the ASCII form the packed form cannot tell from other non-ACGT bytes; src/filter_common.rs:229). */
+int dcn_newline_bits(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
+                     uint32_t *nl_bits);
+
 /* ---- B2: batch classify on pre-hashed records --------------------------------------------------
  * Replaces unpaired_should_keep / paired_should_keep (src/remote_filter.rs:230-301), i.e. the body of
  * the server's POST handlers (src/server.rs:120-164).  A paired request carries one pooled hash list
@@ -123,6 +151,8 @@ int dcn_stats_reset(dcn_ctx *ctx);
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Milliseconds of the last host-pointer call: H2D copies, kernels, D2H copies (CUDA events). */
 int dcn_last_timing(dcn_ctx *ctx, float *h2d_ms, float *kernel_ms, float *d2h_ms);
+/* Host packing time (ms, wall clock) of the last dcn_filter_batch call; 0 when it shipped ASCII. */
+int dcn_last_pack_ms(dcn_ctx *ctx, float *pack_ms);
 /* Random 32-byte-sector read ceiling over the resident table: about *n_probes independent loads;
  * on return *n_probes is the exact number issued and *ms the kernel time. */
 int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms);

@@ -14,6 +14,7 @@
 #include "../../deacon_server_b200/csrc/dcn_plan.cuh"
 #include "../../deacon_server_b200/csrc/dcn_tile.cuh"
 #include "../../deacon_server_b200/csrc/dcn_generic.cuh"
+#include "../../deacon_server_b200/csrc/dcn_host_pack.h"
 
 using namespace dcn;
 
@@ -141,8 +142,11 @@ int emu_table_build(const uint64_t *keys, uint64_t n, double load, uint64_t **sl
 }
 void emu_free(void *p) { free(p); }
 
+}  // extern "C"
+
 // mirrors dcn_filter_batch_device for k=31, w=15; returns 0 or a negative error
-int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const uint8_t *bases_in,
+template <bool PACKED>
+static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty, const uint8_t *bases_in,
                      const uint64_t *rec_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
                      double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total) {
     using G = Geo<31, 15>;
@@ -151,7 +155,20 @@ int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const ui
     uint8_t *bases = (uint8_t *)aligned_alloc(16, ((n_bases + 15) / 16 + 1) * 16);
     memcpy(bases, bases_in, n_bases);
     FilterParams P;
-    P.bases = bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = rec_off; P.n_rec = n_rec;
+    P.bases = bases; P.pk_codes = nullptr; P.pk_inv = nullptr; P.nl_bits = nullptr; P.nl_bit0 = 0;
+    P.base0 = 0; P.n_bases = n_bases; P.rec_off = rec_off; P.n_rec = n_rec;
+    std::vector<uint32_t> pk_codes(2 * ((n_bases + 31) / 32) + 2), nl_bits((n_rec + 31) / 32 + 1, 0);
+    std::vector<uint16_t> pk_inv(2 * ((n_bases + 31) / 32) + 2);
+    if (PACKED) {   // what dcn_filter_batch's ingest stage ships instead of the bytes
+        pack_ascii(bases, n_bases, pk_codes.data(), pk_inv.data(), 1);
+        for (uint32_t r = 0; r < n_rec; r++) {
+            uint64_t len = rec_off[r + 1] - rec_off[r];
+            if (len < (uint64_t)G::K) continue;
+            uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;
+            if (bases[rec_off[r] + n - 1] == (uint8_t)'\n') nl_bits[r >> 5] |= 1u << (r & 31);
+        }
+        P.bases = nullptr; P.pk_codes = pk_codes.data(); P.pk_inv = pk_inv.data(); P.nl_bits = nl_bits.data();
+    }
     P.rpu = paired ? 2 : 1; P.n_units = n_rec / P.rpu;
     P.prefix_len = prefix_len; P.abs_thr = abs_thr; P.rel_thr = rel_thr; P.deplete = deplete;
     P.table.slots = slots; P.table.n_buckets = nb; P.table.has_empty_key = has_empty;
@@ -173,7 +190,7 @@ int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const ui
     ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); });
     for (uint32_t tile = 0; tile < n_tiles; tile++)
         if (tile_first[tile] < tile_end[tile])
-            filter_tile<G>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
+            filter_tile<G, PACKED>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
     int rc = 0;
     if (n_long) {  // mirrors prep_long_kernel + the chunk loop of filter_fused_kernel + finalize_long_kernel
         std::vector<uint32_t> long_units;
@@ -187,7 +204,7 @@ int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const ui
             hits[u] = 0; total[u] = 0;
             for (uint32_t r = u * P.rpu; r < (u + 1) * P.rpu; r++) {
                 uint64_t gs = rec_off[r], rl = rec_off[r + 1] - gs;
-                uint32_t nc = chunks_of<G>(effective_len64<G, FLAVOUR_FILTER>(bases, gs, rl, prefix_len));
+                uint32_t nc = chunks_of<G>(filter_eff_len<G>(P, r, gs, rl));
                 for (uint32_t c = 0; c < nc; c++) desc.push_back(ChunkDesc{r, c});
             }
         }
@@ -197,7 +214,7 @@ int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const ui
         std::vector<unsigned __int128> slots(cap, 0);
         uint32_t overflow = 0;
         DedupView dd{slots.data(), cap - 1, &overflow};
-        for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G>(ex, *s, P, dd, desc[i]);
+        for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G, PACKED>(ex, *s, P, dd, desc[i]);
         for (uint32_t u : long_units)
             keep[u] = meets_criteria(hits[u], total[u], abs_thr, rel_thr, deplete) ? 1 : 0;
         if (overflow) rc = -6;
@@ -206,6 +223,21 @@ int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const ui
     free(bases);
     return rc;
 }
+
+extern "C" {
+
+int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const uint8_t *bases_in,
+                     const uint64_t *rec_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
+                     double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total, int packed) {
+    if (packed)
+        return emu_filter_batch_t<true>(slots, nb, has_empty, bases_in, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr,
+                                        deplete, keep, hits, total);
+    return emu_filter_batch_t<false>(slots, nb, has_empty, bases_in, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr,
+                                     deplete, keep, hits, total);
+}
+
+void emu_pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd) { pack_ascii(bases, n, codes, inv, simd); }
+int emu_pack_has_simd() { return pack_has_simd() ? 1 : 0; }
 
 // mirrors dcn_index_build_device's extraction (k=31, w=15): unordered hashes, duplicates included
 long long emu_index_extract(const uint8_t *bases_in, const uint64_t *rec_off, uint32_t n_rec, const uint32_t *entropy_pass,

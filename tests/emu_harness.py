@@ -12,10 +12,11 @@ u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uin
 
 
 def build():
-    srcs = [os.path.join(_HERE, "dcn_emu.cpp")] + [os.path.join(_CSRC, f) for f in ("dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh", "dcn_generic.cuh")]
+    srcs = [os.path.join(_HERE, "dcn_emu.cpp")] + [os.path.join(_CSRC, f) for f in (
+        "dcn_host_pack.cpp", "dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh", "dcn_generic.cuh", "dcn_host_pack.h")]
     if os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs):
         return _SO
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _SO, srcs[0]])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", _SO, srcs[0], srcs[1]])
     return _SO
 
 
@@ -33,7 +34,7 @@ def _p(a, t):
     return a.ctypes.data_as(t)
 
 
-def filter_batch(keys, bases, off, paired=False, prefix=0, abs_thr=2, rel=0.01, deplete=False, load=0.5):
+def filter_batch(keys, bases, off, paired=False, prefix=0, abs_thr=2, rel=0.01, deplete=False, load=0.5, packed=False):
     L = lib()
     keys = np.ascontiguousarray(keys, np.uint64)
     slots, nb, he = u64p(), C.c_uint64(), C.c_int()
@@ -46,9 +47,19 @@ def filter_batch(keys, bases, off, paired=False, prefix=0, abs_thr=2, rel=0.01, 
     tot = np.zeros(max(nu, 1), np.uint32)
     b = bases if len(bases) else np.zeros(1, np.uint8)
     rc = L.emu_filter_batch(slots, nb, he, _p(b, u8p), _p(off, u64p), C.c_uint32(n_rec), int(paired), C.c_uint32(prefix),
-                            C.c_uint32(abs_thr), C.c_double(rel), int(deplete), _p(keep, u8p), _p(hits, u32p), _p(tot, u32p))
+                            C.c_uint32(abs_thr), C.c_double(rel), int(deplete), _p(keep, u8p), _p(hits, u32p), _p(tot, u32p),
+                            int(packed))
     L.emu_free(slots)
     return rc, keep[:nu], hits[:nu], tot[:nu]
+
+
+def pack_ascii(bases, simd=True):
+    n = len(bases)
+    nw = 2 * ((n + 31) // 32)
+    codes, inv = np.zeros(max(nw, 1), np.uint32), np.zeros(max(nw, 1), np.uint16)
+    b = bases if n else np.zeros(1, np.uint8)
+    lib().emu_pack_ascii(_p(b, u8p), C.c_uint64(n), _p(codes, u32p), inv.ctypes.data_as(C.POINTER(C.c_uint16)), int(simd))
+    return codes[:nw], inv[:nw]
 
 
 def index_extract(bases, off, entropy_bitmap=None):

@@ -70,3 +70,21 @@ def test_host_classification_matches_oracle():
                 assert api.calculate_required_hits(abs_, rel, total) == O.required_hits(abs_, rel, total)
     assert api.meets_filtering_criteria(1, 48, 2, 0.01, True) is True    # tests/filter_tests.rs:943-1015
     assert api.meets_filtering_criteria(0, 0, 2, 0.01, False) is False
+
+
+def test_product_packer_matches_definition():
+    """dcn_pack_ascii (the ingest stage of dcn_filter_batch; runs on the host, no GPU needed):
+    code = (byte >> 1) & 3 (src/filter_common.rs:238), non-ACGT mask (:245-258)."""
+    rng = np.random.default_rng(11)
+    for n in (0, 1, 31, 32, 33, 100_003):
+        b = rng.integers(0, 256, n).astype(np.uint8)
+        if n > 1000:
+            b[: n // 2] = np.frombuffer(b"ACGTacgtN", np.uint8)[rng.integers(0, 9, n // 2)]
+        codes, inv = api.pack_ascii(b)
+        pad = np.zeros(len(codes) * 16, np.uint8)
+        pad[:n] = b
+        code = ((pad >> 1) & 3).astype(np.uint32).reshape(-1, 16)
+        want_c = (code << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1).astype(np.uint32)
+        bad = ~np.isin(pad & 0xDF, np.frombuffer(b"ACGT", np.uint8))
+        want_i = (bad.reshape(-1, 16).astype(np.uint32) << np.arange(16, dtype=np.uint32)).sum(axis=1).astype(np.uint16)
+        assert np.array_equal(codes, want_c) and np.array_equal(inv, want_i), n

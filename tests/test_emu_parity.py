@@ -17,11 +17,13 @@ def _index_for(case):
     return idx
 
 
+@pytest.mark.parametrize("packed", [False, True], ids=["ascii", "packed"])
 @pytest.mark.parametrize("case", CASES.make_cases(), ids=lambda c: c["name"])
-def test_short_path_matches_oracle(case):
+def test_short_path_matches_oracle(case, packed):
     idx = _index_for(case)
     bases, off = H.concat(case["records"])
-    rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"])
+    rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"],
+                                 packed=packed)
     assert rc == 0
     ok, oh, ot = O.filter_batch(idx, bases, off, paired=case["paired"], prefix_len=case["prefix"], abs_thr=case["abs"],
                                 rel_thr=case["rel"], deplete=case["deplete"])
@@ -41,11 +43,13 @@ def test_high_load_factor_table_probing():
         assert rc == 0 and np.array_equal(h, oh) and np.array_equal(t, ot) and np.array_equal(k, ok)
 
 
+@pytest.mark.parametrize("packed", [False, True], ids=["ascii", "packed"])
 @pytest.mark.parametrize("case", CASES.make_long_cases(), ids=lambda c: c["name"])
-def test_long_path_matches_oracle(case):
+def test_long_path_matches_oracle(case, packed):
     idx = _index_for(case)
     bases, off = H.concat(case["records"])
-    rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"])
+    rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"],
+                                 packed=packed)
     assert rc == 0
     ok, oh, ot = O.filter_batch(idx, bases, off, paired=case["paired"], prefix_len=case["prefix"], abs_thr=case["abs"],
                                 rel_thr=case["rel"], deplete=case["deplete"])
@@ -75,3 +79,24 @@ def test_index_extraction_matches_oracle_set():
     got = np.unique(E.index_extract(bases, off))
     want = O.index_build((bases, off), 31, 15).keys()
     assert np.array_equal(got, want)
+
+
+def test_host_packer_simd_matches_scalar_and_definition():
+    """dcn_host_pack.cpp: the AVX2/BMI2 packer == the scalar loop == the definition
+    (code = (byte >> 1) & 3, src/filter_common.rs:238; non-ACGT mask, :245-258), all 256 byte values."""
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 15, 16, 31, 32, 33, 63, 64, 65, 127, 128, 129, 1000, 4097):
+        b = rng.integers(0, 256, n).astype(np.uint8)
+        if n >= 64:
+            b[:40] = np.frombuffer(b"ACGTacgtNnRYKM\n-*" * 3, np.uint8)[:40]
+        c0, i0 = E.pack_ascii(b, simd=0)
+        for level in (1, 2):   # 1 = best the CPU has (AVX-512 BW where present), 2 = the AVX2 + BMI2 path
+            c1, i1 = E.pack_ascii(b, simd=level)
+            assert np.array_equal(c1, c0) and np.array_equal(i1, i0), (n, level)
+        pad = np.zeros(len(c0) * 16, np.uint8)
+        pad[:n] = b
+        code = ((pad >> 1) & 3).astype(np.uint32).reshape(-1, 16)
+        want_c = (code << (2 * np.arange(16, dtype=np.uint32))).sum(axis=1).astype(np.uint32)
+        bad = ~np.isin(pad & 0xDF, np.frombuffer(b"ACGT", np.uint8))
+        want_i = (bad.reshape(-1, 16).astype(np.uint32) << np.arange(16, dtype=np.uint32)).sum(axis=1).astype(np.uint16)
+        assert np.array_equal(c0, want_c) and np.array_equal(i0, want_i), n

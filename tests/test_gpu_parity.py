@@ -34,6 +34,21 @@ def _check(gpu, idx, case):
     assert np.array_equal(t, ot), "total minimizers differ"
     assert np.array_equal(h, oh), "distinct hit counts differ"
     assert np.array_equal(k, ok), "keep decisions differ"
+    # the same call with host packing off (ASCII bytes over PCIe, converted on the GPU)
+    gpu.host_pack_threads(0)
+    try:
+        k2, h2, t2 = gpu.filter_batch(bases, off, paired=case["paired"], prefix_length=case["prefix"], abs_threshold=case["abs"],
+                                      rel_threshold=case["rel"], deplete=case["deplete"])
+    finally:
+        gpu.host_pack_threads(4)
+    assert np.array_equal(t2, ot) and np.array_equal(h2, oh) and np.array_equal(k2, ok), "ASCII ingest differs"
+    # and with the batch packed by the caller (dcn_pack_ascii + dcn_newline_bits -> dcn_filter_batch_packed)
+    from deacon_server_b200 import api
+    codes, inv = api.pack_ascii(bases)
+    nl = api.newline_bits(bases, off, 31, case["prefix"])
+    k3, h3, t3 = gpu.filter_batch_packed(codes, inv, nl, off, paired=case["paired"], prefix_length=case["prefix"],
+                                         abs_threshold=case["abs"], rel_threshold=case["rel"], deplete=case["deplete"])
+    assert np.array_equal(t3, ot) and np.array_equal(h3, oh) and np.array_equal(k3, ok), "caller-packed ingest differs"
 
 
 @pytest.mark.parametrize("case", CASES.make_cases(), ids=lambda c: c["name"])

@@ -108,13 +108,40 @@ hh = torch.zeros(NP, dtype=torch.int32).pin_memory()
 ht = torch.zeros(NP, dtype=torch.int32).pin_memory()
 def e2e():
     gpu.filter_batch_ptr(hbases.data_ptr(), hoff.data_ptr(), NR, True, 0, 2, 0.01, True, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
-e2e()
+for threads, fr in ((0, -1), (16, 1.0), (16, -1)):
+    gpu.host_pack_threads(threads)
+    gpu.host_pack_fraction(fr)
+    e2e()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e()
+    dt = (time.perf_counter() - t0) / args.steps
+    print(f"e2e pinned, pack threads {threads} fraction {fr}: {dt*1e3:.2f} ms/step, {nb/dt/1e9:.2f} Gbp/s; timing {gpu.last_timing()} pack_ms {gpu.last_pack_ms():.2f}")
+    assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu())
+# caller-packed input (dcn_filter_batch_packed), pinned
+from deacon_server_b200 import api as A
+codes_np, inv_np = A.pack_ascii(hbases.numpy())
+hc = torch.from_numpy(codes_np.view(np.int32)).pin_memory()
+hi = torch.from_numpy(inv_np.view(np.int16)).pin_memory()
+def e2e_packed():
+    gpu.filter_batch_packed_ptr(hc.data_ptr(), hi.data_ptr(), None, hoff.data_ptr(), NR, True, 0, 2, 0.01, True, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
+e2e_packed()
 t0 = time.perf_counter()
 for _ in range(args.steps):
-    e2e()
+    e2e_packed()
 dt = (time.perf_counter() - t0) / args.steps
-print(f"e2e pinned: {dt*1e3:.2f} ms/step, {nb/dt/1e9:.2f} Gbp/s; timing {gpu.last_timing()}")
+print(f"e2e caller-packed pinned: {dt*1e3:.2f} ms/step, {nb/dt/1e9:.2f} Gbp/s; timing {gpu.last_timing()}")
 assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu())
+# pageable (non-pinned) caller buffers
+pb, po = bases.cpu().numpy().copy(), off.cpu().numpy().copy()
+gpu.host_pack_fraction(-1)
+for threads in (0, 16):
+    gpu.host_pack_threads(threads)
+    t0 = time.perf_counter()
+    k2, h2, t2 = gpu.filter_batch(pb, po.astype(np.uint64), paired=True, deplete=True)
+    dt = time.perf_counter() - t0
+    print(f"e2e pageable, pack threads {threads}: {dt*1e3:.2f} ms/step, {nb/dt/1e9:.2f} Gbp/s")
+    assert np.array_equal(k2, keep.cpu().numpy())
 t0 = time.perf_counter()
 ob, oo = O.filter_batch(full, hb, ho, paired=True, deplete=True, threads=os.cpu_count())[:2]
 dt = time.perf_counter() - t0
