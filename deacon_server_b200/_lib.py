@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdeacon_cuda.so")
+LIB_PATH = os.environ.get("DCN_LIB") or os.path.join(_HERE, "libdeacon_cuda.so")   # DCN_LIB: kernel-variant experiments
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)

@@ -70,6 +70,15 @@ struct DevExec {
         put(t, pv, base + x - v, total);
         __syncthreads();
     }
+    // Records of the tile this CTA processes next: their offsets are pulled into L2 from the middle of
+    // the current tile (the tile range itself was loaded one tile ahead), so the next tile's first
+    // dependent loads (rec_off -> last byte of each record) do not start from DRAM.
+    const uint64_t *pf_off = nullptr;
+    uint32_t pf_lo = 0, pf_hi = 0;
+    __device__ __forceinline__ void midtile_prefetch(int t) {
+        const uint32_t i = pf_lo + 16u * (uint32_t)t;   // 16 offsets per 128-byte line
+        if (t < 16 && i <= pf_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_off + i));
+    }
     __device__ __forceinline__ void ballot2(int t, uint32_t idx, bool valid, bool hit, uint32_t *vm, uint32_t *hm) {
         uint32_t a = __ballot_sync(0xFFFFFFFFu, valid), b = __ballot_sync(0xFFFFFFFFu, hit);
         if ((t & 31) == 0 && idx < (uint32_t)G::PKCAP) { vm[idx >> 5] = a; hm[idx >> 5] = b; }
@@ -193,9 +202,31 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     const PlanCfg cfg = plan_make_cfg<G>(st->max_short);
     const uint32_t n_tiles = plan_num_tiles(P.n_bases - P.base0, cfg);
     const uint32_t n_long = st->n_long;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        uint32_t a = tile_first[tile], b = tile_end[tile];
+    // Software pipeline over this CTA's tiles: the unit range of tile i+1 is loaded and its bases are
+    // pulled into L2 while tile i is processed.
+    uint32_t tile = blockIdx.x, a = 0, b = 0;
+    if (tile < n_tiles) { a = tile_first[tile]; b = tile_end[tile]; }
+    ex.pf_off = P.rec_off;
+    while (tile < n_tiles) {
+        const uint32_t nt = tile + gridDim.x;
+        uint32_t a2 = 0, b2 = 0;
+        if (nt < n_tiles) {
+            a2 = tile_first[nt]; b2 = tile_end[nt];
+            // tile nt owns the units that start in [nt * S, (nt + 1) * S): at most S + max_short + 15 bases
+            const uint64_t lo = (uint64_t)nt * cfg.S, n_rel = P.n_bases - P.base0;
+            const uint64_t off = lo + 128ull * threadIdx.x;
+            if (128u * threadIdx.x < cfg.S + cfg.max_short + 16u && off < n_rel) {
+                if (PACKED) {   // 128 bases = 32 bytes of codes + 16 bytes of mask
+                    if ((threadIdx.x & 3u) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pk_codes + (off >> 4)));
+                    if ((threadIdx.x & 7u) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.pk_inv + (off >> 4)));
+                } else {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(P.bases + off));
+                }
+            }
+        }
+        ex.pf_lo = a2 * P.rpu; ex.pf_hi = b2 * P.rpu;   // a2 == b2 == 0: one harmless line
         if (a < b) filter_tile<G, PACKED>(ex, s, P, cfg, n_long, a, b);
+        tile = nt; a = a2; b = b2;
     }
     if (n_long) {  // long units: chunks, spread over the CTAs in reverse so short and long work interleave
         __syncthreads();

@@ -31,10 +31,11 @@ struct Geo {
     static constexpr int BCAP = WCAP + L - 1;   // bases a tile may reference
     static constexpr int NBW = 132;             // 32-bit words of the per-position bit arrays
     static constexpr int MAXR = 512;            // records per sub-batch
-    static constexpr int PKCAP = 2048;          // picks per pass; a denser run of units is split (see filter_tile)
+    static constexpr int PKCAP = 1024;          // picks per pass; a denser run of units is split (see filter_tile)
     static constexpr int HP = 20;               // hrow pitch in words (16 data + 4 pad: conflict-free LDS.128)
 };
 
+struct alignas(16) Bucket { uint64_t k0, k1, k2, k3; };   // one 32-byte bucket of the HBM table
 struct u32x2 { uint32_t x, y; };
 struct u32x4 { uint32_t x, y, z, w; };
 
@@ -42,8 +43,8 @@ template <class G>
 struct alignas(16) TileSmem {
     u32x4 ag[G::NV + 6];              // per vector: E_fw, E_rc (own role), N_fw, N_rc (right-neighbour role)
     union {                           // hrow is dead once the window minima are taken; picks reuse it
-        uint32_t hrow[G::NT * G::HP]; // ntHash of the 16 k-mers of each thread
-        uint32_t pk_pos[G::PKCAP];    // local position | start-rank << 16 | in-index << 30 | valid << 31
+        uint32_t hrow[G::NT * G::HP]; // ntHash (upper 16 bits) of the 16 k-mers of each thread
+        uint32_t pk_pos[G::NT * G::HP];   // local position | start-rank << 16 | in-index << 30 | valid << 31
     };
     uint64_t pk_hash[G::PKCAP];       // xxh3 of each pick
     u32x2 tb0[256];                   // 4-base aggregate table (fw, rc)
@@ -65,8 +66,6 @@ struct alignas(16) TileSmem {
     uint32_t wsum[16];
     uint32_t npicks;
 };
-static_assert(Geo<31, 15>::NT * Geo<31, 15>::HP >= Geo<31, 15>::PKCAP, "pk_pos must fit inside hrow");
-
 template <class G>
 struct TilePriv {
     uint32_t c0;           // own 16 codes
@@ -238,9 +237,10 @@ DCN_HD void phase_hash(int t, TileSmem<G> &s, TilePriv<G> &pv) {
         rc = rotr32(rc ^ o.y ^ n.y, 1);
         pv.h[i] = fw + rc;
     }
+    // only the upper 16 bits take part in the window comparison: keep them masked
     uint32_t *row = &s.hrow[t * G::HP];
 #pragma unroll
-    for (int i = 0; i < 16; i++) row[i] = pv.h[i];
+    for (int i = 0; i < 16; i++) { pv.h[i] &= 0xFFFF0000u; row[i] = pv.h[i]; }
 }
 
 // ------------------------------------------------------------------ phase 3: window minima
@@ -272,7 +272,7 @@ DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
     // left keys: (h >> 16) << 16 | i  -> min = smallest hash, leftmost;  SURVEY A.3 steps 1-2
     uint32_t key[30], oL[16], oR[16];
 #pragma unroll
-    for (int i = 0; i < 30; i++) key[i] = (hv[i] & 0xFFFF0000u) | (uint32_t)i;
+    for (int i = 0; i < 30; i++) key[i] = hv[i] + (uint32_t)i;   // hv is masked: + == |
     {
 #pragma unroll
         for (int i = 13; i >= 0; i--) key[i] = umin32(key[i], key[i + 1]);      // suffix min of block A
@@ -285,7 +285,7 @@ DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
     }
     // right keys: ~(h >> 16) << 16 | i -> max = smallest hash, rightmost;  A.3 step 3
 #pragma unroll
-    for (int i = 0; i < 30; i++) key[i] = (~hv[i] & 0xFFFF0000u) | (uint32_t)i;
+    for (int i = 0; i < 30; i++) key[i] = (0xFFFF0000u + (uint32_t)i) - hv[i];   // == (~hv & 0xFFFF0000) | i
     {
 #pragma unroll
         for (int i = 13; i >= 0; i--) key[i] = umax32(key[i], key[i + 1]);
@@ -418,8 +418,6 @@ DCN_HD uint64_t pick_hash(const TileSmem<G> &s, uint32_t p) {
 }
 
 // ------------------------------------------------------------------ table probe
-struct Bucket { uint64_t k0, k1, k2, k3; };
-
 DCN_HD Bucket load_bucket(const uint64_t *slots, uint64_t b) {
     Bucket r;
     const uint64_t *p = slots + 4 * b;
@@ -482,6 +480,32 @@ DCN_HD void set_bits(uint32_t *arr, uint32_t a, uint32_t b) {
         arr[w] |= mask;
 #endif
         a = end;
+    }
+}
+
+DCN_HD void set_bit(uint32_t *arr, uint32_t p) {
+#ifdef __CUDA_ARCH__
+    atomicOr(&arr[p >> 5], 1u << (p & 31u));
+#else
+    arr[p >> 5] |= 1u << (p & 31u);
+#endif
+}
+
+// bits of the 32-position word that starts at `lo` whose position is < a or >= b
+DCN_HD uint32_t outside_mask(uint32_t lo, uint32_t a, uint32_t b) {
+    uint32_t m = 0;
+    if (lo < a) m = (a - lo >= 32u) ? 0xFFFFFFFFu : ((1u << (a - lo)) - 1u);
+    if (lo + 32u > b) m |= (b <= lo) ? 0xFFFFFFFFu : (0xFFFFFFFFu << (b - lo));
+    return m;
+}
+// Start state of the per-position bit arrays, written by all threads (one word each, no atomics):
+// windows may only start in [dead_lo, dead_hi), sequence only exists in [brk_lo, brk_hi).
+template <class G>
+DCN_HD void init_structure_words(int t, TileSmem<G> &s, uint32_t dead_lo, uint32_t dead_hi, uint32_t brk_lo, uint32_t brk_hi) {
+    for (int i = t; i < G::NBW + 2; i += G::NT) {
+        s.dead[i] = outside_mask(32u * (uint32_t)i, dead_lo, dead_hi);
+        s.brk[i] = outside_mask(32u * (uint32_t)i, brk_lo, brk_hi);
+        s.ustart[i] = 0;
     }
 }
 
@@ -549,11 +573,10 @@ DCN_HD void phase_structure(int t, TileSmem<G> &s, uint32_t rpu, uint32_t n_rec_
     for (uint32_t i = (uint32_t)t; i < n_rec_t; i += G::NT) {
         const uint32_t se = s.rec_se[i];
         const uint32_t sL = se & 0xFFFFu, eL = se >> 16, eff = s.rec_eff[i];
-        set_bits(s.brk, sL, sL + 1);
-        if (i % rpu == 0) { set_bits(s.ustart, sL, sL + 1); s.ustartpos[i / rpu] = (uint16_t)sL; }
+        set_bit(s.brk, sL);
+        if (i % rpu == 0) { set_bit(s.ustart, sL); s.ustartpos[i / rpu] = (uint16_t)sL; }
         if (eff < eL) { set_bits(s.dead, eff, eL); set_bits(s.brk, eff, eL); }
-        if (i == 0 && sL > 0) { set_bits(s.dead, 0, sL); set_bits(s.brk, 0, sL); }
-        if (i == n_rec_t - 1) { set_bits(s.dead, eL, G::NBW * 32); set_bits(s.brk, eL, G::NBW * 32); }
+        // positions before the first record and after the last one were marked by init_structure_words
     }
 }
 
@@ -588,9 +611,11 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
     const uint64_t first_start = P.rec_off[r_begin] - P.base0;
     const uint64_t origin = first_start & ~15ull;   // relative to base0, like every offset below
     const TileSrc src = filter_src(P);
+    const uint32_t span_lo = (uint32_t)(first_start - origin);
+    const uint32_t span_hi = (uint32_t)(P.rec_off[r_begin + n_rec_t] - P.base0 - origin);
 
     ex.par([&](int t, Priv &pv) {
-        for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
+        init_structure_words<G>(t, s, span_lo, span_hi, span_lo, span_hi);
         phase_structure_load<G>(t, s, P, r_begin, n_rec_t, origin);
         phase_convert<G, FLAVOUR_FILTER, PACKED>(t, s, pv, src, origin);
     });
@@ -598,7 +623,10 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
         phase_structure<G>(t, s, P.rpu, n_rec_t);
         phase_hash<G>(t, s, pv);
     });
-    ex.par([&](int t, Priv &pv) { phase_slide<G>(t, s, pv); });
+    ex.par([&](int t, Priv &pv) {
+        ex.midtile_prefetch(t);
+        phase_slide<G>(t, s, pv);
+    });
     ex.scan([&](int t, Priv &pv) { return phase_emit_fix<G>(t, s, pv); },
             [&](int t, Priv &pv, uint32_t excl, uint32_t total) { phase_emit<G>(t, s, pv, excl, total); });
     const uint32_t npicks = s.npicks;
@@ -606,7 +634,8 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
 
     // hash every pick and probe the table: two picks per thread are in flight at a time (hash A,
     // request A, hash B, request B, then test A and B), the answer is kept as bit 30 of the pick;
-    // unit -> pick-range tables on the side
+    // unit -> pick-range tables on the side.  (Staging the buckets in shared memory with cp.async so
+    // that the duplicate test overlaps the HBM latency was measured 7 % slower: round-1 notes.)
     ex.par([&](int t, Priv &) {
         phase_unit_first<G>(t, s, n_units_t, npicks);
         for (uint32_t idx = (uint32_t)t; idx < npicks; idx += 2 * G::NT) {
@@ -791,19 +820,18 @@ DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const TileSrc &src, uint64_t
     const uint64_t eff_end = gs + eff_len;
     *origin_out = origin;
 
+    const uint64_t e64 = eff_end - origin;                           // bases beyond the effective sequence
+    const uint32_t e = e64 < (uint64_t)((G::NBW + 2) * 32) ? (uint32_t)e64 : (uint32_t)((G::NBW + 2) * 32);
     ex.par([&](int t, Priv &pv) {
-        for (int i = t; i < G::NBW + 2; i += G::NT) { s.brk[i] = 0; s.dead[i] = 0; s.ustart[i] = 0; }
+        // windows of this chunk start in [la, la + carry + nw); later ones belong to later chunks
+        init_structure_words<G>(t, s, la, la + carry + nw, la, e);
         phase_convert<G, FLAV, PACKED>(t, s, pv, src, origin);
     });
     ex.par([&](int t, Priv &pv) {
         if (t == 0) {
             s.wsum[8] = 0; s.wsum[9] = 0;                            // per-chunk tallies of the consumer phase
-            if (la > 0) { set_bits(s.dead, 0, la); set_bits(s.brk, 0, la); }
-            if (!carry) set_bits(s.brk, la, la + 1);                 // record start: first window always emits
-            set_bits(s.ustart, la, la + 1);                          // one "unit": every pick gets rank 0
-            set_bits(s.dead, la + carry + nw, G::NBW * 32);          // windows of later chunks
-            uint64_t e = eff_end - origin;                           // bases beyond the effective sequence
-            if (e < (uint64_t)(G::NBW * 32)) set_bits(s.brk, (uint32_t)e, G::NBW * 32);
+            if (!carry) set_bit(s.brk, la);                          // record start: first window always emits
+            set_bit(s.ustart, la);                                   // one "unit": every pick gets rank 0
         }
         phase_hash<G>(t, s, pv);
     });

@@ -86,6 +86,7 @@ struct HostExec {
     template <class F>
     void par_nosync(F f) { par(f); }
     void barrier() {}
+    void midtile_prefetch(int) {}
     template <class Get, class Put>
     void scan(Get get, Put put) {
         std::vector<uint32_t> v(G::NT);

@@ -21,6 +21,7 @@ ap.add_argument("--pairs-m", type=float, default=2)
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--load", type=float, default=0.5)
 ap.add_argument("--check", type=int, default=20000)
+ap.add_argument("--no-e2e", action="store_true")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -100,6 +101,8 @@ print(f"random 32B sector ceiling: {n/rms/1e6:.2f} Gsectors/s ({n*32/rms/1e6:.1f
 probes = float(tot.sum())
 print(f"fused kernel probe rate: {probes/ms/1e6:.2f} Gprobes/s")
 
+if args.no_e2e:
+    sys.exit(0)
 # e2e with pinned host buffers
 hbases = bases.cpu().pin_memory()
 hoff = off.cpu().pin_memory()
