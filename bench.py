@@ -169,6 +169,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import deacon_server_b200 as d
+    from deacon_server_b200 import parallel as par
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -224,10 +225,7 @@ def run_ours(args):
     for i in range(args.steps):
         step(args.warmup + i)
     counters = gpu.stats()                       # syncs; the six ProcessingStats counters of this rank
-    cvec = torch.tensor([counters[k] for k in ("total_seqs", "filtered_seqs", "total_bp", "output_bp", "filtered_bp",
-                                               "output_seq_counter")], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(cvec)                    # the path's only collective: NCCL sum of 6 counters
+    counters = par.reduce_counters(counters, dev)   # the path's only collective: NCCL sum of 6 x u64
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -269,6 +267,35 @@ def run_ours(args):
     e2e_s = float(evec.item())
     clk = clocks.stop()
 
+    # ---- the same end to end with the batch already packed by the caller (dcn_filter_batch_packed: what a
+    # host-side FASTQ parser can emit directly); reported beside e2e, never instead of it
+    from deacon_server_b200 import api as A
+    codes_np, inv_np = A.pack_ascii(hb[0].numpy())
+    hc = torch.from_numpy(codes_np.view(np.int32)).pin_memory()
+    hi = torch.from_numpy(inv_np.view(np.int16)).pin_memory()
+
+    def packed_step():
+        gpu.filter_batch_packed_ptr(hc.data_ptr(), hi.data_ptr(), None, hoff.data_ptr(), NR, True, 0, 2, 0.01, True,
+                                    hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
+
+    packed_step()
+    barrier()
+    p_steps = max(1, min(e2e_steps, 5))
+    t0 = time.perf_counter()
+    for i in range(p_steps):
+        packed_step()
+    torch.cuda.synchronize()
+    pvec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(pvec, op=dist.ReduceOp.MAX)
+    packed_s = float(pvec.item())
+    step(0)
+    torch.cuda.synchronize()
+    assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu()) and torch.equal(ht, tot.cpu()), \
+        "caller-packed path and device-pointer path disagree"
+    for i in range(1):
+        e2e_step(e2e_steps - 1)   # leave the last e2e batch's result in the host buffers for the check below
+
     # parity of the last e2e step against the device-resident result of the same batch
     step((e2e_steps - 1) % n_host)
     torch.cuda.synchronize()
@@ -309,7 +336,12 @@ def run_ours(args):
                        "table_bytes": gpu.index_info()["table_bytes"]},
             "e2e": {"value": round(e2e_value, 3), "unit": "Gbp/s", "h2d_bytes_per_step": nb + (NR + 1) * 8,
                     "d2h_bytes_per_step": 9 * NP, "steps": e2e_steps, "host_buffers": "pinned",
-                    "api": "dcn_filter_batch (C ABI)"},
+                    "api": "dcn_filter_batch (C ABI), ASCII records in host memory"},
+            "e2e_packed_input": {"value": round(1e-9 * nb * p_steps * world / packed_s, 3), "unit": "Gbp/s",
+                                 "h2d_bytes_per_step": int(codes_np.nbytes + inv_np.nbytes + (NR + 1) * 8),
+                                 "d2h_bytes_per_step": 9 * NP, "steps": p_steps,
+                                 "api": "dcn_filter_batch_packed (C ABI): 2-bit codes + non-ACGT bits packed by the caller "
+                                        "(packing time not included)"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "filter_fused_kernel<Geo<31,15>>", "achieved": round(achieved, 2),
                          "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
@@ -322,8 +354,7 @@ def run_ours(args):
                          "note": "integer-issue bound, not HBM bound: see DESIGN.md"},
             "cpu_baseline": cpu,
             "clocks": clk,
-            "counters": {k: int(v) for k, v in zip(("total_seqs", "filtered_seqs", "total_bp", "output_bp", "filtered_bp",
-                                                      "output_seq_counter"), cvec.tolist())},
+            "counters": counters,
             "kept_pairs_last_step": kept_last,
         }
         print(json.dumps(out))

@@ -340,7 +340,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     const int pg = (int)std::min<uint64_t>((n_units + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
     const size_t smem = sizeof(TileSmem<G31>);
     const uint64_t tiles_lb = n_rel / G31::BCAP + 1;
-    const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * 4);
+    const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * (1024 / G31::NT));
 
     // A batch can only contain a long unit if it holds more than DCN_MAX_SHORT bases; otherwise the
     // stats readback (one small sync) is skipped.
@@ -1060,7 +1060,7 @@ int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t 
         IndexParams P;
         P.bases = d_bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = d_rec_off; P.n_rec = n_rec;
         P.entropy_pass = d_entropy; P.out = ctx->ib_alt.as<uint64_t>(); P.out_cap = cap; P.out_count = d_count;
-        extract_index_kernel<G31><<<ctx->sm_count * 4, G31::NT, sizeof(TileSmem<G31>), st>>>(P, d_stats, reinterpret_cast<ChunkDesc *>(ctx->ib_desc.p));
+        extract_index_kernel<G31><<<ctx->sm_count * (1024 / G31::NT), G31::NT, sizeof(TileSmem<G31>), st>>>(P, d_stats, reinterpret_cast<ChunkDesc *>(ctx->ib_desc.p));
         ctx->launches += 2;
         CK(cudaMemcpyAsync(&n_picks, d_count, sizeof(n_picks), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -166,7 +166,7 @@ __global__ void finalize_long_kernel(FilterParams P, const BatchStats *st, const
 
 // ------------------------------------------------------------------ index-flavour extraction kernel
 template <class G>
-__global__ void __launch_bounds__(G::NT, 4)
+__global__ void __launch_bounds__(G::NT, 1024 / G::NT)
 extract_index_kernel(IndexParams P, const BatchStats *st, const ChunkDesc *__restrict__ desc) {
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
     TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);
@@ -190,7 +190,7 @@ __global__ void prep_tiles_kernel(const uint64_t *__restrict__ rec_off, uint32_t
 // ------------------------------------------------------------------ the fused filter kernel
 // Persistent CTAs; tile i -> CTA (i mod grid).  4 CTAs per SM (64 registers, ~53 KB shared memory each).
 template <class G, bool PACKED>
-__global__ void __launch_bounds__(G::NT, 4)
+__global__ void __launch_bounds__(G::NT, 1024 / G::NT)
 filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ tile_first,
                     const uint32_t *__restrict__ tile_end, DedupView dd, const ChunkDesc *__restrict__ desc) {
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];

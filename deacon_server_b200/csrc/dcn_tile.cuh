@@ -25,13 +25,16 @@ struct Geo {
     static_assert(W_ == 15, "fast path is specialised for w = 15 (R = w + 1 = 16 windows per thread)");
     static_assert(K_ >= 17 && K_ <= 31, "fast path needs 17 <= k <= 31 (k-mer spans exactly 3 threads' words)");
     static constexpr int K = K_, W = W_, L = K_ + W_ - 1;
-    static constexpr int NT = 256;              // threads per CTA
+#ifndef DCN_NT
+#define DCN_NT 256
+#endif
+    static constexpr int NT = DCN_NT;           // threads per CTA
     static constexpr int NV = NT + 2;           // 16-byte vectors loaded per tile
     static constexpr int WCAP = NT * 16 - 16;   // window starts per tile (thread 255 only hashes)
     static constexpr int BCAP = WCAP + L - 1;   // bases a tile may reference
-    static constexpr int NBW = 132;             // 32-bit words of the per-position bit arrays
-    static constexpr int MAXR = 512;            // records per sub-batch
-    static constexpr int PKCAP = 1024;          // picks per pass; a denser run of units is split (see filter_tile)
+    static constexpr int NBW = NT / 2 + 4;      // 32-bit words of the per-position bit arrays
+    static constexpr int MAXR = 2 * NT;         // records per sub-batch
+    static constexpr int PKCAP = 4 * NT < 1024 ? 1024 : 4 * NT;   // picks per pass (>= the 980 windows of one short unit); a denser run of units is split (see filter_tile)
     static constexpr int HP = 20;               // hrow pitch in words (16 data + 4 pad: conflict-free LDS.128)
 };
 
@@ -82,13 +85,15 @@ struct TilePriv {
 template <class G>
 DCN_HD void init_tables(int t, TileSmem<G> &s) {
     // tb0[b]: bases c0..c3 of byte b at group 0: fw = XOR rotl(F[c_m], 30-m), rc = XOR rotl(F[c_m^2], m)
-    uint32_t fw = 0, rc = 0;
-    for (int m = 0; m < 4; m++) {
-        uint32_t c = ((uint32_t)t >> (2 * m)) & 3u;
-        fw ^= rotl32(nt_f(c), (uint32_t)(30 - m));
-        rc ^= rotl32(nt_f(c ^ 2u), (uint32_t)m);
+    for (int b = t; b < 256; b += G::NT) {
+        uint32_t fw = 0, rc = 0;
+        for (int m = 0; m < 4; m++) {
+            uint32_t c = ((uint32_t)b >> (2 * m)) & 3u;
+            fw ^= rotl32(nt_f(c), (uint32_t)(30 - m));
+            rc ^= rotl32(nt_f(c ^ 2u), (uint32_t)m);
+        }
+        s.tb0[b].x = fw; s.tb0[b].y = rc;
     }
-    s.tb0[t].x = fw; s.tb0[t].y = rc;
     if (t < 4) {
         uint32_t c = (uint32_t)t;
         s.tin[t].x = nt_f(c);                          s.tin[t].y = rotl32(nt_f(c ^ 2u), G::K);

@@ -1,0 +1,89 @@
+"""Multi-GPU host logic of the filter path: one process per GPU, the index replicated
+on every GPU, record batches sharded by rank, NO collective on the data path.  The only exchange is
+the sum of the six ProcessingStats counters (src/local_filter.rs:179-187) at the end of a run - one
+all-reduce of 6 x u64 (NCCL when the tensors live on a GPU, gloo on the CPU for the host-logic tests).
+
+Nothing here computes minimizers or lookups: `engine` is a DeaconGpu (or anything with its
+filter_batch signature).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+COUNTER_NAMES = ("total_seqs", "filtered_seqs", "total_bp", "output_bp", "filtered_bp", "output_seq_counter")
+
+
+def shard_units(n_units: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced unit range [u0, u1) of `rank`: sizes differ by at most one unit and a
+    pair is never split (units, not records, are dealt out)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(n_units, world)
+    u0 = rank * base + min(rank, extra)
+    return u0, u0 + base + (1 if rank < extra else 0)
+
+
+def shard_batch(bases: np.ndarray, rec_off: np.ndarray, paired: bool, rank: int, world: int):
+    """-> (bases view, rec_off rebased to 0, u0, u1) of this rank's share of a batch."""
+    rec_off = np.ascontiguousarray(rec_off, np.uint64)
+    rpu = 2 if paired else 1
+    n_units = (len(rec_off) - 1) // rpu
+    u0, u1 = shard_units(n_units, rank, world)
+    lo, hi = int(rec_off[u0 * rpu]), int(rec_off[u1 * rpu])
+    return bases[lo:hi], rec_off[u0 * rpu:u1 * rpu + 1] - np.uint64(lo), u0, u1
+
+
+def counters_of(rec_off: np.ndarray, keep: np.ndarray, paired: bool) -> dict:
+    """The six counters of one shard from its lengths and decisions (what stats_kernel accumulates on
+    the device; src/local_filter.rs:347-371 single, 488-525 paired)."""
+    rpu = 2 if paired else 1
+    rec_off = np.asarray(rec_off, np.uint64)
+    n_units = (len(rec_off) - 1) // rpu
+    ulen = (rec_off[rpu::rpu][:n_units] - rec_off[0::rpu][:n_units]).astype(np.int64)
+    k = np.asarray(keep[:n_units], bool)
+    total_bp, out_bp = int(ulen.sum()), int(ulen[k].sum())
+    n_keep = int(k.sum()) * rpu
+    return {"total_seqs": n_units * rpu, "filtered_seqs": n_units * rpu - n_keep, "total_bp": total_bp,
+            "output_bp": out_bp, "filtered_bp": total_bp - out_bp, "output_seq_counter": n_keep}
+
+
+def reduce_counters(counters: dict, device=None) -> dict:
+    """Sum the six counters over all ranks (the path's only collective).  Without an initialised
+    process group (single GPU) this is the identity."""
+    import torch
+    import torch.distributed as dist
+    vec = torch.tensor([int(counters[k]) for k in COUNTER_NAMES], dtype=torch.int64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return {k: int(v) for k, v in zip(COUNTER_NAMES, vec.tolist())}
+
+
+def gather_decisions(keep: np.ndarray, n_units_total: int, device=None) -> np.ndarray:
+    """Re-assemble the per-unit keep flags of all shards in input order (the host re-interleaves
+    outputs).  Used by drivers that write one output stream; not on the timed path."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return np.asarray(keep, np.uint8)
+    world = dist.get_world_size()
+    width = -(-n_units_total // world)
+    mine = torch.zeros(width, dtype=torch.uint8, device=device)
+    mine[:len(keep)] = torch.from_numpy(np.ascontiguousarray(keep, np.uint8)).to(mine.device)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    out = np.empty(n_units_total, np.uint8)
+    for r, p in enumerate(parts):
+        u0, u1 = shard_units(n_units_total, r, world)
+        out[u0:u1] = p[:u1 - u0].cpu().numpy()
+    return out
+
+
+def filter_sharded(engine, bases: np.ndarray, rec_off: np.ndarray, paired: bool = False, device=None, **kw):
+    """Filter this rank's share of a batch with `engine.filter_batch` and reduce the counters.
+    -> (keep, hits, total) of the local shard, (u0, u1), reduced counters."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    sb, so, u0, u1 = shard_batch(bases, rec_off, paired, rank, world)
+    keep, hits, total = engine.filter_batch(sb, so, paired=paired, **kw)
+    return (keep, hits, total), (u0, u1), reduce_counters(counters_of(so, keep, paired), device)

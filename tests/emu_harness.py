@@ -6,7 +6,8 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu")
-_SO = os.path.join(_HERE, "libdcn_emu.so")
+_FLAGS = os.environ.get("DCN_EMU_FLAGS", "").split()          # e.g. -DDCN_NT=128: kernel-geometry experiments
+_SO = os.path.join(_HERE, "libdcn_emu%s.so" % ("_" + "_".join(f.strip("-").replace("=", "") for f in _FLAGS) if _FLAGS else ""))
 _CSRC = os.path.join(os.path.dirname(_HERE), "..", "deacon_server_b200", "csrc")
 u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 
@@ -16,7 +17,7 @@ def build():
         "dcn_host_pack.cpp", "dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh", "dcn_generic.cuh", "dcn_host_pack.h")]
     if os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs):
         return _SO
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", "-o", _SO, srcs[0], srcs[1]])
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", *_FLAGS, "-o", _SO, srcs[0], srcs[1]])
     return _SO
 
 

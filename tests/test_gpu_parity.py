@@ -109,6 +109,12 @@ def test_config1_shape_and_counters(gpu):
     assert st["total_seqs"] == len(reads) and st["total_bp"] == int(lens.sum())
     assert st["output_seq_counter"] == int(ok.sum()) and st["filtered_seqs"] == len(reads) - int(ok.sum())
     assert st["output_bp"] == int(lens[ok.astype(bool)].sum()) and st["filtered_bp"] == int(lens[~ok.astype(bool)].sum())
+    from deacon_server_b200 import parallel as P
+    assert P.counters_of(off, k, paired=False) == st                      # host mirror of stats_kernel
+    assert P.reduce_counters(st) == st                                     # single process: identity
+    gpu.stats_reset()
+    k2, _, _ = gpu.filter_batch(bases, off, paired=True, deplete=True)
+    assert P.counters_of(off, k2, paired=True) == gpu.stats()
 
 
 def test_chunked_pipeline_many_chunks(gpu, monkeypatch):
