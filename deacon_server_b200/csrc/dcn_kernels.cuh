@@ -21,7 +21,9 @@ struct DevExec {
     __device__ __forceinline__ void par_nosync(F f) { f((int)threadIdx.x, pv); }
     __device__ __forceinline__ void barrier() { __syncthreads(); }
     __device__ __forceinline__ uint32_t ballot(int, bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
-    __device__ __forceinline__ uint32_t bcast0(int, uint32_t v) { return __shfl_sync(0xFFFFFFFFu, v, 0); }
+    __device__ __forceinline__ uint64_t bcast64(int, uint64_t v, uint32_t src) {
+        return (uint64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)v, (int)src);
+    }
     // lanes of this warp holding the same 64-bit value
     __device__ __forceinline__ uint32_t match64(int, uint64_t v, bool) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
     // add the number of lanes with a / b set to two shared-memory counters
@@ -78,10 +80,6 @@ struct DevExec {
     __device__ __forceinline__ void midtile_prefetch(int t) {
         const uint32_t i = pf_lo + 16u * (uint32_t)t;   // 16 offsets per 128-byte line
         if (t < 16 && i <= pf_hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_off + i));
-    }
-    __device__ __forceinline__ void ballot2(int t, uint32_t idx, bool valid, bool hit, uint32_t *vm, uint32_t *hm) {
-        uint32_t a = __ballot_sync(0xFFFFFFFFu, valid), b = __ballot_sync(0xFFFFFFFFu, hit);
-        if ((t & 31) == 0 && idx < (uint32_t)G::PKCAP) { vm[idx >> 5] = a; hm[idx >> 5] = b; }
     }
 };
 

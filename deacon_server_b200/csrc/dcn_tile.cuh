@@ -47,7 +47,7 @@ struct alignas(16) TileSmem {
     u32x4 ag[G::NV + 6];              // per vector: E_fw, E_rc (own role), N_fw, N_rc (right-neighbour role)
     union {                           // hrow is dead once the window minima are taken; picks reuse it
         uint32_t hrow[G::NT * G::HP]; // ntHash (upper 16 bits) of the 16 k-mers of each thread
-        uint32_t pk_pos[G::NT * G::HP];   // local position | start-rank << 16 | in-index << 30 | valid << 31
+        uint32_t pk_pos[G::NT * G::HP];   // local position | in-index << 30 | valid << 31
     };
     uint64_t pk_hash[G::PKCAP];       // xxh3 of each pick
     u32x2 tb0[256];                   // 4-base aggregate table (fw, rc)
@@ -56,13 +56,10 @@ struct alignas(16) TileSmem {
     uint32_t inv[(G::NV + 6 + 1) / 2 + 2];  // non-ACGT bits, 32 positions per word
     uint32_t brk[G::NBW + 2];         // position is a record start or lies outside every effective sequence
     uint32_t dead[G::NBW + 2];        // no window may start here
-    uint32_t ustart[G::NBW + 2];      // a unit (record or pair) starts here
     uint32_t lastpick[G::NT];
-    uint32_t poff[G::NT];             // exclusive pick offset | exclusive start-rank << 16
-    uint32_t emk[G::NT];              // emit mask | ustart bits << 16
-    uint32_t vmask[G::PKCAP / 32], hmask[G::PKCAP / 32];
+    uint32_t poff[G::NT];             // exclusive pick offset
+    uint32_t emk[G::NT];              // emit mask
     uint16_t ufirst[G::MAXR + 2];     // first pick index of each unit
-    uint16_t rkfirst[G::MAXR + 2];    // first pick index by start-rank
     uint16_t ustartpos[G::MAXR + 2];
     uint32_t rec_se[G::MAXR];         // record start | end << 16 (tile-local), loaded one phase early
     uint16_t rec_eff[G::MAXR];        // end of the record's effective sequence (tile-local)
@@ -76,9 +73,8 @@ struct TilePriv {
     uint32_t h[16];        // ntHash of own 16 k-mers
     uint32_t rel4[4];      // pick position relative to 16t, 8 bits per window
     uint32_t emask;        // windows that emit a pick
-    uint32_t ust16;        // unit-start bits of own 16 positions
     uint32_t valid16;
-    uint32_t pickoff, rankoff;
+    uint32_t pickoff;
 };
 
 // ------------------------------------------------------------------ tables
@@ -263,7 +259,7 @@ DCN_HD uint64_t bits64_at(const uint32_t *arr, int t) {
 
 template <class G>
 DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
-    pv.emask = 0; pv.valid16 = 0; pv.ust16 = 0;
+    pv.emask = 0; pv.valid16 = 0;
     pv.rel4[0] = pv.rel4[1] = pv.rel4[2] = pv.rel4[3] = 0;
     if (t >= G::NT - 1) { s.lastpick[t] = 0xFFFFFFFFu; return; }
 
@@ -353,7 +349,6 @@ DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
     uint32_t valid16 = ~invalid16 & 0xFFFFu;
     uint32_t first16 = (uint32_t)bw & ~dead16 & 0xFFFFu;      // first window of a record: always emits
     pv.valid16 = valid16;
-    pv.ust16 = (uint32_t)bits64_at(s.ustart, t) & 0xFFFFu;
     // emit(j) = valid(j) && (first(j) || (valid(j-1) && pick(j) != pick(j-1)));  A.3 step 5
     pv.emask = valid16 & (first16 | ((valid16 << 1) & neq));  // bit 0 completed in phase_emit_fix
     s.lastpick[t] = (valid16 & 0x8000u) ? (uint32_t)(16 * t) + rel[15] : 0xFFFFFFFFu;
@@ -367,19 +362,18 @@ DCN_HD uint32_t phase_emit_fix(int t, TileSmem<G> &s, TilePriv<G> &pv) {
         uint32_t mine = (uint32_t)(16 * t) + (pv.rel4[0] & 0xFFu);
         if (lp != 0xFFFFFFFFu && lp != mine) pv.emask |= 1u;
     }
-    return popc32(pv.emask) | (popc32(pv.ust16) << 16);
+    return popc32(pv.emask);
 }
 
 // ------------------------------------------------------------------ phase 4: compact picks
 template <class G>
 DCN_HD void phase_emit(int t, TileSmem<G> &s, TilePriv<G> &pv, uint32_t excl, uint32_t total,
                        uint32_t cap = (uint32_t)G::PKCAP) {
-    pv.pickoff = excl & 0xFFFFu;
-    pv.rankoff = excl >> 16;
+    pv.pickoff = excl;
     s.poff[t] = excl;
-    s.emk[t] = pv.emask | (pv.ust16 << 16);
-    if (t == 0) s.npicks = total & 0xFFFFu;
-    if ((total & 0xFFFFu) > cap) return;   // the caller splits the run and retries
+    s.emk[t] = pv.emask;
+    if (t == 0) s.npicks = total;
+    if (total > cap) return;   // the caller splits the run and retries
     uint32_t em = pv.emask;
     uint32_t idx = pv.pickoff;
     const uint64_t relA = pv.rel4[0] | ((uint64_t)pv.rel4[1] << 32), relB = pv.rel4[2] | ((uint64_t)pv.rel4[3] << 32);
@@ -391,8 +385,7 @@ DCN_HD void phase_emit(int t, TileSmem<G> &s, TilePriv<G> &pv, uint32_t excl, ui
 #endif
         em &= em - 1;
         const uint32_t rel = (uint32_t)(((i & 8) ? relB : relA) >> (8 * (i & 7))) & 0xFFu;
-        const uint32_t rank = pv.rankoff + popc32(pv.ust16 & ((2u << i) - 1u)) - 1u;
-        s.pk_pos[idx++] = ((uint32_t)(16 * t) + rel) | ((rank & 0x3FFFu) << 16);
+        s.pk_pos[idx++] = (uint32_t)(16 * t) + rel;
     }
 }
 
@@ -456,21 +449,6 @@ DCN_HD bool table_contains(const TableView &tv, uint64_t h) {
     return table_contains_from(tv, h, b, load_bucket(tv.slots, b));
 }
 
-// popcount of bits [a, b) of a bit array
-DCN_HD uint32_t popc_range(const uint32_t *m, uint32_t a, uint32_t b) {
-    uint32_t n = 0;
-    while (a < b) {
-        uint32_t w = a >> 5, lo = a & 31u;
-        uint32_t end = (w + 1) << 5;
-        if (end > b) end = b;
-        uint32_t width = end - a;
-        uint32_t mask = width == 32 ? 0xFFFFFFFFu : (((1u << width) - 1u) << lo);
-        n += popc32(m[w] & mask);
-        a = end;
-    }
-    return n;
-}
-
 // set bits [a, b) of a 32-bit-word bit array (shared memory on device)
 DCN_HD void set_bits(uint32_t *arr, uint32_t a, uint32_t b) {
     while (a < b) {
@@ -510,7 +488,6 @@ DCN_HD void init_structure_words(int t, TileSmem<G> &s, uint32_t dead_lo, uint32
     for (int i = t; i < G::NBW + 2; i += G::NT) {
         s.dead[i] = outside_mask(32u * (uint32_t)i, dead_lo, dead_hi);
         s.brk[i] = outside_mask(32u * (uint32_t)i, brk_lo, brk_hi);
-        s.ustart[i] = 0;
     }
 }
 
@@ -579,13 +556,13 @@ DCN_HD void phase_structure(int t, TileSmem<G> &s, uint32_t rpu, uint32_t n_rec_
         const uint32_t se = s.rec_se[i];
         const uint32_t sL = se & 0xFFFFu, eL = se >> 16, eff = s.rec_eff[i];
         set_bit(s.brk, sL);
-        if (i % rpu == 0) { set_bit(s.ustart, sL); s.ustartpos[i / rpu] = (uint16_t)sL; }
+        if (i % rpu == 0) s.ustartpos[i / rpu] = (uint16_t)sL;
         if (eff < eL) { set_bits(s.dead, eff, eL); set_bits(s.brk, eff, eL); }
         // positions before the first record and after the last one were marked by init_structure_words
     }
 }
 
-// first pick index of every unit, and of every distinct unit-start position (rank)
+// first pick index of every unit: the picks emitted by windows that start before the unit's first base
 template <class G>
 DCN_HD void phase_unit_first(int t, TileSmem<G> &s, uint32_t n_units_t, uint32_t npicks) {
     for (uint32_t u = (uint32_t)t; u < n_units_t; u += G::NT) {
@@ -593,14 +570,7 @@ DCN_HD void phase_unit_first(int t, TileSmem<G> &s, uint32_t n_units_t, uint32_t
         uint32_t tt = pos >> 4, ii = pos & 15u;
         // a unit that starts in the last 16-position chunk or beyond has no window in this tile
         bool tail = tt >= (uint32_t)(G::NT - 1);
-        uint32_t po = tail ? 0u : s.poff[tt], em = tail ? 0u : s.emk[tt];
-        uint32_t uf = tail ? npicks : (po & 0xFFFFu) + popc32(em & 0xFFFFu & ((1u << ii) - 1u));
-        s.ufirst[u] = (uint16_t)uf;
-        bool last_at_pos = (u + 1 == n_units_t) || (s.ustartpos[u + 1] != pos);
-        if (last_at_pos && !tail) {
-            uint32_t rank = (po >> 16) + popc32((em >> 16) & ((1u << ii) - 1u));
-            s.rkfirst[rank] = (uint16_t)uf;
-        }
+        s.ufirst[u] = (uint16_t)(tail ? npicks : s.poff[tt] + popc32(s.emk[tt] & ((1u << ii) - 1u)));
         if (u == 0) s.ufirst[n_units_t] = (uint16_t)npicks;
     }
 }
@@ -671,72 +641,57 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
             }
         }
     });
-    // probe + distinct-hit test (src/filter_common.rs:143-145: contains && seen.insert).
-    // A pick is a duplicate iff an EARLIER valid pick of the same unit has the same hash.  Picks of
-    // one warp-round (32 consecutive list entries) are compared with a warp match; the earlier
-    // picks of the unit that straddles into this round are brought in by a second match when they
-    // fit the lanes that do not belong to that unit, else scanned in shared memory.
-    ex.par([&](int t, Priv &) {
-        const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
-        const uint32_t lane = (uint32_t)t & 31u;
-        const uint32_t lt = (1u << lane) - 1u;
-        for (uint32_t r = 0; r < rounds; r++) {
-            const uint32_t idx = r * G::NT + (uint32_t)t;
-            const uint32_t wbase = idx - lane;
-            bool valid = false, found = false, hit = false, inlist = idx < npicks;
-            uint64_t h = 0;
-            uint32_t first = 0xFFFFFFFFu;
-            if (inlist) {
-                uint32_t pp = s.pk_pos[idx];
-                valid = (pp & 0x80000000u) != 0;
-                found = (pp & 0x40000000u) != 0;
-                first = s.rkfirst[(pp >> 16) & 0x3FFFu];
-                if (valid) h = s.pk_hash[idx];
-            }
-            const uint32_t vmask = ex.ballot(t, valid);
-            const uint32_t same = ex.match64(t, h, valid);
-            bool dup = false;
-            if (valid) {
-                uint32_t unit_lanes = first <= wbase ? 0xFFFFFFFFu : (first - wbase >= 32 ? 0u : 0xFFFFFFFFu << (first - wbase));
-                dup = (same & vmask & unit_lanes & lt) != 0;
-            }
-            // the unit of lane 0 may have started in an earlier warp-round
-            const uint32_t first0 = ex.bcast0(t, first);
-            const uint32_t in0 = ex.ballot(t, inlist && first == first0);       // lanes of that unit (a prefix)
-            const uint32_t m = (first0 != 0xFFFFFFFFu && first0 < wbase) ? wbase - first0 : 0u;   // its earlier picks
-            if (m) {
-                const uint32_t c = popc32(in0);
-                if (m + c <= 32u) {
-                    // lanes [32 - m, 32) present the earlier picks, lanes [0, c) their own pick
-                    const bool is_e = lane >= 32u - m;
-                    const uint32_t j = first0 + (lane - (32u - m));
-                    bool e_valid = false;
-                    uint64_t v = h;
-                    if (is_e) { e_valid = (s.pk_pos[j] & 0x80000000u) != 0; v = s.pk_hash[j]; }
-                    const uint32_t emask = ex.ballot(t, e_valid);
-                    const uint32_t same2 = ex.match64(t, v, true);
-                    if (valid && lane < c && (same2 & emask)) dup = true;
-                } else if (valid && first == first0 && !dup) {
-                    const uint32_t hlo = (uint32_t)h;
-                    const uint32_t *h32 = reinterpret_cast<const uint32_t *>(s.pk_hash);
-                    for (uint32_t j = first0; j < wbase && !dup; j++)
-                        if (h32[2 * j] == hlo) dup = (s.pk_hash[j] == h) && (s.pk_pos[j] & 0x80000000u);
-                }
-            }
-            hit = valid && found && !dup;
-            ex.ballot2(t, idx, valid, hit, s.vmask, s.hmask);
-        }
-    });
-    // per-unit totals and the threshold test (no trailing barrier, see above)
+    // Distinct hits per unit (src/filter_common.rs:143-145: contains && seen.insert) and the threshold
+    // test, one warp per unit: the unit's picks are consecutive list entries, 32 per pass.  A pick is a
+    // duplicate iff an EARLIER valid pick of the same unit has the same hash: within a pass one warp
+    // match answers that; a pick of a later pass (units with more than 32 picks) is compared with the
+    // previous pass through a broadcast per candidate, with older passes by a scan of the list.
+    // No trailing barrier: the first phase of the next tile touches none of the arrays read here.
     ex.par_nosync([&](int t, Priv &) {
-        for (uint32_t u = (uint32_t)t; u < n_units_t; u += G::NT) {
-            uint32_t a = s.ufirst[u], b = s.ufirst[u + 1];
-            uint32_t total = popc_range(s.vmask, a, b);
-            uint32_t hits = popc_range(s.hmask, a, b);
-            uint32_t gu = u_begin + u;
-            P.total[gu] = total;
-            P.hits[gu] = hits;
-            P.keep[gu] = meets_criteria(hits, total, P.abs_thr, P.rel_thr, P.deplete) ? 1 : 0;
+        const uint32_t lane = (uint32_t)t & 31u, lt = (1u << lane) - 1u;
+        for (uint32_t u = (uint32_t)t >> 5; u < n_units_t; u += (uint32_t)G::NT / 32u) {
+            const uint32_t a = s.ufirst[u], b = s.ufirst[u + 1];
+            uint32_t hits = 0, total = 0, vprev = 0;
+            uint64_t hprev = 0;
+            for (uint32_t base = a; base < b; base += 32u) {
+                const uint32_t idx = base + lane;
+                bool valid = false, found = false;
+                uint64_t h = 0;
+                if (idx < b) {
+                    const uint32_t pp = s.pk_pos[idx];
+                    valid = (pp & 0x80000000u) != 0;
+                    found = (pp & 0x40000000u) != 0;
+                    if (valid) h = s.pk_hash[idx];
+                }
+                const uint32_t vmask = ex.ballot(t, valid);
+                const uint32_t same = ex.match64(t, h, valid);
+                bool fresh = valid && found && (same & vmask & lt) == 0;
+                if (base > a) {
+                    uint32_t cand = ex.ballot(t, fresh);
+                    while (cand) {   // warp-uniform: one round per candidate of this pass
+                        const uint32_t l = popc32((cand & (0u - cand)) - 1u);
+                        cand &= cand - 1u;
+                        const uint64_t hv = ex.bcast64(t, h, l);
+                        const uint32_t hitprev = ex.ballot(t, ((vprev >> lane) & 1u) != 0 && hprev == hv);
+                        if (lane == l && hitprev) fresh = false;
+                    }
+                    if (fresh && base > a + 32u) {   // passes before the previous one
+                        const uint32_t hlo = (uint32_t)h;
+                        const uint32_t *h32 = reinterpret_cast<const uint32_t *>(s.pk_hash);
+                        for (uint32_t j = a; j < base - 32u && fresh; j++)
+                            if (h32[2 * j] == hlo && s.pk_hash[j] == h && (s.pk_pos[j] & 0x80000000u)) fresh = false;
+                    }
+                }
+                hits += popc32(ex.ballot(t, fresh));
+                total += popc32(vmask);
+                hprev = h; vprev = vmask;
+            }
+            if (lane == 0) {
+                const uint32_t gu = u_begin + u;
+                P.total[gu] = total;
+                P.hits[gu] = hits;
+                P.keep[gu] = meets_criteria(hits, total, P.abs_thr, P.rel_thr, P.deplete) ? 1 : 0;
+            }
         }
     });
     return true;
@@ -836,7 +791,6 @@ DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const TileSrc &src, uint64_t
         if (t == 0) {
             s.wsum[8] = 0; s.wsum[9] = 0;                            // per-chunk tallies of the consumer phase
             if (!carry) set_bit(s.brk, la);                          // record start: first window always emits
-            set_bit(s.ustart, la);                                   // one "unit": every pick gets rank 0
         }
         phase_hash<G>(t, s, pv);
     });

@@ -44,10 +44,10 @@ struct HostExec {
         for (int l = 0; l < 32; l++) m |= (uint32_t)(prev_at(w + l) & 1) << l;
         return m;
     }
-    uint32_t bcast0(int t, uint32_t v) {
+    uint64_t bcast64(int t, uint64_t v, uint32_t src) {
         size_t slot = vote_slot(t);
         cur_v[slot] = v;
-        return (uint32_t)prev_at(slot - (size_t)(t & 31));
+        return prev_at(slot - (size_t)(t & 31) + src);
     }
     uint32_t match64(int t, uint64_t v, bool) {
         size_t slot = vote_slot(t);
@@ -102,12 +102,6 @@ struct HostExec {
         if (!valid) return;
         unsigned long long pos = (*count)++;
         if (pos < cap) out[pos] = v;
-    }
-    void ballot2(int t, uint32_t idx, bool valid, bool hit, uint32_t *vm, uint32_t *hm) {
-        if (idx >= (uint32_t)G::PKCAP) return;
-        if ((t & 31) == 0) { vm[idx >> 5] = 0; hm[idx >> 5] = 0; }
-        if (valid) vm[idx >> 5] |= 1u << (idx & 31);
-        if (hit) hm[idx >> 5] |= 1u << (idx & 31);
     }
 };
 
