@@ -52,6 +52,11 @@ SIGNATURES = {
                                          C.c_uint8, C.c_float, C.c_int, u64p, C.c_void_p]),
     "dcn_index_build_keys": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64]),
     "dcn_index_build_keys_device": (C.c_void_p, [C.c_void_p]),
+    "dcn_idx_decode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, u8p, u8p, u8p, u64p, u64p]),
+    "dcn_index_diff_sequences": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, u64p]),
+    "dcn_idx_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
+    "dcn_working_set_info": (C.c_int, [C.c_void_p, u64p, u8p, u8p]),
+    "dcn_index_make_resident": (C.c_int, [C.c_void_p]),
     "dcn_stats_get": (C.c_int, [C.c_void_p, u64p]),
     "dcn_stats_reset": (C.c_int, [C.c_void_p]),
     "dcn_last_timing": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),

@@ -328,6 +328,63 @@ class DeaconGpu:
             self.header = IndexHeader(2, k, w)
         return keys[:n.value]
 
+    # ---- .idx codec + set algebra on the GPU (working key set of the ctx)
+    SET_REPLACE, SET_UNION, SET_SUBTRACT = 0, 1, 2
+
+    def idx_decode(self, data, mode: int = 0, make_resident: bool = False):
+        """load_minimizer_hashes' decode (src/index.rs:80-107) on the GPU -> (header, keys in file, keys in the set)."""
+        buf = np.frombuffer(data, np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        ver, k, w, nf, ns = C.c_uint8(), C.c_uint8(), C.c_uint8(), C.c_uint64(), C.c_uint64()
+        ptr = buf.ctypes.data if len(buf) else None
+        self._check(self._lib.dcn_idx_decode(self._ctx, ptr, len(buf), mode, int(make_resident), C.byref(ver), C.byref(k),
+                                             C.byref(w), C.byref(nf), C.byref(ns)))
+        hdr = IndexHeader(ver.value, k.value, w.value)
+        if make_resident:
+            self.header = hdr
+        return hdr, nf.value, ns.value
+
+    def working_set_info(self) -> dict:
+        n, k, w = C.c_uint64(), C.c_uint8(), C.c_uint8()
+        self._check(self._lib.dcn_working_set_info(self._ctx, C.byref(n), C.byref(k), C.byref(w)))
+        return {"n_keys": n.value, "kmer_length": k.value, "window_size": w.value}
+
+    def working_keys(self) -> np.ndarray:
+        """Sorted unique keys of the working set."""
+        n = self.working_set_info()["n_keys"]
+        keys = np.zeros(max(1, n), np.uint64)
+        self._check(self._lib.dcn_index_build_keys(self._ctx, keys.ctypes.data, len(keys)))
+        return keys[:n]
+
+    def idx_encode(self) -> bytes:
+        """write_minimizers (src/index.rs:130-164) of the working set, encoded on the GPU."""
+        ln = C.c_uint64()
+        rc = self._lib.dcn_idx_encode(self._ctx, None, 0, C.byref(ln))
+        if rc not in (0, -6):
+            self._check(rc)
+        out = np.zeros(ln.value, np.uint8)
+        self._check(self._lib.dcn_idx_encode(self._ctx, out.ctypes.data, len(out), C.byref(ln)))
+        return out.tobytes()
+
+    def index_union(self, data) -> int:
+        """index::union step (src/index.rs:626-650): working set |= keys of this .idx -> size of the set."""
+        return self.idx_decode(data, self.SET_UNION)[2]
+
+    def index_diff(self, data) -> int:
+        """index::diff, index - index (src/index.rs:515-528): working set -= keys of this .idx."""
+        return self.idx_decode(data, self.SET_SUBTRACT)[2]
+
+    def index_diff_sequences(self, bases, rec_off) -> int:
+        """stream_diff_fastx (src/index.rs:311-419): working set -= minimizers of these records."""
+        bases = np.ascontiguousarray(bases, np.uint8)
+        rec_off = np.ascontiguousarray(rec_off, np.uint64)
+        n = C.c_uint64()
+        bptr = bases.ctypes.data if len(bases) else rec_off.ctypes.data
+        self._check(self._lib.dcn_index_diff_sequences(self._ctx, bptr, rec_off.ctypes.data, len(rec_off) - 1, C.byref(n)))
+        return n.value
+
+    def index_make_resident(self):
+        self._check(self._lib.dcn_index_make_resident(self._ctx))
+
     # ---- counters / measurement
     def stats(self) -> dict:
         c = (C.c_uint64 * 6)()

@@ -98,7 +98,9 @@ struct dcn_ctx {
     DevBuf longs, dedup;   // long-path scratch of the device-pointer API
     // index build
     DevBuf ib_bases, ib_off, ib_desc, ib_keys, ib_alt, ib_tmp, ib_entropy, ib_stats;
-    uint64_t ib_n = 0;     // sorted unique keys of the last build (in ib_keys)
+    uint64_t ib_n = 0;     // the working key set: sorted unique keys of the last build / decode / union / diff (in ib_keys)
+    uint8_t ws_k = 0, ws_w = 0;   // its header (src/index.rs:17-22)
+    DevBuf ws_table, ws_flags;    // scratch table for set difference
     // generic (k, w) path and B3 extraction: staging, chunk plan, CSR outputs
     DevBuf gx_bases, gx_off, gx_rc, gx_cc, gx_tmp, gx_h, gx_p, gx_oo, gx_entropy;
     static const int NSLOT = 3;
@@ -469,6 +471,7 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->ib_entropy.release(); ctx->ib_stats.release();
     ctx->gx_bases.release(); ctx->gx_off.release(); ctx->gx_rc.release(); ctx->gx_cc.release(); ctx->gx_tmp.release();
     ctx->gx_h.release(); ctx->gx_p.release(); ctx->gx_oo.release(); ctx->gx_entropy.release();
+    ctx->ws_table.release(); ctx->ws_flags.release();
     ctx->pool.reset();
     for (int i = 0; i < dcn_ctx::NSLOT; i++) {
         Slot &s = ctx->slot[i];
@@ -981,6 +984,7 @@ int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t 
 // FxHashSet::extend (src/index.rs:267-284) == radix sort + unique of the n_picks hashes in ib_alt
 static int index_sort_unique(dcn_ctx *ctx, uint64_t n_picks, uint8_t k, uint8_t w, int make_resident, uint64_t *n_keys_out,
                              cudaStream_t st) {
+    ctx->ws_k = k; ctx->ws_w = w; ctx->ib_n = 0;
     if (n_picks == 0) {
         if (make_resident) return dcn_index_upload_device(ctx, nullptr, 0, k, w, st);
         return DCN_OK;
@@ -1009,30 +1013,24 @@ static int index_sort_unique(dcn_ctx *ctx, uint64_t n_picks, uint8_t k, uint8_t 
     return DCN_OK;
 }
 
-int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
-                           uint64_t n_bases, uint8_t k, uint8_t w, float entropy_thr, int make_resident,
-                           uint64_t *n_keys_out, void *stream) {
-    if (!ctx) return DCN_ERR_ARG;
-    int rc0 = check_kw(ctx, k, w, DCN_FLAVOUR_INDEX);
-    if (rc0) return rc0;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    ctx->ib_n = 0;
-    if (n_keys_out) *n_keys_out = 0;
+// Index-flavour extraction of every record into ctx->ib_alt (unordered, duplicates included).
+static int index_extract_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                                uint64_t n_bases, uint8_t k, uint8_t w, float entropy_thr, cudaStream_t st, uint64_t *n_out) {
+    *n_out = 0;
     CK(ctx->ib_stats.ensure(64 + 16));
-    if (k != 31 || w != 15) {   // generic extraction (ordered CSR, offsets unused), then the same sort + unique
+    if (k != 31 || w != 15) {   // generic extraction (ordered CSR, offsets unused)
         uint64_t m = 0;
         bool written = false;
-        rc0 = generic_extract_device(ctx, DCN_FLAVOUR_INDEX, d_bases, d_rec_off, n_rec, k, w, 0, entropy_thr, false, 0, st, &m, &written);
+        int rc0 = generic_extract_device(ctx, DCN_FLAVOUR_INDEX, d_bases, d_rec_off, n_rec, k, w, 0, entropy_thr, false, 0, st, &m, &written);
         if (rc0) return rc0;
         if (m) {
             CK(ctx->ib_alt.ensure(m * sizeof(uint64_t)));
             CK(cudaMemcpyAsync(ctx->ib_alt.p, ctx->gx_h.p, m * sizeof(uint64_t), cudaMemcpyDeviceToDevice, st));
         }
-        return index_sort_unique(ctx, m, k, w, make_resident, n_keys_out, st);
+        *n_out = m;
+        return DCN_OK;
     }
     if (reinterpret_cast<uintptr_t>(d_bases) & 15u) return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
-
     const uint32_t *d_entropy = nullptr;
     if (entropy_thr != 0.0f) {
         std::vector<uint32_t> bits;
@@ -1044,7 +1042,6 @@ int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t 
     }
     const uint32_t desc_cap = (uint32_t)(n_bases / ChunkGeo<G31>::CSTRIDE + n_rec + 16);
     CK(ctx->ib_desc.ensure((size_t)desc_cap * sizeof(ChunkDesc)));
-    CK(ctx->ib_stats.ensure(64 + 16));
     BatchStats *d_stats = ctx->ib_stats.as<BatchStats>();
     unsigned long long *d_count = reinterpret_cast<unsigned long long *>(ctx->ib_stats.as<uint8_t>() + 64);
 
@@ -1069,6 +1066,22 @@ int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t 
         if (attempt == 1) return ctx->fail(DCN_ERR_OVERFLOW, "minimizer buffer overflowed twice");
         cap = n_picks + 1024;
     }
+    *n_out = n_picks;
+    return DCN_OK;
+}
+
+int dcn_index_build_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                           uint64_t n_bases, uint8_t k, uint8_t w, float entropy_thr, int make_resident,
+                           uint64_t *n_keys_out, void *stream) {
+    if (!ctx) return DCN_ERR_ARG;
+    int rc0 = check_kw(ctx, k, w, DCN_FLAVOUR_INDEX);
+    if (rc0) return rc0;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    ctx->ib_n = 0;
+    if (n_keys_out) *n_keys_out = 0;
+    uint64_t n_picks = 0;
+    if ((rc0 = index_extract_device(ctx, d_bases, d_rec_off, n_rec, n_bases, k, w, entropy_thr, st, &n_picks))) return rc0;
     return index_sort_unique(ctx, n_picks, k, w, make_resident, n_keys_out, st);
 }
 
@@ -1095,6 +1108,257 @@ int dcn_index_build_keys(dcn_ctx *ctx, uint64_t *out_keys, uint64_t cap) {
     return DCN_OK;
 }
 const uint64_t *dcn_index_build_keys_device(dcn_ctx *ctx) { return ctx && ctx->ib_n ? ctx->ib_keys.as<uint64_t>() : nullptr; }
+
+// ---------------------------------------------------------------------------- .idx codec + set algebra on the GPU
+// bincode-2 varint (src/index.rs:57-72 via bincode config::standard): < 251 one byte; 0xFB + u16; 0xFC + u32; 0xFD + u64
+static bool host_read_varint(const uint8_t *p, uint64_t len, uint64_t &pos, uint64_t &v) {
+    if (pos >= len) return false;
+    const uint8_t t = p[pos++];
+    if (t < 251) { v = t; return true; }
+    const int n = t == 0xFB ? 2 : t == 0xFC ? 4 : t == 0xFD ? 8 : 0;   // 0xFE (u128) cannot hold a u64 field
+    if (!n || pos + (uint64_t)n > len) return false;
+    v = 0;
+    for (int i = 0; i < n; i++) v |= (uint64_t)p[pos + i] << (8 * i);
+    pos += (uint64_t)n;
+    return true;
+}
+
+namespace {
+struct NotInTable {   // predicate of the set difference: key absent from the scratch table
+    TableView tv;
+    __device__ bool operator()(const uint64_t &key) const { return !table_contains(tv, key); }
+};
+
+// body of a .idx file whose every key is a 9-byte token (0xFD + 8 bytes LE): token i starts at byte 9 i.
+// bad[0] is set when a tag is not 0xFD (the caller then falls back to the sequential scan).
+__global__ void idx_decode9_kernel(const uint8_t *__restrict__ body, uint64_t n, uint64_t *__restrict__ keys, uint32_t *bad) {
+    const uint64_t *w = reinterpret_cast<const uint64_t *>(body);   // 8-byte aligned, padded by 16 bytes
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t at = 9 * i;
+        if (body[at] != 0xFDu) *bad = 1;
+        const uint64_t a = at + 1, q = a >> 3;
+        const uint32_t sh = (uint32_t)(a & 7u) * 8u;
+        const uint64_t lo = w[q], hi = w[q + 1];
+        keys[i] = sh ? (lo >> sh) | (hi << (64u - sh)) : lo;
+    }
+}
+
+__device__ __forceinline__ uint32_t varint_len(uint64_t v) { return v < 251 ? 1u : v < (1ull << 16) ? 3u : v < (1ull << 32) ? 5u : 9u; }
+
+__global__ void idx_token_len_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ len) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x)
+        len[i] = i < n ? varint_len(keys[i]) : 0;
+}
+__global__ void idx_count_short_kernel(const uint64_t *__restrict__ keys, uint64_t n, unsigned long long *n_short) {
+    unsigned long long c = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        c += keys[i] < (1ull << 32);
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_short, c);
+}
+// off == nullptr: every token is 9 bytes
+__global__ void idx_encode_kernel(const uint64_t *__restrict__ keys, uint64_t n, const uint64_t *__restrict__ off, uint8_t *__restrict__ out) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = keys[i];
+        uint8_t *p = out + (off ? off[i] : 9 * i);
+        const uint32_t l = off ? varint_len(v) : 9u;
+        if (l == 1) { p[0] = (uint8_t)v; continue; }
+        p[0] = l == 3 ? 0xFBu : l == 5 ? 0xFCu : 0xFDu;
+        for (uint32_t b = 0; b + 1 < l; b++) p[1 + b] = (uint8_t)(v >> (8 * b));
+    }
+}
+}  // namespace
+
+// keys of a decoded .idx body -> device buffer `dst` (n entries)
+static int idx_body_to_device(dcn_ctx *ctx, const uint8_t *body, uint64_t body_len, uint64_t n, DevBuf &dst, cudaStream_t st) {
+    CK(dst.ensure(std::max<uint64_t>(n, 1) * 8));
+    if (n == 0) return DCN_OK;
+    if (body_len == 9 * n) {   // the usual layout: xxh3 values below 2^32 are a 2^-32 event
+        CK(ctx->gx_bases.ensure(body_len + 32));
+        CK(ctx->ib_stats.ensure(64 + 16));
+        uint32_t *d_bad = reinterpret_cast<uint32_t *>(ctx->ib_stats.as<uint8_t>() + 72);
+        CK(cudaMemsetAsync(d_bad, 0, 4, st));
+        CK(cudaMemsetAsync(ctx->gx_bases.as<uint8_t>() + (body_len & ~7ull), 0, 24, st));   // the last word pair is read whole
+        CK(cudaMemcpyAsync(ctx->gx_bases.p, body, body_len, cudaMemcpyHostToDevice, st));
+        idx_decode9_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->gx_bases.as<uint8_t>(), n, dst.as<uint64_t>(), d_bad);
+        ctx->launches += 1;
+        uint32_t bad = 0;
+        CK(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (!bad) return DCN_OK;
+    }
+    // short tokens present: sequential scan of the stream on the host (the codec is host-side in the reference too)
+    std::vector<uint64_t> keys(n);
+    uint64_t pos = 0;
+    for (uint64_t i = 0; i < n; i++)
+        if (!host_read_varint(body, body_len, pos, keys[i])) return ctx->fail(DCN_ERR_ARG, "Failed to deserialise hash: truncated or malformed index body");
+    CK(cudaMemcpyAsync(dst.p, keys.data(), n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return DCN_OK;
+}
+
+// working set := working set \ B, B = n_b keys (any order, duplicates allowed) in device memory
+static int working_set_subtract(dcn_ctx *ctx, const uint64_t *d_b, uint64_t n_b, cudaStream_t st) {
+    if (ctx->ib_n == 0 || n_b == 0) return DCN_OK;
+    const uint64_t nb = table_buckets_for(n_b, 0.5);
+    CK(ctx->ws_table.ensure(nb * 4 * sizeof(uint64_t)));
+    CK(ctx->ws_flags.ensure(64));
+    unsigned long long *cnt = ctx->ws_flags.as<unsigned long long>();
+    CK(cudaMemsetAsync(cnt, 0, 64, st));
+    table_fill_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->ws_table.as<uint64_t>(), nb * 4);
+    table_insert_kernel<<<grid_for(ctx, n_b, 256), 256, 0, st>>>(ctx->ws_table.as<uint64_t>(), nb, d_b, n_b, cnt);
+    unsigned long long c[2] = {0, 0};
+    CK(cudaMemcpyAsync(c, cnt, sizeof(c), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    NotInTable pred;
+    pred.tv.slots = ctx->ws_table.as<uint64_t>(); pred.tv.n_buckets = nb; pred.tv.has_empty_key = c[1] != 0;
+    CK(ctx->ib_alt.ensure(ctx->ib_n * 8));
+    size_t tb = 0;
+    unsigned long long *d_n = cnt + 4;
+    CK(cub::DeviceSelect::If(nullptr, tb, ctx->ib_keys.as<uint64_t>(), ctx->ib_alt.as<uint64_t>(), d_n, (int64_t)ctx->ib_n, pred, st));
+    CK(ctx->ib_tmp.ensure(tb));
+    CK(cub::DeviceSelect::If(ctx->ib_tmp.p, tb, ctx->ib_keys.as<uint64_t>(), ctx->ib_alt.as<uint64_t>(), d_n, (int64_t)ctx->ib_n, pred, st));
+    ctx->launches += 4;
+    unsigned long long kept = 0;
+    CK(cudaMemcpyAsync(&kept, d_n, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    std::swap(ctx->ib_keys, ctx->ib_alt);   // a stable selection of a sorted set stays sorted
+    ctx->ib_n = kept;
+    return DCN_OK;
+}
+
+int dcn_idx_decode(dcn_ctx *ctx, const uint8_t *file, uint64_t len, int mode, int make_resident, uint8_t *version,
+                   uint8_t *k, uint8_t *w, uint64_t *n_in_file, uint64_t *n_set) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!file || len < 3) return ctx->fail(DCN_ERR_ARG, "Failed to deserialise index header");
+    if (mode < DCN_SET_REPLACE || mode > DCN_SET_SUBTRACT) return ctx->fail(DCN_ERR_ARG, "unknown mode");
+    if (version) *version = file[0];
+    if (k) *k = file[1];
+    if (w) *w = file[2];
+    if (file[0] != 2) return ctx->fail(DCN_ERR_ARG, "Unsupported index format version (src/index.rs:34-40): only version 2");
+    uint64_t pos = 3, count = 0;
+    if (!host_read_varint(file, len, pos, count)) return ctx->fail(DCN_ERR_ARG, "Failed to deserialise minimizer count");
+    if (n_in_file) *n_in_file = count;
+    if (count > len) return ctx->fail(DCN_ERR_ARG, "minimizer count exceeds the file size");
+    if (mode != DCN_SET_REPLACE && (file[1] != ctx->ws_k || file[2] != ctx->ws_w))
+        return ctx->fail(DCN_ERR_ARG, "Incompatible headers: k, w differ from the first index (src/index.rs:474-485, 626-640)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (mode == DCN_SET_REPLACE) {
+        if ((rc = idx_body_to_device(ctx, file + pos, len - pos, count, ctx->ib_alt, st))) return rc;
+        rc = index_sort_unique(ctx, count, file[1], file[2], 0, nullptr, st);
+    } else if (mode == DCN_SET_UNION) {
+        if ((rc = idx_body_to_device(ctx, file + pos, len - pos, count, ctx->gx_h, st))) return rc;
+        const uint64_t tot = ctx->ib_n + count;
+        CK(ctx->ib_alt.ensure(std::max<uint64_t>(tot, 1) * 8));
+        if (ctx->ib_n) CK(cudaMemcpyAsync(ctx->ib_alt.p, ctx->ib_keys.p, ctx->ib_n * 8, cudaMemcpyDeviceToDevice, st));
+        if (count) CK(cudaMemcpyAsync(ctx->ib_alt.as<uint64_t>() + ctx->ib_n, ctx->gx_h.p, count * 8, cudaMemcpyDeviceToDevice, st));
+        rc = index_sort_unique(ctx, tot, ctx->ws_k, ctx->ws_w, 0, nullptr, st);
+    } else {
+        if ((rc = idx_body_to_device(ctx, file + pos, len - pos, count, ctx->gx_h, st))) return rc;
+        rc = working_set_subtract(ctx, ctx->gx_h.as<uint64_t>(), count, st);
+    }
+    if (rc) return rc;
+    if (n_set) *n_set = ctx->ib_n;
+    if (make_resident) return dcn_index_upload_device(ctx, ctx->ib_keys.as<uint64_t>(), ctx->ib_n, ctx->ws_k, ctx->ws_w, st);
+    return DCN_OK;
+}
+
+int dcn_index_diff_sequences(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint64_t *n_set) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!rec_off || (!bases && n_rec && rec_off[n_rec] > 0)) return ctx->fail(DCN_ERR_ARG, "null input pointer");
+    if (!ctx->ws_k) return ctx->fail(DCN_ERR_NO_INDEX, "no working key set: build or decode an index first");
+    if (n_rec && rec_off[0] != 0) return ctx->fail(DCN_ERR_ARG, "rec_off[0] must be 0");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n_bases = n_rec ? rec_off[n_rec] : 0;
+    CK(ctx->ib_bases.ensure(n_bases + 64));
+    CK(ctx->ib_off.ensure(((size_t)n_rec + 1) * 8));
+    if (n_bases) CK(cudaMemcpyAsync(ctx->ib_bases.p, bases, n_bases, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->ib_off.p, rec_off, ((size_t)n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
+    // the working set lives in ib_keys; extraction writes ib_alt, which the subtraction then reuses as its output:
+    // move the extracted hashes out of the way first
+    uint64_t m = 0;
+    int rc = index_extract_device(ctx, ctx->ib_bases.as<uint8_t>(), ctx->ib_off.as<uint64_t>(), n_rec, n_bases, ctx->ws_k, ctx->ws_w,
+                                  0.0f, st, &m);   // entropy 0.0: src/index.rs:378-381
+    if (rc) return rc;
+    CK(ctx->gx_h.ensure(std::max<uint64_t>(m, 1) * 8));
+    if (m) CK(cudaMemcpyAsync(ctx->gx_h.p, ctx->ib_alt.p, m * 8, cudaMemcpyDeviceToDevice, st));
+    if ((rc = working_set_subtract(ctx, ctx->gx_h.as<uint64_t>(), m, st))) return rc;
+    if (n_set) *n_set = ctx->ib_n;
+    return DCN_OK;
+}
+
+int dcn_idx_encode(dcn_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *len) {
+    if (!ctx || !len) return DCN_ERR_ARG;
+    if (!ctx->ws_k) return ctx->fail(DCN_ERR_NO_INDEX, "no working key set: build or decode an index first");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const uint64_t n = ctx->ib_n;
+    uint8_t head[12] = {2, ctx->ws_k, ctx->ws_w};
+    uint64_t hl = 3;
+    if (n < 251) head[hl++] = (uint8_t)n;
+    else {
+        const int nb = n < (1ull << 16) ? 2 : n < (1ull << 32) ? 4 : 8;
+        head[hl++] = nb == 2 ? 0xFB : nb == 4 ? 0xFC : 0xFD;
+        for (int i = 0; i < nb; i++) head[hl++] = (uint8_t)(n >> (8 * i));
+    }
+    uint64_t body = 9 * n;
+    const uint64_t *d_off = nullptr;
+    if (n) {
+        CK(ctx->ws_flags.ensure(64));
+        unsigned long long *d_short = ctx->ws_flags.as<unsigned long long>();
+        CK(cudaMemsetAsync(d_short, 0, 8, st));
+        idx_count_short_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->ib_keys.as<uint64_t>(), n, d_short);
+        unsigned long long n_short = 0;
+        CK(cudaMemcpyAsync(&n_short, d_short, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (n_short) {   // variable token lengths: lengths -> exclusive scan -> offsets
+            CK(ctx->gx_cc.ensure((n + 1) * 8));
+            uint64_t *l = ctx->gx_cc.as<uint64_t>();
+            idx_token_len_kernel<<<grid_for(ctx, n + 1, 256), 256, 0, st>>>(ctx->ib_keys.as<uint64_t>(), n, l);
+            size_t tb = 0;
+            CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, l, l, (int64_t)n + 1, st));
+            CK(ctx->gx_tmp.ensure(tb));
+            CK(cub::DeviceScan::ExclusiveSum(ctx->gx_tmp.p, tb, l, l, (int64_t)n + 1, st));
+            CK(cudaMemcpyAsync(&body, l + n, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            d_off = l;
+            ctx->launches += 3;
+        }
+    }
+    *len = hl + body;
+    if (!out || cap < hl + body) return ctx->fail(DCN_ERR_OVERFLOW, "output buffer too small: *len holds the required size");
+    memcpy(out, head, hl);
+    if (n) {
+        CK(ctx->gx_bases.ensure(body + 16));
+        idx_encode_kernel<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->ib_keys.as<uint64_t>(), n, d_off, ctx->gx_bases.as<uint8_t>());
+        ctx->launches += 2;
+        CK(cudaMemcpyAsync(out + hl, ctx->gx_bases.p, body, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+    }
+    return DCN_OK;
+}
+
+int dcn_working_set_info(dcn_ctx *ctx, uint64_t *n_keys, uint8_t *k, uint8_t *w) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!ctx->ws_k) return ctx->fail(DCN_ERR_NO_INDEX, "no working key set: build or decode an index first");
+    if (n_keys) *n_keys = ctx->ib_n;
+    if (k) *k = ctx->ws_k;
+    if (w) *w = ctx->ws_w;
+    return DCN_OK;
+}
+
+int dcn_index_make_resident(dcn_ctx *ctx) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!ctx->ws_k) return ctx->fail(DCN_ERR_NO_INDEX, "no working key set: build or decode an index first");
+    CK(cudaSetDevice(ctx->device));
+    return dcn_index_upload_device(ctx, ctx->ib_keys.as<uint64_t>(), ctx->ib_n, ctx->ws_k, ctx->ws_w, ctx->stream);
+}
 
 // ---------------------------------------------------------------------------- counters
 int dcn_stats_get(dcn_ctx *ctx, uint64_t counters[6]) {

@@ -141,6 +141,31 @@ int dcn_index_build_keys(dcn_ctx *ctx, uint64_t *out_keys, uint64_t cap);
 /* device pointer to the sorted unique keys of the last build (valid until the next build) */
 const uint64_t *dcn_index_build_keys_device(dcn_ctx *ctx);
 
+/* ---- .idx container and set algebra on the working key set ---------------------------
+ * A ctx holds one "working key set": the sorted unique keys of the last dcn_index_build, dcn_idx_decode, union
+ * or difference, with its (k, w).  dcn_index_build_keys[_device] read it; dcn_idx_encode serialises it.
+ *
+ * dcn_idx_decode replaces load_minimizer_hashes' decode + insert loop (src/index.rs:80-107): `file` is a whole
+ * .idx file (3-byte header, bincode varint count, varint keys).  The usual all-9-byte-token body is decoded by a
+ * kernel straight from the uploaded bytes; bodies with short tokens are scanned sequentially on the host.
+ *   mode DCN_SET_REPLACE   working set := file            (index info / load)
+ *        DCN_SET_UNION     working set := working ∪ file  (index::union, src/index.rs:563-664)
+ *        DCN_SET_SUBTRACT  working set := working \ file  (index::diff, index - index, src/index.rs:421-537)
+ * Headers must agree for UNION / SUBTRACT ("Incompatible headers", src/index.rs:474-485, 626-640). */
+enum { DCN_SET_REPLACE = 0, DCN_SET_UNION = 1, DCN_SET_SUBTRACT = 2 };
+int dcn_idx_decode(dcn_ctx *ctx, const uint8_t *file, uint64_t len, int mode, int make_resident,
+                   uint8_t *version, uint8_t *k, uint8_t *w, uint64_t *n_in_file, uint64_t *n_set);
+/* stream_diff_fastx (src/index.rs:311-419): working set -= minimizers of these records (index flavour,
+ * entropy 0, the working set's k and w). */
+int dcn_index_diff_sequences(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint64_t *n_set);
+/* write_minimizers (src/index.rs:130-164): header + varint count + varint keys (ascending).  Returns
+ * DCN_ERR_OVERFLOW with *len = required size when cap is too small (out may be NULL to query). */
+int dcn_idx_encode(dcn_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *len);
+/* `deacon index info` (src/index.rs:539-560): size and header of the working key set. */
+int dcn_working_set_info(dcn_ctx *ctx, uint64_t *n_keys, uint8_t *k, uint8_t *w);
+/* Make the working key set the resident (probed) index. */
+int dcn_index_make_resident(dcn_ctx *ctx);
+
 /* ---- a13: the six summary counters (ProcessingStats, src/local_filter.rs:179-187) ----------------
  * counters[6] = {total_seqs, filtered_seqs, total_bp, output_bp, filtered_bp, output_seq_counter},
  * accumulated over every dcn_filter_batch call since the last reset.  These are the values the

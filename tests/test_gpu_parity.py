@@ -409,3 +409,70 @@ def test_lookup_equals_filter_on_same_reads(gpu):
     res = gpu.paired_should_keep([(x, [], []) for x in lists], 31, 2, 0.01, True)
     assert [r[0] for r in res] == [bool(x) for x in k1]
     assert [r[1] for r in res] == [int(x) for x in h1] and [r[2] for r in res] == [int(x) for x in t1]
+
+
+# --------------------------------------------------------------------------- .idx codec + union / diff on the GPU
+def _mixed_keys(seed, n):
+    rng = np.random.default_rng(seed)
+    return np.unique(rng.integers(0, 2**64, n, dtype=np.uint64))
+
+
+def test_idx_decode_encode_matches_oracle_codec(gpu):
+    """dcn_idx_decode / dcn_idx_encode == the oracle's restatement of src/index.rs:57-72,130-164, for the usual
+    all-9-byte body (GPU decode) and for bodies with short varints (sequential scan)."""
+    for keys in (_mixed_keys(1, 200_000),
+                 np.array([0, 5, 250, 251, 70000, 2**32 - 1, 2**32, 2**64 - 1], np.uint64),
+                 np.concatenate([np.arange(0, 300, dtype=np.uint64), _mixed_keys(2, 5000)]),
+                 np.zeros(0, np.uint64)):
+        keys = np.unique(keys)
+        data = O.idx_encode(np.random.default_rng(3).permutation(keys), 31, 15)       # a set in arbitrary order, like the reference writes
+        hdr, n_file, n_set = gpu.idx_decode(data)
+        assert (hdr.format_version, hdr.kmer_length, hdr.window_size) == (2, 31, 15) and n_file == n_set == len(keys)
+        assert np.array_equal(gpu.working_keys(), keys)
+        out = gpu.idx_encode()
+        assert out == O.idx_encode(keys, 31, 15)                                       # byte-identical to the oracle's writer on sorted keys
+        ver, k, w, back = O.idx_decode(out)
+        assert (ver, k, w) == (2, 31, 15) and np.array_equal(back, keys)
+    from deacon_server_b200 import DeaconCudaError
+    with pytest.raises(DeaconCudaError, match="version"):
+        gpu.idx_decode(bytes([1, 31, 15, 0]))
+    with pytest.raises(DeaconCudaError, match="truncated|malformed"):
+        gpu.idx_decode(O.idx_encode(_mixed_keys(4, 100), 31, 15)[:-3])
+
+
+def test_index_union_and_diff_match_set_algebra(gpu):
+    """index::union (src/index.rs:563-664) and index::diff index - index (:421-537)."""
+    a, b, c = _mixed_keys(11, 300_000), _mixed_keys(12, 200_000), _mixed_keys(13, 1000)
+    b = np.unique(np.concatenate([b, a[::3]]))          # overlap
+    gpu.idx_decode(O.idx_encode(a, 31, 15))
+    assert gpu.index_union(O.idx_encode(b, 31, 15)) == len(np.union1d(a, b))
+    assert gpu.index_union(O.idx_encode(c, 31, 15)) == len(np.union1d(np.union1d(a, b), c))
+    assert np.array_equal(gpu.working_keys(), np.union1d(np.union1d(a, b), c))
+    gpu.idx_decode(O.idx_encode(a, 31, 15))
+    assert gpu.index_diff(O.idx_encode(b, 31, 15)) == len(np.setdiff1d(a, b))
+    assert np.array_equal(gpu.working_keys(), np.setdiff1d(a, b))
+    assert gpu.idx_encode() == O.idx_encode(np.setdiff1d(a, b), 31, 15)
+    from deacon_server_b200 import DeaconCudaError
+    with pytest.raises(DeaconCudaError, match="Incompatible headers"):
+        gpu.index_union(O.idx_encode(c, 21, 11))
+    # the working set becomes the resident index and answers lookups
+    gpu.index_make_resident()
+    d = np.setdiff1d(a, b)
+    q = np.concatenate([d[:50], b[:50]])
+    k, h, t = gpu.lookup_batch(q, np.array([0, 50, 100], np.uint64), 1, 0.0, False)
+    assert list(map(int, h)) == [50, int(np.isin(b[:50], d).sum())]
+
+
+@pytest.mark.parametrize("k,w", [(31, 15), (21, 11)])
+def test_index_diff_against_sequences(gpu, k, w):
+    """index diff IDX reads.fa (stream_diff_fastx, src/index.rs:311-419) == index - index of the same sequences
+    (the equality tests/index_tests.rs:168-285 checks)."""
+    g = H.random_genome(300_000, 21 + k)
+    second = [g[50_000:120_000].copy(), g[200_000:200_040].copy(), np.frombuffer(b"ACGTNNNNRYKMacgtnryk" * 100, np.uint8).copy()]
+    bases, off = H.concat([g])
+    a = gpu.index_build(bases, off, k, w, 0.0, make_resident=False)
+    sb, so = H.concat(second)
+    remaining = gpu.index_diff_sequences(sb, so)
+    want = np.setdiff1d(a, O.index_build((sb, so), k, w).keys())
+    assert remaining == len(want) and np.array_equal(gpu.working_keys(), want)
+    assert len(want) < len(a)
