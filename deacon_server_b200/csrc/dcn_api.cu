@@ -451,6 +451,8 @@ dcn_ctx *dcn_ctx_create(int device) {
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(extract_tiles_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(extract_index_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     if (!ok) {
@@ -947,6 +949,71 @@ int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_o
 }
 
 // ---------------------------------------------------------------------------- B3 extraction
+// Fast path: filter flavour, k = 31, w = 15, no record above DCN_MAX_SHORT bases -> the tile pipeline.
+// Leaves the CSR in ctx->gx_h / gx_p / gx_oo like generic_extract_device.
+static int tile_extract_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_off, uint32_t n_rec, uint64_t n_bases,
+                               uint32_t prefix_len, bool want_pos, uint64_t cap_limit, cudaStream_t st, uint64_t *n_out,
+                               bool *written) {
+    *n_out = 0; *written = false;
+    const size_t pbytes = plan_bytes(n_bases);
+    CK(ctx->plan.ensure(pbytes));
+    const uint64_t n_tiles_max = (pbytes - 64) / (2 * sizeof(uint32_t));
+    BatchStats *d_stats = ctx->plan.as<BatchStats>();
+    uint32_t *tile_first = reinterpret_cast<uint32_t *>(ctx->plan.as<uint8_t>() + 64);
+    uint32_t *tile_end = tile_first + n_tiles_max;
+    CK(ctx->gx_rc.ensure(((size_t)n_rec + 1) * 8));   // rec_cnt (scanned in place into the CSR offsets)
+    CK(ctx->gx_oo.ensure(((size_t)n_rec + 1) * 8));
+    CK(ctx->gx_cc.ensure(((size_t)n_rec + 1) * 8 + 64));   // rec_tmp + cursor
+    FilterParams P;
+    memset(&P, 0, sizeof(P));
+    P.bases = d_bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = d_off; P.n_rec = n_rec; P.rpu = 1; P.n_units = n_rec;
+    P.prefix_len = prefix_len;
+    unsigned long long *d_cursor = reinterpret_cast<unsigned long long *>(ctx->gx_cc.as<uint8_t>() + ((size_t)n_rec + 1) * 8);
+    const int pb = 256;
+    const int pg = (int)std::min<uint64_t>(((uint64_t)n_rec + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
+    const int grid = (int)std::min<uint64_t>(n_bases / G31::BCAP + 1, (uint64_t)ctx->sm_count * (1024 / G31::NT));
+    uint64_t cap = (uint64_t)((double)n_bases * 0.13) + 4096;   // ~0.095 picks per base for 150-base records
+    unsigned long long used = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        CK(ctx->ib_alt.ensure(cap * 8));     // temp hashes
+        CK(ctx->ib_tmp.ensure(cap * 4));     // temp positions
+        CK(cudaMemsetAsync(ctx->plan.p, 0, pbytes, st));
+        CK(cudaMemsetAsync(d_cursor, 0, 8, st));
+        CK(cudaMemsetAsync(ctx->gx_rc.p, 0, ((size_t)n_rec + 1) * 8, st));
+        P.xo.tmp_h = ctx->ib_alt.as<uint64_t>(); P.xo.tmp_p = ctx->ib_tmp.as<uint32_t>(); P.xo.tmp_cap = cap;
+        P.xo.cursor = d_cursor; P.xo.rec_cnt = ctx->gx_rc.as<uint64_t>(); P.xo.rec_tmp = ctx->gx_cc.as<uint64_t>();
+        prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, 1, n_rec, d_stats);
+        prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, 1, n_rec, 0, d_stats, tile_first, tile_end);
+        extract_tiles_kernel<G31><<<grid, G31::NT, sizeof(TileSmem<G31>), st>>>(P, d_stats, tile_first, tile_end);
+        ctx->launches += 3;
+        CK(cudaMemcpyAsync(&used, d_cursor, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (used <= cap) break;
+        if (attempt == 1) return ctx->fail(DCN_ERR_OVERFLOW, "pick buffer overflowed twice");
+        cap = used + 1024;
+    }
+    // records that own no window keep count 0 (memset); exclusive scan -> CSR offsets
+    size_t tb = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, tb, ctx->gx_rc.as<uint64_t>(), ctx->gx_oo.as<uint64_t>(), (int64_t)n_rec + 1, st));
+    CK(ctx->gx_tmp.ensure(tb));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->gx_tmp.p, tb, ctx->gx_rc.as<uint64_t>(), ctx->gx_oo.as<uint64_t>(), (int64_t)n_rec + 1, st));
+    uint64_t m = 0;
+    CK(cudaMemcpyAsync(&m, ctx->gx_oo.as<uint64_t>() + n_rec, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = m;
+    ctx->launches += 1;
+    if (cap_limit && m > cap_limit) return DCN_OK;
+    CK(ctx->gx_h.ensure(std::max<uint64_t>(m, 1) * 8));
+    if (want_pos) CK(ctx->gx_p.ensure(std::max<uint64_t>(m, 1) * 4));
+    extract_compact_kernel<<<grid_for(ctx, (uint64_t)n_rec * 32, 256), 256, 0, st>>>(P.xo, ctx->gx_oo.as<uint64_t>(), n_rec, ctx->gx_h.as<uint64_t>(),
+                                                                                  want_pos ? ctx->gx_p.as<uint32_t>() : nullptr);
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    *written = true;
+    return DCN_OK;
+}
+
 int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k,
                 uint8_t w, uint32_t prefix_len, float entropy_thr, uint64_t *out_hashes, uint32_t *out_pos,
                 uint64_t *out_off, uint64_t out_cap) {
@@ -967,9 +1034,15 @@ int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t 
     else CK(cudaMemsetAsync(ctx->gx_off.p, 0, 8, st));
     uint64_t m = 0;
     bool written = false;
-    rc = generic_extract_device(ctx, flavour, ctx->gx_bases.as<uint8_t>(), ctx->gx_off.as<uint64_t>(), n_rec, k, w,
-                                flavour == DCN_FLAVOUR_FILTER ? prefix_len : 0, entropy_thr, out_pos != nullptr, out_cap ? out_cap : 1,
-                                st, &m, &written);
+    bool tiles = flavour == DCN_FLAVOUR_FILTER && k == 31 && w == 15 && n_rec > 0 && n_bases > 0 && !getenv("DCN_EXTRACT_GENERIC");
+    for (uint32_t r = 0; tiles && r < n_rec; r++) tiles = rec_off[r + 1] - rec_off[r] <= DCN_MAX_SHORT;
+    if (tiles)
+        rc = tile_extract_device(ctx, ctx->gx_bases.as<uint8_t>(), ctx->gx_off.as<uint64_t>(), n_rec, n_bases, prefix_len,
+                                 out_pos != nullptr, out_cap ? out_cap : 1, st, &m, &written);
+    else
+        rc = generic_extract_device(ctx, flavour, ctx->gx_bases.as<uint8_t>(), ctx->gx_off.as<uint64_t>(), n_rec, k, w,
+                                    flavour == DCN_FLAVOUR_FILTER ? prefix_len : 0, entropy_thr, out_pos != nullptr, out_cap ? out_cap : 1,
+                                    st, &m, &written);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out_off, ctx->gx_oo.p, ((size_t)n_rec + 1) * 8, cudaMemcpyDeviceToHost, st));
     if (written && m) {

@@ -35,6 +35,7 @@ struct DevExec {
         }
     }
     __device__ __forceinline__ void global_add(uint32_t *p, uint32_t v) { if (v) atomicAdd(p, v); }
+    __device__ __forceinline__ uint64_t global_add64(unsigned long long *p, uint64_t v) { return atomicAdd(p, (unsigned long long)v); }
     // warp-aggregated append to a global array
     __device__ __forceinline__ void append64(int t, bool valid, uint64_t v, uint64_t *out, uint64_t cap,
                                              unsigned long long *count) {
@@ -223,7 +224,7 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
             }
         }
         ex.pf_lo = a2 * P.rpu; ex.pf_hi = b2 * P.rpu;   // a2 == b2 == 0: one harmless line
-        if (a < b) filter_tile<G, PACKED>(ex, s, P, cfg, n_long, a, b);
+        if (a < b) filter_tile<G, PACKED, MODE_FILTER>(ex, s, P, cfg, n_long, a, b);
         tile = nt; a = a2; b = b2;
     }
     if (n_long) {  // long units: chunks, spread over the CTAs in reverse so short and long work interleave
@@ -231,6 +232,56 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
         const uint32_t n_chunks = st->n_chunks;
         for (uint32_t w = gridDim.x - 1 - blockIdx.x; w < n_chunks; w += gridDim.x)
             filter_long_chunk<G, PACKED>(ex, s, P, dd, desc[w]);
+    }
+}
+
+// ------------------------------------------------------------------ B3: extraction through the tile pipeline
+// get_minimizer_hashes_and_positions (src/filter_common.rs:211-310) for a batch of short records
+// (every record <= DCN_MAX_SHORT bases, k = 31, w = 15): phases 1-4 of the fused kernel, then hashes
+// and record-relative positions into per-tile blocks of the temp arrays.
+template <class G>
+__global__ void __launch_bounds__(G::NT, 1024 / G::NT)
+extract_tiles_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ tile_first,
+                     const uint32_t *__restrict__ tile_end) {
+    extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
+    TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);
+    DevExec<G> ex;
+    ex.wsum = s.wsum;
+    init_tables<G>((int)threadIdx.x, s);
+    __syncthreads();
+    const PlanCfg cfg = plan_make_cfg<G>(st->max_short);
+    const uint32_t n_tiles = plan_num_tiles(P.n_bases - P.base0, cfg);
+    ex.pf_off = P.rec_off;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t a = tile_first[tile], b = tile_end[tile];
+        if (a < b) {
+            filter_tile<G, false, MODE_EXTRACT>(ex, s, P, cfg, 0u, a, b);
+            __syncthreads();   // the extraction phases end without a barrier; the next tile rewrites wsum / the pick list
+        }
+    }
+}
+
+// CSR compaction: one warp per record moves its valid picks from the tile block to out_off[r] ..
+__global__ void extract_compact_kernel(ExtractOut xo, const uint64_t *__restrict__ out_off, uint32_t n_rec,
+                                       uint64_t *__restrict__ out_h, uint32_t *__restrict__ out_p) {
+    const uint32_t lane = threadIdx.x & 31u, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rec; r += warps) {
+        const uint64_t rt = xo.rec_tmp[r], start = rt >> 16;
+        const uint32_t n = (uint32_t)(rt & 0xFFFFu);
+        uint64_t at = out_off[r];
+        for (uint32_t base = 0; base < n; base += 32u) {
+            const uint32_t i = base + lane;
+            uint32_t pp = 0;
+            if (i < n) pp = xo.tmp_p[start + i];
+            const bool valid = (pp & 0x80000000u) != 0;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+            if (valid) {
+                const uint64_t o = at + (uint64_t)__popc(m & ((1u << lane) - 1u));
+                out_h[o] = xo.tmp_h[start + i];
+                if (out_p) out_p[o] = pp & 0x7FFFFFFFu;
+            }
+            at += (uint64_t)__popc(m);
+        }
     }
 }
 

@@ -492,6 +492,17 @@ DCN_HD void init_structure_words(int t, TileSmem<G> &s, uint32_t dead_lo, uint32
 }
 
 // ------------------------------------------------------------------ filter parameters
+// B3 (extraction only) through the tile pipeline: a tile reserves a block of the temp arrays for its
+// picks, the per-record valid counts go through a scan, and a copy kernel compacts the blocks into CSR.
+struct ExtractOut {
+    uint64_t *tmp_h;                 // xxh3 of each pick (block of the tile, list order)
+    uint32_t *tmp_p;                 // position in the record's effective sequence | valid << 31
+    uint64_t tmp_cap;
+    unsigned long long *cursor;      // next free temp entry (may run past tmp_cap: the host retries)
+    uint64_t *rec_cnt;               // valid picks of each record
+    uint64_t *rec_tmp;               // temp start of each record << 16 | picks (valid or not)
+};
+
 struct FilterParams {
     const uint8_t *bases;     // concatenated ASCII records (device), 16-byte aligned; nullptr when packed
     const uint32_t *pk_codes; // host-packed form (see TileSrc): 2-bit codes ...
@@ -512,6 +523,7 @@ struct FilterParams {
     uint8_t *keep;            // per unit
     uint32_t *hits;
     uint32_t *total;
+    ExtractOut xo;            // extraction mode only
 };
 
 // effective length of a record (src/filter_common.rs:217-229): raw-length guard, prefix, one '\n'.
@@ -577,7 +589,9 @@ DCN_HD void phase_unit_first(int t, TileSmem<G> &s, uint32_t n_units_t, uint32_t
 
 // Returns false (after one barrier-consistent decision, nothing written) when the run emits more
 // than PKCAP picks: the caller then splits the run.  A single short unit (<= 1024 bases) never does.
-template <class G, bool PACKED, class Ex>
+enum TileMode { MODE_FILTER = 0, MODE_EXTRACT = 1 };
+
+template <class G, bool PACKED, int MODE, class Ex>
 DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
     using Priv = TilePriv<G>;
     const uint32_t r_begin = u_begin * P.rpu;
@@ -606,6 +620,53 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
             [&](int t, Priv &pv, uint32_t excl, uint32_t total) { phase_emit<G>(t, s, pv, excl, total); });
     const uint32_t npicks = s.npicks;
     if (npicks > (uint32_t)G::PKCAP) { ex.barrier(); return false; }
+
+    if (MODE == MODE_EXTRACT) {
+        // B3: hash every pick (no probe); thread 0 reserves the tile's block of the temp arrays
+        ex.par([&](int t, Priv &) {
+            phase_unit_first<G>(t, s, n_units_t, npicks);
+            if (t == 0) {
+                const uint64_t base = ex.global_add64(P.xo.cursor, npicks);
+                s.wsum[10] = (uint32_t)base; s.wsum[11] = (uint32_t)(base >> 32);
+            }
+            for (uint32_t idx = (uint32_t)t; idx < npicks; idx += G::NT) {
+                const uint32_t pp = s.pk_pos[idx];
+                if (pick_kmer_valid<G>(s, pp & 0xFFFFu)) {
+                    s.pk_hash[idx] = pick_hash<G>(s, pp & 0xFFFFu);
+                    s.pk_pos[idx] = pp | 0x80000000u;
+                }
+            }
+        });
+        // one warp per record: its picks (list order = position order) go to the tile's block, with the
+        // position made relative to the record; the valid count feeds the CSR offsets
+        ex.par_nosync([&](int t, Priv &) {
+            const uint32_t lane = (uint32_t)t & 31u;
+            const uint64_t tbase = (uint64_t)s.wsum[10] | ((uint64_t)s.wsum[11] << 32);
+            for (uint32_t u = (uint32_t)t >> 5; u < n_units_t; u += (uint32_t)G::NT / 32u) {
+                const uint32_t a = s.ufirst[u], b = s.ufirst[u + 1], sL = s.ustartpos[u];
+                uint32_t cnt = 0;
+                for (uint32_t base = a; base < b; base += 32u) {
+                    const uint32_t idx = base + lane;
+                    bool valid = false;
+                    if (idx < b) {
+                        const uint32_t pp = s.pk_pos[idx];
+                        valid = (pp & 0x80000000u) != 0;
+                        const uint64_t at = tbase + idx;
+                        if (at < P.xo.tmp_cap) {
+                            P.xo.tmp_p[at] = ((pp & 0xFFFFu) - sL) | (pp & 0x80000000u);
+                            if (valid) P.xo.tmp_h[at] = s.pk_hash[idx];
+                        }
+                    }
+                    cnt += popc32(ex.ballot(t, valid));
+                }
+                if (lane == 0) {
+                    P.xo.rec_cnt[u_begin + u] = cnt;
+                    P.xo.rec_tmp[u_begin + u] = ((tbase + a) << 16) | (uint64_t)(b - a);
+                }
+            }
+        });
+        return true;
+    }
 
     // hash every pick and probe the table: two picks per thread are in flight at a time (hash A,
     // request A, hash B, request B, then test A and B), the answer is kept as bit 30 of the pick;
@@ -698,13 +759,13 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
 }
 
 // a run of short units, split in halves while it emits more picks than one pass can hold
-template <class G, bool PACKED, class Ex>
+template <class G, bool PACKED, int MODE, class Ex>
 DCN_HD void filter_short_run(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint32_t u_begin, uint32_t u_end) {
     uint32_t lo = u_begin;
     uint32_t span = u_end - u_begin;
     while (lo < u_end) {
         uint32_t hi = lo + span < u_end ? lo + span : u_end;
-        if (filter_short_tile<G, PACKED>(ex, s, P, lo, hi)) {
+        if (filter_short_tile<G, PACKED, MODE>(ex, s, P, lo, hi)) {
             if (hi < u_end) ex.barrier();  // the next pass rewrites tables the last phase still reads
             lo = hi;
         } else {
@@ -715,13 +776,13 @@ DCN_HD void filter_short_run(Ex &ex, TileSmem<G> &s, const FilterParams &P, uint
 
 // All units whose first base lies in one tile: runs of short units go through
 // filter_short_tile; long units are skipped here (they are cut into chunks by the long path).
-template <class G, bool PACKED, class Ex>
+template <class G, bool PACKED, int MODE, class Ex>
 DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const PlanCfg &cfg, uint32_t n_long,
                         uint32_t u_first, uint32_t u_end) {
     const uint64_t rpu = P.rpu;
     // common case: the batch has no long unit and the tile's records fit one pass
     if (n_long == 0 && (uint64_t)(u_end - u_first) * rpu <= (uint64_t)G::MAXR) {
-        filter_short_run<G, PACKED>(ex, s, P, u_first, u_end);
+        filter_short_run<G, PACKED, MODE>(ex, s, P, u_first, u_end);
         return;
     }
     uint32_t u = u_first;
@@ -732,7 +793,7 @@ DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const Pla
         while (v < u_end && (uint64_t)(v - u + 1) * rpu <= (uint64_t)G::MAXR &&
                P.rec_off[(uint64_t)(v + 1) * rpu] - P.rec_off[(uint64_t)v * rpu] <= cfg.max_short)
             v++;
-        filter_short_run<G, PACKED>(ex, s, P, u, v);
+        filter_short_run<G, PACKED, MODE>(ex, s, P, u, v);
         ex.barrier();  // a following pass rewrites the tables the last phase still reads
         u = v;
     }

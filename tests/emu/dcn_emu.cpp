@@ -98,6 +98,7 @@ struct HostExec {
     }
     void tally2(int, bool a, bool b, uint32_t *ca, uint32_t *cb) { *ca += a; *cb += b; }
     void global_add(uint32_t *p, uint32_t v) { *p += v; }
+    uint64_t global_add64(unsigned long long *p, uint64_t v) { uint64_t o = *p; *p += v; return o; }
     void append64(int, bool valid, uint64_t v, uint64_t *out, uint64_t cap, unsigned long long *count) {
         if (!valid) return;
         unsigned long long pos = (*count)++;
@@ -185,7 +186,7 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
     ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); });
     for (uint32_t tile = 0; tile < n_tiles; tile++)
         if (tile_first[tile] < tile_end[tile])
-            filter_tile<G, PACKED>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
+            filter_tile<G, PACKED, MODE_FILTER>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
     int rc = 0;
     if (n_long) {  // mirrors prep_long_kernel + the chunk loop of filter_fused_kernel + finalize_long_kernel
         std::vector<uint32_t> long_units;

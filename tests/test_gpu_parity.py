@@ -323,6 +323,44 @@ def test_extract_matches_oracle(gpu, k, w):
             assert np.array_equal(h[int(oo[i]):int(oo[i + 1])], O.extract_index(r, k, w, thr)), (k, w, thr, i)
 
 
+@pytest.mark.parametrize("case", [c for c in CASES.make_cases() if c["name"] in (
+    "single_150_search", "ragged_0_420_N_lower", "ragged_prefix_80", "ragged_prefix_20_below_k", "lengths_around_k_and_l",
+    "trailing_newline", "trailing_newline_prefix", "tiny_records", "empty_records_only", "low_complexity", "dense_picks_polyA",
+    "non_acgt_bytes", "units_up_to_1024")], ids=lambda c: c["name"])
+def test_extract_tile_pipeline_matches_oracle(gpu, case):
+    """dcn_extract's fast path (short records, k=31 w=15: phases 1-4 of the fused kernel + CSR compaction): hashes and
+    positions per record == get_minimizer_hashes_and_positions (src/filter_common.rs:211-310), and == the generic kernels."""
+    recs = [r for r in case["records"] if len(r) <= 1024]
+    bases, off = H.concat(recs)
+    h, p, oo = gpu.extract(bases, off, 0, 31, 15, case["prefix"])
+    for i, r in enumerate(recs):
+        wh, wp = O.extract_filter(r, 31, 15, case["prefix"])
+        a, b = int(oo[i]), int(oo[i + 1])
+        assert np.array_equal(h[a:b], wh) and np.array_equal(p[a:b], wp), (case["name"], i)
+    os.environ["DCN_EXTRACT_GENERIC"] = "1"
+    try:
+        h2, p2, oo2 = gpu.extract(bases, off, 0, 31, 15, case["prefix"])
+    finally:
+        del os.environ["DCN_EXTRACT_GENERIC"]
+    assert np.array_equal(h, h2) and np.array_equal(p, p2) and np.array_equal(oo, oo2)
+
+
+def test_extract_then_lookup_equals_filter(gpu):
+    """Client/server split of the batch engine (src/remote_filter.rs:762-790): B3 on the client, B2 on the server,
+    must reproduce B1's decisions - all three on the GPU."""
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(500_000, 131)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    reads = H.sample_reads(g, 60_000, 150, 132)
+    bases, off = H.concat(reads)
+    h, p, oo = gpu.extract(bases, off, 0, 31, 15, 0)
+    pair_off = oo[::2].copy()                                   # pooled hash list per pair (src/filter_common.rs:312-348)
+    k2, h2, t2 = gpu.lookup_batch(h, pair_off, 2, 0.01, True)
+    k1, h1, t1 = gpu.filter_batch(bases, off, paired=True, deplete=True)
+    assert np.array_equal(k1, k2) and np.array_equal(h1, h2) and np.array_equal(t1, t2)
+
+
 def test_extract_single_record_api_and_overflow(gpu):
     from deacon_server_b200 import DeaconCudaError
     g = H.random_genome(5000, 77)

@@ -3,6 +3,7 @@ device-resident, CUDA events.  Prints one JSON object per line; results are quot
   --what lookup   B2 dcn_lookup_batch_device on pre-hashed pairs (config 5 server path): probes/s vs the random-sector ceiling
   --what long     config 3: ONT-like reads (gamma(2) lengths, mean 10 kbp, 5 % substitutions), search mode
   --what build    config 4: index build with -e 0.5 on a reference with low-complexity inserts
+  --what idx      .idx container: GPU encode of the built key set and GPU decode + table build of that file
 """
 import argparse
 import json
@@ -19,7 +20,7 @@ import bench as B  # noqa: E402
 import deacon_server_b200 as d  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--what", default="lookup,long,build")
+ap.add_argument("--what", default="lookup,long,build,idx")
 ap.add_argument("--genome-mbp", type=float, default=3100.0)
 ap.add_argument("--pairs-m", type=float, default=5.0)
 ap.add_argument("--long-gbp", type=float, default=2.0, help="bases of long reads per step")
@@ -154,3 +155,22 @@ if "build" in what:
         res[str(thr)] = {"keys": nk, "seconds": round(time.perf_counter() - t1, 4), "first_call_seconds": round(t1 - t0, 4)}
     print(json.dumps({"what": "config 4: index build (extract + radix sort + unique), 2 % low-complexity inserts",
                       "reference_mbp": args.genome_mbp, "by_entropy_threshold": res}))
+
+if "idx" in what:
+    import ctypes as C
+    nk = gpu.index_build_device(genome, coff, B.CONTIGS, G, 31, 15, 0.0, False, stream=st)
+    torch.cuda.synchronize()
+    ln = C.c_uint64()
+    gpu._lib.dcn_idx_encode(gpu._ctx, None, 0, C.byref(ln))
+    buf = torch.empty(ln.value, dtype=torch.uint8).pin_memory()
+    t0 = time.perf_counter()
+    gpu._check(gpu._lib.dcn_idx_encode(gpu._ctx, buf.data_ptr(), buf.numel(), C.byref(ln)))
+    t_enc = time.perf_counter() - t0
+    ver, k, w, nf, ns = C.c_uint8(), C.c_uint8(), C.c_uint8(), C.c_uint64(), C.c_uint64()
+    t0 = time.perf_counter()
+    gpu._check(gpu._lib.dcn_idx_decode(gpu._ctx, buf.data_ptr(), buf.numel(), 0, 1, C.byref(ver), C.byref(k), C.byref(w), C.byref(nf), C.byref(ns)))
+    t_dec = time.perf_counter() - t0
+    assert nf.value == ns.value == nk
+    print(json.dumps({"what": ".idx container on the GPU (pinned host buffer)", "keys": nk, "file_bytes": ln.value,
+                      "encode_s": round(t_enc, 3), "decode_sort_upload_table_s": round(t_dec, 3),
+                      "decode_gb_per_s": round(ln.value / t_dec / 1e9, 1)}))
