@@ -176,6 +176,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    bound = par.bind_to_gpu(local) if world > 1 and not os.environ.get("DCN_NO_BIND") else []
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -332,6 +333,7 @@ def run_ours(args):
                        "pairs_per_step": NP, "pairs_total_per_gpu": NP * args.steps, "distinct_batches": n_batches,
                        "l2_policy": "inputs larger than L2 (1.5 GB batch, distinct batches cycled)",
                        "parallelism": f"read-sharded x{world}, index replicated",
+                       "cpu_binding_rank0": f"{len(bound)} CPUs local to the GPU" if bound else "none",
                        "index_build_s": round(t_index, 3), "setup_s": round(t_setup, 2),
                        "table_bytes": gpu.index_info()["table_bytes"]},
             "e2e": {"value": round(e2e_value, 3), "unit": "Gbp/s", "h2d_bytes_per_step": nb + (NR + 1) * 8,
@@ -357,7 +359,7 @@ def run_ours(args):
             "counters": counters,
             "kept_pairs_last_step": kept_last,
         }
-        print(json.dumps(out))
+        _emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -443,10 +445,19 @@ def run_reference(args):
                             "sample": f"{S} pairs ({nb / 1e6:.0f} Mbp) per step, oracle/deacon_oracle.c on {threads} threads "
                                       "(the Rust reference cannot be built here: no cargo/rustc)"},
            "e2e": {"value": round(value, 4), "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    _emit(out)
+
+
+def _emit(obj):
+    """The one JSON line of the contract goes to the real stdout; everything else any library prints on
+    fd 1 while we run (NCCL prints its version banner there) is sent to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

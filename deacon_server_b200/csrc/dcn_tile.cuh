@@ -51,7 +51,8 @@ struct alignas(16) TileSmem {
     };
     uint64_t pk_hash[G::PKCAP];       // xxh3 of each pick
     u32x2 tb0[256];                   // 4-base aggregate table (fw, rc)
-    u32x2 tin[4], tout[4], tsb[4];    // rolling-step tables: incoming / outgoing base, single base
+    u32x2 tio[16];                    // rolling-step table indexed by outgoing code | incoming code << 2 (fw, rc parts)
+    u32x2 tsb[4];                     // single base at the neighbour-role rotation
     uint32_t codes[G::NV + 6];        // 16 bases x 2 bit per word
     uint32_t inv[(G::NV + 6 + 1) / 2 + 2];  // non-ACGT bits, 32 positions per word
     uint32_t brk[G::NBW + 2];         // position is a record start or lies outside every effective sequence
@@ -90,10 +91,13 @@ DCN_HD void init_tables(int t, TileSmem<G> &s) {
         }
         s.tb0[b].x = fw; s.tb0[b].y = rc;
     }
+    if (t < 16) {   // one step of the rolling hash: fw = rotl(fw, 1) ^ x, rc = rotr(rc ^ y, 1)
+        uint32_t oc = (uint32_t)t & 3u, ic = (uint32_t)t >> 2;
+        s.tio[t].x = rotl32(nt_f(oc), G::K) ^ nt_f(ic);
+        s.tio[t].y = nt_f(oc ^ 2u) ^ rotl32(nt_f(ic ^ 2u), G::K);
+    }
     if (t < 4) {
         uint32_t c = (uint32_t)t;
-        s.tin[t].x = nt_f(c);                          s.tin[t].y = rotl32(nt_f(c ^ 2u), G::K);
-        s.tout[t].x = rotl32(nt_f(c), G::K);           s.tout[t].y = nt_f(c ^ 2u);
         s.tsb[t].x = rotl32(nt_f(c), 15);              s.tsb[t].y = rotl32(nt_f(c ^ 2u), 15);
     }
 }
@@ -228,14 +232,19 @@ DCN_HD void phase_hash(int t, TileSmem<G> &s, TilePriv<G> &pv) {
         fw = rotr32(fw, 31 - G::K);
     }
     pv.h[0] = fw + rc;
+    // step j (k-mer 16t+j -> 16t+j+1) drops base j and takes base K+j.  The two code streams are
+    // interleaved once, so that a step's table index (out | in << 2) is one shift + one mask:
+    // even steps read nibble j/2 of mE, odd steps nibble (j-1)/2 of mO.
+    const uint32_t in = fshr(c1, c2, 2u * (uint32_t)(G::K - 16));        // base K+j at bits 2j
+    const uint32_t mE = (c0 & 0x33333333u) | ((in & 0x33333333u) << 2);
+    const uint32_t mO = ((c0 >> 2) & 0x33333333u) | (in & 0xCCCCCCCCu);
 #pragma unroll
     for (int i = 1; i < 16; i++) {
-        uint32_t oc = (c0 >> (2 * (i - 1))) & 3u;
-        int in_idx = G::K - 1 + i;  // base index relative to 16t, in [K, K+14]
-        uint32_t ic = in_idx < 32 ? (c1 >> (2 * (in_idx - 16))) & 3u : (c2 >> (2 * (in_idx - 32))) & 3u;
-        u32x2 o = s.tout[oc], n = s.tin[ic];
-        fw = rotl32(fw, 1) ^ o.x ^ n.x;
-        rc = rotr32(rc ^ o.y ^ n.y, 1);
+        const int j = i - 1;
+        const uint32_t idx = (((j & 1) ? mO : mE) >> (4 * (j >> 1))) & 15u;
+        const u32x2 e = s.tio[idx];
+        fw = rotl32(fw, 1) ^ e.x;
+        rc = rotr32(rc ^ e.y, 1);
         pv.h[i] = fw + rc;
     }
     // only the upper 16 bits take part in the window comparison: keep them masked

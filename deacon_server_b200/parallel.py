@@ -13,6 +13,30 @@ import numpy as np
 COUNTER_NAMES = ("total_seqs", "filtered_seqs", "total_bp", "output_bp", "filtered_bp", "output_seq_counter")
 
 
+def bind_to_gpu(local_rank: int) -> list[int]:
+    """Pin this process to the CPUs NVML reports as local to its GPU, so the pinned staging buffers it allocates
+    afterwards (first touch) sit on the GPU's NUMA node: with 8 GPUs on a two-socket host the H2D copies otherwise
+    cross the socket interconnect.  Returns the CPU list (empty = left unchanged)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.replace(",", "").isdigit() else local_rank
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = [i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1]
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if cpus and len(cpus) < len(allowed):
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return []
+
+
 def shard_units(n_units: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous, balanced unit range [u0, u1) of `rank`: sizes differ by at most one unit and a
     pair is never split (units, not records, are dealt out)."""
