@@ -353,7 +353,10 @@ def run_ours(args):
                          "minimizers_per_bp": round(minim_per_step / nb, 5),
                          "lookup_gprobes_per_s": round(minim_per_step / (fused_avg_ms * 1e-3) / 1e9, 3),
                          "random_sector_ceiling_gsectors_per_s": round(nprobe / (rms * 1e-3) / 1e9, 3),
-                         "note": "integer-issue bound, not HBM bound: see DESIGN.md"},
+                         "int_alu_pipe_pct_of_peak": traffic.get("alu_pipe_pct_of_peak") if traffic else None,
+                         "issue_slots_pct": traffic.get("issue_active_pct") if traffic else None,
+                         "note": "integer-ALU bound, not HBM bound (ncu: profiles/r1_final_fused_ncu_summary.json); "
+                                 "the lookup kernel alone (dcn_lookup_batch) runs at 82 % of the random-sector ceiling: DESIGN.md"},
             "cpu_baseline": cpu,
             "clocks": clk,
             "counters": counters,

@@ -342,7 +342,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     const int pg = (int)std::min<uint64_t>((n_units + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
     const size_t smem = sizeof(TileSmem<G31>);
     const uint64_t tiles_lb = n_rel / G31::BCAP + 1;
-    const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * (1024 / G31::NT));
+    const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * DCN_CTAS_PER_SM);
 
     // A batch can only contain a long unit if it holds more than DCN_MAX_SHORT bases; otherwise the
     // stats readback (one small sync) is skipped.

@@ -188,8 +188,11 @@ __global__ void prep_tiles_kernel(const uint64_t *__restrict__ rec_off, uint32_t
 
 // ------------------------------------------------------------------ the fused filter kernel
 // Persistent CTAs; tile i -> CTA (i mod grid).  4 CTAs per SM (64 registers, ~53 KB shared memory each).
+#ifndef DCN_CTAS_PER_SM
+#define DCN_CTAS_PER_SM (1024 / DCN_NT)
+#endif
 template <class G, bool PACKED>
-__global__ void __launch_bounds__(G::NT, 1024 / G::NT)
+__global__ void __launch_bounds__(G::NT, DCN_CTAS_PER_SM)
 filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ tile_first,
                     const uint32_t *__restrict__ tile_end, DedupView dd, const ChunkDesc *__restrict__ desc) {
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];

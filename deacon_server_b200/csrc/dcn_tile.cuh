@@ -33,7 +33,10 @@ struct Geo {
     static constexpr int WCAP = NT * 16 - 16;   // window starts per tile (thread 255 only hashes)
     static constexpr int BCAP = WCAP + L - 1;   // bases a tile may reference
     static constexpr int NBW = NT / 2 + 4;      // 32-bit words of the per-position bit arrays
-    static constexpr int MAXR = 2 * NT;         // records per sub-batch
+#ifndef DCN_MAXR
+#define DCN_MAXR (2 * DCN_NT)
+#endif
+    static constexpr int MAXR = DCN_MAXR;       // records per sub-batch
     static constexpr int PKCAP = 4 * NT < 1024 ? 1024 : 4 * NT;   // picks per pass (>= the 980 windows of one short unit); a denser run of units is split (see filter_tile)
     static constexpr int HP = 20;               // hrow pitch in words (16 data + 4 pad: conflict-free LDS.128)
 };
