@@ -514,3 +514,64 @@ def test_index_diff_against_sequences(gpu, k, w):
     want = np.setdiff1d(a, O.index_build((sb, so), k, w).keys())
     assert remaining == len(want) and np.array_equal(gpu.working_keys(), want)
     assert len(want) < len(a)
+
+
+# --------------------------------------------------------------------------- ABI contract: errors, contexts
+def test_error_codes_and_messages(gpu):
+    """Every failure is an error code + dcn_last_error text (SURVEY 8b: the reference returns anyhow::Result or panics;
+    the library never aborts and never falls back to the CPU)."""
+    import ctypes as C
+    import deacon_server_b200 as d
+    from deacon_server_b200 import DeaconCudaError, IndexHeader
+    lib = d.load()
+    fresh = d.DeaconGpu(0)
+    try:
+        b = np.frombuffer(b"ACGT" * 40, np.uint8)
+        off = np.array([0, 160], np.uint64)
+        with pytest.raises(DeaconCudaError) as e:
+            fresh.filter_batch(b, off)
+        assert e.value.code == -3 and "no index resident" in str(e.value)                     # DCN_ERR_NO_INDEX
+        with pytest.raises(DeaconCudaError) as e:
+            fresh.lookup_batch(np.array([1], np.uint64), np.array([0, 1], np.uint64))
+        assert e.value.code == -3
+        with pytest.raises(DeaconCudaError) as e:
+            fresh.idx_encode()
+        assert e.value.code == -3
+        fresh.index_upload(np.array([5, 6, 7], np.uint64), IndexHeader(2, 31, 15))
+        with pytest.raises(DeaconCudaError) as e:
+            fresh.filter_batch(np.tile(b, 3), np.array([0, 160, 320, 480], np.uint64), paired=True)
+        assert e.value.code == -2 and "even record count" in str(e.value)                       # DCN_ERR_ARG
+        k = np.zeros(1, np.uint8)
+        assert lib.dcn_filter_batch(fresh._ctx, b.ctypes.data, off.ctypes.data, 1, 0, 0, 2, 0.01, 0, None, None, None) == -2
+        assert lib.dcn_filter_batch(None, b.ctypes.data, off.ctypes.data, 1, 0, 0, 2, 0.01, 0, k.ctypes.data, None, None) == -2
+        with pytest.raises(DeaconCudaError, match="load factor"):
+            fresh.set_load_factor(0.99)
+        with pytest.raises(DeaconCudaError, match="unknown flavour"):
+            fresh.extract(b, off, flavour=7)
+        # zero records is a no-op, not an error
+        kk, hh, tt = fresh.filter_batch(np.zeros(0, np.uint8), np.array([0], np.uint64))
+        assert len(kk) == 0
+        assert lib.dcn_ctx_create(99) is None and b"out of range" in lib.dcn_last_error(None)
+    finally:
+        fresh.close()
+
+
+def test_two_contexts_are_independent(gpu):
+    """One ctx per index / per worker (SURVEY 8b threading): different tables, same GPU, interleaved calls."""
+    import deacon_server_b200 as d
+    from deacon_server_b200 import IndexHeader
+    g1, g2 = H.random_genome(80_000, 201), H.random_genome(80_000, 202)
+    i1, i2 = O.index_build([g1], 31, 15), O.index_build([g2], 31, 15)
+    other = d.DeaconGpu(0)
+    try:
+        gpu.index_upload(i1.keys(), IndexHeader(2, 31, 15))
+        other.index_upload(i2.keys(), IndexHeader(2, 31, 15))
+        reads = H.sample_reads(g1, 1500, 150, 203) + H.sample_reads(g2, 1500, 150, 204)
+        bases, off = H.concat(reads)
+        for _ in range(2):
+            a = gpu.filter_batch(bases, off)
+            b = other.filter_batch(bases, off)
+            assert np.array_equal(a[1], O.filter_batch(i1, bases, off)[1]) and np.array_equal(b[1], O.filter_batch(i2, bases, off)[1])
+        assert int(a[1][:1500].sum()) > 10 * int(a[1][1500:].sum()) and int(b[1][1500:].sum()) > 10 * int(b[1][:1500].sum())
+    finally:
+        other.close()
