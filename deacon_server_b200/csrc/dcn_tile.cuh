@@ -260,6 +260,15 @@ DCN_HD void phase_hash(int t, TileSmem<G> &s, TilePriv<G> &pv) {
 DCN_HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 DCN_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
+// low bytes of four words -> one word
+DCN_HD uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+#ifdef __CUDA_ARCH__
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+#else
+    return (a & 0xFFu) | ((b & 0xFFu) << 8) | ((c & 0xFFu) << 16) | ((d & 0xFFu) << 24);
+#endif
+}
+
 // 64-bit window of a bit array starting at bit 16*t
 DCN_HD uint64_t bits64_at(const uint32_t *arr, int t) {
     int w0 = t >> 1;
@@ -272,7 +281,7 @@ DCN_HD uint64_t bits64_at(const uint32_t *arr, int t) {
 template <class G>
 DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
     pv.emask = 0; pv.valid16 = 0;
-    pv.rel4[0] = pv.rel4[1] = pv.rel4[2] = pv.rel4[3] = 0;
+    pv.rel4[0] = pv.rel4[1] = pv.rel4[2] = pv.rel4[3] = 0;   // thread NT-1 owns no window
     if (t >= G::NT - 1) { s.lastpick[t] = 0xFFFFFFFFu; return; }
 
     uint32_t hv[30];
@@ -313,10 +322,6 @@ DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
     // canonical strand: #(T|G) > #(A|C) over the L bases of the window (A.3 step 4).
     // T/G <=> bit 1 of the 2-bit code.
     const uint32_t c0 = pv.c0, c1 = s.codes[t + 1], c2 = s.codes[t + 2], c3 = s.codes[t + 3];
-    auto tgbit = [&](int b) -> uint32_t {  // TG bit of base b (0..63) relative to 16t
-        uint32_t w = b < 16 ? c0 : b < 32 ? c1 : b < 48 ? c2 : c3;
-        return (w >> (2 * (b & 15) + 1)) & 1u;
-    };
     uint32_t cnt = 0;
     {
         // bases 0 .. L-1
@@ -330,17 +335,37 @@ DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
             cnt += popc32(c2 & (0xAAAAAAAAu & ((1u << (2 * (rem & 15))) - 1u)));
         }
     }
-    uint32_t rel[16];
-    uint32_t neq = 0;
+    // The 16 windows of the thread, four at a time in byte lanes.  cnt(i) = cnt(0) + sum_{j<=i} (in(j) - out(j)),
+    // in(j) = T/G flag of base L-1+j, out(j) = flag of base j-1: the flags sit in the 2-bit lanes of the code
+    // words; a multiply spreads four of them into four bytes, a second multiply prefix-sums the bytes.
+    constexpr int LW = (G::L - 1) / 16, LS = 2 * ((G::L - 1) % 16);
+    const uint32_t xw_lo = ((LW == 0 ? c0 : LW == 1 ? c1 : c2) >> 1) & 0x55555555u;
+    const uint32_t xw_hi = ((LW == 0 ? c1 : LW == 1 ? c2 : c3) >> 1) & 0x55555555u;
+    const uint32_t xin = fshr(xw_lo, xw_hi, (uint32_t)LS) & ~3u;        // lane j = in(j); lane 0 belongs to cnt(0)
+    const uint32_t xout = ((c0 >> 1) & 0x55555555u) << 2;               // lane j = out(j); lane 0 = 0
+    constexpr uint32_t THR = (uint32_t)(G::L + 1) / 2;                  // canonical <=> cnt >= THR (L is odd)
+    uint32_t neq = 0, prev_hi = 0;
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        if (i > 0) cnt += tgbit(i - 1 + G::L) - tgbit(i - 1);
-        bool canonical = 2 * cnt > (uint32_t)G::L;
-        rel[i] = (canonical ? oL[i] : oR[i]) & 0xFFFFu;
-        if (i > 0 && rel[i] != rel[i - 1]) neq |= 1u << i;
+    for (int g = 0; g < 4; g++) {
+        const uint32_t spi = (((xin >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
+        const uint32_t spo = (((xout >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
+        const uint32_t cnt4 = cnt * 0x01010101u + spi * 0x01010101u - spo * 0x01010101u;   // cnt of windows 4g .. 4g+3
+        cnt = cnt4 >> 24;
+        const uint32_t canon = ((cnt4 + (0x80u - THR) * 0x01010101u) >> 7) & 0x01010101u;
+        const uint32_t msk = canon * 0xFFu;                                                  // 0xFF in the bytes of canonical windows
+        // pick positions (low byte of the keys: the index 0..29) of the four windows, left and right flavour
+        const uint32_t l4 = pack_low_bytes(oL[4 * g], oL[4 * g + 1], oL[4 * g + 2], oL[4 * g + 3]);
+        const uint32_t r4 = pack_low_bytes(oR[4 * g], oR[4 * g + 1], oR[4 * g + 2], oR[4 * g + 3]);
+        const uint32_t rel = (l4 & msk) | (r4 & ~msk);                                       // A.3 step 4
+        pv.rel4[g] = rel;
+        // pick(i) != pick(i-1): compare every byte with the one before it (window 0 with itself)
+        const uint32_t before = (rel << 8) | (g == 0 ? (rel & 0xFFu) : prev_hi);
+        const uint32_t xd = rel ^ before;
+        const uint32_t nz = ((((xd & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | xd) >> 7) & 0x01010101u;
+        neq |= (((nz * 0x00204081u) >> 21) & 0xFu) << (4 * g);
+        prev_hi = rel >> 24;
     }
-#pragma unroll
-    for (int i = 0; i < 16; i++) pv.rel4[i >> 2] |= rel[i] << (8 * (i & 3));
+    const uint32_t rel15 = prev_hi;
 
     // window validity from the record structure: window j is valid iff j is not dead and no
     // break bit lies in (j, j + L - 1].
@@ -363,7 +388,7 @@ DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
     pv.valid16 = valid16;
     // emit(j) = valid(j) && (first(j) || (valid(j-1) && pick(j) != pick(j-1)));  A.3 step 5
     pv.emask = valid16 & (first16 | ((valid16 << 1) & neq));  // bit 0 completed in phase_emit_fix
-    s.lastpick[t] = (valid16 & 0x8000u) ? (uint32_t)(16 * t) + rel[15] : 0xFFFFFFFFu;
+    s.lastpick[t] = (valid16 & 0x8000u) ? (uint32_t)(16 * t) + rel15 : 0xFFFFFFFFu;
 }
 
 // bit 0 of the emit mask needs the last pick of the thread to the left
