@@ -46,6 +46,8 @@ SIGNATURES = {
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_extract": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint8,
                               C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
+    "dcn_extract_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint8, C.c_uint8,
+                                     C.c_uint32, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, u64p, C.c_void_p]),
     "dcn_index_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint8, C.c_float,
                                   C.c_int, u64p]),
     "dcn_index_build_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint8,
@@ -59,6 +61,7 @@ SIGNATURES = {
     "dcn_index_make_resident": (C.c_int, [C.c_void_p]),
     "dcn_stats_get": (C.c_int, [C.c_void_p, u64p]),
     "dcn_stats_reset": (C.c_int, [C.c_void_p]),
+    "dcn_stats_accumulate_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
     "dcn_last_timing": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
     "dcn_measure_random_access": (C.c_int, [C.c_void_p, u64p, f32p]),
     "dcn_launch_count": (C.c_uint64, [C.c_void_p]),

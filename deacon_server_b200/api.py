@@ -302,6 +302,25 @@ class DeaconGpu:
         m = int(out_off[n])
         return hashes[:m], pos[:m], out_off
 
+    def extract_device(self, d_bases, d_rec_off, n_rec, n_bases, d_hashes, d_pos, d_off, k=31, w=15, prefix_length=0,
+                       flavour=0, entropy_threshold=0.0, stream: int = 0) -> int:
+        """B3 on device-resident records into device CSR buffers -> number of minimizers."""
+        n = C.c_uint64()
+        self._check(self._lib.dcn_extract_device(
+            self._ctx, flavour, d_bases.data_ptr(), d_rec_off.data_ptr(), n_rec, n_bases, k, w, prefix_length, entropy_threshold,
+            d_hashes.data_ptr(), d_pos.data_ptr() if d_pos is not None else None, d_off.data_ptr(), d_hashes.numel(),
+            C.byref(n), stream))
+        return n.value
+
+    def lookup_batch_device(self, d_hashes, d_rec_off, n_rec, d_keep, d_hits, d_total, abs_threshold=2, rel_threshold=0.01,
+                            deplete=False, stream: int = 0):
+        self._check(self._lib.dcn_lookup_batch_device(self._ctx, d_hashes.data_ptr(), d_rec_off.data_ptr(), n_rec, abs_threshold,
+                                                      rel_threshold, int(deplete), d_keep.data_ptr(), d_hits.data_ptr(),
+                                                      d_total.data_ptr(), stream))
+
+    def stats_accumulate_device(self, d_rec_off, n_rec, paired, d_keep, stream: int = 0):
+        self._check(self._lib.dcn_stats_accumulate_device(self._ctx, d_rec_off.data_ptr(), n_rec, int(paired), d_keep.data_ptr(), stream))
+
     def get_minimizer_hashes_and_positions(self, seq, prefix_length, kmer_length, window_size):
         """src/filter_common.rs:211 -> (hashes, positions)."""
         bases, off = _concat([seq])

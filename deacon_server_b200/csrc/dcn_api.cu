@@ -1014,6 +1014,47 @@ static int tile_extract_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint6
     return DCN_OK;
 }
 
+int dcn_extract_device(dcn_ctx *ctx, int flavour, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                       uint64_t n_bases, uint8_t k, uint8_t w, uint32_t prefix_len, float entropy_thr, uint64_t *d_out_hashes,
+                       uint32_t *d_out_pos, uint64_t *d_out_off, uint64_t out_cap, uint64_t *n_out, void *stream) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (flavour != DCN_FLAVOUR_FILTER && flavour != DCN_FLAVOUR_INDEX) return ctx->fail(DCN_ERR_ARG, "unknown flavour");
+    if (!d_rec_off || !d_out_off || !n_out || (!d_out_hashes && out_cap)) return ctx->fail(DCN_ERR_ARG, "null pointer");
+    int rc = check_kw(ctx, k, w, flavour);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    *n_out = 0;
+    bool tiles = flavour == DCN_FLAVOUR_FILTER && k == 31 && w == 15 && n_rec > 0 && n_bases > 0 &&
+                 (reinterpret_cast<uintptr_t>(d_bases) & 15u) == 0 && !getenv("DCN_EXTRACT_GENERIC");
+    if (tiles) {   // the tile pipeline takes whole short records only: ask the device for the longest one
+        CK(ctx->plan.ensure(256));
+        BatchStats hs;
+        CK(cudaMemsetAsync(ctx->plan.p, 0, sizeof(BatchStats), st));
+        prep_stats_kernel<<<grid_for(ctx, n_rec, 256), 256, 0, st>>>(d_rec_off, 1, n_rec, ctx->plan.as<BatchStats>());
+        CK(cudaMemcpyAsync(&hs, ctx->plan.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->launches += 1;
+        tiles = hs.n_long == 0;
+    }
+    uint64_t m = 0;
+    bool written = false;
+    if (tiles)
+        rc = tile_extract_device(ctx, d_bases, d_rec_off, n_rec, n_bases, prefix_len, d_out_pos != nullptr, out_cap ? out_cap : 1, st, &m, &written);
+    else
+        rc = generic_extract_device(ctx, flavour, d_bases, d_rec_off, n_rec, k, w, flavour == DCN_FLAVOUR_FILTER ? prefix_len : 0,
+                                    entropy_thr, d_out_pos != nullptr, out_cap ? out_cap : 1, st, &m, &written);
+    if (rc) return rc;
+    *n_out = m;
+    CK(cudaMemcpyAsync(d_out_off, ctx->gx_oo.p, ((size_t)n_rec + 1) * 8, cudaMemcpyDeviceToDevice, st));
+    if (m > out_cap) return ctx->fail(DCN_ERR_OVERFLOW, "out_cap too small: *n_out holds the required capacity");
+    if (written && m) {
+        CK(cudaMemcpyAsync(d_out_hashes, ctx->gx_h.p, m * 8, cudaMemcpyDeviceToDevice, st));
+        if (d_out_pos) CK(cudaMemcpyAsync(d_out_pos, ctx->gx_p.p, m * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    return DCN_OK;
+}
+
 int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k,
                 uint8_t w, uint32_t prefix_len, float entropy_thr, uint64_t *out_hashes, uint32_t *out_pos,
                 uint64_t *out_off, uint64_t out_cap) {
@@ -1441,6 +1482,22 @@ int dcn_stats_get(dcn_ctx *ctx, uint64_t counters[6]) {
     CK(cudaMemcpy(counters, ctx->counters.p, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return DCN_OK;
 }
+int dcn_stats_accumulate_device(dcn_ctx *ctx, const uint64_t *d_rec_off, uint32_t n_rec, int paired, const uint8_t *d_keep,
+                                void *stream) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!d_rec_off || !d_keep) return ctx->fail(DCN_ERR_ARG, "null pointer");
+    const uint32_t rpu = paired ? 2u : 1u;
+    if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
+    const uint32_t n_units = n_rec / rpu;
+    if (!n_units) return DCN_OK;
+    CK(cudaSetDevice(ctx->device));
+    stats_kernel<<<grid_for(ctx, n_units, 256), 256, 0, (cudaStream_t)stream>>>(d_rec_off, rpu, n_units, d_keep,
+                                                                               ctx->counters.as<unsigned long long>());
+    ctx->launches += 1;
+    CK(cudaGetLastError());
+    return DCN_OK;
+}
+
 int dcn_stats_reset(dcn_ctx *ctx) {
     if (!ctx) return DCN_ERR_ARG;
     CK(cudaSetDevice(ctx->device));

@@ -127,6 +127,13 @@ int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t 
                 uint8_t k, uint8_t w, uint32_t prefix_len, float entropy_thr,
                 uint64_t *out_hashes, uint32_t *out_pos, uint64_t *out_off, uint64_t out_cap);
 
+/* Device-pointer form (the GPU-resident client of the batch engine: extraction -> dcn_lookup_batch_device).
+ * d_bases 16-byte aligned; *n_out = minimizers found (also when DCN_ERR_OVERFLOW is returned). */
+int dcn_extract_device(dcn_ctx *ctx, int flavour, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                       uint64_t n_bases, uint8_t k, uint8_t w, uint32_t prefix_len, float entropy_thr,
+                       uint64_t *d_out_hashes, uint32_t *d_out_pos, uint64_t *d_out_off, uint64_t out_cap,
+                       uint64_t *n_out, void *stream);
+
 /* ---- index build (config 4) ---------------------------------------------------------------------
  * Replaces index::build's extraction + FxHashSet::extend (src/index.rs:225-284): index-flavour
  * extraction of every record, radix sort + unique on the GPU.  The sorted unique key set stays in the
@@ -172,6 +179,10 @@ int dcn_index_make_resident(dcn_ctx *ctx);
  * multi-GPU driver all-reduces over NCCL. */
 int dcn_stats_get(dcn_ctx *ctx, uint64_t counters[6]);
 int dcn_stats_reset(dcn_ctx *ctx);
+/* The client of the batch engine owns the reads and therefore the counters (src/remote_filter.rs:793-835): add the
+ * counters of a batch whose decisions came from dcn_lookup_batch_device.  d_rec_off = offsets of the READS. */
+int dcn_stats_accumulate_device(dcn_ctx *ctx, const uint64_t *d_rec_off, uint32_t n_rec, int paired, const uint8_t *d_keep,
+                                void *stream);
 
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Milliseconds of the last host-pointer call: H2D copies, kernels, D2H copies (CUDA events). */

@@ -91,15 +91,35 @@ def test_reference_behavioural_known_answers_k31_w15(gpu):
     assert ran >= 6
 
 
-def test_config1_shape_and_counters(gpu):
-    """BASELINE config 1 shape, scaled: single-end 150 bp reads vs a random reference, -a 2 -r 0.01;
-    also checks the six ProcessingStats counters (src/local_filter.rs:179-187, 347-371)."""
-    from deacon_server_b200 import IndexHeader
-    g = H.random_genome(1_000_000, 1)
+def _config1_reads(g, n, seed):
+    """50 % sampled from the genome (random strand, 1 % substitutions), 50 % random,
+    0.1 % of the reads carry one N - vectorised so that the full 1 M-read size is generated in a second."""
+    rng = np.random.default_rng(seed)
+    pos = rng.integers(0, len(g) - 150, n)
+    reads = g[pos[:, None] + np.arange(150)[None, :]]
+    rc = rng.random(n) < 0.5
+    reads[rc] = H._COMP[reads[rc][:, ::-1]]
+    rnd = rng.random(n) < 0.5
+    reads[rnd] = H.ACGT[rng.integers(0, 4, (int(rnd.sum()), 150))]
+    sub = rng.random((n, 150)) < 0.01
+    sub[rnd] = False
+    reads[sub] = H.ACGT[rng.integers(0, 4, int(sub.sum()))]
+    withn = np.flatnonzero(rng.random(n) < 0.001)
+    reads[withn, rng.integers(0, 150, len(withn))] = ord("N")
+    return np.ascontiguousarray(reads.reshape(-1)), np.arange(n + 1, dtype=np.uint64) * np.uint64(150)
+
+
+def test_config1_full_size_and_counters(gpu):
+    """BASELINE config 1 at its full size: 1 M single-end 150 bp reads vs a 10 Mbp random reference indexed with
+    k=31 w=15 (index built on the GPU and checked against the oracle's), search mode, -a 2 -r 0.01; every
+    (keep, hits, total) against the oracle, and the six ProcessingStats counters (src/local_filter.rs:179-187, 347-371)."""
+    g = H.random_genome(10_000_000, 1)
+    gb, go = H.concat([g])
+    keys = gpu.index_build(gb, go, 31, 15, 0.0, make_resident=True)
     idx = O.index_build([g], 31, 15, threads=8)
-    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
-    reads = H.sample_reads(g, 100_000, 150, 2)
-    bases, off = H.concat(reads)
+    assert np.array_equal(keys, idx.keys()) and 1_200_000 < len(keys) < 1_300_000
+    bases, off = _config1_reads(g, 1_000_000, 2)
+    reads = [None] * 1_000_000
     gpu.stats_reset()
     k, h, t = gpu.filter_batch(bases, off)
     ok, oh, ot = O.filter_batch(idx, bases, off, threads=8)
@@ -107,6 +127,7 @@ def test_config1_shape_and_counters(gpu):
     st = gpu.stats()
     lens = np.diff(off).astype(np.int64)
     assert st["total_seqs"] == len(reads) and st["total_bp"] == int(lens.sum())
+    assert 0.45 < ok.mean() < 0.55 and int(oh.max()) >= 14
     assert st["output_seq_counter"] == int(ok.sum()) and st["filtered_seqs"] == len(reads) - int(ok.sum())
     assert st["output_bp"] == int(lens[ok.astype(bool)].sum()) and st["filtered_bp"] == int(lens[~ok.astype(bool)].sum())
     from deacon_server_b200 import parallel as P

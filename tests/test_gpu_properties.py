@@ -136,6 +136,38 @@ def test_extract_then_lookup_equals_filter_large(gpu, world):
     assert np.array_equal(k2, k1.cpu().numpy()) and np.array_equal(h2.view(np.int32), h1.cpu().numpy())
 
 
+def test_device_resident_client_server_chain(gpu, world):
+    """dcn_extract_device -> dcn_lookup_batch_device -> dcn_stats_accumulate_device (the GPU-resident form of the
+    remote engine, BASELINE configs[4]) == the fused local filter and its counters."""
+    dev = _dev()
+    reads = world["reads"][:2 * 1_000_000]
+    n_rec = reads.shape[0]
+    nu = n_rec // 2
+    bases = reads.reshape(-1).contiguous()
+    off = torch.arange(n_rec + 1, device=dev, dtype=torch.int64) * 150
+    st = torch.cuda.current_stream().cuda_stream
+    gpu.stats_reset()
+    k1, h1, t1 = _filter_dev(gpu, reads)
+    want = gpu.stats()
+    d_h = torch.empty(int(0.11 * bases.numel()), dtype=torch.int64, device=dev)
+    d_p = torch.empty(d_h.numel(), dtype=torch.int32, device=dev)
+    d_o = torch.empty(n_rec + 1, dtype=torch.int64, device=dev)
+    m = gpu.extract_device(bases, off, n_rec, bases.numel(), d_h, d_p, d_o, stream=st)
+    torch.cuda.synchronize()
+    assert m == int(d_o[-1]) == int(t1.sum())
+    keep = torch.zeros(nu, dtype=torch.uint8, device=dev)
+    hits = torch.zeros(nu, dtype=torch.int32, device=dev)
+    tot = torch.zeros(nu, dtype=torch.int32, device=dev)
+    gpu.lookup_batch_device(d_h, d_o[::2].contiguous(), nu, keep, hits, tot, 2, 0.01, True, stream=st)
+    gpu.stats_reset()
+    gpu.stats_accumulate_device(off, n_rec, True, keep, stream=st)
+    assert torch.equal(keep, k1) and torch.equal(hits, h1) and torch.equal(tot, t1)
+    assert gpu.stats() == want
+    from deacon_server_b200 import DeaconCudaError
+    with pytest.raises(DeaconCudaError, match="out_cap"):
+        gpu.extract_device(bases, off, n_rec, bases.numel(), d_h[:1000], d_p, d_o, stream=st)
+
+
 def test_index_set_algebra_large(gpu, world):
     genome, coff, st = world["genome"], world["coff"], world["stream"]
     n_all = world["n_keys"]
