@@ -42,6 +42,8 @@ SIGNATURES = {
     "dcn_last_pack_ms": (C.c_int, [C.c_void_p, f32p]),
     "dcn_lookup_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcn_lookup_batch_flags": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_lookup_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_double,
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_extract": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint8,

@@ -274,18 +274,73 @@ class DeaconGpu:
                                                int(deplete), keep.ctypes.data, hits.ctypes.data, total.ctypes.data))
         return keep[:n], hits[:n], total[:n]
 
-    def unpaired_should_keep(self, input_minimizers_and_positions, kmer_length, abs_threshold, rel_threshold, deplete,
-                             debug=False):
-        """src/remote_filter.rs:230-264: list of (hashes, positions, seq) -> list of (keep, hits, total, kmers)."""
-        lists = [np.asarray(rec[0], np.uint64) for rec in input_minimizers_and_positions]
+    def lookup_batch_flags(self, hashes: np.ndarray, rec_off: np.ndarray, abs_threshold=2, rel_threshold=0.01, deplete=False):
+        """lookup_batch + per-hash flag: counted hit (in the index, first of its value in the record)."""
+        hashes = np.ascontiguousarray(hashes, np.uint64)
+        rec_off = np.ascontiguousarray(rec_off, np.uint64)
+        n = len(rec_off) - 1
+        keep, hits, total = np.zeros(max(n, 1), np.uint8), np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint32)
+        flags = np.zeros(max(len(hashes), 1), np.uint8)
+        hptr = hashes.ctypes.data if len(hashes) else keep.ctypes.data
+        self._check(self._lib.dcn_lookup_batch_flags(self._ctx, hptr, rec_off.ctypes.data, n, abs_threshold, rel_threshold,
+                                                     int(deplete), keep.ctypes.data, hits.ctypes.data, total.ctypes.data,
+                                                     flags.ctypes.data))
+        return keep[:n], hits[:n], total[:n], flags[:len(hashes)]
+
+    def _should_keep(self, recs, kmer_length, abs_threshold, rel_threshold, deplete, debug, paired):
+        lists = [np.asarray(rec[0], np.uint64) for rec in recs]
         off = np.zeros(len(lists) + 1, np.uint64)
         if lists:
             off[1:] = np.cumsum([len(x) for x in lists], dtype=np.uint64)
         hashes = np.concatenate(lists) if lists and int(off[-1]) else np.zeros(0, np.uint64)
-        k, h, t = self.lookup_batch(hashes, off, abs_threshold, rel_threshold, deplete)
-        return [(bool(k[i]), int(h[i]), int(t[i]), []) for i in range(len(lists))]
+        if not debug:
+            k, h, t = self.lookup_batch(hashes, off, abs_threshold, rel_threshold, deplete)
+            return [(bool(k[i]), int(h[i]), int(t[i]), []) for i in range(len(lists))]
+        k, h, t, fl = self.lookup_batch_flags(hashes, off, abs_threshold, rel_threshold, deplete)
+        out = []
+        for i, rec in enumerate(recs):
+            kmers = []
+            positions, seqs = rec[1], rec[2]
+            for j in np.flatnonzero(fl[int(off[i]):int(off[i + 1])]):
+                if j >= len(positions):
+                    continue
+                pos = int(positions[j])
+                if paired:      # src/filter_common.rs:186-195: one sequence per hash (always empty in practice, SURVEY C.6)
+                    if j >= len(seqs):
+                        continue
+                    seq = bytes(seqs[j])
+                    if pos + kmer_length > len(seq):
+                        continue
+                else:           # src/filter_common.rs:146-151
+                    seq = bytes(seqs)
+                kmers.append(seq[pos:pos + kmer_length].decode("utf-8", "replace"))
+            out.append((bool(k[i]), int(h[i]), int(t[i]), kmers))
+        return out
 
-    paired_should_keep = unpaired_should_keep  # src/remote_filter.rs:266-301: same shape, pooled hashes
+    def unpaired_should_keep(self, input_minimizers_and_positions, kmer_length, abs_threshold, rel_threshold, deplete,
+                             debug=False):
+        """src/remote_filter.rs:230-264: list of (hashes, positions, seq) -> list of (keep, hits, total, kmers)."""
+        return self._should_keep(input_minimizers_and_positions, kmer_length, abs_threshold, rel_threshold, deplete, debug, False)
+
+    def paired_should_keep(self, input_minimizers_and_positions, kmer_length, abs_threshold, rel_threshold, deplete,
+                           debug=False):
+        """src/remote_filter.rs:266-301: list of (pooled hashes, positions, sequences) -> the same tuples."""
+        return self._should_keep(input_minimizers_and_positions, kmer_length, abs_threshold, rel_threshold, deplete, debug, True)
+
+    def should_keep_sequence_debug(self, record_id: str, seq, prefix_length=0, abs_threshold=2, rel_threshold=0.01, deplete=False):
+        """The `--debug` line of the default engine for one single-end record (src/local_filter.rs:351-363):
+        extraction (B3) + lookup with hit flags (B2) on the GPU, k-mer strings cut from the sequence on the host."""
+        hdr = self.header or IndexHeader()
+        h, p = self.get_minimizer_hashes_and_positions(seq, prefix_length, hdr.kmer_length, hdr.window_size)
+        eff = bytes(seq)
+        if prefix_length > 0 and len(eff) > prefix_length:
+            eff = eff[:prefix_length]
+        if eff.endswith(b"\n"):
+            eff = eff[:-1]
+        (keep, hits, total, kmers), = self.unpaired_should_keep([(h, p, eff)], hdr.kmer_length, abs_threshold, rel_threshold,
+                                                                 deplete, debug=True)
+        line = f"DEBUG: {record_id} hits={hits}/{total} keep={'true' if keep else 'false'} kmers=[{','.join(kmers)}]"
+        return keep, hits, total, kmers, line
 
     # ---- B3 / index build
     def extract(self, bases, rec_off, flavour=0, k=31, w=15, prefix_length=0, entropy_threshold=0.0, cap=None):

@@ -876,9 +876,9 @@ int dcn_pack_ascii(const uint8_t *bases, uint64_t n_bases, uint32_t *codes, uint
 }
 
 // ---------------------------------------------------------------------------- B2 lookup
-int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t *d_rec_off, uint32_t n_rec,
-                            uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep, uint32_t *d_hits,
-                            uint32_t *d_total, void *stream) {
+static int lookup_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t *d_rec_off, uint32_t n_rec,
+                         uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep, uint32_t *d_hits,
+                         uint32_t *d_total, uint8_t *d_flags, void *stream) {
     if (!ctx) return DCN_ERR_ARG;
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
     if (n_rec == 0) return DCN_OK;
@@ -906,7 +906,7 @@ int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64
             dd.slots = ctx->dedup.as<unsigned __int128>(); dd.mask = dedup_cap - 1;
         }
         const int grid = (int)std::min<uint64_t>(((uint64_t)n_rec * 32 + 255) / 256, (uint64_t)ctx->sm_count * 8);
-        lookup_kernel<<<grid, 256, 0, st>>>(d_hashes, d_rec_off, n_rec, tv, dd, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total);
+        lookup_kernel<<<grid, 256, 0, st>>>(d_hashes, d_rec_off, n_rec, tv, dd, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, d_flags);
         ctx->launches += 2;
         CK(cudaGetLastError());
         if (!hs.n_long) break;
@@ -920,8 +920,19 @@ int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64
     return DCN_OK;
 }
 
+int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t *d_rec_off, uint32_t n_rec,
+                            uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep, uint32_t *d_hits,
+                            uint32_t *d_total, void *stream) {
+    return lookup_device(ctx, d_hashes, d_rec_off, n_rec, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, nullptr, stream);
+}
+
 int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_off, uint32_t n_rec, uint32_t abs_thr,
                      double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    return dcn_lookup_batch_flags(ctx, hashes, rec_off, n_rec, abs_thr, rel_thr, deplete, keep, hits, total, nullptr);
+}
+
+int dcn_lookup_batch_flags(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_off, uint32_t n_rec, uint32_t abs_thr,
+                           double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total, uint8_t *hit_flags) {
     if (!ctx) return DCN_ERR_ARG;
     if (!rec_off || !keep || !hits || !total) return ctx->fail(DCN_ERR_ARG, "null pointer");
     if (n_rec == 0) return DCN_OK;
@@ -933,14 +944,16 @@ int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_o
     cudaStream_t st = s.stream;
     const size_t o_off = align_up(n_hash * 8, 8), o_tot = (size_t)n_rec * 4, o_keep = (size_t)n_rec * 8;
     CK(s.in.ensure(o_off + ((size_t)n_rec + 1) * 8));
-    CK(s.out.ensure((size_t)n_rec * 9));
+    const size_t o_flags = align_up((size_t)n_rec * 9, 16);
+    CK(s.out.ensure(o_flags + (hit_flags ? n_hash : 0)));
     uint8_t *din = s.in.as<uint8_t>(), *dout = s.out.as<uint8_t>();
     if (n_hash) CK(cudaMemcpyAsync(din, hashes, n_hash * 8, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(din + o_off, rec_off, (size_t)(n_rec + 1) * 8, cudaMemcpyHostToDevice, st));
-    int rc = dcn_lookup_batch_device(ctx, reinterpret_cast<uint64_t *>(din), reinterpret_cast<uint64_t *>(din + o_off), n_rec, abs_thr,
-                                     rel_thr, deplete, dout + o_keep, reinterpret_cast<uint32_t *>(dout),
-                                     reinterpret_cast<uint32_t *>(dout + o_tot), st);
+    int rc = lookup_device(ctx, reinterpret_cast<uint64_t *>(din), reinterpret_cast<uint64_t *>(din + o_off), n_rec, abs_thr,
+                           rel_thr, deplete, dout + o_keep, reinterpret_cast<uint32_t *>(dout),
+                           reinterpret_cast<uint32_t *>(dout + o_tot), hit_flags ? dout + o_flags : nullptr, st);
     if (rc) return rc;
+    if (hit_flags && n_hash) CK(cudaMemcpyAsync(hit_flags, dout + o_flags, n_hash, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(keep, dout + o_keep, n_rec, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(hits, dout, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(total, dout + o_tot, (size_t)n_rec * 4, cudaMemcpyDeviceToHost, st));

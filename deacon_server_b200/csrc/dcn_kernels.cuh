@@ -297,7 +297,8 @@ __global__ void extract_compact_kernel(ExtractOut xo, const uint64_t *__restrict
 __global__ void __launch_bounds__(256)
 lookup_kernel(const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ rec_off, uint32_t n_rec,
               TableView table, DedupView dd, uint32_t abs_thr, double rel_thr, int deplete,
-              uint8_t *__restrict__ keep, uint32_t *__restrict__ hits_out, uint32_t *__restrict__ total_out) {
+              uint8_t *__restrict__ keep, uint32_t *__restrict__ hits_out, uint32_t *__restrict__ total_out,
+              uint8_t *__restrict__ hit_flags) {   // optional: 1 where a hash is a counted (first, in-index) hit
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
@@ -330,6 +331,7 @@ lookup_kernel(const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ 
                 }
                 fresh = found && !dup;
             }
+            if (hit_flags && in) hit_flags[i] = fresh ? 1 : 0;
             hits += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, fresh));
         }
         if (lane == 0) {

@@ -113,6 +113,11 @@ int dcn_newline_bits(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_r
 int dcn_lookup_batch(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_off, uint32_t n_rec,
                      uint32_t abs_thr, double rel_thr, int deplete,
                      uint8_t *keep, uint32_t *hits, uint32_t *total);
+/* Same, plus hit_flags[i] = 1 where hashes[i] is a counted hit (in the index and first of its value in the record):
+ * what `--debug` needs to print the matching k-mers (sequence_matches / pair_matches, src/filter_common.rs:129-198). */
+int dcn_lookup_batch_flags(dcn_ctx *ctx, const uint64_t *hashes, const uint64_t *rec_off, uint32_t n_rec,
+                           uint32_t abs_thr, double rel_thr, int deplete,
+                           uint8_t *keep, uint32_t *hits, uint32_t *total, uint8_t *hit_flags);
 int dcn_lookup_batch_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t *d_rec_off, uint32_t n_rec,
                             uint32_t abs_thr, double rel_thr, int deplete,
                             uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream);

@@ -596,3 +596,33 @@ def test_two_contexts_are_independent(gpu):
         assert int(a[1][:1500].sum()) > 10 * int(a[1][1500:].sum()) and int(b[1][1500:].sum()) > 10 * int(b[1][:1500].sum())
     finally:
         other.close()
+
+
+def test_debug_hit_kmers_match_reference_semantics(gpu):
+    """--debug: the k-mers of the counted hits, in hash-list order (sequence_matches, src/filter_common.rs:129-155),
+    and the DEBUG line of the default engine (src/local_filter.rs:354-363)."""
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(50_000, 301)
+    idx = O.index_build([g], 31, 15)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    read = np.concatenate([g[1000:1150], g[1000:1100]])            # the second part repeats minimizers of the first
+    read[60] = ord("N")
+    hashes, pos = O.extract_filter(read, 31, 15, 0)
+    want, seen = [], set()
+    for h, p in zip(hashes, pos):                                   # the reference's loop, restated
+        if int(h) in idx and int(h) not in seen:
+            seen.add(int(h))
+            want.append(bytes(read[int(p):int(p) + 31]).decode())
+    (keep, hits, total, kmers), = gpu.unpaired_should_keep([(hashes, pos, read)], 31, 2, 0.01, False, debug=True)
+    assert kmers == want and hits == len(want) and total == len(hashes) and len(want) < len(hashes)
+    keep2, hits2, total2, kmers2, line = gpu.should_keep_sequence_debug("read1", read)
+    assert (keep2, hits2, total2, kmers2) == (keep, hits, total, kmers)
+    assert line == f"DEBUG: read1 hits={hits}/{total} keep=true kmers=[{','.join(want)}]"
+    # flags of many records at once agree with per-record oracle counts
+    reads = H.sample_reads(g, 500, 150, 302)
+    lists = [O.extract_filter(r, 31, 15, 0)[0] for r in reads]
+    off = np.zeros(len(lists) + 1, np.uint64)
+    off[1:] = np.cumsum([len(x) for x in lists], dtype=np.uint64)
+    k, h, t, fl = gpu.lookup_batch_flags(np.concatenate(lists), off)
+    ok, oh, ot = O.lookup_batch(idx, np.concatenate(lists), off)
+    assert np.array_equal(h, oh) and np.array_equal(np.add.reduceat(fl.astype(np.uint32), off[:-1].astype(np.int64))[oh > 0], oh[oh > 0])
