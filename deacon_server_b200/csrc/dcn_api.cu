@@ -430,7 +430,6 @@ dcn_ctx *dcn_ctx_create(int device) {
         g_create_error = "this library is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major * 10 + prop.minor);
         return nullptr;
     }
-    if (const char *e = getenv("DCN_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     dcn_ctx *ctx = new dcn_ctx();
     memset(ctx->kev0, 0, sizeof(ctx->kev0));
     memset(ctx->kev1, 0, sizeof(ctx->kev1));

@@ -464,13 +464,6 @@ DCN_HD Bucket load_bucket(const uint64_t *slots, uint64_t b) {
 #endif
     return r;
 }
-DCN_HD void prefetch_bucket(const uint64_t *slots, uint64_t b) {
-#ifdef __CUDA_ARCH__
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(slots + 4 * b));
-#else
-    (void)slots; (void)b;
-#endif
-}
 // continue a probe whose first bucket has been loaded
 DCN_HD bool table_contains_from(const TableView &tv, uint64_t h, uint64_t b, Bucket k) {
     if (h == DCN_EMPTY) return tv.has_empty_key != 0;
@@ -935,19 +928,28 @@ DCN_HD void filter_long_chunk(Ex &ex, TileSmem<G> &s, const FilterParams &P, con
     uint64_t origin;
     const uint32_t npicks = chunk_picks<G, FLAVOUR_FILTER, PACKED>(ex, s, filter_src(P), gs, eff_len, cd.chunk, &origin);
     ex.par([&](int t, Priv &) {
+        // two picks per thread in flight (hash A, request A, hash B, request B, then test and record A and B)
         const uint32_t rounds = (npicks + G::NT - 1) / G::NT;
-        for (uint32_t r = 0; r < rounds; r++) {
-            const uint32_t idx = r * G::NT + (uint32_t)t;
-            bool valid = false, fresh = false;
-            if (idx < npicks) {
-                uint32_t p = s.pk_pos[idx] & 0xFFFFu;
-                valid = pick_kmer_valid<G>(s, p);
-                if (valid) {
-                    uint64_t h = pick_hash<G>(s, p);
-                    if (table_contains(P.table, h)) fresh = dedup_insert(dd, h, unit);
-                }
+        for (uint32_t r = 0; r < rounds; r += 2) {
+            const uint32_t idxA = r * G::NT + (uint32_t)t, idxB = idxA + G::NT;
+            bool vA = false, vB = false;
+            uint64_t hA = 0, hB = 0, bA = 0, bB = 0;
+            Bucket kA, kB;
+            kA.k0 = kA.k1 = kA.k2 = kA.k3 = 0; kB = kA;
+            if (idxA < npicks) {
+                const uint32_t p = s.pk_pos[idxA] & 0xFFFFu;
+                vA = pick_kmer_valid<G>(s, p);
+                if (vA) { hA = pick_hash<G>(s, p); bA = table_bucket(hA, P.table.n_buckets); kA = load_bucket(P.table.slots, bA); }
             }
-            ex.tally2(t, valid, fresh, &s.wsum[8], &s.wsum[9]);
+            if (idxB < npicks) {
+                const uint32_t p = s.pk_pos[idxB] & 0xFFFFu;
+                vB = pick_kmer_valid<G>(s, p);
+                if (vB) { hB = pick_hash<G>(s, p); bB = table_bucket(hB, P.table.n_buckets); kB = load_bucket(P.table.slots, bB); }
+            }
+            const bool fA = vA && table_contains_from(P.table, hA, bA, kA) && dedup_insert(dd, hA, unit);
+            const bool fB = vB && table_contains_from(P.table, hB, bB, kB) && dedup_insert(dd, hB, unit);
+            ex.tally2(t, vA, fA, &s.wsum[8], &s.wsum[9]);
+            ex.tally2(t, vB, fB, &s.wsum[8], &s.wsum[9]);
         }
     });
     ex.par([&](int t, Priv &) {
