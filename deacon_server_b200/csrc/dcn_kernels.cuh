@@ -200,6 +200,7 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     DevExec<G> ex;
     ex.wsum = s.wsum;
     init_tables<G>((int)threadIdx.x, s);
+    init_required<G>((int)threadIdx.x, s, P.abs_thr, P.rel_thr);
     __syncthreads();
     const PlanCfg cfg = plan_make_cfg<G>(st->max_short);
     const uint32_t n_tiles = plan_num_tiles(P.n_bases - P.base0, cfg);

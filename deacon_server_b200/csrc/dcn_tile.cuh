@@ -69,6 +69,7 @@ struct alignas(16) TileSmem {
     uint16_t rec_eff[G::MAXR];        // end of the record's effective sequence (tile-local)
     uint32_t wsum[16];
     uint32_t npicks;
+    uint16_t req[256];                // required_hits(total) for total < 256 (src/filter_common.rs:84-96), filled once per CTA
 };
 template <class G>
 struct TilePriv {
@@ -102,6 +103,15 @@ DCN_HD void init_tables(int t, TileSmem<G> &s) {
     if (t < 4) {
         uint32_t c = (uint32_t)t;
         s.tsb[t].x = rotl32(nt_f(c), 15);              s.tsb[t].y = rotl32(nt_f(c ^ 2u), 15);
+    }
+}
+
+// required hits per total, so that the per-unit threshold test is a table lookup instead of f64 arithmetic
+template <class G>
+DCN_HD void init_required(int t, TileSmem<G> &s, uint32_t abs_thr, double rel_thr) {
+    for (int i = t; i < 256; i += G::NT) {
+        const uint64_t r = required_hits(abs_thr, rel_thr, (uint64_t)i);
+        s.req[i] = (uint16_t)(r > 0xFFFFull ? 0xFFFFull : r);   // hits <= total < 256: saturation keeps every comparison exact
     }
 }
 
@@ -469,7 +479,9 @@ DCN_HD bool table_contains_from(const TableView &tv, uint64_t h, uint64_t b, Buc
     if (h == DCN_EMPTY) return tv.has_empty_key != 0;
     for (;;) {
         if (k.k0 == h || k.k1 == h || k.k2 == h || k.k3 == h) return true;
-        if (k.k0 == DCN_EMPTY || k.k1 == DCN_EMPTY || k.k2 == DCN_EMPTY || k.k3 == DCN_EMPTY) return false;
+        // slots of a bucket fill in order (an insert takes the first empty slot and nothing is ever deleted):
+        // the bucket has room, i.e. the probe sequence ends here, iff its last slot is empty
+        if (k.k3 == DCN_EMPTY) return false;
         if (++b == tv.n_buckets) b = 0;
         k = load_bucket(tv.slots, b);
     }
@@ -781,7 +793,10 @@ DCN_HD bool filter_short_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, uin
                 const uint32_t gu = u_begin + u;
                 P.total[gu] = total;
                 P.hits[gu] = hits;
-                P.keep[gu] = meets_criteria(hits, total, P.abs_thr, P.rel_thr, P.deplete) ? 1 : 0;
+                bool keep;
+                if (total < 256u) { const uint32_t req = s.req[total]; keep = P.deplete ? hits < req : hits >= req; }
+                else keep = meets_criteria(hits, total, P.abs_thr, P.rel_thr, P.deplete);
+                P.keep[gu] = keep ? 1 : 0;
             }
         }
     });

@@ -183,7 +183,7 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
     memset(s, 0xA5, sizeof(*s));  // shared memory starts out as garbage on the device
     HostExec<G> ex;
     ex.smem_ptr = s; ex.smem_bytes = sizeof(*s);
-    ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); });
+    ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); init_required<G>(t, *s, abs_thr, rel_thr); });
     for (uint32_t tile = 0; tile < n_tiles; tile++)
         if (tile_first[tile] < tile_end[tile])
             filter_tile<G, PACKED, MODE_FILTER>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
