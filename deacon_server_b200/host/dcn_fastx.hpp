@@ -8,6 +8,8 @@
 #pragma once
 #include <dlfcn.h>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -365,10 +367,16 @@ struct Rec {
 };
 
 struct Chunk {
-    std::unique_ptr<char[]> buf;
-    size_t len = 0;
+    std::shared_ptr<const void> hold;   // what the record views point into: a read buffer or the file mapping
     std::vector<Rec> recs;
     bool fastq = false;
+};
+
+// a whole uncompressed file mapped read-only: its records are parsed in place, no read() copy
+struct Mapping {
+    char *p = nullptr;
+    size_t n = 0;
+    ~Mapping() { if (p) munmap(p, n); }
 };
 
 // copy the newline-free sequence of a record (record.seq() of paraseq / needletail) to dst
@@ -504,14 +512,71 @@ inline const char *sync_fasta(const char *buf, const char *from, const char *end
 // ------------------------------------------------------------------ block reader
 class FastxReader {
   public:
-    FastxReader(const std::string &path, Pool *pool, size_t block_bytes = 32u << 20)
-        : src_(open_source(path)), pool_(pool), block_(block_bytes), path_(path) {}
+    FastxReader(const std::string &path, Pool *pool, size_t block_bytes = 32u << 20) : pool_(pool), block_(block_bytes), path_(path) {
+        if (path != "-") {   // a regular uncompressed file is mapped; pipes and compressed files are streamed
+            int fd = ::open(path.c_str(), O_RDONLY);
+            if (fd < 0) throw Error("Failed to open file " + path + ": " + std::strerror(errno));
+            struct stat st;
+            if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+                void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+                if (m != MAP_FAILED) {
+                    const unsigned char *h = static_cast<const unsigned char *>(m);
+                    const size_t n = (size_t)st.st_size;
+                    const bool packed = (n >= 2 && h[0] == 0x1f && h[1] == 0x8b) || (n >= 4 && h[0] == 0x28 && h[1] == 0xb5 && h[2] == 0x2f && h[3] == 0xfd) ||
+                                        (n >= 6 && h[0] == 0xfd && h[1] == '7' && h[2] == 'z' && h[3] == 'X' && h[4] == 'Z' && h[5] == 0);
+                    if (packed) munmap(m, n);
+                    else {
+                        map_ = std::make_shared<Mapping>();
+                        map_->p = static_cast<char *>(m); map_->n = n;
+                        madvise(m, n, MADV_SEQUENTIAL);
+                    }
+                }
+            }
+            ::close(fd);
+        }
+        if (!map_) src_ = open_source(path);
+    }
 
     // Next block of whole records; nullptr at the end of the input.
-    std::shared_ptr<Chunk> next() {
+    std::shared_ptr<Chunk> next() { return map_ ? next_mapped() : next_streamed(); }
+
+    bool is_fastq() const { return fastq_; }
+
+  private:
+    void sniff(const char *p) {
+        if (format_known_) return;
+        if (*p == '@') fastq_ = true;
+        else if (*p == '>') fastq_ = false;
+        else throw Error("Failed to create reader for " + path_ + ": input is neither FASTA nor FASTQ");
+        format_known_ = true;
+    }
+    std::shared_ptr<Chunk> next_mapped() {
+        const char *base = map_->p, *file_end = base + map_->n;
+        size_t want = block_;
+        while (!finished_) {
+            const char *p = detail::skip_blank(base + pos_, file_end);
+            if (p == file_end) { finished_ = true; return nullptr; }
+            sniff(p);
+            const char *e = (size_t)(file_end - p) > want ? p + want : file_end;
+            eof_ = e == file_end;
+            auto ch = std::make_shared<Chunk>();
+            ch->hold = map_;
+            ch->fastq = fastq_;
+            const char *consumed = parse_block(p, e, *ch);
+            if (eof_) {
+                if (detail::skip_blank(consumed, e) != e) throw Error("Truncated record at the end of " + path_);
+                finished_ = true;
+            }
+            pos_ = (size_t)(consumed - base);
+            if (!ch->recs.empty()) return ch;
+            want *= 2;   // no complete record in the block (one very long sequence): look further
+        }
+        return nullptr;
+    }
+    std::shared_ptr<Chunk> next_streamed() {
         while (!finished_) {
             size_t cap = std::max(block_, carry_.size() * 2);
-            std::unique_ptr<char[]> buf(new char[cap + 1]);
+            std::shared_ptr<char> buf(new char[cap + 1], std::default_delete<char[]>());
             size_t len = carry_.size();
             if (len) memcpy(buf.get(), carry_.data(), len);
             carry_.clear();
@@ -521,20 +586,14 @@ class FastxReader {
                 len += r;
             }
             auto ch = std::make_shared<Chunk>();
-            ch->buf = std::move(buf);
-            ch->len = len;
-            const char *b = ch->buf.get(), *e = b + len;
+            ch->hold = buf;
+            const char *b = buf.get(), *e = b + len;
             const char *p = detail::skip_blank(b, e);
             if (p == e) {
                 if (eof_) { finished_ = true; return nullptr; }
                 continue;
             }
-            if (!format_known_) {
-                if (*p == '@') fastq_ = true;
-                else if (*p == '>') fastq_ = false;
-                else throw Error("Failed to create reader for " + path_ + ": input is neither FASTA nor FASTQ");
-                format_known_ = true;
-            }
+            sniff(p);
             ch->fastq = fastq_;
             const char *consumed = parse_block(p, e, *ch);
             if (eof_) {
@@ -548,9 +607,6 @@ class FastxReader {
         }
         return nullptr;
     }
-    bool is_fastq() const { return fastq_; }
-
-  private:
     const char *parse_range(const char *p, const char *stop, const char *end, bool eof, std::vector<Rec> &out) {
         while (p < stop) {
             Rec r;
@@ -599,6 +655,8 @@ class FastxReader {
     }
 
     std::unique_ptr<ByteSource> src_;
+    std::shared_ptr<Mapping> map_;
+    size_t pos_ = 0;
     Pool *pool_;
     size_t block_;
     std::string path_;

@@ -286,6 +286,12 @@ FilterSummary run_filter(const FilterConfig &cfg) {
                 paired_stdin ? "interleaved" : paired ? "paired" : "single", options.c_str());
     }
 
+    // Batches of 64 Mbp by default: large enough for full PCIe / kernel rate, small enough that pinning the three
+    // staging buffers (a few hundred MB at ~2 GB/s) does not show in the start-up time.
+    const uint64_t target_bases = std::max<uint64_t>(1, cfg.batch_mbp) * 1000000ull;
+    const size_t n_slots = cfg.devices.size() + 2;
+    std::vector<PinSlot> slots(n_slots);
+
     // one context per GPU, the index replicated in each
     std::vector<std::unique_ptr<Gpu>> gpus;
     IdxInfo idx;
@@ -304,10 +310,9 @@ FilterSummary run_filter(const FilterConfig &cfg) {
     std::unique_ptr<Sink> writer2;
     if (cfg.output2_path && cfg.input2_path) writer2 = get_writer(*cfg.output2_path, cfg.compression_level);
 
-    Pool pool((int)host_threads(cfg.threads));
-    const uint64_t target_bases = std::max<uint64_t>(1, cfg.batch_mbp) * 1000000ull;
-    const size_t n_slots = gpus.size() + 2;
-    std::vector<PinSlot> slots(n_slots);
+    // one fork-join pool per stage that uses one, so that parsing and gathering overlap instead of taking turns
+    const int T = (int)host_threads(cfg.threads);
+    Pool pool(std::max(1, T / 2)), read_pool1(std::max(1, T / 2)), read_pool2(paired && !paired_stdin ? std::max(1, T / 2) : 1);
     Channel<PinSlot *> free_slots(n_slots);
     for (auto &s : slots) free_slots.push(&s);
     Channel<std::shared_ptr<Chunk>> q_in1(3), q_in2(3);
@@ -332,11 +337,26 @@ FilterSummary run_filter(const FilterConfig &cfg) {
         };
     };
 
+    // busy seconds per stage (DCN_HOST_TIMING=1 prints them): where a file-to-file run spends its time
+    std::atomic<uint64_t> busy_ns[4] = {{0}, {0}, {0}, {0}};
+    struct Busy {
+        std::atomic<uint64_t> &acc;
+        Clock::time_point t0 = Clock::now();
+        ~Busy() { acc += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(Clock::now() - t0).count(); }
+    };
+
     // ---- stage 1: read + parse
-    auto read_stage = [&](const std::string &path, Channel<std::shared_ptr<Chunk>> &q) {
-        FastxReader reader(path, &pool);
-        while (auto ch = reader.next())
+    auto read_stage = [&](const std::string &path, Channel<std::shared_ptr<Chunk>> &q, Pool &parse_pool) {
+        FastxReader reader(path, &parse_pool);
+        for (;;) {
+            std::shared_ptr<Chunk> ch;
+            {
+                Busy t{busy_ns[0]};
+                ch = reader.next();
+            }
+            if (!ch) break;
             if (!q.push(ch)) return;
+        }
         q.done();
     };
 
@@ -348,6 +368,7 @@ FilterSummary run_filter(const FilterConfig &cfg) {
             if (b->recs.empty()) return true;
             PinSlot *slot = nullptr;
             if (!free_slots.pop(slot)) return false;
+            Busy t{busy_ns[1]};
             const size_t n = b->recs.size();
             uint64_t nb = 0;
             for (const Rec *r : b->recs) nb += r->seq_len;
@@ -431,6 +452,7 @@ FilterSummary run_filter(const FilterConfig &cfg) {
             const uint32_t n_units = paired ? n_rec / 2 : n_rec;
             b->keep.assign(n_units, 0); b->hits.assign(n_units, 0); b->total.assign(n_units, 0);
             const uint8_t *bases = reinterpret_cast<const uint8_t *>(b->pin->bases);
+            Busy t{busy_ns[2]};
             if (cfg.debug && !paired) {
                 // extraction with positions (B3) + lookup with hit flags (B2): the k-mers of the DEBUG line
                 uint64_t cap = b->n_bases / 4 + n_rec + 16;
@@ -465,6 +487,7 @@ FilterSummary run_filter(const FilterConfig &cfg) {
         std::string out1, out2, dbg;
         std::unique_ptr<Batch> in;
         auto emit = [&](Batch &b) {
+            Busy t{busy_ns[3]};
             const size_t rpu = paired ? 2 : 1;
             const size_t n_units = b.recs.size() / rpu;
             for (size_t u = 0; u < n_units; u++) {
@@ -523,9 +546,10 @@ FilterSummary run_filter(const FilterConfig &cfg) {
         }
     };
 
+    const auto filter_start = Clock::now();
     std::vector<std::thread> threads;
-    threads.emplace_back(guarded([&] { read_stage(cfg.input_path, q_in1); }));
-    if (paired && !paired_stdin) threads.emplace_back(guarded([&] { read_stage(*cfg.input2_path, q_in2); }));
+    threads.emplace_back(guarded([&] { read_stage(cfg.input_path, q_in1, read_pool1); }));
+    if (paired && !paired_stdin) threads.emplace_back(guarded([&] { read_stage(*cfg.input2_path, q_in2, read_pool2); }));
     threads.emplace_back(guarded(assemble_stage));
     for (size_t gi = 0; gi < gpus.size(); gi++) threads.emplace_back(guarded([&, gi] { gpu_stage(gi); }));
     threads.emplace_back(guarded(write_stage));
@@ -547,6 +571,10 @@ FilterSummary run_filter(const FilterConfig &cfg) {
             throw Error("internal error: the GPU's summary counters disagree with the records written");
     }
 
+    if (getenv("DCN_HOST_TIMING"))
+        fprintf(stderr, "host stages busy: read+parse %.3fs, gather %.3fs, gpu %.3fs, write %.3fs; filter phase %.3fs (%.2f Gbp/s); wall %.3fs\n",
+                busy_ns[0] * 1e-9, busy_ns[1] * 1e-9, busy_ns[2] * 1e-9, busy_ns[3] * 1e-9, seconds_since(filter_start),
+                (double)stats.total_bp / seconds_since(filter_start) / 1e9, seconds_since(start_time));
     const double total_time = seconds_since(start_time);
     const double seqs_per_sec = (double)stats.total_seqs / total_time, bp_per_sec = (double)stats.total_bp / total_time;
     auto prop = [](uint64_t a, uint64_t b) { return b > 0 ? (double)a / (double)b : 0.0; };

@@ -57,7 +57,7 @@ struct FilterConfig {
     bool debug = false;
     bool quiet = false;
     std::vector<int> devices = {0};  // extension: GPUs to shard the batches over (index replicated)
-    uint64_t batch_mbp = 256;        // extension: bases per GPU batch, in millions
+    uint64_t batch_mbp = 64;         // extension: bases per GPU batch, in millions
 
     FilterSummary execute() const;   // filter::run (src/local_filter.rs:575)
 };

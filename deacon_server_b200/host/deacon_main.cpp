@@ -42,7 +42,7 @@ const char *FILTER_USAGE =
     "      --debug                          Output sequences with minimizer hits to stderr\n"
     "  -q, --quiet                          Suppress progress reporting\n"
     "      --devices <LIST>                 GPUs to shard the batches over, e.g. 0,1,2,3 [default: 0]\n"
-    "      --batch-mbp <N>                  Bases per GPU batch, in millions [default: 256]\n";
+    "      --batch-mbp <N>                  Bases per GPU batch, in millions [default: 64]\n";
 
 const char *INDEX_USAGE =
     "Usage: deacon-b200 index <COMMAND>\n\n"
