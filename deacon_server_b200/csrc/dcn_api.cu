@@ -143,8 +143,6 @@ static size_t plan_bytes(uint64_t n_rel_bases) {
     return 64 + (size_t)n_tiles * 2 * sizeof(uint32_t);
 }
 
-static uint64_t next_pow2(uint64_t x) { uint64_t p = 1; while (p < x) p <<= 1; return p; }
-
 // src/minimizers.rs:73-121 evaluated on the host for every base-count triple: the same f32
 // operations in the same order (p = count / total; entropy -= p * log2f(p); entropy / 2 >= thr).
 // `stride` values per axis: 32 for the k = 31 tile kernel, 64 for the generic path (k <= 57).
@@ -275,7 +273,7 @@ static int enqueue_filter_generic(dcn_ctx *ctx, DevBuf &plan, DevBuf &tmp, DevBu
     tv.slots = ctx->table.as<uint64_t>(); tv.n_buckets = ctx->n_buckets; tv.has_empty_key = ctx->has_empty;
     const uint64_t n_rel = n_bases_abs - base0;
     // expected picks ~ 2 / (w + 1) per base; twice that many slots, grown x4 on overflow
-    uint64_t dedup_cap = next_pow2(std::max<uint64_t>(4096, 4 * n_rel / ((uint64_t)ctx->w + 1)));
+    uint64_t dedup_cap = std::max<uint64_t>(4096, 4 * n_rel / ((uint64_t)ctx->w + 1));
     for (int attempt = 0; attempt < 4; attempt++) {
         CK(cudaMemsetAsync(d_stats, 0, sizeof(BatchStats), st));
         CK(cudaMemsetAsync(d_hits, 0, (size_t)n_units * 4, st));
@@ -283,7 +281,7 @@ static int enqueue_filter_generic(dcn_ctx *ctx, DevBuf &plan, DevBuf &tmp, DevBu
         CK(dedup.ensure(dedup_cap * 16));
         CK(cudaMemsetAsync(dedup.p, 0, dedup_cap * 16, st));
         DedupView dd;
-        dd.slots = dedup.as<unsigned __int128>(); dd.mask = dedup_cap - 1; dd.overflow = &d_stats->overflow;
+        dd.slots = dedup.as<unsigned __int128>(); dd.cap = dedup_cap; dd.overflow = &d_stats->overflow;
         if (n_chunks) {
             generic_filter_kernel<<<grid_for(ctx, n_chunks, 128), 128, 0, st>>>(B, n_chunks, rpu, tv, dd, d_hits, d_total);
             ctx->launches += 1;
@@ -361,19 +359,20 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             CK(cudaStreamSynchronize(st));
         }
         DedupView dd;
-        dd.slots = nullptr; dd.mask = 0; dd.overflow = &d_stats->overflow;
+        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow;
         uint32_t *long_units = nullptr;
         ChunkDesc *desc = nullptr;
         if (hs.n_long) {
-            // distinct hits of long units go through a global (hash, unit) set: expected picks are
-            // ~0.13 per base; start at 0.5 entries per base and grow on overflow (exactness is kept
-            // by retrying, never by dropping)
-            if (!dedup_cap) dedup_cap = next_pow2(std::max<uint64_t>(4096, hs.long_bases / 2));
+            // distinct hits of long units go through a global (hash, unit) set: only hits are inserted and
+            // picks are ~0.13 per base, so 0.25 entries per base is at most half full; it grows x4 on
+            // overflow (exactness is kept by retrying, never by dropping).  The set is cleared per call:
+            // its size is what the long path pays up front (4 bytes per long base).
+            if (!dedup_cap) dedup_cap = std::max<uint64_t>(4096, hs.long_bases / 4);
             const uint32_t desc_cap = (uint32_t)(hs.long_bases / ChunkGeo<G31>::CSTRIDE + (uint64_t)hs.n_long * rpu + 16);
             CK(dedup.ensure(dedup_cap * 16));
             CK(longs.ensure((size_t)hs.n_long * 4 + 64 + (size_t)desc_cap * sizeof(ChunkDesc)));
             CK(cudaMemsetAsync(dedup.p, 0, dedup_cap * 16, st));
-            dd.slots = dedup.as<unsigned __int128>(); dd.mask = dedup_cap - 1;
+            dd.slots = dedup.as<unsigned __int128>(); dd.cap = dedup_cap;
             long_units = longs.as<uint32_t>();
             desc = reinterpret_cast<ChunkDesc *>(longs.as<uint8_t>() + (((size_t)hs.n_long * 4 + 63) & ~(size_t)63));
             prep_long_kernel<G31><<<pg, pb, 0, st>>>(P, d_stats, long_units, desc, desc_cap);
@@ -897,12 +896,12 @@ static int lookup_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t 
         CK(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         DedupView dd;
-        dd.slots = nullptr; dd.mask = 0; dd.overflow = &d_stats->overflow;
+        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow;
         if (hs.n_long) {
-            if (!dedup_cap) dedup_cap = next_pow2(std::max<uint64_t>(4096, hs.long_bases * 2));
+            if (!dedup_cap) dedup_cap = std::max<uint64_t>(4096, hs.long_bases * 2);
             CK(ctx->dedup.ensure(dedup_cap * 16));
             CK(cudaMemsetAsync(ctx->dedup.p, 0, dedup_cap * 16, st));
-            dd.slots = ctx->dedup.as<unsigned __int128>(); dd.mask = dedup_cap - 1;
+            dd.slots = ctx->dedup.as<unsigned __int128>(); dd.cap = dedup_cap;
         }
         const int grid = (int)std::min<uint64_t>(((uint64_t)n_rec * 32 + 255) / 256, (uint64_t)ctx->sm_count * 8);
         lookup_kernel<<<grid, 256, 0, st>>>(d_hashes, d_rec_off, n_rec, tv, dd, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, d_flags);

@@ -910,13 +910,13 @@ DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const TileSrc &src, uint64_t
 // 16-byte entries {hash, unit + 1}; all-zero = empty.  Exact: the full key is stored.
 struct DedupView {
     unsigned __int128 *slots;
-    uint64_t mask;        // capacity - 1 (power of two)
+    uint64_t cap;         // entries (any size: the start slot is mulhi(mix, cap))
     uint32_t *overflow;   // set when an insert gives up
 };
 
 DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
     const unsigned __int128 val = ((unsigned __int128)((uint64_t)unit + 1) << 64) | h;
-    uint64_t slot = (h ^ ((uint64_t)unit * 0x9E3779B97F4A7C15ULL)) & d.mask;
+    uint64_t slot = mulhi64(h ^ ((uint64_t)unit * 0x9E3779B97F4A7C15ULL), d.cap);
     for (uint32_t probes = 0; probes < 4096; probes++) {
 #ifdef __CUDA_ARCH__
         unsigned __int128 old = atomicCAS(&d.slots[slot], (unsigned __int128)0, val);
@@ -926,7 +926,7 @@ DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
 #endif
         if (old == 0) return true;
         if (old == val) return false;
-        slot = (slot + 1) & d.mask;
+        if (++slot == d.cap) slot = 0;
     }
     *d.overflow = 1;
     return false;

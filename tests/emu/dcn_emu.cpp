@@ -204,12 +204,11 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
                 for (uint32_t c = 0; c < nc; c++) desc.push_back(ChunkDesc{r, c});
             }
         }
-        uint64_t cap = 4096;
-        while (cap < long_bases / 2) cap <<= 1;
+        uint64_t cap = std::max<uint64_t>(4096, long_bases / 4);
         if (dedup_cap_override) cap = dedup_cap_override;
         std::vector<unsigned __int128> slots(cap, 0);
         uint32_t overflow = 0;
-        DedupView dd{slots.data(), cap - 1, &overflow};
+        DedupView dd{slots.data(), cap, &overflow};
         for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G, PACKED>(ex, *s, P, dd, desc[i]);
         for (uint32_t u : long_units)
             keep[u] = meets_criteria(hits[u], total[u], abs_thr, rel_thr, deplete) ? 1 : 0;
@@ -322,7 +321,7 @@ extern "C" int emu_generic_filter(const uint64_t *slots, uint64_t nb, int has_em
     while (cap < 4 * rec_off[n_rec] / ((uint64_t)w + 1)) cap <<= 1;
     std::vector<unsigned __int128> set(cap, 0);
     uint32_t overflow = 0;
-    DedupView dd{set.data(), cap - 1, &overflow};
+    DedupView dd{set.data(), cap, &overflow};
     for (uint32_t u = 0; u < n_units; u++) hits[u] = total[u] = 0;
     for (uint64_t g = rco[n_rec]; g-- > 0;) {
         uint32_t r = 0, nt = 0, nh = 0;
