@@ -240,6 +240,19 @@ def test_index_union_diff_through_the_cli(world):
     assert p.returncode == 1 and b"Incompatible headers" in p.stderr
 
 
+def test_batches_sharded_over_two_gpus_give_the_same_files(world):
+    """--devices 0,1: batches dealt to one context per GPU (index replicated), written back in input order."""
+    import deacon_server_b200 as d
+    if d.load().dcn_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    dd = world["dir"]
+    reads = H.sample_reads(world["genome"], 20000, (50, 250), 71)
+    (dd / "many.fq").write_bytes(fastq(fastq_records(reads)))
+    run("filter", "-d", "-q", dd / "ref.idx", dd / "many.fq", "-o", dd / "g1.fq", "--batch-mbp", 1, "--devices", 0)
+    run("filter", "-d", "-q", dd / "ref.idx", dd / "many.fq", "-o", dd / "g2.fq", "--batch-mbp", 1, "--devices", "0,1")
+    assert (dd / "g1.fq").read_bytes() == (dd / "g2.fq").read_bytes()
+
+
 def test_missing_index_and_unreadable_inputs(world):
     d = world["dir"]
     p = run("filter", d / "nope.idx", d / "reads.fq", check=False)
