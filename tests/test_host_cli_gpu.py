@@ -253,6 +253,28 @@ def test_batches_sharded_over_two_gpus_give_the_same_files(world):
     assert (dd / "g1.fq").read_bytes() == (dd / "g2.fq").read_bytes()
 
 
+def test_empty_input_and_a_record_larger_than_a_batch(world):
+    d = world["dir"]
+    (d / "empty.fq").write_bytes(b"")
+    run("filter", "-q", d / "ref.idx", d / "empty.fq", "-o", d / "empty_out.fq", "-s", d / "empty.json")
+    s = json.load(open(d / "empty.json"))
+    assert (d / "empty_out.fq").read_bytes() == b"" and s["seqs_in"] == 0 and s["bp_in"] == 0 and s["seqs_out_proportion"] == 0.0
+    # one 2.5 Mbp record (a stretch of the reference with 3 % substitutions) between short ones, batches of 1 Mbp
+    big = np.concatenate([world["genome"]] * 7)[:2_500_000].copy()
+    rng = np.random.default_rng(5)
+    m = rng.random(len(big)) < 0.03
+    big[m] = H.ACGT[rng.integers(0, 4, int(m.sum()))]
+    reads = H.sample_reads(world["genome"], 50, 150, 81)
+    seqs = reads[:25] + [big] + reads[25:]
+    names = [b"r%d" % i for i in range(len(seqs))]
+    (d / "mixed.fa").write_bytes(fasta(seqs, width=60, names=names))
+    run("filter", "-q", d / "ref.idx", d / "mixed.fa", "-o", d / "mixed_out.fa", "--batch-mbp", 1, "-r", 0.02)
+    recs = [(n, bytes(r), None) for n, r in zip(names, seqs)]
+    keep, hits, total = oracle_keep(world["idx"], [r[1] for r in recs], False, rel_thr=0.02)
+    assert keep[25] == 1 and total[25] > 100_000
+    assert (d / "mixed_out.fa").read_bytes() == expected_output(recs, keep, False)[0]
+
+
 def test_missing_index_and_unreadable_inputs(world):
     d = world["dir"]
     p = run("filter", d / "nope.idx", d / "reads.fq", check=False)
