@@ -167,19 +167,45 @@ struct Stats {   // ProcessingStats (src/local_filter.rs:179-187)
     uint64_t total_seqs = 0, filtered_seqs = 0, total_bp = 0, output_bp = 0, filtered_bp = 0, output_seq_counter = 0;
 };
 
-void append_record(std::string &out, const Rec &r, bool fastq, const char *seq, uint64_t counter, bool rename) {
-    // format_record_to_buffer (src/local_filter.rs:60-92)
-    if (!rename && r.verbatim) { out.append(r.raw, r.raw_len); return; }
-    out.push_back(fastq ? '@' : '>');
-    if (rename) out += std::to_string(counter);
-    else out.append(r.id, r.id_len);
-    out.push_back('\n');
-    out.append(seq, r.seq_len);
-    if (fastq) {
-        out.append("\n+\n", 3);
-        out.append(r.qual, r.seq_len);
+// format_record_to_buffer (src/local_filter.rs:60-92), split into "how many bytes" and "write them" so that the kept
+// records of a batch can be laid out by a prefix sum and written by several threads
+unsigned decimal_digits(uint64_t v) {
+    unsigned d = 1;
+    while (v >= 10) { v /= 10; d++; }
+    return d;
+}
+size_t record_size(const Rec &r, bool fastq, uint64_t counter, bool rename) {
+    if (!rename && r.verbatim) return r.raw_len;
+    const size_t id = rename ? decimal_digits(counter) : r.id_len;
+    return 1 + id + 1 + (size_t)r.seq_len + (fastq ? 3 + (size_t)r.seq_len : 0) + 1;
+}
+char *put_record(char *dst, const Rec &r, bool fastq, const char *seq, uint64_t counter, bool rename) {
+    if (!rename && r.verbatim) { memcpy(dst, r.raw, r.raw_len); return dst + r.raw_len; }
+    *dst++ = fastq ? '@' : '>';
+    if (rename) {
+        const unsigned d = decimal_digits(counter);
+        for (unsigned i = d; i-- > 0; counter /= 10) dst[i] = (char)('0' + counter % 10);
+        dst += d;
+    } else {
+        memcpy(dst, r.id, r.id_len);
+        dst += r.id_len;
     }
-    out.push_back('\n');
+    *dst++ = '\n';
+    memcpy(dst, seq, r.seq_len);
+    dst += r.seq_len;
+    if (fastq) {
+        memcpy(dst, "\n+\n", 3);
+        dst += 3;
+        memcpy(dst, r.qual, r.seq_len);
+        dst += r.seq_len;
+    }
+    *dst++ = '\n';
+    return dst;
+}
+void append_record(std::string &out, const Rec &r, bool fastq, const char *seq, uint64_t counter, bool rename) {
+    const size_t at = out.size();
+    out.resize(at + record_size(r, fastq, counter, rename));
+    put_record(&out[at], r, fastq, seq, counter, rename);
 }
 
 }  // namespace
@@ -313,6 +339,7 @@ FilterSummary run_filter(const FilterConfig &cfg) {
     // one fork-join pool per stage that uses one, so that parsing and gathering overlap instead of taking turns
     const int T = (int)host_threads(cfg.threads);
     Pool pool(std::max(1, T / 2)), read_pool1(std::max(1, T / 2)), read_pool2(paired && !paired_stdin ? std::max(1, T / 2) : 1);
+    Pool write_pool(cfg.debug ? 1 : std::max(1, T / 2));
     Channel<PinSlot *> free_slots(n_slots);
     for (auto &s : slots) free_slots.push(&s);
     Channel<std::shared_ptr<Chunk>> q_in1(3), q_in2(3);
@@ -534,10 +561,68 @@ FilterSummary run_filter(const FilterConfig &cfg) {
             if (!out1.empty()) { writer->write(out1.data(), out1.size()); out1.clear(); }
             if (!out2.empty()) { writer2->write(out2.data(), out2.size()); out2.clear(); }
         };
+        // The same without --debug, on the write pool: blocks of units are sized, laid out by a prefix sum (record
+        // counter and byte offset of each block) and formatted in parallel into one buffer per output, written once.
+        std::unique_ptr<char[]> buf1, buf2;
+        size_t cap1 = 0, cap2 = 0;
+        auto emit_parallel = [&](Batch &b) {
+            Busy t{busy_ns[3]};
+            const size_t rpu = paired ? 2 : 1;
+            const size_t n_units = b.recs.size() / rpu;
+            const size_t n_blk = std::max<size_t>(1, std::min<size_t>(n_units / 1024 + 1, (size_t)write_pool.size() * 4));
+            const size_t per = (n_units + n_blk - 1) / n_blk;
+            struct Blk { Stats st; uint64_t first_counter = 0; size_t bytes1 = 0, bytes2 = 0, off1 = 0, off2 = 0; };
+            std::vector<Blk> blk(n_blk);
+            auto walk = [&](size_t i, bool sizes, bool fill) {   // one pass over block i
+                Blk &k = blk[i];
+                uint64_t counter = k.first_counter;
+                char *d1 = fill ? buf1.get() + k.off1 : nullptr, *d2 = fill && writer2 ? buf2.get() + k.off2 : nullptr;
+                if (!fill) { k.st = Stats(); k.bytes1 = k.bytes2 = 0; }
+                for (size_t u = i * per, ue = std::min(n_units, u + per); u < ue; u++) {
+                    const Rec &r1 = *b.recs[u * rpu];
+                    const Rec *r2 = paired ? b.recs[u * rpu + 1] : nullptr;
+                    const bool keep = b.keep[u] != 0;
+                    if (!fill) {
+                        const uint64_t bp = (uint64_t)r1.seq_len + (r2 ? r2->seq_len : 0);
+                        k.st.total_seqs += rpu; k.st.total_bp += bp;
+                        if (keep) { k.st.output_bp += bp; k.st.output_seq_counter += rpu; }
+                        else { k.st.filtered_seqs += rpu; k.st.filtered_bp += bp; }
+                    }
+                    if (!keep || !(sizes || fill)) continue;
+                    const bool q1 = b.fastq[u * rpu] != 0;
+                    if (fill) d1 = put_record(d1, r1, q1, b.pin->bases + b.pin->off[u * rpu], counter + 1, cfg.rename);
+                    else k.bytes1 += record_size(r1, q1, counter + 1, cfg.rename);
+                    if (r2) {
+                        const bool q2 = b.fastq[u * rpu + 1] != 0;
+                        const char *s2 = b.pin->bases + b.pin->off[u * rpu + 1];
+                        if (fill) (writer2 ? d2 : d1) = put_record(writer2 ? d2 : d1, *r2, q2, s2, counter + 2, cfg.rename);
+                        else (writer2 ? k.bytes2 : k.bytes1) += record_size(*r2, q2, counter + 2, cfg.rename);
+                    }
+                    counter += rpu;
+                }
+            };
+            // sizes depend on the counters only when renaming: then count first, size second
+            write_pool.run(n_blk, [&](size_t i) { walk(i, !cfg.rename, false); });
+            uint64_t counter = stats.output_seq_counter;
+            for (auto &k : blk) { k.first_counter = counter; counter += k.st.output_seq_counter; }
+            if (cfg.rename) write_pool.run(n_blk, [&](size_t i) { walk(i, true, false); });
+            size_t tot1 = 0, tot2 = 0;
+            for (auto &k : blk) { k.off1 = tot1; k.off2 = tot2; tot1 += k.bytes1; tot2 += k.bytes2; }
+            if (tot1 > cap1) { cap1 = tot1 + tot1 / 4; buf1.reset(new char[cap1]); }
+            if (tot2 > cap2) { cap2 = tot2 + tot2 / 4; buf2.reset(new char[cap2]); }
+            if (tot1 + tot2) write_pool.run(n_blk, [&](size_t i) { walk(i, false, true); });
+            if (tot1) writer->write(buf1.get(), tot1);
+            if (tot2) writer2->write(buf2.get(), tot2);
+            for (auto &k : blk) {
+                stats.total_seqs += k.st.total_seqs; stats.filtered_seqs += k.st.filtered_seqs; stats.total_bp += k.st.total_bp;
+                stats.output_bp += k.st.output_bp; stats.filtered_bp += k.st.filtered_bp; stats.output_seq_counter += k.st.output_seq_counter;
+            }
+        };
         while (q_out.pop(in)) {
             pending[in->seq_no] = std::move(in);
             for (auto it = pending.find(next_no); it != pending.end(); it = pending.find(next_no)) {
-                emit(*it->second);
+                if (cfg.debug) emit(*it->second);
+                else emit_parallel(*it->second);
                 PinSlot *slot = it->second->pin;
                 pending.erase(it);
                 next_no++;
