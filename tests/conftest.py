@@ -11,6 +11,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # the product library and the host driver are built artefacts (git-ignored): build them if a fresh checkout has none
+    pkg = os.path.join(ROOT, "deacon_server_b200")
+    if not (os.path.exists(os.path.join(pkg, "libdeacon_cuda.so")) and os.path.exists(os.path.join(pkg, "deacon-b200"))):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
