@@ -356,7 +356,7 @@ def run_ours(args):
                          "int_alu_pipe_pct_of_peak": traffic.get("alu_pipe_pct_of_peak") if traffic else None,
                          "issue_slots_pct": traffic.get("issue_active_pct") if traffic else None,
                          "note": "integer-ALU bound, not HBM bound (ncu: profiles/r1_final_fused_ncu_summary.json); "
-                                 "the lookup kernel alone (dcn_lookup_batch) runs at 82 % of the random-sector ceiling: DESIGN.md"},
+                                 "the lookup kernel alone (dcn_lookup_batch) runs at 89 % of the random-sector ceiling: DESIGN.md"},
             "cpu_baseline": cpu,
             "clocks": clk,
             "counters": counters,

@@ -303,8 +303,21 @@ lookup_kernel(const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ 
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rec; r += warps) {
-        const uint64_t a = rec_off[r], b = rec_off[r + 1];
+    // Software pipeline over the warp's records, three stages deep: while record r is probed, the first 32 hashes of
+    // record r + warps and the offsets of record r + 2 warps are already requested, so a warp keeps three dependent-load
+    // chains (offsets -> hashes -> bucket) in flight.
+    uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint64_t a = 0, b = 0, h0 = 0, an = 0, bn = 0;
+    if (r < n_rec) {
+        a = rec_off[r]; b = rec_off[r + 1];
+        if (a + lane < b) h0 = hashes[a + lane];
+    }
+    if (r + warps < n_rec) { an = rec_off[r + warps]; bn = rec_off[r + warps + 1]; }
+    while (r < n_rec) {
+        const uint32_t rn = r + warps, rnn = rn + warps;
+        uint64_t ann = 0, bnn = 0, hn = 0;
+        if (rnn < n_rec) { ann = rec_off[rnn]; bnn = rec_off[rnn + 1]; }
+        if (rn < n_rec && an + lane < bn) hn = hashes[an + lane];
         const bool big = b - a > DCN_MAX_SHORT;
         uint32_t hits = 0;
         for (uint64_t base = a; base < b; base += 32) {
@@ -313,7 +326,7 @@ lookup_kernel(const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ 
             uint64_t h = 0;
             bool found = false;
             if (in) {
-                h = hashes[i];
+                h = base == a ? h0 : hashes[i];
                 found = table_contains(table, h);
             }
             bool fresh;
@@ -341,6 +354,7 @@ lookup_kernel(const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ 
             total_out[r] = (uint32_t)total;
             keep[r] = meets_criteria(hits, total, abs_thr, rel_thr, deplete) ? 1 : 0;
         }
+        r = rn; a = an; b = bn; h0 = hn; an = ann; bn = bnn;
     }
 }
 

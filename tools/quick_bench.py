@@ -22,6 +22,7 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--load", type=float, default=0.5)
 ap.add_argument("--check", type=int, default=20000)
 ap.add_argument("--no-e2e", action="store_true")
+ap.add_argument("--sweep", default="", help="e2e ingest sweep: threads:fraction,threads:fraction,... (replaces the default three settings)")
 args = ap.parse_args()
 
 dev = torch.device("cuda:0")
@@ -111,7 +112,8 @@ hh = torch.zeros(NP, dtype=torch.int32).pin_memory()
 ht = torch.zeros(NP, dtype=torch.int32).pin_memory()
 def e2e():
     gpu.filter_batch_ptr(hbases.data_ptr(), hoff.data_ptr(), NR, True, 0, 2, 0.01, True, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
-for threads, fr in ((0, -1), (16, 1.0), (16, -1)):
+settings = [(int(a), float(b)) for a, b in (x.split(":") for x in args.sweep.split(","))] if args.sweep else [(0, -1), (16, 1.0), (16, -1)]
+for threads, fr in settings:
     gpu.host_pack_threads(threads)
     gpu.host_pack_fraction(fr)
     e2e()
