@@ -65,6 +65,7 @@ SIGNATURES = {
     "dcn_stats_reset": (C.c_int, [C.c_void_p]),
     "dcn_stats_accumulate_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]),
     "dcn_last_timing": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
+    "dcn_last_transfer_bytes": (C.c_int, [C.c_void_p, u64p, u64p]),
     "dcn_measure_random_access": (C.c_int, [C.c_void_p, u64p, f32p]),
     "dcn_launch_count": (C.c_uint64, [C.c_void_p]),
     "dcn_fused_time_take": (C.c_int, [C.c_void_p, f32p, u32p]),

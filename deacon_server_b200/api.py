@@ -474,6 +474,12 @@ class DeaconGpu:
         self._check(self._lib.dcn_last_timing(self._ctx, C.byref(a), C.byref(b), C.byref(c)))
         return {"h2d_ms": a.value, "kernel_ms": b.value, "d2h_ms": c.value}
 
+    def last_transfer_bytes(self):
+        """(h2d, d2h) bytes the last host-pointer filter call moved over PCIe."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._check(self._lib.dcn_last_transfer_bytes(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def last_pack_ms(self) -> float:
         a = C.c_float()
         self._check(self._lib.dcn_last_pack_ms(self._ctx, C.byref(a)))

@@ -358,6 +358,12 @@ lookup_kernel(const uint64_t *__restrict__ hashes, const uint64_t *__restrict__ 
     }
 }
 
+// ------------------------------------------------------------------ record offsets of a chunk of equal-length records
+// (host ingest: such a chunk's rec_off is first + i * len, so it is written here instead of being copied over PCIe)
+__global__ void uniform_offsets_kernel(uint64_t *__restrict__ off, uint32_t n, uint64_t first, uint64_t len) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) off[i] = first + (uint64_t)i * len;
+}
+
 // ------------------------------------------------------------------ summary counters (a13)
 // src/local_filter.rs:347-371 (single) / 488-525 (pair): seqs and bp in / kept / filtered.
 __global__ void stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,

@@ -192,6 +192,10 @@ int dcn_stats_accumulate_device(dcn_ctx *ctx, const uint64_t *d_rec_off, uint32_
 /* ---- measurement helpers ------------------------------------------------------------------------
  * Milliseconds of the last host-pointer call: H2D copies, kernels, D2H copies (CUDA events). */
 int dcn_last_timing(dcn_ctx *ctx, float *h2d_ms, float *kernel_ms, float *d2h_ms);
+/* Bytes the last dcn_filter_batch / dcn_filter_batch_packed call copied over PCIe in each direction.  Less than
+ * the caller's buffers when a chunk's records all have one length: its rec_off is then an arithmetic sequence
+ * and is written by a kernel on the device instead of being copied (8 bytes per record saved). */
+int dcn_last_transfer_bytes(dcn_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 /* Host packing time (ms, wall clock) of the last dcn_filter_batch call; 0 when it shipped ASCII. */
 int dcn_last_pack_ms(dcn_ctx *ctx, float *pack_ms);
 /* Random 32-byte-sector read ceiling over the resident table: about *n_probes independent loads;

@@ -154,6 +154,42 @@ def test_chunked_pipeline_many_chunks(gpu, monkeypatch):
     assert np.array_equal(t, ot) and np.array_equal(h, oh) and np.array_equal(k, ok)
 
 
+def test_equal_length_chunks_do_not_ship_their_offsets(gpu):
+    """Host ingest: a chunk whose records all have one length gets its rec_off written on the device (arithmetic sequence)
+    instead of copied; one odd record anywhere in the chunk switches that chunk back to the copy.  Results never change."""
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(300_000, 15)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    gpu.host_pack_threads(0)   # ASCII route: the bytes moved are the bases plus whatever offsets are shipped
+    try:
+        rng = np.random.default_rng(16)
+        n = 500_000                                                   # 75 MB: three chunks
+        pos = rng.integers(0, len(g) - 151, n)
+        reads = g[(pos[:, None] + np.arange(150)[None, :])]
+        bases = reads.reshape(-1).copy()
+        off = np.arange(n + 1, dtype=np.uint64) * np.uint64(150)
+        for paired in (False, True):
+            k, h, t = gpu.filter_batch(bases, off, paired=paired)
+            ok, oh, ot = O.filter_batch(idx, bases, off, paired=paired, threads=8)
+            assert np.array_equal(t, ot) and np.array_equal(h, oh) and np.array_equal(k, ok)
+            h2d, d2h = gpu.last_transfer_bytes()
+            assert len(bases) <= h2d < len(bases) + 64 and d2h == 9 * len(k)
+        # one 151-base record in the last chunk: only that chunk ships its offsets
+        lens = np.full(n, 150, np.uint64)
+        lens[n - 7] = 151
+        off2 = np.zeros(n + 1, np.uint64)
+        off2[1:] = np.cumsum(lens)
+        bases2 = np.insert(bases, int(off2[n - 7]) + 150, ord("A"))
+        k, h, t = gpu.filter_batch(bases2, off2)
+        ok, oh, ot = O.filter_batch(idx, bases2, off2, threads=8)
+        assert np.array_equal(t, ot) and np.array_equal(h, oh) and np.array_equal(k, ok)
+        h2d, _ = gpu.last_transfer_bytes()
+        assert len(bases2) + 8 * 10_000 < h2d < len(bases2) + 8 * (n + 1)
+    finally:
+        gpu.host_pack_threads(4)
+
+
 def test_device_pointer_api_matches_host_api(gpu):
     import torch
     from deacon_server_b200 import IndexHeader
