@@ -69,6 +69,12 @@ struct Slot {  // one stage of the host-pointer pipeline
     uint32_t u0 = 0, u1 = 0;
 };
 
+struct PackBlob {   // pinned staging of one host-packed chunk (filter_pipeline: two per packer thread)
+    HostBuf buf;
+    cudaEvent_t h2d_done = nullptr;
+    enum State { FREE, READY, ENQUEUED } state = FREE;
+};
+
 // what the fused kernel reads: ASCII bytes, or the host-packed form (dcn_host_pack.h)
 struct FilterInput {
     const uint8_t *bases = nullptr;
@@ -103,11 +109,11 @@ struct dcn_ctx {
     DevBuf ws_table, ws_flags;    // scratch table for set difference
     // generic (k, w) path and B3 extraction: staging, chunk plan, CSR outputs
     DevBuf gx_bases, gx_off, gx_rc, gx_cc, gx_tmp, gx_h, gx_p, gx_oo, gx_entropy;
-    static const int NSLOT = 3;
+    static const int NSLOT = 4;
     Slot slot[NSLOT];
     // host ingest (packing) pool; pack_threads = 0 ships ASCII over PCIe instead
     int pack_threads = -1;   // -1: decide at first use (DCN_PACK_THREADS or min(hardware threads, 16))
-    std::unique_ptr<HostPool> pool;
+    std::vector<PackBlob> blobs;
     float t_pack = 0;
     // Ingest: a chunk is either packed by the host pool (CPU reads 1 B/bp, PCIe carries 0.4 B/bp) or shipped
     // as ASCII (PCIe carries 1 B/bp, no CPU work); `pack_fraction` of the chunks take the first route.
@@ -473,7 +479,11 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     ctx->gx_bases.release(); ctx->gx_off.release(); ctx->gx_rc.release(); ctx->gx_cc.release(); ctx->gx_tmp.release();
     ctx->gx_h.release(); ctx->gx_p.release(); ctx->gx_oo.release(); ctx->gx_entropy.release();
     ctx->ws_table.release(); ctx->ws_flags.release();
-    ctx->pool.reset();
+    for (auto &bl : ctx->blobs) {
+        bl.buf.release();
+        if (bl.h2d_done) cudaEventDestroy(bl.h2d_done);
+    }
+    ctx->blobs.clear();
     for (int i = 0; i < dcn_ctx::NSLOT; i++) {
         Slot &s = ctx->slot[i];
         s.in.release(); s.out.release(); s.plan.release(); s.longs.release(); s.dedup.release();
@@ -589,29 +599,81 @@ int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static int pack_pool(dcn_ctx *ctx) {   // -> threads used for host packing (0 = ship ASCII)
+static int pack_threads_of(dcn_ctx *ctx) {   // -> host threads available for packing (0 = ship ASCII only)
     if (ctx->pack_threads < 0) {
         const char *e = getenv("DCN_PACK_THREADS");
-        int n = e ? atoi(e) : (int)std::min<unsigned>(std::thread::hardware_concurrency(), 16u);
+        // default: leave four hardware threads to the caller, the enqueueing thread and the driver's own threads
+        // (measured on a 16-vCPU box: 12 packers 61 Gbp/s end to end, 16 packers 46)
+        const int hc = (int)std::thread::hardware_concurrency();
+        int n = e ? atoi(e) : std::min(std::max(hc - 4, 1), 16);
         ctx->pack_threads = std::max(0, std::min(n, 256));
     }
-    if (ctx->pack_threads > 0 && (!ctx->pool || ctx->pool->size() != ctx->pack_threads))
-        ctx->pool.reset(new HostPool(ctx->pack_threads));
     return ctx->pack_threads;
 }
 
-// Host-pointer form (SURVEY.md 8f.1 "pinned double-buffered streams"): unit-aligned chunks go
-// through NSLOT pipeline stages, each with its own stream.  For the default index parameters a
-// chunk is first packed by the host pool (2-bit codes + non-ACGT bits, plus its record offsets and
-// newline flags) into ONE pinned staging blob, so 0.375 + ~0.06 B/bp cross PCIe in a single copy
-// while earlier chunks are still in their kernels; other (k, w) ship the ASCII bytes.  Results come
-// back through a pinned blob and are scattered into the caller's arrays when the stage is reused.
+// Host-pointer form (SURVEY.md 8f.1 "pinned double-buffered streams"): unit-aligned chunks of 32 MB go through
+// NSLOT pipeline stages, each with its own stream; results come back through a pinned blob and are scattered into
+// the caller's arrays when the stage is reused.  A chunk reaches the GPU by one of two routes:
+//   ASCII   the bytes are copied as they are (1 B/bp over PCIe, no CPU work), the GPU converts them;
+//   packed  a host thread packs the chunk (2-bit codes + non-ACGT bits, plus record offsets and newline flags:
+//           what PackedSeqVec::from_ascii and the mask loop of src/filter_common.rs:238-258 compute) into one
+//           pinned blob and 0.43 B/bp cross PCIe.
+// The copy engine and the host cores work at the same time (measured on the round-1 box: a pinned H2D stream keeps
+// 55 GB/s beside 12 packing threads doing 64 GB/s, tools/hybrid_probe.py), so with pinned caller buffers the two
+// routes share a batch dynamically: the enqueueing thread takes ASCII chunks from the front of the chunk list at
+// the pace of the link, persistent-for-the-call packer threads take whole chunks from its back, and a packed chunk
+// is enqueued as soon as it is ready (chunks may complete in any order: results are scattered by unit index).
+// Pageable caller buffers take the packed route only (a direct copy would be staged by the driver at ~8 GB/s).
 struct HostSrc {   // caller's host buffers: ASCII, or already packed (dcn_filter_batch_packed)
     const uint8_t *bases = nullptr;
     const uint32_t *codes = nullptr;
     const uint16_t *inv = nullptr;
     const uint32_t *nl = nullptr;
 };
+
+namespace {
+
+struct ChunkPlan {
+    uint32_t u0, u1, nr, nu;
+    uint64_t a0, b1, nb;   // chunk origin (64-aligned), end, bases covered
+    // blob layouts
+    size_t n_words, o_inv, o_off_p, o_nl, in_packed, o_off_a, in_ascii, out_bytes;
+};
+
+struct ChunkStats {
+    BatchStats st;
+    bool uniform;        // every record has length rec_len0: rec_off is first + i * rec_len0
+    uint64_t rec_len0;
+};
+
+// unit-length statistics of a chunk (what prep_stats_kernel computes on the device) and the equal-length test
+static ChunkStats chunk_stats(const uint64_t *off0, uint32_t nu, uint32_t rpu) {
+    ChunkStats c;
+    memset(&c.st, 0, sizeof(c.st));
+    const uint64_t nr = (uint64_t)nu * rpu;
+    c.rec_len0 = nr ? off0[1] - off0[0] : 0;
+    // a branch-free pass the compiler vectorises, left at the first block with a mismatch
+    uint64_t diff = 0;
+    for (uint64_t r = 0; r < nr && !diff;) {
+        const uint64_t blk_end = std::min(nr, r + 2048);
+        for (; r < blk_end; r++) diff |= (off0[r + 1] - off0[r]) ^ c.rec_len0;
+    }
+    c.uniform = diff == 0 && nr > 0;
+    if (c.uniform) {   // the unit statistics follow from the one length
+        const uint64_t len = c.rec_len0 * rpu;
+        if (len > DCN_MAX_SHORT) { c.st.n_long = nu; c.st.long_bases = len * nu; }
+        else c.st.max_short = (uint32_t)len;
+        return c;
+    }
+    for (uint32_t u = 0; u < nu; u++) {
+        const uint64_t len = off0[(uint64_t)(u + 1) * rpu] - off0[(uint64_t)u * rpu];
+        if (len > DCN_MAX_SHORT) { c.st.n_long++; c.st.long_bases += len; }
+        else if ((uint32_t)len > c.st.max_short) c.st.max_short = (uint32_t)len;
+    }
+    return c;
+}
+
+}  // namespace
 
 static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec_off, uint32_t n_rec, int paired,
                            uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
@@ -634,23 +696,59 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         if (mb < 1) mb = 1;
         return mb << 20;
     }();
-    const bool can_pack = !prepacked && ctx->k == 31 && ctx->w == 15 && pack_pool(ctx) > 0;
-    double frac = 0;   // fraction of chunks the host packs
-    if (can_pack) {
+
+    // ---- routes
+    int n_packers = 0;           // host threads packing atoms
+    bool ascii_route = true;     // the enqueueing thread may ship chunks as ASCII
+    double pack_share = 0;       // share of the atoms the packers may take
+    const uint64_t total_bases = rec_off[(uint64_t)n_units * rpu] - rec_off[0];
+    if (!prepacked && ctx->k == 31 && ctx->w == 15 && pack_threads_of(ctx) > 0) {
         cudaPointerAttributes pa;
         const bool pinned = cudaPointerGetAttributes(&pa, bases) == cudaSuccess && pa.type == cudaMemoryTypeHost;
         cudaGetLastError();
         static const double env_frac = []() { const char *e = getenv("DCN_PACK_FRACTION"); return e ? atof(e) : -1.0; }();
         const double forced = ctx->pack_fraction >= 0 ? ctx->pack_fraction : env_frac;
-        if (forced >= 0) frac = std::min(1.0, forced);
-        // Measured on the round-1 box (16 vCPUs, ~60 GB/s of host memory bandwidth, PCIe 5 x16 at 53 GB/s): every
-        // ASCII byte has to leave host memory once, read either by the copy engine or by a packing core, so for
-        // pinned buffers packing buys nothing there (50 Gbp/s either way) and the cores stay free for the caller.
-        // Pageable buffers are different: a direct copy is staged by the driver at ~8 GB/s, the pool reaches ~25.
-        else frac = pinned ? 0.0 : 1.0;
+        if (forced >= 0) { pack_share = std::min(1.0, forced); ascii_route = pack_share < 1.0; }
+        else if (!pinned) { pack_share = 1.0; ascii_route = false; }
+        else pack_share = total_bases >= 6 * chunk_bases ? 1.0 : 0.0;   // dynamic split; not worth the threads for a few chunks
+        if (pack_share > 0) n_packers = pack_threads_of(ctx);
     }
-    double frac_acc = 0.5;
-    uint64_t packed_bytes = 0;
+
+    // ---- plan: the batch is cut into unit-aligned ATOMS.  The ASCII route ships up to `atoms_per_chunk` consecutive
+    // atoms as one chunk (one copy, one kernel); a packer thread takes one atom at a time, so the two routes meet with
+    // at most one atom's packing time (~1.5 ms) of imbalance instead of a chunk's.
+    const uint32_t atoms_per_chunk = n_packers > 0 ? 4 : 1;
+    const uint64_t atom_bases = std::max<uint64_t>(chunk_bases / atoms_per_chunk, 1);
+    std::vector<uint32_t> atom_u;   // atom i covers units [atom_u[i], atom_u[i + 1])
+    atom_u.push_back(0);
+    for (uint32_t u0 = 0; u0 < n_units;) {
+        // largest u1 with rec_off[u1*rpu] - rec_off[u0*rpu] <= atom_bases (at least one unit)
+        const uint64_t b0 = rec_off[(uint64_t)u0 * rpu];
+        uint32_t lo = u0 + 1, hi = n_units;
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo + 1) / 2;
+            if (rec_off[(uint64_t)mid * rpu] - b0 <= atom_bases) lo = mid; else hi = mid - 1;
+        }
+        atom_u.push_back(lo);
+        u0 = lo;
+    }
+    const int n_atoms = (int)atom_u.size() - 1;
+    auto make_chunk = [&](int a_first, int a_last) {   // atoms [a_first, a_last)
+        ChunkPlan c;
+        c.u0 = atom_u[(size_t)a_first]; c.u1 = atom_u[(size_t)a_last]; c.nu = c.u1 - c.u0; c.nr = c.nu * rpu;
+        c.b1 = rec_off[(uint64_t)c.u1 * rpu];
+        c.a0 = rec_off[(uint64_t)c.u0 * rpu] & ~63ull;   // chunk origin: keeps 16-byte loads and 32-base pack blocks aligned
+        c.nb = c.b1 - c.a0;
+        c.n_words = 2 * ((c.nb + 31) / 32);
+        c.o_inv = c.n_words * 4; c.o_off_p = align_up(c.o_inv + c.n_words * 2, 8); c.o_nl = c.o_off_p + ((size_t)c.nr + 1) * 8;
+        c.in_packed = c.o_nl + align_up(((size_t)c.nr + 31) / 32 * 4, 8);
+        c.o_off_a = align_up(c.nb + 16, 16); c.in_ascii = c.o_off_a + ((size_t)c.nr + 1) * 8;
+        c.out_bytes = (size_t)c.nu * 9;
+        return c;
+    };
+    const int pack_budget = (int)std::min<double>(n_atoms, pack_share * n_atoms + 0.5);   // atoms the packers may take
+    n_packers = std::min(n_packers, pack_budget);
+    if (n_packers == 0) ascii_route = true;
 
     ctx->t_h2d = ctx->t_kernel = ctx->t_d2h = ctx->t_pack = 0;
     ctx->bytes_h2d = ctx->bytes_d2h = 0;
@@ -671,192 +769,233 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         return DCN_OK;
     };
 
-    uint32_t u0 = 0;
-    int which = 0;
-    int rc = DCN_OK;
-    while (u0 < n_units) {
-        // largest u1 with rec_off[u1*rpu] - rec_off[u0*rpu] <= chunk_bases (at least one unit)
-        const uint64_t b0 = rec_off[(uint64_t)u0 * rpu];
-        uint32_t lo = u0 + 1, hi = n_units;
-        while (lo < hi) {
-            uint32_t mid = lo + (hi - lo + 1) / 2;
-            if (rec_off[(uint64_t)mid * rpu] - b0 <= chunk_bases) lo = mid; else hi = mid - 1;
-        }
-        const uint32_t u1 = lo;
-        const uint64_t b1 = rec_off[(uint64_t)u1 * rpu];
-        const uint64_t a0 = b0 & ~63ull;   // chunk origin: keeps 16-byte loads and 32-base pack blocks aligned
-        const uint64_t nb = b1 - a0;
-        const uint32_t nr = (u1 - u0) * rpu, nu = u1 - u0;
-        const uint64_t *off0 = rec_off + (uint64_t)u0 * rpu;
+    // ---- shared state of the two routes
+    std::mutex m;
+    std::condition_variable cv;
+    int head = 0, tail = n_atoms, taken_by_packers = 0;   // ASCII takes atoms from head, a packer atom --tail
+    struct Ready { int a0, a1, blob; ChunkStats cs; int err; };   // atoms [a0, a1); blob < 0: not packed
+    std::vector<Ready> ready;
+    bool abort_packers = false;
+    uint64_t packed_bytes = 0;
+    if ((int)ctx->blobs.size() < 2 * n_packers) ctx->blobs.resize((size_t)2 * n_packers);
+    const auto t_pack0 = std::chrono::steady_clock::now();
+    double pack_busy_ms = 0, pack_wait_ms = 0;   // summed over the packer threads
+    double enq_retire_ms = 0, enq_ready_ms = 0;  // the enqueueing thread's waits: for a stage, for a packed atom
+    static const bool trace = getenv("DCN_HOST_TRACE") != nullptr;
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
 
-        bool packed = false;
-        if (frac > 0) {   // error diffusion: the packed share of the chunks approaches `frac`
-            frac_acc += frac;
-            if (frac_acc >= 1.0) { packed = true; frac_acc -= 1.0; }
+    auto packer = [&](int t) {
+        cudaSetDevice(ctx->device);
+        int flip = 0;
+        for (;;) {
+            int ci;
+            {
+                std::lock_guard<std::mutex> g(m);
+                if (abort_packers || tail <= head || taken_by_packers >= pack_budget) return;
+                ci = --tail; taken_by_packers++;
+            }
+            const ChunkPlan c = make_chunk(ci, ci + 1);
+            const int bi = 2 * t + flip;
+            flip ^= 1;
+            PackBlob &bl = ctx->blobs[(size_t)bi];
+            Ready r{ci, ci + 1, bi, ChunkStats(), 0};
+            const auto tw0 = std::chrono::steady_clock::now();
+            {   // the blob's previous copy must have left the host
+                std::unique_lock<std::mutex> g(m);
+                cv.wait(g, [&] { return bl.state != PackBlob::READY || abort_packers; });
+                if (abort_packers) return;
+            }
+            if (bl.state == PackBlob::ENQUEUED) cudaEventSynchronize(bl.h2d_done);
+            bl.state = PackBlob::FREE;
+            const auto t0 = std::chrono::steady_clock::now();
+            const double wait_ms = std::chrono::duration<double, std::milli>(t0 - tw0).count();
+            if (bl.buf.ensure(c.in_packed) != cudaSuccess || (!bl.h2d_done && cudaEventCreateWithFlags(&bl.h2d_done, cudaEventDisableTiming) != cudaSuccess)) {
+                r.err = 1;
+            } else {
+                uint8_t *hin = bl.buf.as<uint8_t>();
+                const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
+                r.cs = chunk_stats(off0, c.nu, rpu);
+                if (!r.cs.uniform) memcpy(hin + c.o_off_p, off0, ((size_t)c.nr + 1) * 8);
+                uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
+                uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + c.o_inv);
+                uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + c.o_nl);
+                // Packing and the newline flags advance together, 1024 records at a time, so the flag loop finds the
+                // records' last bytes in the core's cache instead of missing once per record after the whole atom.
+                uint64_t cur = 0;   // bases [a0, a0 + cur) are packed; a multiple of 64 until the last piece
+                for (uint32_t rg = 0; rg < c.nr || cur < c.nb; rg += 1024) {
+                    const uint32_t rg_end = (uint32_t)std::min<uint64_t>((uint64_t)rg + 1024, c.nr);
+                    const uint64_t upto = rg_end >= c.nr ? c.nb : ((off0[rg_end] - c.a0) & ~63ull);
+                    if (upto > cur) {
+                        pack_ascii(bases + c.a0 + cur, upto - cur, h_codes + cur / 16, h_inv + cur / 16, 1);
+                        cur = upto;
+                    }
+                    for (uint32_t rw = rg; rw < rg_end; rw += 32) {     // newline flags, 32 records per word
+                        uint32_t bits = 0;
+                        for (uint32_t q = rw; q < std::min(rw + 32, rg_end); q++) {
+                            const uint64_t len = off0[q + 1] - off0[q];
+                            if (len < (uint64_t)ctx->k) continue;                                          // src/filter_common.rs:217-219
+                            const uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;   // :222-226
+                            if (bases[off0[q] + n - 1] == (uint8_t)'\n') bits |= 1u << (q - rw);           // :229
+                        }
+                        h_nl[rw / 32] = bits;
+                    }
+                }
+            }
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            {
+                std::lock_guard<std::mutex> g(m);
+                bl.state = PackBlob::READY;
+                ready.push_back(r);
+                packed_bytes += c.nb;
+                pack_busy_ms += ms;
+                pack_wait_ms += wait_ms;
+            }
+            cv.notify_all();
         }
+    };
+    std::vector<std::thread> packers;
+    for (int t = 0; t < n_packers; t++) packers.emplace_back(packer, t);
+    auto stop_packers = [&] {
+        {
+            std::lock_guard<std::mutex> g(m);
+            abort_packers = true;
+        }
+        cv.notify_all();
+        for (auto &t : packers) t.join();
+        packers.clear();
+    };
+    struct JoinOnExit {   // every return path (the CK macro returns) must leave no thread behind
+        std::function<void()> f;
+        ~JoinOnExit() { f(); }
+    } join_on_exit{stop_packers};
+
+    // ---- the enqueueing thread
+    int which = 0, rc = DCN_OK, processed = 0;
+    while (processed < n_atoms && rc == DCN_OK) {
+        Ready r{-1, -1, -1, ChunkStats(), 0};
+        {
+            std::unique_lock<std::mutex> g(m);
+            for (;;) {
+                if (!ready.empty()) { r = ready.back(); ready.pop_back(); break; }
+                // ASCII route, or the packers' budget is used up and the rest goes as ASCII
+                if ((ascii_route || taken_by_packers >= pack_budget) && head < tail) {
+                    r.a0 = head;
+                    head = r.a1 = std::min<int>(tail, head + (int)atoms_per_chunk);
+                    break;
+                }
+                const double w0 = now_ms();
+                cv.wait(g);   // only packed atoms are left and none is ready yet
+                enq_ready_ms += now_ms() - w0;
+            }
+        }
+        if (r.err) { rc = ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed in a packer thread"); break; }
+        const ChunkPlan c = make_chunk(r.a0, r.a1);
+        const bool packed = r.blob >= 0;
+        const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
         Slot &s = ctx->slot[which];
+        const double w0 = now_ms();
         if ((rc = retire(s))) break;  // the stage's previous chunk (NSLOT chunks ago)
-        // blob layouts
-        const size_t n_words = 2 * ((nb + 31) / 32);
-        const size_t o_inv = n_words * 4, o_off_p = align_up(o_inv + n_words * 2, 8), o_nl = o_off_p + ((size_t)nr + 1) * 8;
-        const size_t in_packed = o_nl + align_up(((size_t)nr + 31) / 32 * 4, 8);
-        const size_t o_off_a = align_up(nb + 16, 16), in_ascii = o_off_a + ((size_t)nr + 1) * 8;
-        const size_t out_bytes = (size_t)nu * 9;
-        if (s.in.ensure((packed || prepacked) ? in_packed + 8 : in_ascii) != cudaSuccess || s.out.ensure(out_bytes) != cudaSuccess ||
-            s.h_out.ensure(out_bytes) != cudaSuccess || (packed && s.h_in.ensure(in_packed) != cudaSuccess)) {
+        enq_retire_ms += now_ms() - w0;
+        if (s.in.ensure((packed || prepacked) ? c.in_packed + 8 : c.in_ascii) != cudaSuccess || s.out.ensure(c.out_bytes) != cudaSuccess ||
+            s.h_out.ensure(c.out_bytes) != cudaSuccess) {
             rc = ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
             break;
         }
         uint8_t *din = s.in.as<uint8_t>();
         FilterInput in;
         const uint64_t *d_off;
-        // unit-length statistics of the chunk (what prep_stats_kernel computes on the device)
-        const int T = ctx->pool ? ctx->pool->size() * 2 : 1;
-        std::vector<BatchStats> part((size_t)T);
-        memset(part.data(), 0, sizeof(BatchStats) * (size_t)T);
-        // ... and whether every record of the chunk has the same length: then the offsets are an arithmetic sequence
-        // and are written on the device instead of crossing PCIe (8 bytes per record: 5 % of an ASCII chunk of
-        // 150-base reads, 12 % of a packed one)
-        const uint64_t rec_len0 = nr ? off0[1] - off0[0] : 0;
-        std::vector<uint8_t> part_uniform((size_t)T, 1);
-        const uint32_t upiece = (nu + (uint32_t)T - 1) / (uint32_t)T;
-        auto stats_task = [&](int i) {
-            BatchStats &b = part[(size_t)i];
-            const uint32_t ua = std::min<uint64_t>((uint64_t)i * upiece, nu), ub = std::min<uint64_t>((uint64_t)ua + upiece, nu);
-            // equal-length test first: a branch-free pass the compiler vectorises, left at the first block with a mismatch
-            uint64_t diff = 0;
-            for (uint64_t r = (uint64_t)ua * rpu, r_end = (uint64_t)ub * rpu; r < r_end && !diff;) {
-                const uint64_t blk_end = std::min(r_end, r + 2048);
-                for (; r < blk_end; r++) diff |= (off0[r + 1] - off0[r]) ^ rec_len0;
-            }
-            part_uniform[(size_t)i] = diff == 0 ? 1 : 0;
-            if (diff == 0) {   // the unit statistics follow from the one length
-                const uint64_t len = rec_len0 * rpu;
-                if (ub > ua) {
-                    if (len > DCN_MAX_SHORT) { b.n_long = ub - ua; b.long_bases = len * (ub - ua); }
-                    else b.max_short = (uint32_t)len;
-                }
-                return;
-            }
-            for (uint32_t u = ua; u < ub; u++) {
-                const uint64_t len = off0[(uint64_t)(u + 1) * rpu] - off0[(uint64_t)u * rpu];
-                if (len > DCN_MAX_SHORT) { b.n_long++; b.long_bases += len; }
-                else if ((uint32_t)len > b.max_short) b.max_short = (uint32_t)len;
-            }
-        };
-        auto chunk_uniform = [&] {
-            for (uint8_t u : part_uniform) if (!u) return false;
-            return nr > 0;
-        };
-        // offsets of the chunk on the device: copied, or generated when the records all have one length
-        auto ship_offsets = [&](uint8_t *dst) -> cudaError_t {
-            if (chunk_uniform()) {
-                uniform_offsets_kernel<<<grid_for(ctx, (uint64_t)nr + 1, 256), 256, 0, s.stream>>>(reinterpret_cast<uint64_t *>(dst), nr + 1, off0[0], rec_len0);
+        const ChunkStats cs = packed ? r.cs : chunk_stats(off0, c.nu, rpu);
+        // offsets of the chunk on the device: copied, or generated when the records all have one length (then rec_off
+        // is an arithmetic sequence: 8 bytes per record stay off PCIe, 5 % of an ASCII chunk of 150-base reads)
+        auto ship_offsets = [&](uint8_t *dst, const void *host_src) -> cudaError_t {
+            if (cs.uniform) {
+                uniform_offsets_kernel<<<grid_for(ctx, (uint64_t)c.nr + 1, 256), 256, 0, s.stream>>>(reinterpret_cast<uint64_t *>(dst), c.nr + 1, off0[0], cs.rec_len0);
                 ctx->launches += 1;
                 ctx->n_uniform_chunks++;
                 return cudaGetLastError();
             }
-            ctx->bytes_h2d += ((uint64_t)nr + 1) * 8;
-            return cudaMemcpyAsync(dst, off0, ((size_t)nr + 1) * 8, cudaMemcpyHostToDevice, s.stream);
+            ctx->bytes_h2d += ((uint64_t)c.nr + 1) * 8;
+            return cudaMemcpyAsync(dst, host_src, ((size_t)c.nr + 1) * 8, cudaMemcpyHostToDevice, s.stream);
         };
+        CK(cudaEventRecord(s.ev_start, s.stream));
         if (prepacked) {   // slices of the caller's packed arrays, copied as they are
-            for (int i = 0; i < T; i++) stats_task(i);   // on this thread: hidden behind the copies already queued
-            const uint64_t r_first = (uint64_t)u0 * rpu;
-            CK(cudaEventRecord(s.ev_start, s.stream));
-            CK(cudaMemcpyAsync(din, src.codes + a0 / 16, n_words * 4, cudaMemcpyHostToDevice, s.stream));
-            CK(cudaMemcpyAsync(din + o_inv, src.inv + a0 / 16, n_words * 2, cudaMemcpyHostToDevice, s.stream));
-            ctx->bytes_h2d += n_words * 6;
-            CK(ship_offsets(din + o_off_p));
+            const uint64_t r_first = (uint64_t)c.u0 * rpu;
+            CK(cudaMemcpyAsync(din, src.codes + c.a0 / 16, c.n_words * 4, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaMemcpyAsync(din + c.o_inv, src.inv + c.a0 / 16, c.n_words * 2, cudaMemcpyHostToDevice, s.stream));
+            ctx->bytes_h2d += c.n_words * 6;
+            CK(ship_offsets(din + c.o_off_p, off0));
             if (src.nl) {
-                const uint64_t w0 = r_first / 32, w1 = (r_first + nr + 31) / 32;
-                CK(cudaMemcpyAsync(din + o_nl, src.nl + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s.stream));
+                const uint64_t w0 = r_first / 32, w1 = (r_first + c.nr + 31) / 32;
+                CK(cudaMemcpyAsync(din + c.o_nl, src.nl + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s.stream));
                 ctx->bytes_h2d += (w1 - w0) * 4;
-                in.nl = reinterpret_cast<const uint32_t *>(din + o_nl);
+                in.nl = reinterpret_cast<const uint32_t *>(din + c.o_nl);
                 in.nl_bit0 = (uint32_t)(r_first % 32);
             }
             in.codes = reinterpret_cast<const uint32_t *>(din);
-            in.inv = reinterpret_cast<const uint16_t *>(din + o_inv);
-            d_off = reinterpret_cast<const uint64_t *>(din + o_off_p);
+            in.inv = reinterpret_cast<const uint16_t *>(din + c.o_inv);
+            d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_p);
         } else if (packed) {
-            const auto t0 = std::chrono::steady_clock::now();
-            uint8_t *hin = s.h_in.as<uint8_t>();
-            uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
-            uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + o_inv);
-            uint64_t *h_off = reinterpret_cast<uint64_t *>(hin + o_off_p);
-            uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + o_nl);
-            const uint64_t piece = align_up((nb + T - 1) / T, 64);           // bases per task
-            const uint32_t rpiece = (uint32_t)align_up(((size_t)nr + 1 + T - 1) / T, 32);   // records per task
-            const uint8_t *src = bases + a0;
-            ctx->pool->run(T, [&](int i) {
-                stats_task(i);
-                const uint64_t p0 = (uint64_t)i * piece;
-                if (p0 < nb) {
-                    const uint64_t pn = std::min(piece, nb - p0);
-                    pack_ascii(src + p0, pn, h_codes + p0 / 16, h_inv + p0 / 16, 1);
-                }
-                const uint32_t r0 = (uint32_t)i * rpiece;
-                if (r0 <= nr) {
-                    const uint32_t r1 = std::min<uint64_t>((uint64_t)r0 + rpiece, (uint64_t)nr + 1);
-                    memcpy(h_off + r0, off0 + r0, (size_t)(r1 - r0) * 8);
-                    for (uint32_t rw = r0; rw < r1 && rw < nr; rw += 32) {     // newline flags, 32 records per word
-                        uint32_t bits = 0;
-                        for (uint32_t r = rw; r < std::min(rw + 32, std::min(r1, nr)); r++) {
-                            const uint64_t len = off0[r + 1] - off0[r];
-                            if (len < (uint64_t)ctx->k) continue;                              // src/filter_common.rs:217-219
-                            const uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;   // :222-226
-                            if (bases[off0[r] + n - 1] == (uint8_t)'\n') bits |= 1u << (r - rw);      // :229
-                        }
-                        h_nl[rw / 32] = bits;
-                    }
-                }
-            });
-            ctx->t_pack += std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            packed_bytes += nb;
+            PackBlob &bl = ctx->blobs[(size_t)r.blob];
+            const uint8_t *hin = bl.buf.as<uint8_t>();
+            if (cs.uniform) {   // codes + non-ACGT bits, then the newline flags; the offsets are generated
+                CK(cudaMemcpyAsync(din, hin, c.o_off_p, cudaMemcpyHostToDevice, s.stream));
+                CK(cudaMemcpyAsync(din + c.o_nl, hin + c.o_nl, c.in_packed - c.o_nl, cudaMemcpyHostToDevice, s.stream));
+                ctx->bytes_h2d += c.o_off_p + (c.in_packed - c.o_nl);
+                CK(ship_offsets(din + c.o_off_p, nullptr));
+            } else {
+                CK(cudaMemcpyAsync(din, hin, c.in_packed, cudaMemcpyHostToDevice, s.stream));
+                ctx->bytes_h2d += c.in_packed;
+            }
+            CK(cudaEventRecord(bl.h2d_done, s.stream));
+            {
+                std::lock_guard<std::mutex> g(m);
+                bl.state = PackBlob::ENQUEUED;
+            }
+            cv.notify_all();
             ctx->n_packed_chunks++;
-            CK(cudaEventRecord(s.ev_start, s.stream));
-            CK(cudaMemcpyAsync(din, hin, in_packed, cudaMemcpyHostToDevice, s.stream));
-            ctx->bytes_h2d += in_packed;
             in.codes = reinterpret_cast<const uint32_t *>(din);
-            in.inv = reinterpret_cast<const uint16_t *>(din + o_inv);
-            in.nl = reinterpret_cast<const uint32_t *>(din + o_nl);
-            d_off = reinterpret_cast<const uint64_t *>(din + o_off_p);
+            in.inv = reinterpret_cast<const uint16_t *>(din + c.o_inv);
+            in.nl = reinterpret_cast<const uint32_t *>(din + c.o_nl);
+            d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_p);
         } else {
-            for (int i = 0; i < T; i++) stats_task(i);
             ctx->n_ascii_chunks++;
-            CK(cudaEventRecord(s.ev_start, s.stream));
-            if (nb) CK(cudaMemcpyAsync(din, bases + a0, (size_t)nb, cudaMemcpyHostToDevice, s.stream));
-            ctx->bytes_h2d += nb;
-            CK(ship_offsets(din + o_off_a));
+            if (c.nb) CK(cudaMemcpyAsync(din, bases + c.a0, (size_t)c.nb, cudaMemcpyHostToDevice, s.stream));
+            ctx->bytes_h2d += c.nb;
+            CK(ship_offsets(din + c.o_off_a, off0));
             in.bases = din;
-            d_off = reinterpret_cast<const uint64_t *>(din + o_off_a);
+            d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_a);
         }
         CK(cudaEventRecord(s.ev_h2d, s.stream));
-        BatchStats hstats;
-        memset(&hstats, 0, sizeof(hstats));
-        for (const BatchStats &b : part) {
-            hstats.max_short = std::max(hstats.max_short, b.max_short);
-            hstats.n_long += b.n_long;
-            hstats.long_bases += b.long_bases;
-        }
         uint8_t *dout = s.out.as<uint8_t>();
-        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, a0, b1, d_off, nr, paired, prefix_len, abs_thr, rel_thr, deplete,
-                            dout + (size_t)nu * 8, reinterpret_cast<uint32_t *>(dout), reinterpret_cast<uint32_t *>(dout + (size_t)nu * 4),
-                            s.stream, &hstats);
+        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, c.a0, c.b1, d_off, c.nr, paired, prefix_len, abs_thr, rel_thr, deplete,
+                            dout + (size_t)c.nu * 8, reinterpret_cast<uint32_t *>(dout), reinterpret_cast<uint32_t *>(dout + (size_t)c.nu * 4),
+                            s.stream, &cs.st);
         if (rc) break;
         CK(cudaEventRecord(s.ev_kernel, s.stream));
-        CK(cudaMemcpyAsync(s.h_out.p, dout, out_bytes, cudaMemcpyDeviceToHost, s.stream));
-        ctx->bytes_d2h += out_bytes;
+        CK(cudaMemcpyAsync(s.h_out.p, dout, c.out_bytes, cudaMemcpyDeviceToHost, s.stream));
+        ctx->bytes_d2h += c.out_bytes;
         CK(cudaEventRecord(s.ev_done, s.stream));
-        s.busy = true; s.u0 = u0; s.u1 = u1;
+        s.busy = true; s.u0 = c.u0; s.u1 = c.u1;
         which = (which + 1) % dcn_ctx::NSLOT;
-        u0 = u1;
+        processed += r.a1 - r.a0;
     }
+    stop_packers();
     for (int i = 0; i < dcn_ctx::NSLOT; i++) {   // oldest first
         int r2 = retire(ctx->slot[(which + i) % dcn_ctx::NSLOT]);
         if (!rc) rc = r2;
     }
     if (rc) { cudaDeviceSynchronize(); for (auto &sl : ctx->slot) sl.busy = false; }
-    if (!rc && packed_bytes && ctx->t_pack > 0) ctx->pack_gbps = (double)packed_bytes / 1e6 / ctx->t_pack;
+    for (auto &bl : ctx->blobs) bl.state = PackBlob::FREE;   // every copy has completed
+    if (trace)
+        fprintf(stderr, "[dcn host] %d atoms, %d packers: %llu packed / %llu ascii chunks so far; call %.2f ms; enqueuer waited %.2f ms on stages, "
+                "%.2f ms on packers; packers busy %.2f ms, waiting for a blob %.2f ms (sums over threads); h2d %.1f MB\n",
+                n_atoms, n_packers, (unsigned long long)ctx->n_packed_chunks, (unsigned long long)ctx->n_ascii_chunks,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack0).count(), enq_retire_ms, enq_ready_ms,
+                pack_busy_ms, pack_wait_ms, ctx->bytes_h2d / 1e6);
+    if (packed_bytes) {
+        ctx->t_pack = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_pack0).count();
+        if (pack_busy_ms > 0) ctx->pack_gbps = (double)packed_bytes / 1e6 / pack_busy_ms * std::max(1, n_packers);
+    }
     return rc;
 }
 
@@ -905,7 +1044,7 @@ int dcn_host_pack_threads(dcn_ctx *ctx, int n_threads) {
     if (n_threads < 0 || n_threads > 256) return ctx->fail(DCN_ERR_ARG, "n_threads must be in 0..=256");
     ctx->pack_threads = n_threads;
     ctx->pack_gbps = 0;
-    if (n_threads == 0) ctx->pool.reset();
+
     return DCN_OK;
 }
 

@@ -190,6 +190,63 @@ def test_equal_length_chunks_do_not_ship_their_offsets(gpu):
         gpu.host_pack_threads(4)
 
 
+def test_two_route_ingest_pinned_ragged(gpu):
+    """Host ingest with pinned caller buffers: the batch is cut into atoms, the copy engine ships ASCII chunks from the
+    front while packer threads pack atoms from the back (dcn_api.cu filter_pipeline).  Ragged records (some shorter
+    than k, some ending in a newline, some with N) so every atom ships its offsets and newline flags; whatever way
+    the two routes split the batch, the results are the oracle's."""
+    import torch
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(500_000, 21)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    rng = np.random.default_rng(22)
+    n = 1_400_000
+    lens = rng.integers(100, 251, n).astype(np.uint64)
+    lens[rng.integers(0, n, 2000)] = rng.integers(0, 31, 2000).astype(np.uint64)        # shorter than k, some empty
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])                                                                # ~245 MB: 7-8 chunks of 32 MB
+    assert total > 7 * (32 << 20)
+    # reads = one long random walk over the genome (half of it host), cut at the record boundaries
+    start = rng.integers(0, len(g) - 400, total // 256 + 2)
+    bases = g[(start[:, None] + np.arange(256)[None, :])].reshape(-1)[:total].copy()
+    rnd = rng.integers(0, 2, total // 4096 + 1).astype(bool).repeat(4096)[:total]
+    bases[rnd] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rnd.sum()))]
+    bases[rng.integers(0, total, 5000)] = ord("N")
+    nl = rng.integers(0, n, 3000)
+    nl = nl[lens[nl] >= 31]
+    bases[(off[nl + 1] - 1).astype(np.int64)] = ord("\n")                              # records ending in a newline
+    hb = torch.from_numpy(bases).pin_memory()
+    ho = torch.from_numpy(off.view(np.int64)).pin_memory()
+    np_units = n // 2
+    hk = torch.zeros(np_units, dtype=torch.uint8).pin_memory()
+    hh = torch.zeros(np_units, dtype=torch.int32).pin_memory()
+    ht = torch.zeros(np_units, dtype=torch.int32).pin_memory()
+    ok, oh, ot = O.filter_batch(idx, bases, off, paired=True, deplete=True, threads=8)
+    assert 0.2 < ok.mean() < 0.8
+    try:
+        for threads, fraction in ((6, -1.0), (3, 0.5), (6, 1.0), (0, -1.0)):
+            gpu.host_pack_threads(threads)
+            gpu.host_pack_fraction(fraction)
+            for _ in range(2):                                                          # the second call reuses the packers' blobs
+                hk.zero_(); hh.zero_(); ht.zero_()
+                gpu.filter_batch_ptr(hb.data_ptr(), ho.data_ptr(), n, True, 0, 2, 0.01, True, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
+                assert np.array_equal(ht.numpy().view(np.uint32), ot) and np.array_equal(hh.numpy().view(np.uint32), oh)
+                assert np.array_equal(hk.numpy(), ok)
+                h2d, d2h = gpu.last_transfer_bytes()
+                assert d2h == 9 * np_units
+                if threads == 0:
+                    assert h2d >= total + 8 * n                                         # ASCII only: every base and offset crosses
+                elif fraction == 1.0:
+                    assert h2d < 0.5 * total                                            # packed only: 0.375 B/bp + offsets + flags
+                else:
+                    assert h2d < total + 8 * n                                          # some atoms went packed
+    finally:
+        gpu.host_pack_fraction(-1.0)
+        gpu.host_pack_threads(4)
+
+
 def test_device_pointer_api_matches_host_api(gpu):
     import torch
     from deacon_server_b200 import IndexHeader
