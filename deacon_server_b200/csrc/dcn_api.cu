@@ -65,14 +65,8 @@ struct Slot {  // one stage of the host-pointer pipeline
     HostBuf h_in, h_out;                  // pinned mirrors of `in` (packed mode only) and `out`
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_start = nullptr, ev_h2d = nullptr, ev_kernel = nullptr, ev_done = nullptr;
-    bool busy = false;
+    bool busy = false, packed = false;
     uint32_t u0 = 0, u1 = 0;
-};
-
-struct PackBlob {   // pinned staging of one host-packed chunk (filter_pipeline: two per packer thread)
-    HostBuf buf;
-    cudaEvent_t h2d_done = nullptr;
-    enum State { FREE, READY, ENQUEUED } state = FREE;
 };
 
 // what the fused kernel reads: ASCII bytes, or the host-packed form (dcn_host_pack.h)
@@ -113,14 +107,14 @@ struct dcn_ctx {
     Slot slot[NSLOT];
     // host ingest (packing) pool; pack_threads = 0 ships ASCII over PCIe instead
     int pack_threads = -1;   // -1: decide at first use (DCN_PACK_THREADS or min(hardware threads, 16))
-    std::vector<PackBlob> blobs;
+    std::vector<Slot> pslot;   // two stages per packer thread (filter_pipeline), created by the threads themselves
     float t_pack = 0;
     // Ingest: a chunk is either packed by the host pool (CPU reads 1 B/bp, PCIe carries 0.4 B/bp) or shipped
     // as ASCII (PCIe carries 1 B/bp, no CPU work); `pack_fraction` of the chunks take the first route.
     double pack_gbps = 0;       // packing rate of the last call that packed (ASCII GB/s), for reporting
     double pack_fraction = -1;  // < 0: automatic (pinned caller buffers: 0, pageable: 1); DCN_PACK_FRACTION overrides
     uint64_t n_packed_chunks = 0, n_ascii_chunks = 0, n_uniform_chunks = 0;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
     uint64_t bytes_h2d = 0, bytes_d2h = 0;   // what the last host-pointer filter call moved over PCIe
     // CUDA-event pairs around every launch of the fused kernel (ring), for dcn_fused_time_take
@@ -128,7 +122,9 @@ struct dcn_ctx {
     cudaEvent_t kev0[KEV], kev1[KEV];
     uint32_t kev_head = 0, kev_count = 0;
 
+    std::mutex err_m;   // the pipeline's packer threads report errors too
     int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+        std::lock_guard<std::mutex> g(err_m);
         err = what;
         if (e != cudaSuccess) { err += ": "; err += cudaGetErrorString(e); }
         return code;
@@ -313,7 +309,8 @@ static int enqueue_filter_generic(dcn_ctx *ctx, DevBuf &plan, DevBuf &tmp, DevBu
 static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &dedup, const FilterInput &in,
                           uint64_t base0, uint64_t n_bases_abs, const uint64_t *d_off, uint32_t n_rec, int paired,
                           uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep,
-                          uint32_t *d_hits, uint32_t *d_total, cudaStream_t st, const BatchStats *host_stats = nullptr) {
+                          uint32_t *d_hits, uint32_t *d_total, cudaStream_t st, const BatchStats *host_stats = nullptr,
+                          bool time_fused = true) {   // false: no event pair around the fused kernel (the ring is not thread-safe)
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
     const uint32_t rpu = paired ? 2u : 1u;
     if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
@@ -386,12 +383,14 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             ctx->launches += 1;
         }
         const uint32_t ke = ctx->kev_head % dcn_ctx::KEV;
-        CK(cudaEventRecord(ctx->kev0[ke], st));
+        if (time_fused) CK(cudaEventRecord(ctx->kev0[ke], st));
         if (in.codes) filter_fused_kernel<G31, true><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
         else filter_fused_kernel<G31, false><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
-        CK(cudaEventRecord(ctx->kev1[ke], st));
-        ctx->kev_head++;
-        if (ctx->kev_count < dcn_ctx::KEV) ctx->kev_count++;
+        if (time_fused) {
+            CK(cudaEventRecord(ctx->kev1[ke], st));
+            ctx->kev_head++;
+            if (ctx->kev_count < dcn_ctx::KEV) ctx->kev_count++;
+        }
         ctx->launches += 1;
         if (hs.n_long) {
             finalize_long_kernel<<<std::max(1, (int)std::min<uint32_t>((hs.n_long + 255) / 256, 1024)), 256, 0, st>>>(P, d_stats, long_units);
@@ -479,13 +478,8 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     ctx->gx_bases.release(); ctx->gx_off.release(); ctx->gx_rc.release(); ctx->gx_cc.release(); ctx->gx_tmp.release();
     ctx->gx_h.release(); ctx->gx_p.release(); ctx->gx_oo.release(); ctx->gx_entropy.release();
     ctx->ws_table.release(); ctx->ws_flags.release();
-    for (auto &bl : ctx->blobs) {
-        bl.buf.release();
-        if (bl.h2d_done) cudaEventDestroy(bl.h2d_done);
-    }
-    ctx->blobs.clear();
-    for (int i = 0; i < dcn_ctx::NSLOT; i++) {
-        Slot &s = ctx->slot[i];
+    for (size_t i = 0; i < dcn_ctx::NSLOT + ctx->pslot.size(); i++) {
+        Slot &s = i < dcn_ctx::NSLOT ? ctx->slot[i] : ctx->pslot[i - dcn_ctx::NSLOT];
         s.in.release(); s.out.release(); s.plan.release(); s.longs.release(); s.dedup.release();
         s.h_in.release(); s.h_out.release();
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -714,10 +708,11 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         if (pack_share > 0) n_packers = pack_threads_of(ctx);
     }
 
-    // ---- plan: the batch is cut into unit-aligned ATOMS.  The ASCII route ships up to `atoms_per_chunk` consecutive
-    // atoms as one chunk (one copy, one kernel); a packer thread takes one atom at a time, so the two routes meet with
-    // at most one atom's packing time (~1.5 ms) of imbalance instead of a chunk's.
-    const uint32_t atoms_per_chunk = n_packers > 0 ? 4 : 1;
+    // ---- plan: the batch is cut into unit-aligned ATOMS of 4 MB.  The ASCII route ships up to `atoms_per_chunk`
+    // consecutive atoms as one chunk (one copy, one kernel); a packer thread takes up to half a chunk at a time while
+    // plenty of atoms are left and single atoms near the end, so the two routes meet with at most one atom's packing
+    // time (~0.7 ms) of imbalance instead of a chunk's.
+    const uint32_t atoms_per_chunk = n_packers > 0 ? 8 : 1;
     const uint64_t atom_bases = std::max<uint64_t>(chunk_bases / atoms_per_chunk, 1);
     std::vector<uint32_t> atom_u;   // atom i covers units [atom_u[i], atom_u[i + 1])
     atom_u.push_back(0);
@@ -752,9 +747,26 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
 
     ctx->t_h2d = ctx->t_kernel = ctx->t_d2h = ctx->t_pack = 0;
     ctx->bytes_h2d = ctx->bytes_d2h = 0;
-    auto retire = [&](Slot &s) -> int {  // wait for a stage and scatter its results
+    static const int trace_level = []() { const char *e = getenv("DCN_HOST_TRACE"); return e ? atoi(e) : 0; }();
+    cudaEvent_t ev_call = nullptr;
+    if (trace_level >= 2) {
+        cudaEventCreate(&ev_call);
+        cudaEventRecord(ev_call, ctx->slot[0].stream);
+    }
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_call0 = now_ms();
+
+    // what one thread of the pipeline adds up; merged into the ctx under `m` when the thread is done
+    struct Acc {
+        uint64_t h2d = 0, d2h = 0, n_packed = 0, n_ascii = 0, n_uniform = 0, packed_bases = 0;
+        float t_h2d = 0, t_kernel = 0, t_d2h = 0;
+        double wait_ms = 0, pack_ms = 0;   // waiting for a stage to come back; packing
+    };
+    auto retire = [&](Slot &s, Acc &acc) -> int {  // wait for a stage and scatter its results (disjoint unit ranges per stage)
         if (!s.busy) return DCN_OK;
+        const double w0 = now_ms();
         CK(cudaEventSynchronize(s.ev_done));
+        acc.wait_ms += now_ms() - w0;
         const uint32_t nu = s.u1 - s.u0;
         const uint8_t *o = s.h_out.as<uint8_t>();
         memcpy(hits + s.u0, o, (size_t)nu * 4);
@@ -764,237 +776,240 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         cudaEventElapsedTime(&a, s.ev_start, s.ev_h2d);
         cudaEventElapsedTime(&b, s.ev_h2d, s.ev_kernel);
         cudaEventElapsedTime(&c, s.ev_kernel, s.ev_done);
-        ctx->t_h2d += a; ctx->t_kernel += b; ctx->t_d2h += c;
+        acc.t_h2d += a; acc.t_kernel += b; acc.t_d2h += c;
+        if (trace_level >= 2 && ev_call) {   // device timeline of the chunk, ms since the call's first enqueue
+            float t0 = 0;
+            cudaEventElapsedTime(&t0, ev_call, s.ev_start);
+            fprintf(stderr, "[dcn chunk] units %u..%u %s start %.3f h2d_end %.3f kernel_end %.3f done %.3f\n", s.u0, s.u1,
+                    s.packed ? "packed" : "ascii", t0, t0 + a, t0 + a + b, t0 + a + b + c);
+        }
         s.busy = false;
         return DCN_OK;
     };
 
-    // ---- shared state of the two routes
-    std::mutex m;
-    std::condition_variable cv;
-    int head = 0, tail = n_atoms, taken_by_packers = 0;   // ASCII takes atoms from head, a packer atom --tail
-    struct Ready { int a0, a1, blob; ChunkStats cs; int err; };   // atoms [a0, a1); blob < 0: not packed
-    std::vector<Ready> ready;
-    bool abort_packers = false;
-    uint64_t packed_bytes = 0;
-    if ((int)ctx->blobs.size() < 2 * n_packers) ctx->blobs.resize((size_t)2 * n_packers);
-    const auto t_pack0 = std::chrono::steady_clock::now();
-    double pack_busy_ms = 0, pack_wait_ms = 0;   // summed over the packer threads
-    double enq_retire_ms = 0, enq_ready_ms = 0;  // the enqueueing thread's waits: for a stage, for a packed atom
-    static const bool trace = getenv("DCN_HOST_TRACE") != nullptr;
-    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-
-    auto packer = [&](int t) {
-        cudaSetDevice(ctx->device);
-        int flip = 0;
-        for (;;) {
-            int ci;
-            {
-                std::lock_guard<std::mutex> g(m);
-                if (abort_packers || tail <= head || taken_by_packers >= pack_budget) return;
-                ci = --tail; taken_by_packers++;
-            }
-            const ChunkPlan c = make_chunk(ci, ci + 1);
-            const int bi = 2 * t + flip;
-            flip ^= 1;
-            PackBlob &bl = ctx->blobs[(size_t)bi];
-            Ready r{ci, ci + 1, bi, ChunkStats(), 0};
-            const auto tw0 = std::chrono::steady_clock::now();
-            {   // the blob's previous copy must have left the host
-                std::unique_lock<std::mutex> g(m);
-                cv.wait(g, [&] { return bl.state != PackBlob::READY || abort_packers; });
-                if (abort_packers) return;
-            }
-            if (bl.state == PackBlob::ENQUEUED) cudaEventSynchronize(bl.h2d_done);
-            bl.state = PackBlob::FREE;
-            const auto t0 = std::chrono::steady_clock::now();
-            const double wait_ms = std::chrono::duration<double, std::milli>(t0 - tw0).count();
-            if (bl.buf.ensure(c.in_packed) != cudaSuccess || (!bl.h2d_done && cudaEventCreateWithFlags(&bl.h2d_done, cudaEventDisableTiming) != cudaSuccess)) {
-                r.err = 1;
-            } else {
-                uint8_t *hin = bl.buf.as<uint8_t>();
-                const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
-                r.cs = chunk_stats(off0, c.nu, rpu);
-                if (!r.cs.uniform) memcpy(hin + c.o_off_p, off0, ((size_t)c.nr + 1) * 8);
-                uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
-                uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + c.o_inv);
-                uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + c.o_nl);
-                // Packing and the newline flags advance together, 1024 records at a time, so the flag loop finds the
-                // records' last bytes in the core's cache instead of missing once per record after the whole atom.
-                uint64_t cur = 0;   // bases [a0, a0 + cur) are packed; a multiple of 64 until the last piece
-                for (uint32_t rg = 0; rg < c.nr || cur < c.nb; rg += 1024) {
-                    const uint32_t rg_end = (uint32_t)std::min<uint64_t>((uint64_t)rg + 1024, c.nr);
-                    const uint64_t upto = rg_end >= c.nr ? c.nb : ((off0[rg_end] - c.a0) & ~63ull);
-                    if (upto > cur) {
-                        pack_ascii(bases + c.a0 + cur, upto - cur, h_codes + cur / 16, h_inv + cur / 16, 1);
-                        cur = upto;
-                    }
-                    for (uint32_t rw = rg; rw < rg_end; rw += 32) {     // newline flags, 32 records per word
-                        uint32_t bits = 0;
-                        for (uint32_t q = rw; q < std::min(rw + 32, rg_end); q++) {
-                            const uint64_t len = off0[q + 1] - off0[q];
-                            if (len < (uint64_t)ctx->k) continue;                                          // src/filter_common.rs:217-219
-                            const uint64_t n = (prefix_len > 0 && len > prefix_len) ? prefix_len : len;   // :222-226
-                            if (bases[off0[q] + n - 1] == (uint8_t)'\n') bits |= 1u << (q - rw);           // :229
-                        }
-                        h_nl[rw / 32] = bits;
-                    }
-                }
-            }
-            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            {
-                std::lock_guard<std::mutex> g(m);
-                bl.state = PackBlob::READY;
-                ready.push_back(r);
-                packed_bytes += c.nb;
-                pack_busy_ms += ms;
-                pack_wait_ms += wait_ms;
-            }
-            cv.notify_all();
-        }
-    };
-    std::vector<std::thread> packers;
-    for (int t = 0; t < n_packers; t++) packers.emplace_back(packer, t);
-    auto stop_packers = [&] {
-        {
-            std::lock_guard<std::mutex> g(m);
-            abort_packers = true;
-        }
-        cv.notify_all();
-        for (auto &t : packers) t.join();
-        packers.clear();
-    };
-    struct JoinOnExit {   // every return path (the CK macro returns) must leave no thread behind
-        std::function<void()> f;
-        ~JoinOnExit() { f(); }
-    } join_on_exit{stop_packers};
-
-    // ---- the enqueueing thread
-    int which = 0, rc = DCN_OK, processed = 0;
-    while (processed < n_atoms && rc == DCN_OK) {
-        Ready r{-1, -1, -1, ChunkStats(), 0};
-        {
-            std::unique_lock<std::mutex> g(m);
-            for (;;) {
-                if (!ready.empty()) { r = ready.back(); ready.pop_back(); break; }
-                // ASCII route, or the packers' budget is used up and the rest goes as ASCII
-                if ((ascii_route || taken_by_packers >= pack_budget) && head < tail) {
-                    r.a0 = head;
-                    head = r.a1 = std::min<int>(tail, head + (int)atoms_per_chunk);
-                    break;
-                }
-                const double w0 = now_ms();
-                cv.wait(g);   // only packed atoms are left and none is ready yet
-                enq_ready_ms += now_ms() - w0;
-            }
-        }
-        if (r.err) { rc = ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed in a packer thread"); break; }
-        const ChunkPlan c = make_chunk(r.a0, r.a1);
-        const bool packed = r.blob >= 0;
+    // Enqueue one chunk on stage `s`: copies in, the kernels, results out.  `route`: 0 ASCII bytes, 1 the caller's packed
+    // arrays, 2 the blob a packer thread has just written to s.h_in.  Called by the enqueueing thread (stages ctx->slot)
+    // and by every packer thread (its own two stages): it touches nothing shared but atomics and the device.
+    auto ship = [&](Slot &s, const ChunkPlan &c, int route, const ChunkStats &cs, Acc &acc, bool time_fused) -> int {
         const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
-        Slot &s = ctx->slot[which];
-        const double w0 = now_ms();
-        if ((rc = retire(s))) break;  // the stage's previous chunk (NSLOT chunks ago)
-        enq_retire_ms += now_ms() - w0;
-        if (s.in.ensure((packed || prepacked) ? c.in_packed + 8 : c.in_ascii) != cudaSuccess || s.out.ensure(c.out_bytes) != cudaSuccess ||
-            s.h_out.ensure(c.out_bytes) != cudaSuccess) {
-            rc = ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
-            break;
-        }
+        if (s.in.ensure(route ? c.in_packed + 8 : c.in_ascii) != cudaSuccess || s.out.ensure(c.out_bytes) != cudaSuccess ||
+            s.h_out.ensure(c.out_bytes) != cudaSuccess)
+            return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
         uint8_t *din = s.in.as<uint8_t>();
         FilterInput in;
         const uint64_t *d_off;
-        const ChunkStats cs = packed ? r.cs : chunk_stats(off0, c.nu, rpu);
         // offsets of the chunk on the device: copied, or generated when the records all have one length (then rec_off
         // is an arithmetic sequence: 8 bytes per record stay off PCIe, 5 % of an ASCII chunk of 150-base reads)
         auto ship_offsets = [&](uint8_t *dst, const void *host_src) -> cudaError_t {
             if (cs.uniform) {
                 uniform_offsets_kernel<<<grid_for(ctx, (uint64_t)c.nr + 1, 256), 256, 0, s.stream>>>(reinterpret_cast<uint64_t *>(dst), c.nr + 1, off0[0], cs.rec_len0);
                 ctx->launches += 1;
-                ctx->n_uniform_chunks++;
+                acc.n_uniform++;
                 return cudaGetLastError();
             }
-            ctx->bytes_h2d += ((uint64_t)c.nr + 1) * 8;
+            acc.h2d += ((uint64_t)c.nr + 1) * 8;
             return cudaMemcpyAsync(dst, host_src, ((size_t)c.nr + 1) * 8, cudaMemcpyHostToDevice, s.stream);
         };
         CK(cudaEventRecord(s.ev_start, s.stream));
-        if (prepacked) {   // slices of the caller's packed arrays, copied as they are
+        if (route == 1) {   // slices of the caller's packed arrays, copied as they are
             const uint64_t r_first = (uint64_t)c.u0 * rpu;
             CK(cudaMemcpyAsync(din, src.codes + c.a0 / 16, c.n_words * 4, cudaMemcpyHostToDevice, s.stream));
             CK(cudaMemcpyAsync(din + c.o_inv, src.inv + c.a0 / 16, c.n_words * 2, cudaMemcpyHostToDevice, s.stream));
-            ctx->bytes_h2d += c.n_words * 6;
+            acc.h2d += c.n_words * 6;
             CK(ship_offsets(din + c.o_off_p, off0));
             if (src.nl) {
                 const uint64_t w0 = r_first / 32, w1 = (r_first + c.nr + 31) / 32;
                 CK(cudaMemcpyAsync(din + c.o_nl, src.nl + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, s.stream));
-                ctx->bytes_h2d += (w1 - w0) * 4;
+                acc.h2d += (w1 - w0) * 4;
                 in.nl = reinterpret_cast<const uint32_t *>(din + c.o_nl);
                 in.nl_bit0 = (uint32_t)(r_first % 32);
             }
             in.codes = reinterpret_cast<const uint32_t *>(din);
             in.inv = reinterpret_cast<const uint16_t *>(din + c.o_inv);
             d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_p);
-        } else if (packed) {
-            PackBlob &bl = ctx->blobs[(size_t)r.blob];
-            const uint8_t *hin = bl.buf.as<uint8_t>();
+        } else if (route == 2) {
+            const uint8_t *hin = s.h_in.as<uint8_t>();
             if (cs.uniform) {   // codes + non-ACGT bits, then the newline flags; the offsets are generated
                 CK(cudaMemcpyAsync(din, hin, c.o_off_p, cudaMemcpyHostToDevice, s.stream));
                 CK(cudaMemcpyAsync(din + c.o_nl, hin + c.o_nl, c.in_packed - c.o_nl, cudaMemcpyHostToDevice, s.stream));
-                ctx->bytes_h2d += c.o_off_p + (c.in_packed - c.o_nl);
+                acc.h2d += c.o_off_p + (c.in_packed - c.o_nl);
                 CK(ship_offsets(din + c.o_off_p, nullptr));
             } else {
                 CK(cudaMemcpyAsync(din, hin, c.in_packed, cudaMemcpyHostToDevice, s.stream));
-                ctx->bytes_h2d += c.in_packed;
+                acc.h2d += c.in_packed;
             }
-            CK(cudaEventRecord(bl.h2d_done, s.stream));
-            {
-                std::lock_guard<std::mutex> g(m);
-                bl.state = PackBlob::ENQUEUED;
-            }
-            cv.notify_all();
-            ctx->n_packed_chunks++;
+            acc.n_packed++;
             in.codes = reinterpret_cast<const uint32_t *>(din);
             in.inv = reinterpret_cast<const uint16_t *>(din + c.o_inv);
             in.nl = reinterpret_cast<const uint32_t *>(din + c.o_nl);
             d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_p);
         } else {
-            ctx->n_ascii_chunks++;
+            acc.n_ascii++;
             if (c.nb) CK(cudaMemcpyAsync(din, bases + c.a0, (size_t)c.nb, cudaMemcpyHostToDevice, s.stream));
-            ctx->bytes_h2d += c.nb;
+            acc.h2d += c.nb;
             CK(ship_offsets(din + c.o_off_a, off0));
             in.bases = din;
             d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_a);
         }
         CK(cudaEventRecord(s.ev_h2d, s.stream));
         uint8_t *dout = s.out.as<uint8_t>();
-        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, c.a0, c.b1, d_off, c.nr, paired, prefix_len, abs_thr, rel_thr, deplete,
-                            dout + (size_t)c.nu * 8, reinterpret_cast<uint32_t *>(dout), reinterpret_cast<uint32_t *>(dout + (size_t)c.nu * 4),
-                            s.stream, &cs.st);
-        if (rc) break;
+        const int rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, c.a0, c.b1, d_off, c.nr, paired, prefix_len, abs_thr, rel_thr, deplete,
+                                      dout + (size_t)c.nu * 8, reinterpret_cast<uint32_t *>(dout), reinterpret_cast<uint32_t *>(dout + (size_t)c.nu * 4),
+                                      s.stream, &cs.st, time_fused);
+        if (rc) return rc;
         CK(cudaEventRecord(s.ev_kernel, s.stream));
         CK(cudaMemcpyAsync(s.h_out.p, dout, c.out_bytes, cudaMemcpyDeviceToHost, s.stream));
-        ctx->bytes_d2h += c.out_bytes;
+        acc.d2h += c.out_bytes;
         CK(cudaEventRecord(s.ev_done, s.stream));
-        s.busy = true; s.u0 = c.u0; s.u1 = c.u1;
+        s.busy = true; s.u0 = c.u0; s.u1 = c.u1; s.packed = route != 0;
+        return DCN_OK;
+    };
+
+    // ---- shared state of the two routes
+    std::mutex m;
+    int head = 0, tail = n_atoms, taken_by_packers = 0;   // ASCII takes atoms from head, a packer from tail
+    int first_rc = DCN_OK;                                  // first failure of any thread; stops the others
+    Acc sum;
+    double pack_busy_ms = 0, pack_wait_ms = 0;              // summed over the packer threads
+    auto merge = [&](const Acc &a, int rc) {
+        std::lock_guard<std::mutex> g(m);
+        sum.h2d += a.h2d; sum.d2h += a.d2h; sum.n_packed += a.n_packed; sum.n_ascii += a.n_ascii; sum.n_uniform += a.n_uniform;
+        sum.packed_bases += a.packed_bases;
+        sum.t_h2d += a.t_h2d; sum.t_kernel += a.t_kernel; sum.t_d2h += a.t_d2h;
+        if (rc && !first_rc) first_rc = rc;
+    };
+    // stages per packer thread: enough that a thread never waits for its own earlier atoms, whose copies queue behind
+    // the ASCII chunks already handed to the copy engine (2 stages: the threads idled a quarter of the call)
+    constexpr int PST = 4;
+    if ((int)ctx->pslot.size() < PST * n_packers) ctx->pslot.resize((size_t)PST * n_packers);
+
+    // A packer thread is a small pipeline of its own: claim atoms from the back of the batch (a few at a time while
+    // plenty are left, one at a time near the end so all threads finish together), pack them into the pinned blob of
+    // one of its stages, enqueue copy + kernels + results on that stage's stream, and collect the stage's previous
+    // results before the blob is written again.  Nothing goes through the enqueueing thread: at ~90 us of CUDA API
+    // calls per chunk, one thread enqueueing every packed atom was the limit of the whole pipeline (64 Gbp/s).
+    auto packer = [&](int t) {
+        Acc acc;
+        int rc = DCN_OK;
+        std::vector<uint64_t> bad32;
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(ctx->device));
+            for (int i = 0; i < PST; i++) {
+                Slot &s = ctx->pslot[(size_t)(PST * t + i)];
+                if (s.stream) continue;
+                CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+                CK(cudaEventCreate(&s.ev_start)); CK(cudaEventCreate(&s.ev_h2d));
+                CK(cudaEventCreate(&s.ev_kernel)); CK(cudaEventCreate(&s.ev_done));
+            }
+            for (int flip = 0;; flip = (flip + 1) % PST) {
+                int a_lo, a_hi;
+                {
+                    std::lock_guard<std::mutex> g(m);
+                    if (first_rc || tail <= head || taken_by_packers >= pack_budget) break;
+                    int grab = std::max(1, std::min<int>((int)atoms_per_chunk / 2, (tail - head) / (2 * n_packers)));
+                    grab = std::min(grab, std::min(tail - head, pack_budget - taken_by_packers));
+                    a_hi = tail; a_lo = tail -= grab; taken_by_packers += grab;
+                }
+                const ChunkPlan c = make_chunk(a_lo, a_hi);
+                Slot &s = ctx->pslot[(size_t)(PST * t + flip)];
+                int r = retire(s, acc);   // the blob's previous copy has left the host once its results are back
+                if (r) return r;
+                const double t0 = now_ms();
+                if (s.h_in.ensure(c.in_packed) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed", cudaGetLastError());
+                uint8_t *hin = s.h_in.as<uint8_t>();
+                const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
+                const ChunkStats cs = chunk_stats(off0, c.nu, rpu);
+                if (!cs.uniform) memcpy(hin + c.o_off_p, off0, ((size_t)c.nr + 1) * 8);
+                uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
+                uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + c.o_inv);
+                uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + c.o_nl);
+                // Newline flags (src/filter_common.rs:229): a record's last byte can only be '\n' inside a 32-base
+                // block the packer found a non-ACGT byte in, so the packer lists those blocks and only the records
+                // ending inside them are looked at (a per-record pass over the atom cost 28 % of the packing time).
+                bad32.clear();
+                pack_ascii(bases + c.a0, c.nb, h_codes, h_inv, 1, &bad32);
+                memset(h_nl, 0, ((size_t)c.nr + 31) / 32 * 4);
+                auto rec_end = [&](uint32_t q) {   // one past the last byte the reference looks at
+                    const uint64_t len = off0[q + 1] - off0[q];
+                    return off0[q] + ((prefix_len > 0 && len > prefix_len) ? prefix_len : len);   // :222-226
+                };
+                uint32_t q0 = 0;
+                for (const uint64_t bi : bad32) {
+                    const uint64_t B = c.a0 + 32 * bi;   // block [B, B + 32); rec_end is non-decreasing in q
+                    uint32_t lo = q0, hi = c.nr;         // first record with rec_end > B
+                    while (lo < hi) {
+                        const uint32_t mid = lo + (hi - lo) / 2;
+                        if (rec_end(mid) > B) hi = mid; else lo = mid + 1;
+                    }
+                    q0 = lo;
+                    for (uint32_t q = lo; q < c.nr; q++) {
+                        const uint64_t e = rec_end(q);
+                        if (e > B + 32) break;
+                        if (off0[q + 1] - off0[q] < (uint64_t)ctx->k) continue;                            // :217-219
+                        if (bases[e - 1] == (uint8_t)'\n') h_nl[q / 32] |= 1u << (q % 32);
+                    }
+                }
+                acc.pack_ms += now_ms() - t0;
+                acc.packed_bases += c.nb;
+                if ((r = ship(s, c, 2, cs, acc, false))) return r;
+            }
+            for (int i = 0; i < PST; i++) {
+                const int r = retire(ctx->pslot[(size_t)(PST * t + i)], acc);
+                if (r) return r;
+            }
+            return DCN_OK;
+        };
+        rc = body();
+        merge(acc, rc);
+        std::lock_guard<std::mutex> g(m);
+        pack_busy_ms += acc.pack_ms; pack_wait_ms += acc.wait_ms;
+    };
+    std::vector<std::thread> packers;
+    for (int t = 0; t < n_packers; t++) packers.emplace_back(packer, t);
+
+    // ---- the enqueueing thread: ASCII chunks (or the caller's packed arrays) from the front, at the pace of the link
+    Acc main_acc;
+    int which = 0, rc = DCN_OK;
+    while (ascii_route && rc == DCN_OK) {
+        int a_lo, a_hi;
+        {
+            std::lock_guard<std::mutex> g(m);
+            if (first_rc || head >= tail) break;
+            a_lo = head;
+            a_hi = head = std::min<int>(tail, head + (int)atoms_per_chunk);
+        }
+        const ChunkPlan c = make_chunk(a_lo, a_hi);
+        Slot &s = ctx->slot[which];
+        if ((rc = retire(s, main_acc))) break;  // the stage's previous chunk (NSLOT chunks ago)
+        const ChunkStats cs = chunk_stats(rec_off + (uint64_t)c.u0 * rpu, c.nu, rpu);
+        if ((rc = ship(s, c, prepacked ? 1 : 0, cs, main_acc, true))) break;
         which = (which + 1) % dcn_ctx::NSLOT;
-        processed += r.a1 - r.a0;
     }
-    stop_packers();
     for (int i = 0; i < dcn_ctx::NSLOT; i++) {   // oldest first
-        int r2 = retire(ctx->slot[(which + i) % dcn_ctx::NSLOT]);
+        int r2 = retire(ctx->slot[(which + i) % dcn_ctx::NSLOT], main_acc);
         if (!rc) rc = r2;
     }
-    if (rc) { cudaDeviceSynchronize(); for (auto &sl : ctx->slot) sl.busy = false; }
-    for (auto &bl : ctx->blobs) bl.state = PackBlob::FREE;   // every copy has completed
-    if (trace)
-        fprintf(stderr, "[dcn host] %d atoms, %d packers: %llu packed / %llu ascii chunks so far; call %.2f ms; enqueuer waited %.2f ms on stages, "
-                "%.2f ms on packers; packers busy %.2f ms, waiting for a blob %.2f ms (sums over threads); h2d %.1f MB\n",
-                n_atoms, n_packers, (unsigned long long)ctx->n_packed_chunks, (unsigned long long)ctx->n_ascii_chunks,
-                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_pack0).count(), enq_retire_ms, enq_ready_ms,
-                pack_busy_ms, pack_wait_ms, ctx->bytes_h2d / 1e6);
-    if (packed_bytes) {
-        ctx->t_pack = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_pack0).count();
-        if (pack_busy_ms > 0) ctx->pack_gbps = (double)packed_bytes / 1e6 / pack_busy_ms * std::max(1, n_packers);
+    merge(main_acc, rc);
+    for (auto &t : packers) t.join();
+    rc = first_rc;
+    if (rc) {
+        cudaDeviceSynchronize();
+        for (auto &sl : ctx->slot) sl.busy = false;
+        for (auto &sl : ctx->pslot) sl.busy = false;
+    }
+    ctx->t_h2d = sum.t_h2d; ctx->t_kernel = sum.t_kernel; ctx->t_d2h = sum.t_d2h;
+    ctx->bytes_h2d = sum.h2d; ctx->bytes_d2h = sum.d2h;
+    ctx->n_packed_chunks += sum.n_packed; ctx->n_ascii_chunks += sum.n_ascii; ctx->n_uniform_chunks += sum.n_uniform;
+    if (ev_call) cudaEventDestroy(ev_call);
+    const double call_ms = now_ms() - t_call0;
+    if (trace_level >= 1)
+        fprintf(stderr, "[dcn host] %d atoms, %d packers: %llu packed / %llu ascii chunks; call %.2f ms; enqueuer waited %.2f ms on its stages; "
+                "packers: packing %.2f ms, waiting for a stage %.2f ms (sums over threads); h2d %.1f MB\n",
+                n_atoms, n_packers, (unsigned long long)sum.n_packed, (unsigned long long)sum.n_ascii, call_ms, main_acc.wait_ms,
+                pack_busy_ms, pack_wait_ms, sum.h2d / 1e6);
+    if (sum.packed_bases) {
+        ctx->t_pack = (float)call_ms;
+        if (pack_busy_ms > 0) ctx->pack_gbps = (double)sum.packed_bases / 1e6 / pack_busy_ms * std::max(1, n_packers);
     }
     return rc;
 }
@@ -1741,7 +1756,7 @@ int dcn_last_pack_ms(dcn_ctx *ctx, float *pack_ms) {
     return DCN_OK;
 }
 
-uint64_t dcn_launch_count(dcn_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t dcn_launch_count(dcn_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int dcn_fused_time_take(dcn_ctx *ctx, float *total_ms, uint32_t *n_launches) {
     if (!ctx || !total_ms || !n_launches) return DCN_ERR_ARG;

@@ -31,7 +31,7 @@ static inline void pack32_scalar(const uint8_t *p, uint32_t *codes, uint16_t *in
 
 #ifdef DCN_X86
 __attribute__((target("avx2,bmi2"))) static void pack_blocks_avx2(const uint8_t *p, uint64_t n_blocks, uint32_t *codes,
-                                                                  uint16_t *inv) {
+                                                                  uint16_t *inv, std::vector<uint64_t> *bad32) {
     // letter expected for each low nibble of the byte: 1 -> 'A', 3 -> 'C', 4 -> 'T', 7 -> 'G'
     const __m256i lut = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,
                                          -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
@@ -44,6 +44,7 @@ __attribute__((target("avx2,bmi2"))) static void pack_blocks_avx2(const uint8_t 
         uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(want, _mm256_and_si256(v, mdf)));
         uint32_t bad = ~ok;
         memcpy(inv + 2 * i, &bad, 4);
+        if (bad && bad32) bad32->push_back(i);
         uint64_t x0, x1, x2, x3;
         memcpy(&x0, q, 8); memcpy(&x1, q + 8, 8); memcpy(&x2, q + 16, 8); memcpy(&x3, q + 24, 8);
         uint64_t c = _pext_u64(x0, M) | (_pext_u64(x1, M) << 16) | (_pext_u64(x2, M) << 32) | (_pext_u64(x3, M) << 48);
@@ -56,7 +57,8 @@ __attribute__((target("avx2,bmi2"))) static void pack_blocks_avx2(const uint8_t 
 // (byte & 0xDF) with the letter its low nibble stands for.  `nt` = streaming stores: the output is a
 // pinned staging buffer the GPU's copy engine reads next, so keep it out of the cores' caches.
 __attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_blocks_avx512(const uint8_t *p, uint64_t n_blocks64,
-                                                                                   uint32_t *codes, uint16_t *inv, bool nt) {
+                                                                                   uint32_t *codes, uint16_t *inv, bool nt,
+                                                                                   std::vector<uint64_t> *bad32) {
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1));
     const __m512i m0f = _mm512_set1_epi8(0x0F), mdf = _mm512_set1_epi8((char)0xDF), m03 = _mm512_set1_epi8(0x03);
     const __m512i mul8 = _mm512_set1_epi16(0x0401), mul16 = _mm512_set1_epi32(0x00100001);
@@ -65,6 +67,10 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_blocks_avx
         __m512i v = _mm512_loadu_si512(p + 64 * i);
         __m512i want = _mm512_shuffle_epi8(lut, _mm512_and_si512(v, m0f));
         uint64_t bad = ~_mm512_cmpeq_epi8_mask(want, _mm512_and_si512(v, mdf));
+        if (bad && bad32) {   // rare: reads are almost all ACGT
+            if ((uint32_t)bad) bad32->push_back(2 * i);
+            if (bad >> 32) bad32->push_back(2 * i + 1);
+        }
         __m512i c = _mm512_and_si512(_mm512_srli_epi16(v, 1), m03);
         __m512i c4 = _mm512_maddubs_epi16(c, mul8);          // c0 + 4 c1 per 16-bit lane
         __m512i c8 = _mm512_madd_epi16(c4, mul16);           // + 16 * (c2 + 4 c3) per 32-bit lane
@@ -98,28 +104,32 @@ bool pack_has_simd() {
 #endif
 }
 
-void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd) {
+void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd, std::vector<uint64_t> *bad32) {
     const uint64_t full = n / 32;
     uint64_t done = 0;
 #ifdef DCN_X86
     // simd: 1 = best available, 2 = force the AVX2 path (tests), 0 = scalar
     if (simd == 1 && simd_level() == 2) {
         const bool nt = ((reinterpret_cast<uintptr_t>(codes) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(inv) & 7u) == 0);
-        pack_blocks_avx512(bases, n / 64, codes, inv, nt);
+        pack_blocks_avx512(bases, n / 64, codes, inv, nt, bad32);
         done = (n / 64) * 2;
     } else if (simd && simd_level() >= 1) {
-        pack_blocks_avx2(bases, full, codes, inv);
+        pack_blocks_avx2(bases, full, codes, inv, bad32);
         done = full;
     }
 #else
     (void)simd;
 #endif
-    for (uint64_t i = done; i < full; i++) pack32_scalar(bases + 32 * i, codes + 2 * i, inv + 2 * i);
+    for (uint64_t i = done; i < full; i++) {
+        pack32_scalar(bases + 32 * i, codes + 2 * i, inv + 2 * i);
+        if (bad32 && (inv[2 * i] | inv[2 * i + 1])) bad32->push_back(i);
+    }
     if (n % 32) {
         uint8_t tail[32];
         memset(tail, 0, sizeof(tail));   // byte 0: code 0, not ACGT
         memcpy(tail, bases + 32 * full, n % 32);
         pack32_scalar(tail, codes + 2 * full, inv + 2 * full);
+        if (bad32) bad32->push_back(full);   // the padding is flagged non-ACGT: always listed
     }
 }
 

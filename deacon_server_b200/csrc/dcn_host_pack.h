@@ -18,8 +18,11 @@ namespace dcn {
 // Packs bases[0 .. n): codes[i] holds bases [16 i, 16 i + 16) as 2-bit codes (byte >> 1) & 3, base j
 // at bits 2 j (packed-seq order A=0 C=1 T=2 G=3); inv[i] bit j = base 16 i + j is not one of
 // ACGTacgt.  Both arrays must hold 2 * ceil(n / 32) entries; positions >= n are padded with code 0,
-// non-ACGT 1.  simd = 0 forces the scalar loop (tests compare the two).
-void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd);
+// non-ACGT 1.  simd = 0 forces the scalar loop (tests compare the two).  `bad32`, when given, receives
+// (appended, ascending) the index of every 32-base block that holds a non-ACGT byte or padding: the only
+// places a record-terminating newline can be, so the caller's newline-flag pass visits those and nothing else.
+void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd,
+                std::vector<uint64_t> *bad32 = nullptr);
 bool pack_has_simd();
 
 class HostPool {

@@ -121,7 +121,9 @@ for threads, fr in settings:
     for _ in range(args.steps):
         e2e()
     dt = (time.perf_counter() - t0) / args.steps
-    print(f"e2e pinned, pack threads {threads} fraction {fr}: {dt*1e3:.2f} ms/step, {nb/dt/1e9:.2f} Gbp/s; timing {gpu.last_timing()} pack_ms {gpu.last_pack_ms():.2f}")
+    fms, fn = gpu.fused_time_take()   # the fused kernel's launches of the most recent calls (at most 256)
+    print(f"e2e pinned, pack threads {threads} fraction {fr}: {dt*1e3:.2f} ms/step, {nb/dt/1e9:.2f} Gbp/s; timing {gpu.last_timing()} pack_ms {gpu.last_pack_ms():.2f}; "
+          f"fused kernel {fms / max(fn, 1) * 1e3:.1f} us x {fn} launches; h2d {gpu.last_transfer_bytes()[0] / 1e6:.0f} MB")
     assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu())
 # caller-packed input (dcn_filter_batch_packed), pinned
 from deacon_server_b200 import api as A
