@@ -597,27 +597,32 @@ static int pack_threads_of(dcn_ctx *ctx) {   // -> host threads available for pa
     if (ctx->pack_threads < 0) {
         const char *e = getenv("DCN_PACK_THREADS");
         // default: leave four hardware threads to the caller, the enqueueing thread and the driver's own threads
-        // (measured on a 16-vCPU box: 12 packers 61 Gbp/s end to end, 16 packers 46)
-        const int hc = (int)std::thread::hardware_concurrency();
+        // (measured on a 16-vCPU box: 10-14 packers 70-72 Gbp/s end to end; with all 16 the enqueueing thread starves)
+        int hc = (int)std::thread::hardware_concurrency();
+        cpu_set_t cs;   // a process bound to the CPUs next to its GPU (one rank per GPU) counts only those
+        if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) hc = std::min(hc, (int)CPU_COUNT(&cs));
         int n = e ? atoi(e) : std::min(std::max(hc - 4, 1), 16);
         ctx->pack_threads = std::max(0, std::min(n, 256));
     }
     return ctx->pack_threads;
 }
 
-// Host-pointer form (SURVEY.md 8f.1 "pinned double-buffered streams"): unit-aligned chunks of 32 MB go through
-// NSLOT pipeline stages, each with its own stream; results come back through a pinned blob and are scattered into
-// the caller's arrays when the stage is reused.  A chunk reaches the GPU by one of two routes:
+// Host-pointer form (SURVEY.md 8f.1 "pinned double-buffered streams").  The batch is cut into unit-aligned atoms of
+// 4 MB; a chunk (a run of atoms) goes through a pipeline stage with its own stream: copy in, kernels, results out
+// through a pinned blob, scattered into the caller's arrays when the stage is reused.  A chunk reaches the GPU by
+// one of two routes:
 //   ASCII   the bytes are copied as they are (1 B/bp over PCIe, no CPU work), the GPU converts them;
 //   packed  a host thread packs the chunk (2-bit codes + non-ACGT bits, plus record offsets and newline flags:
 //           what PackedSeqVec::from_ascii and the mask loop of src/filter_common.rs:238-258 compute) into one
 //           pinned blob and 0.43 B/bp cross PCIe.
 // The copy engine and the host cores work at the same time (measured on the round-1 box: a pinned H2D stream keeps
 // 55 GB/s beside 12 packing threads doing 64 GB/s, tools/hybrid_probe.py), so with pinned caller buffers the two
-// routes share a batch dynamically: the enqueueing thread takes ASCII chunks from the front of the chunk list at
-// the pace of the link, persistent-for-the-call packer threads take whole chunks from its back, and a packed chunk
-// is enqueued as soon as it is ready (chunks may complete in any order: results are scattered by unit index).
-// Pageable caller buffers take the packed route only (a direct copy would be staged by the driver at ~8 GB/s).
+// routes share a batch dynamically.  The calling thread ships 32 MB ASCII chunks from the FRONT of the atom list
+// through NSLOT stages, at the pace of the link.  Packer threads (alive for the call) claim atoms from its BACK,
+// up to 16 MB at a time while plenty are left and single atoms near the end, pack them, and enqueue them on stages
+// and streams of their own; the call ends when the two fronts meet.  Stages complete in any order: results are
+// scattered by unit index.  Pageable caller buffers take the packed route only (a direct copy would be staged by
+// the driver at ~8 GB/s).
 struct HostSrc {   // caller's host buffers: ASCII, or already packed (dcn_filter_batch_packed)
     const uint8_t *bases = nullptr;
     const uint32_t *codes = nullptr;
@@ -741,6 +746,22 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         c.out_bytes = (size_t)c.nu * 9;
         return c;
     };
+    // the largest chunks of the two routes, for sizing the stages once (records of >= 64 bases on average assumed;
+    // a chunk that needs more grows its stage)
+    auto layout_for = [&](uint64_t nb_cap) {
+        ChunkPlan c;
+        memset(&c, 0, sizeof(c));
+        c.nb = std::min<uint64_t>(nb_cap, total_bases + 64);
+        c.nr = (uint32_t)std::min<uint64_t>(c.nb / 64 + 2, n_rec); c.nu = c.nr / rpu + 1;
+        c.n_words = 2 * ((c.nb + 31) / 32);
+        c.o_inv = c.n_words * 4; c.o_off_p = align_up(c.o_inv + c.n_words * 2, 8); c.o_nl = c.o_off_p + ((size_t)c.nr + 1) * 8;
+        c.in_packed = c.o_nl + align_up(((size_t)c.nr + 31) / 32 * 4, 8);
+        c.o_off_a = align_up(c.nb + 16, 16); c.in_ascii = c.o_off_a + ((size_t)c.nr + 1) * 8;
+        c.out_bytes = (size_t)c.nu * 9;
+        return c;
+    };
+    const int packer_grab_max = std::max<int>(1, (int)atoms_per_chunk / 2);
+    const ChunkPlan big_ascii = layout_for(chunk_bases + 4096), big_packed = layout_for((uint64_t)packer_grab_max * atom_bases + 4096);
     const int pack_budget = (int)std::min<double>(n_atoms, pack_share * n_atoms + 0.5);   // atoms the packers may take
     n_packers = std::min(n_packers, pack_budget);
     if (n_packers == 0) ascii_route = true;
@@ -792,8 +813,11 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
     // and by every packer thread (its own two stages): it touches nothing shared but atomics and the device.
     auto ship = [&](Slot &s, const ChunkPlan &c, int route, const ChunkStats &cs, Acc &acc, bool time_fused) -> int {
         const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
-        if (s.in.ensure(route ? c.in_packed + 8 : c.in_ascii) != cudaSuccess || s.out.ensure(c.out_bytes) != cudaSuccess ||
-            s.h_out.ensure(c.out_bytes) != cudaSuccess)
+        // sized for the largest chunk the stage is likely to see, not for this one: growing a buffer later costs a
+        // cudaFree / cudaFreeHost (a device-wide sync) in the middle of some call
+        const ChunkPlan &big = route == 2 ? big_packed : big_ascii;
+        if (s.in.ensure(std::max(route ? c.in_packed + 8 : c.in_ascii, route ? big.in_packed + 8 : big.in_ascii)) != cudaSuccess ||
+            s.out.ensure(std::max(c.out_bytes, big.out_bytes)) != cudaSuccess || s.h_out.ensure(std::max(c.out_bytes, big.out_bytes)) != cudaSuccess)
             return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
         uint8_t *din = s.in.as<uint8_t>();
         FilterInput in;
@@ -901,12 +925,18 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
                 CK(cudaEventCreate(&s.ev_start)); CK(cudaEventCreate(&s.ev_h2d));
                 CK(cudaEventCreate(&s.ev_kernel)); CK(cudaEventCreate(&s.ev_done));
             }
+            for (int i = 0; i < PST; i++) {   // all of the thread's staging in its first call (pinning memory is slow)
+                Slot &s = ctx->pslot[(size_t)(PST * t + i)];
+                if (s.h_in.ensure(big_packed.in_packed) != cudaSuccess || s.in.ensure(big_packed.in_packed + 8) != cudaSuccess ||
+                    s.out.ensure(big_packed.out_bytes) != cudaSuccess || s.h_out.ensure(big_packed.out_bytes) != cudaSuccess)
+                    return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
+            }
             for (int flip = 0;; flip = (flip + 1) % PST) {
                 int a_lo, a_hi;
                 {
                     std::lock_guard<std::mutex> g(m);
                     if (first_rc || tail <= head || taken_by_packers >= pack_budget) break;
-                    int grab = std::max(1, std::min<int>((int)atoms_per_chunk / 2, (tail - head) / (2 * n_packers)));
+                    int grab = std::max(1, std::min<int>(packer_grab_max, (tail - head) / (2 * n_packers)));
                     grab = std::min(grab, std::min(tail - head, pack_budget - taken_by_packers));
                     a_hi = tail; a_lo = tail -= grab; taken_by_packers += grab;
                 }
@@ -915,7 +945,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
                 int r = retire(s, acc);   // the blob's previous copy has left the host once its results are back
                 if (r) return r;
                 const double t0 = now_ms();
-                if (s.h_in.ensure(c.in_packed) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed", cudaGetLastError());
+                if (s.h_in.ensure(std::max(c.in_packed, big_packed.in_packed)) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed", cudaGetLastError());
                 uint8_t *hin = s.h_in.as<uint8_t>();
                 const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
                 const ChunkStats cs = chunk_stats(off0, c.nu, rpu);
@@ -971,16 +1001,29 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
     Acc main_acc;
     int which = 0, rc = DCN_OK;
     while (ascii_route && rc == DCN_OK) {
+        Slot &s = ctx->slot[which];
+        if ((rc = retire(s, main_acc))) break;  // the stage's previous chunk (NSLOT chunks ago)
+        if (n_packers > 0) {
+            // Beside packers the route is decided as late as possible: no more than two ASCII copies are handed to the
+            // copy engine ahead of time (one running, one queued: the link never idles), and the chunks shrink as the
+            // two fronts close in, so that when they meet little is left queued while the packer threads sit idle.
+            Slot &prev2 = ctx->slot[(which + dcn_ctx::NSLOT - 2) % dcn_ctx::NSLOT];
+            if (prev2.busy) {
+                const double w0 = now_ms();
+                const cudaError_t e = cudaEventSynchronize(prev2.ev_h2d);   // (no CK here: the packer threads must be joined)
+                if (e != cudaSuccess) { rc = ctx->fail(DCN_ERR_CUDA, "cudaEventSynchronize(ev_h2d)", e); break; }
+                main_acc.wait_ms += now_ms() - w0;
+            }
+        }
         int a_lo, a_hi;
         {
             std::lock_guard<std::mutex> g(m);
             if (first_rc || head >= tail) break;
+            const int grab = n_packers > 0 ? std::max(1, std::min<int>((int)atoms_per_chunk, (tail - head) / 6)) : (int)atoms_per_chunk;
             a_lo = head;
-            a_hi = head = std::min<int>(tail, head + (int)atoms_per_chunk);
+            a_hi = head = std::min<int>(tail, head + grab);
         }
         const ChunkPlan c = make_chunk(a_lo, a_hi);
-        Slot &s = ctx->slot[which];
-        if ((rc = retire(s, main_acc))) break;  // the stage's previous chunk (NSLOT chunks ago)
         const ChunkStats cs = chunk_stats(rec_off + (uint64_t)c.u0 * rpu, c.nu, rpu);
         if ((rc = ship(s, c, prepacked ? 1 : 0, cs, main_acc, true))) break;
         which = (which + 1) % dcn_ctx::NSLOT;

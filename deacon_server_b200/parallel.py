@@ -37,6 +37,21 @@ def bind_to_gpu(local_rank: int) -> list[int]:
     return []
 
 
+def pack_threads_for_rank(local_world: int) -> int:
+    """Host packing threads for one rank of `local_world` on this box (dcn_host_pack_threads): the CPUs this process
+    may run on, shared with the other ranks when it is not bound to a GPU-local subset of its own, minus four for the
+    caller, the enqueueing thread and the driver's threads; 1..16."""
+    import os
+    allowed = len(os.sched_getaffinity(0))
+    total = os.cpu_count() or allowed
+    share = allowed
+    if local_world > 1:
+        # bound to one NUMA node: the node's ranks share it (ranks are dealt out evenly over the nodes)
+        nodes = max(1, round(total / allowed)) if allowed < total else 1
+        share = allowed // max(1, -(-local_world // nodes))
+    return max(1, min(16, share - 4))
+
+
 def shard_units(n_units: int, rank: int, world: int) -> tuple[int, int]:
     """Contiguous, balanced unit range [u0, u1) of `rank`: sizes differ by at most one unit and a
     pair is never split (units, not records, are dealt out)."""

@@ -78,15 +78,17 @@ int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t
                             uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
                             int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream);
 
-/* Host ingest of dcn_filter_batch.  For k=31, w=15 indexes a chunk of the batch can be
- * packed on `n_threads` host threads (2-bit codes + non-ACGT bits: what PackedSeqVec::from_ascii and the mask
- * loop of src/filter_common.rs:238-258 compute per record on the CPU) into pinned staging, so 0.4 B/bp cross
- * PCIe instead of 1 B/bp; otherwise the ASCII bytes are copied and the GPU converts them.  Results are identical.
- * Default threads: DCN_PACK_THREADS, else min(hardware threads, 16); 0 = never pack. */
+/* Host ingest of dcn_filter_batch.  For k=31, w=15 indexes part of the batch can be packed on
+ * `n_threads` host threads (2-bit codes + non-ACGT bits: what PackedSeqVec::from_ascii and the mask loop of
+ * src/filter_common.rs:238-258 compute per record on the CPU) into pinned staging, so 0.4 B/bp cross PCIe instead
+ * of 1 B/bp; the rest is copied as ASCII and converted on the GPU.  Results are identical.
+ * Default threads: DCN_PACK_THREADS, else hardware threads - 4 (at least 1, at most 16); 0 = never pack. */
 int dcn_host_pack_threads(dcn_ctx *ctx, int n_threads);
-/* Share of the chunks that take the packing route.  Negative (default) = automatic: 0 for pinned caller
- * buffers (on the measured box the copy engine alone already runs at the host-memory / PCIe limit), 1 for
- * pageable buffers (a direct copy would be staged by the driver at a few GB/s). */
+/* Share of the batch the packing route may take.  Negative (default) = automatic.  Pinned caller buffers: the two
+ * routes split the batch dynamically -- the copy engine ships ASCII chunks from the front of the batch while the
+ * packer threads work from its back, until they meet (batches under 6 chunks of 32 MB go ASCII only).  Pageable
+ * buffers: 1 (a direct copy would be staged by the driver at a few GB/s).  A value in [0, 1] caps the packers'
+ * share instead (1 = packed only, 0 = ASCII only).  DCN_PACK_FRACTION sets the same from the environment. */
 int dcn_host_pack_fraction(dcn_ctx *ctx, double fraction);
 /* The packer itself (no GPU needed): codes[i] = bases [16i, 16i+16) as (byte >> 1) & 3, base j at bits 2j;
  * inv[i] bit j = base 16i+j is not one of ACGTacgt.  Both arrays hold 2 * ceil(n_bases / 32) entries;
