@@ -7,9 +7,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <sched.h>
+
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>

@@ -133,64 +133,4 @@ void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv
     }
 }
 
-// ------------------------------------------------------------------ thread pool
-HostPool::HostPool(int n_threads) : n_(n_threads < 1 ? 1 : n_threads) {
-    for (int i = 1; i < n_; i++) th_.emplace_back([this] { worker(); });
-}
-
-HostPool::~HostPool() {
-    {
-        std::lock_guard<std::mutex> lk(m_);
-        stop_ = true;
-    }
-    cv_start_.notify_all();
-    for (auto &t : th_) t.join();
-}
-
-void HostPool::drain() {
-    for (;;) {
-        int i = next_.fetch_add(1, std::memory_order_relaxed);
-        if (i >= n_tasks_) return;
-        (*fn_)(i);
-    }
-}
-
-void HostPool::worker() {
-    uint64_t seen = 0;
-    for (;;) {
-        {
-            std::unique_lock<std::mutex> lk(m_);
-            cv_start_.wait(lk, [&] { return stop_ || gen_ != seen; });
-            if (stop_) return;
-            seen = gen_;
-        }
-        drain();
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            if (--busy_ == 0) cv_done_.notify_one();
-        }
-    }
-}
-
-void HostPool::run(int n_tasks, const std::function<void(int)> &fn) {
-    if (n_tasks <= 0) return;
-    if (th_.empty() || n_tasks == 1) {
-        for (int i = 0; i < n_tasks; i++) fn(i);
-        return;
-    }
-    {
-        std::lock_guard<std::mutex> lk(m_);
-        fn_ = &fn;
-        n_tasks_ = n_tasks;
-        next_.store(0, std::memory_order_relaxed);
-        busy_ = (int)th_.size();
-        gen_++;
-    }
-    cv_start_.notify_all();
-    drain();
-    std::unique_lock<std::mutex> lk(m_);
-    cv_done_.wait(lk, [&] { return busy_ == 0; });
-    fn_ = nullptr;
-}
-
 }  // namespace dcn

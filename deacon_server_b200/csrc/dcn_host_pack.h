@@ -1,16 +1,11 @@
 // dcn_host_pack.h -- host-side ingest helpers of the host-pointer pipeline: the
 // 2-bit packing + non-ACGT bitmask the reference computes per record on the CPU
 // (PackedSeqVec::from_ascii and the mask loop, src/filter_common.rs:238-258), done here once per
-// batch by a small thread pool straight into pinned staging buffers, so that 0.375 B/bp instead
-// of 1 B/bp cross PCIe.  Plain C++ (no CUDA): also compiled into the test-only host emulation.
+// batch by the pipeline's packer threads (filter_pipeline, dcn_api.cu) straight into pinned staging
+// buffers, so that 0.375 B/bp instead of 1 B/bp cross PCIe.  Plain C++ (no CUDA): also compiled into the test-only host emulation.
 #pragma once
 #include <stdint.h>
 
-#include <atomic>
-#include <condition_variable>
-#include <functional>
-#include <mutex>
-#include <thread>
 #include <vector>
 
 namespace dcn {
@@ -24,29 +19,5 @@ namespace dcn {
 void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd,
                 std::vector<uint64_t> *bad32 = nullptr);
 bool pack_has_simd();
-
-class HostPool {
-  public:
-    explicit HostPool(int n_threads);   // n_threads - 1 workers; the caller of run() is the last one
-    ~HostPool();
-    HostPool(const HostPool &) = delete;
-    HostPool &operator=(const HostPool &) = delete;
-    int size() const { return n_; }
-    // runs fn(0 .. n_tasks - 1) over the pool and returns when every task is done
-    void run(int n_tasks, const std::function<void(int)> &fn);
-
-  private:
-    void worker();
-    void drain();
-    int n_;
-    std::vector<std::thread> th_;
-    std::mutex m_;
-    std::condition_variable cv_start_, cv_done_;
-    const std::function<void(int)> *fn_ = nullptr;
-    std::atomic<int> next_{0};
-    int n_tasks_ = 0, busy_ = 0;
-    uint64_t gen_ = 0;
-    bool stop_ = false;
-};
 
 }  // namespace dcn

@@ -40,8 +40,13 @@ def bind_to_gpu(local_rank: int) -> list[int]:
 def pack_threads_for_rank(local_world: int) -> int:
     """Host packing threads for one rank of `local_world` on this box (dcn_host_pack_threads): the CPUs this process
     may run on, shared with the other ranks when it is not bound to a GPU-local subset of its own, minus four for the
-    caller, the enqueueing thread and the driver's threads; 1..16."""
+    caller, the enqueueing thread and the driver's threads; at most 16, and 0 (ASCII route only: the copy engine
+    needs no CPU) when fewer than two would be left or when four or more ranks share the host."""
     import os
+    if local_world >= 4:
+        # measured (DESIGN.md 6): with 8 ranks the host's DRAM (~160 GB/s) bounds the ingest, and a packed base costs
+        # 1.86 B of DRAM traffic against 1.0 for a copied one
+        return 0
     allowed = len(os.sched_getaffinity(0))
     total = os.cpu_count() or allowed
     share = allowed
@@ -49,7 +54,8 @@ def pack_threads_for_rank(local_world: int) -> int:
         # bound to one NUMA node: the node's ranks share it (ranks are dealt out evenly over the nodes)
         nodes = max(1, round(total / allowed)) if allowed < total else 1
         share = allowed // max(1, -(-local_world // nodes))
-    return max(1, min(16, share - 4))
+    n = min(16, share - 4)
+    return n if n >= 2 else 0
 
 
 def shard_units(n_units: int, rank: int, world: int) -> tuple[int, int]:

@@ -247,6 +247,47 @@ def test_two_route_ingest_pinned_ragged(gpu):
         gpu.host_pack_threads(4)
 
 
+def test_two_route_ingest_long_reads(gpu):
+    """The same two-route ingest on ONT-like records (config 3 shape): units longer than an atom, long-path units in
+    packed atoms and in ASCII chunks, search mode."""
+    import torch
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(600_000, 31)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    rng = np.random.default_rng(32)
+    lens = np.clip(rng.gamma(2.0, 5000.0, 26_000), 200, 200_000).astype(np.uint64)
+    lens[7] = 6_000_000                                                                # one record longer than an atom
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    assert total > 7 * (32 << 20)
+    start = rng.integers(0, len(g) - 5000, total // 4096 + 2)
+    bases = g[(start[:, None] + np.arange(4096)[None, :])].reshape(-1)[:total].copy()   # 4 kb stretches of the genome
+    rnd = rng.integers(0, 2, total // 65536 + 1).astype(bool).repeat(65536)[:total]
+    bases[rnd] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rnd.sum()))]
+    bases[rng.integers(0, total, 20_000)] = ord("N")
+    hb = torch.from_numpy(bases).pin_memory()
+    ho = torch.from_numpy(off.view(np.int64)).pin_memory()
+    n = len(lens)
+    hk = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    hh = torch.zeros(n, dtype=torch.int32).pin_memory()
+    ht = torch.zeros(n, dtype=torch.int32).pin_memory()
+    ok, oh, ot = O.filter_batch(idx, bases, off, paired=False, deplete=False, threads=8)
+    assert int(oh.max()) > 1000
+    try:
+        for threads, fraction in ((6, -1.0), (4, 0.5), (6, 1.0)):
+            gpu.host_pack_threads(threads)
+            gpu.host_pack_fraction(fraction)
+            hk.zero_(); hh.zero_(); ht.zero_()
+            gpu.filter_batch_ptr(hb.data_ptr(), ho.data_ptr(), n, False, 0, 2, 0.01, False, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
+            assert np.array_equal(ht.numpy().view(np.uint32), ot) and np.array_equal(hh.numpy().view(np.uint32), oh)
+            assert np.array_equal(hk.numpy(), ok)
+    finally:
+        gpu.host_pack_fraction(-1.0)
+        gpu.host_pack_threads(4)
+
+
 def test_device_pointer_api_matches_host_api(gpu):
     import torch
     from deacon_server_b200 import IndexHeader

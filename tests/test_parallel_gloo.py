@@ -89,3 +89,22 @@ def test_counters_match_reference_semantics():
     assert c == {"total_seqs": 4, "filtered_seqs": 2, "total_bp": 420, "output_bp": 250, "filtered_bp": 170, "output_seq_counter": 2}
     c = P.counters_of(off, np.array([0, 1, 1, 0], np.uint8), paired=False)
     assert c == {"total_seqs": 4, "filtered_seqs": 2, "total_bp": 420, "output_bp": 200, "filtered_bp": 220, "output_seq_counter": 2}
+
+
+def test_pack_threads_for_rank(monkeypatch):
+    """Host packing threads a rank gets (parallel.pack_threads_for_rank): its share of the CPUs minus four, none when
+    that leaves fewer than two or when four or more ranks share the host's DRAM."""
+    import os
+    from deacon_server_b200 import parallel as P
+    monkeypatch.setattr(os, "cpu_count", lambda: 16)
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(16)))
+    assert P.pack_threads_for_rank(1) == 12
+    assert P.pack_threads_for_rank(2) == 4
+    assert P.pack_threads_for_rank(8) == 0
+    monkeypatch.setattr(os, "cpu_count", lambda: 224)
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(224)))
+    assert P.pack_threads_for_rank(1) == 16
+    assert P.pack_threads_for_rank(2) == 16
+    assert P.pack_threads_for_rank(4) == 0
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(112)))     # bound to one of two sockets
+    assert P.pack_threads_for_rank(2) == 16
