@@ -744,8 +744,10 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         c.a0 = rec_off[(uint64_t)c.u0 * rpu] & ~63ull;   // chunk origin: keeps 16-byte loads and 32-base pack blocks aligned
         c.nb = c.b1 - c.a0;
         c.n_words = 2 * ((c.nb + 31) / 32);
-        c.o_inv = c.n_words * 4; c.o_off_p = align_up(c.o_inv + c.n_words * 2, 8); c.o_nl = c.o_off_p + ((size_t)c.nr + 1) * 8;
-        c.in_packed = c.o_nl + align_up(((size_t)c.nr + 31) / 32 * 4, 8);
+        // packed blob: codes | non-ACGT bits | newline flags | offsets (last: an equal-length chunk does not ship them)
+        c.o_inv = c.n_words * 4; c.o_nl = align_up(c.o_inv + c.n_words * 2, 8);
+        c.o_off_p = c.o_nl + align_up(((size_t)c.nr + 31) / 32 * 4 + 4, 8);   // + one word: the caller-packed form's flags start mid-word
+        c.in_packed = c.o_off_p + ((size_t)c.nr + 1) * 8;
         c.o_off_a = align_up(c.nb + 16, 16); c.in_ascii = c.o_off_a + ((size_t)c.nr + 1) * 8;
         c.out_bytes = (size_t)c.nu * 9;
         return c;
@@ -758,8 +760,10 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         c.nb = std::min<uint64_t>(nb_cap, total_bases + 64);
         c.nr = (uint32_t)std::min<uint64_t>(c.nb / 64 + 2, n_rec); c.nu = c.nr / rpu + 1;
         c.n_words = 2 * ((c.nb + 31) / 32);
-        c.o_inv = c.n_words * 4; c.o_off_p = align_up(c.o_inv + c.n_words * 2, 8); c.o_nl = c.o_off_p + ((size_t)c.nr + 1) * 8;
-        c.in_packed = c.o_nl + align_up(((size_t)c.nr + 31) / 32 * 4, 8);
+        // packed blob: codes | non-ACGT bits | newline flags | offsets (last: an equal-length chunk does not ship them)
+        c.o_inv = c.n_words * 4; c.o_nl = align_up(c.o_inv + c.n_words * 2, 8);
+        c.o_off_p = c.o_nl + align_up(((size_t)c.nr + 31) / 32 * 4 + 4, 8);   // + one word: the caller-packed form's flags start mid-word
+        c.in_packed = c.o_off_p + ((size_t)c.nr + 1) * 8;
         c.o_off_a = align_up(c.nb + 16, 16); c.in_ascii = c.o_off_a + ((size_t)c.nr + 1) * 8;
         c.out_bytes = (size_t)c.nu * 9;
         return c;
@@ -857,10 +861,9 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
             d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_p);
         } else if (route == 2) {
             const uint8_t *hin = s.h_in.as<uint8_t>();
-            if (cs.uniform) {   // codes + non-ACGT bits, then the newline flags; the offsets are generated
+            if (cs.uniform) {   // codes, non-ACGT bits and newline flags in one copy; the offsets are generated
                 CK(cudaMemcpyAsync(din, hin, c.o_off_p, cudaMemcpyHostToDevice, s.stream));
-                CK(cudaMemcpyAsync(din + c.o_nl, hin + c.o_nl, c.in_packed - c.o_nl, cudaMemcpyHostToDevice, s.stream));
-                acc.h2d += c.o_off_p + (c.in_packed - c.o_nl);
+                acc.h2d += c.o_off_p;
                 CK(ship_offsets(din + c.o_off_p, nullptr));
             } else {
                 CK(cudaMemcpyAsync(din, hin, c.in_packed, cudaMemcpyHostToDevice, s.stream));
@@ -940,7 +943,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
                 {
                     std::lock_guard<std::mutex> g(m);
                     if (first_rc || tail <= head || taken_by_packers >= pack_budget) break;
-                    int grab = std::max(1, std::min<int>(packer_grab_max, (tail - head) / (2 * n_packers)));
+                    int grab = std::max(1, std::min<int>(packer_grab_max, (tail - head) / n_packers));
                     grab = std::min(grab, std::min(tail - head, pack_budget - taken_by_packers));
                     a_hi = tail; a_lo = tail -= grab; taken_by_packers += grab;
                 }
@@ -1006,7 +1009,9 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
     int which = 0, rc = DCN_OK;
     while (ascii_route && rc == DCN_OK) {
         Slot &s = ctx->slot[which];
+        const double h0 = now_ms();
         if ((rc = retire(s, main_acc))) break;  // the stage's previous chunk (NSLOT chunks ago)
+        const double h1 = now_ms();
         if (n_packers > 0) {
             // Beside packers the route is decided as late as possible: no more than two ASCII copies are handed to the
             // copy engine ahead of time (one running, one queued: the link never idles), and the chunks shrink as the
@@ -1027,9 +1032,14 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
             a_lo = head;
             a_hi = head = std::min<int>(tail, head + grab);
         }
+        const double h2 = now_ms();
         const ChunkPlan c = make_chunk(a_lo, a_hi);
         const ChunkStats cs = chunk_stats(rec_off + (uint64_t)c.u0 * rpu, c.nu, rpu);
+        const double h3 = now_ms();
         if ((rc = ship(s, c, prepacked ? 1 : 0, cs, main_acc, true))) break;
+        if (trace_level >= 3)
+            fprintf(stderr, "[dcn main] units %u..%u host ms since call: loop %.3f retired %.3f claimed %.3f stats %.3f shipped %.3f\n",
+                    c.u0, c.u1, h0 - t_call0, h1 - t_call0, h2 - t_call0, h3 - t_call0, now_ms() - t_call0);
         which = (which + 1) % dcn_ctx::NSLOT;
     }
     for (int i = 0; i < dcn_ctx::NSLOT; i++) {   // oldest first
