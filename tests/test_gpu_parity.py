@@ -288,6 +288,52 @@ def test_two_route_ingest_long_reads(gpu):
         gpu.host_pack_threads(4)
 
 
+_SMALL_ATOMS = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
+import helpers as H
+import deacon_server_b200 as d
+from oracle import oracle as O
+g = H.random_genome(150_000, 41)
+idx = O.index_build([g], 31, 15, threads=8)
+gpu = d.DeaconGpu(0)
+gpu.index_upload(idx.keys(), d.IndexHeader(2, 31, 15))
+rng = np.random.default_rng(42)
+n = 120_000
+lens = rng.integers(0, 400, n).astype(np.uint64)
+lens[::997] = 9_000                                    # a few long-path units (> DCN_MAX_SHORT) among the short ones
+off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
+total = int(off[-1])
+start = rng.integers(0, len(g) - 300, total // 128 + 2)
+bases = g[(start[:, None] + np.arange(128)[None, :])].reshape(-1)[:total].copy()
+bases[rng.integers(0, total, total // 500)] = ord("N")
+nl = rng.integers(0, n, n // 10); nl = nl[lens[nl] >= 1]
+bases[(off[nl + 1] - 1).astype(np.int64)] = 10         # every tenth record ends in a newline
+for paired, prefix in ((False, 0), (True, 0), (False, 120)):
+    want = O.filter_batch(idx, bases, off, paired=paired, prefix_len=prefix, deplete=paired, threads=8)
+    for threads, fraction in ((0, -1.0), (5, -1.0), (3, 0.5), (5, 1.0)):
+        gpu.host_pack_threads(threads); gpu.host_pack_fraction(fraction)
+        got = gpu.filter_batch(bases, off, paired=paired, prefix_length=prefix, deplete=paired)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), (paired, prefix, threads, fraction)
+print("small atoms ok")
+"""
+
+
+def test_two_route_ingest_small_atoms(tmp_path):
+    """The two-route ingest with 1 MB chunks (128 KB atoms; DCN_CHUNK_MB is read once per process, hence the
+    subprocess): hundreds of atoms per call, every kind of record boundary inside them -- empty and sub-k records,
+    newline-terminated ones, N runs, long-path units, prefix trimming -- on pageable buffers, all splits."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "small_atoms.py"
+    script.write_text(_SMALL_ATOMS)
+    env = dict(os.environ, DCN_CHUNK_MB="1")
+    r = subprocess.run([sys.executable, str(script), root], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "small atoms ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 def test_device_pointer_api_matches_host_api(gpu):
     import torch
     from deacon_server_b200 import IndexHeader
