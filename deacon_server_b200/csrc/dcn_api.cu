@@ -655,13 +655,7 @@ static ChunkStats chunk_stats(const uint64_t *off0, uint32_t nu, uint32_t rpu) {
     memset(&c.st, 0, sizeof(c.st));
     const uint64_t nr = (uint64_t)nu * rpu;
     c.rec_len0 = nr ? off0[1] - off0[0] : 0;
-    // a branch-free pass the compiler vectorises, left at the first block with a mismatch
-    uint64_t diff = 0;
-    for (uint64_t r = 0; r < nr && !diff;) {
-        const uint64_t blk_end = std::min(nr, r + 2048);
-        for (; r < blk_end; r++) diff |= (off0[r + 1] - off0[r]) ^ c.rec_len0;
-    }
-    c.uniform = diff == 0 && nr > 0;
+    c.uniform = nr > 0 && offsets_equal_length(off0, nr, c.rec_len0);
     if (c.uniform) {   // the unit statistics follow from the one length
         const uint64_t len = c.rec_len0 * rpu;
         if (len > DCN_MAX_SHORT) { c.st.n_long = nu; c.st.long_bases = len * nu; }
@@ -784,6 +778,17 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
     }
     auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_call0 = now_ms();
+    // pinned output arrays receive the device's results directly
+    const bool out_pinned = [&] {
+        const void *outs[3] = {keep, hits, total};
+        for (const void *o : outs) {
+            cudaPointerAttributes pa;
+            const bool pinned = cudaPointerGetAttributes(&pa, o) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+            cudaGetLastError();
+            if (!pinned) return false;
+        }
+        return true;
+    }();
 
     // what one thread of the pipeline adds up; merged into the ctx under `m` when the thread is done
     struct Acc {
@@ -797,10 +802,12 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         CK(cudaEventSynchronize(s.ev_done));
         acc.wait_ms += now_ms() - w0;
         const uint32_t nu = s.u1 - s.u0;
-        const uint8_t *o = s.h_out.as<uint8_t>();
-        memcpy(hits + s.u0, o, (size_t)nu * 4);
-        memcpy(total + s.u0, o + (size_t)nu * 4, (size_t)nu * 4);
-        memcpy(keep + s.u0, o + (size_t)nu * 8, nu);
+        if (!out_pinned) {   // results came back through the stage's pinned blob
+            const uint8_t *o = s.h_out.as<uint8_t>();
+            memcpy(hits + s.u0, o, (size_t)nu * 4);
+            memcpy(total + s.u0, o + (size_t)nu * 4, (size_t)nu * 4);
+            memcpy(keep + s.u0, o + (size_t)nu * 8, nu);
+        }
         float a = 0, b = 0, c = 0;
         cudaEventElapsedTime(&a, s.ev_start, s.ev_h2d);
         cudaEventElapsedTime(&b, s.ev_h2d, s.ev_kernel);
@@ -889,7 +896,13 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
                                       s.stream, &cs.st, time_fused);
         if (rc) return rc;
         CK(cudaEventRecord(s.ev_kernel, s.stream));
-        CK(cudaMemcpyAsync(s.h_out.p, dout, c.out_bytes, cudaMemcpyDeviceToHost, s.stream));
+        if (out_pinned) {   // straight into the caller's arrays: no staging blob, no scatter on this thread
+            CK(cudaMemcpyAsync(hits + c.u0, dout, (size_t)c.nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(total + c.u0, dout + (size_t)c.nu * 4, (size_t)c.nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(keep + c.u0, dout + (size_t)c.nu * 8, c.nu, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            CK(cudaMemcpyAsync(s.h_out.p, dout, c.out_bytes, cudaMemcpyDeviceToHost, s.stream));
+        }
         acc.d2h += c.out_bytes;
         CK(cudaEventRecord(s.ev_done, s.stream));
         s.busy = true; s.u0 = c.u0; s.u1 = c.u1; s.packed = route != 0;

@@ -96,6 +96,34 @@ static int simd_level() {   // 0 scalar, 1 AVX2 + BMI2, 2 AVX-512 BW
 }
 #endif
 
+// ------------------------------------------------------------------ equal-length test of a chunk's records
+#ifdef DCN_X86
+__attribute__((target("avx2"))) static uint64_t first_odd_avx2(const uint64_t *off, uint64_t n, uint64_t len0) {
+    const __m256i want = _mm256_set1_epi64x((long long)len0);
+    uint64_t r = 0;
+    for (; r + 16 <= n; r += 16) {   // 16 records per step; left at the first step that holds an odd one
+        __m256i acc = _mm256_setzero_si256();
+        for (int j = 0; j < 16; j += 4) {
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(off + r + j));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(off + r + j + 1));
+            acc = _mm256_or_si256(acc, _mm256_xor_si256(_mm256_sub_epi64(b, a), want));
+        }
+        if (!_mm256_testz_si256(acc, acc)) break;
+    }
+    return r;
+}
+#endif
+
+bool offsets_equal_length(const uint64_t *off, uint64_t n, uint64_t len0) {
+    uint64_t r = 0;
+#ifdef DCN_X86
+    if (simd_level() >= 1) r = first_odd_avx2(off, n, len0);
+#endif
+    for (; r < n; r++)
+        if (off[r + 1] - off[r] != len0) return false;
+    return true;
+}
+
 bool pack_has_simd() {
 #ifdef DCN_X86
     return simd_level() > 0;

@@ -20,4 +20,8 @@ void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv
                 std::vector<uint64_t> *bad32 = nullptr);
 bool pack_has_simd();
 
+// true iff off[r + 1] - off[r] == len0 for every r < n (off holds n + 1 entries): a chunk whose records all have
+// one length gets its offsets written on the device instead of copied.  Memory-speed (AVX2) scan, early exit.
+bool offsets_equal_length(const uint64_t *off, uint64_t n, uint64_t len0);
+
 }  // namespace dcn
