@@ -1015,7 +1015,14 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         pack_busy_ms += acc.pack_ms; pack_wait_ms += acc.wait_ms;
     };
     std::vector<std::thread> packers;
-    for (int t = 0; t < n_packers; t++) packers.emplace_back(packer, t);
+    for (int t = 0; t < n_packers; t++) {
+        try {
+            packers.emplace_back(packer, t);
+        } catch (const std::exception &) {   // thread limit reached: go on with the threads there are
+            break;
+        }
+    }
+    if (packers.empty() && !ascii_route) ascii_route = true;   // nobody to pack: everything goes as ASCII
 
     // ---- the enqueueing thread: ASCII chunks (or the caller's packed arrays) from the front, at the pace of the link
     Acc main_acc;
