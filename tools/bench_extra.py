@@ -129,6 +129,27 @@ if "long" in what:
                       "mean_len": round(nb / n), "ms": round(ms, 3), "gbp_per_s": round(nb / ms / 1e6, 2),
                       "minimizers_per_bp": round(float(tot.sum()) / nb, 4), "kept": int(keep.sum()),
                       "gprobes_per_s": round(float(tot.sum()) / ms / 1e6, 2)}))
+    # the same batch end to end through dcn_filter_batch from pinned host buffers (two-route ingest)
+    hb = bases[:nb].cpu().pin_memory()
+    ho = off.cpu().pin_memory()
+    hk = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    hh = torch.zeros(n, dtype=torch.int32).pin_memory()
+    ht = torch.zeros(n, dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        gpu.filter_batch_ptr(hb.data_ptr(), ho.data_ptr(), n, False, 0, 2, 0.01, False, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
+
+    for _ in range(3):
+        e2e_step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    dt = (time.perf_counter() - t0) / args.steps
+    assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu()) and torch.equal(ht, tot.cpu())
+    h2d, d2h = gpu.last_transfer_bytes()
+    print(json.dumps({"what": "config 3 end to end (dcn_filter_batch, pinned host buffers)", "bases": nb, "ms": round(dt * 1e3, 2),
+                      "gbp_per_s": round(nb / dt / 1e9, 2), "h2d_bytes": int(h2d), "d2h_bytes": int(d2h),
+                      "results": "identical to the device-resident call"}))
     del bases
 
 if "build" in what:
