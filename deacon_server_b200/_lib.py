@@ -36,6 +36,7 @@ SIGNATURES = {
     "dcn_filter_batch_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_newline_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint32, C.c_void_p]),
+    "dcn_pack_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_host_pack_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "dcn_host_pack_fraction": (C.c_int, [C.c_void_p, C.c_double]),
     "dcn_pack_ascii": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),

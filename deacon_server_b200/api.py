@@ -538,3 +538,21 @@ def newline_bits(bases: np.ndarray, rec_off: np.ndarray, k: int = 31, prefix_len
     if rc:
         raise DeaconCudaError(rc, "dcn_newline_bits failed")
     return out
+
+
+def pack_records(bases: np.ndarray, rec_off: np.ndarray, k: int = 31, prefix_length: int = 0):
+    """pack_ascii over bases[:rec_off[-1]] and newline_bits in one pass (dcn_pack_records) -> (codes, inv, nl_bits)."""
+    bases = np.ascontiguousarray(bases, np.uint8)
+    rec_off = np.ascontiguousarray(rec_off, np.uint64)
+    n = len(rec_off) - 1
+    nb = int(rec_off[-1]) if n else 0
+    nw = 2 * ((nb + 31) // 32)
+    codes = np.zeros(max(nw, 1), np.uint32)
+    inv = np.zeros(max(nw, 1), np.uint16)
+    nl = np.zeros(max(1, (n + 31) // 32), np.uint32)
+    bptr = bases.ctypes.data if len(bases) else codes.ctypes.data
+    rc = _lib.load().dcn_pack_records(bptr, rec_off.ctypes.data, n, k, prefix_length, codes.ctypes.data, inv.ctypes.data,
+                                      nl.ctypes.data)
+    if rc:
+        raise DeaconCudaError(rc, "dcn_pack_records failed")
+    return codes[:nw], inv[:nw], nl

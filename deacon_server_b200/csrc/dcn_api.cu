@@ -973,32 +973,8 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
                 uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
                 uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + c.o_inv);
                 uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + c.o_nl);
-                // Newline flags (src/filter_common.rs:229): a record's last byte can only be '\n' inside a 32-base
-                // block the packer found a non-ACGT byte in, so the packer lists those blocks and only the records
-                // ending inside them are looked at (a per-record pass over the atom cost 28 % of the packing time).
-                bad32.clear();
-                pack_ascii(bases + c.a0, c.nb, h_codes, h_inv, 1, &bad32);
-                memset(h_nl, 0, ((size_t)c.nr + 31) / 32 * 4);
-                auto rec_end = [&](uint32_t q) {   // one past the last byte the reference looks at
-                    const uint64_t len = off0[q + 1] - off0[q];
-                    return off0[q] + ((prefix_len > 0 && len > prefix_len) ? prefix_len : len);   // :222-226
-                };
-                uint32_t q0 = 0;
-                for (const uint64_t bi : bad32) {
-                    const uint64_t B = c.a0 + 32 * bi;   // block [B, B + 32); rec_end is non-decreasing in q
-                    uint32_t lo = q0, hi = c.nr;         // first record with rec_end > B
-                    while (lo < hi) {
-                        const uint32_t mid = lo + (hi - lo) / 2;
-                        if (rec_end(mid) > B) hi = mid; else lo = mid + 1;
-                    }
-                    q0 = lo;
-                    for (uint32_t q = lo; q < c.nr; q++) {
-                        const uint64_t e = rec_end(q);
-                        if (e > B + 32) break;
-                        if (off0[q + 1] - off0[q] < (uint64_t)ctx->k) continue;                            // :217-219
-                        if (bases[e - 1] == (uint8_t)'\n') h_nl[q / 32] |= 1u << (q % 32);
-                    }
-                }
+                // codes, non-ACGT bits and newline flags in one pass over the atom (dcn_host_pack.h)
+                pack_records(bases, c.a0, c.nb, off0, c.nr, ctx->k, prefix_len, h_codes, h_inv, h_nl, bad32);
                 acc.pack_ms += now_ms() - t0;
                 acc.packed_bases += c.nb;
                 if ((r = ship(s, c, 2, cs, acc, false))) return r;
@@ -1137,6 +1113,14 @@ int dcn_host_pack_threads(dcn_ctx *ctx, int n_threads) {
     ctx->pack_threads = n_threads;
     ctx->pack_gbps = 0;
 
+    return DCN_OK;
+}
+
+int dcn_pack_records(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
+                     uint32_t *codes, uint16_t *inv, uint32_t *nl_bits) {
+    if (!rec_off || !codes || !inv || !nl_bits || (!bases && n_rec && rec_off[n_rec] > 0)) return DCN_ERR_ARG;
+    std::vector<uint64_t> bad32;
+    pack_records(bases, 0, n_rec ? rec_off[n_rec] : 0, rec_off, n_rec, k, prefix_len, codes, inv, nl_bits, bad32);
     return DCN_OK;
 }
 

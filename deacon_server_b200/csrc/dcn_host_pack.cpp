@@ -96,6 +96,34 @@ static int simd_level() {   // 0 scalar, 1 AVX2 + BMI2, 2 AVX-512 BW
 }
 #endif
 
+// ------------------------------------------------------------------ packing + newline flags in one pass
+void pack_records(const uint8_t *bases, uint64_t a0, uint64_t nb, const uint64_t *off0, uint32_t nr, uint32_t k,
+                  uint32_t prefix_len, uint32_t *codes, uint16_t *inv, uint32_t *nl, std::vector<uint64_t> &bad32) {
+    bad32.clear();
+    pack_ascii(bases + a0, nb, codes, inv, 1, &bad32);
+    memset(nl, 0, ((size_t)nr + 31) / 32 * 4);
+    auto rec_end = [&](uint32_t q) {   // one past the last byte the reference looks at
+        const uint64_t len = off0[q + 1] - off0[q];
+        return off0[q] + ((prefix_len > 0 && len > prefix_len) ? prefix_len : len);   // src/filter_common.rs:222-226
+    };
+    uint32_t q0 = 0;
+    for (const uint64_t bi : bad32) {
+        const uint64_t B = a0 + 32 * bi;   // block [B, B + 32); rec_end is non-decreasing in q
+        uint32_t lo = q0, hi = nr;         // first record with rec_end > B
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (rec_end(mid) > B) hi = mid; else lo = mid + 1;
+        }
+        q0 = lo;
+        for (uint32_t q = lo; q < nr; q++) {
+            const uint64_t e = rec_end(q);
+            if (e > B + 32) break;
+            if (off0[q + 1] - off0[q] < (uint64_t)k) continue;                               // :217-219
+            if (bases[e - 1] == (uint8_t)'\n') nl[q / 32] |= 1u << (q % 32);                // :229
+        }
+    }
+}
+
 // ------------------------------------------------------------------ equal-length test of a chunk's records
 #ifdef DCN_X86
 __attribute__((target("avx2"))) static uint64_t first_odd_avx2(const uint64_t *off, uint64_t n, uint64_t len0) {

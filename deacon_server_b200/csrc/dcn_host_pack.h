@@ -20,6 +20,14 @@ void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv
                 std::vector<uint64_t> *bad32 = nullptr);
 bool pack_has_simd();
 
+// One pass over a chunk: packs bases[a0 .. a0 + nb) (pack_ascii) and writes the newline flags of its `nr` records
+// (off0[0 .. nr], absolute offsets into `bases`, off0[0] >= a0): bit q of nl = record q has raw length >= k and the
+// last byte of its effective prefix is '\n' (src/filter_common.rs:217-229).  A record can only end in '\n' inside
+// a 32-base block where the packer saw a non-ACGT byte, so only the records ending inside the listed blocks are
+// looked at (a per-record pass over the chunk costs 28 % of the packing time).  `bad32` is scratch.
+void pack_records(const uint8_t *bases, uint64_t a0, uint64_t nb, const uint64_t *off0, uint32_t nr, uint32_t k,
+                  uint32_t prefix_len, uint32_t *codes, uint16_t *inv, uint32_t *nl, std::vector<uint64_t> &bad32);
+
 // true iff off[r + 1] - off[r] == len0 for every r < n (off holds n + 1 entries): a chunk whose records all have
 // one length gets its offsets written on the device instead of copied.  Memory-speed (AVX2) scan, early exit.
 bool offsets_equal_length(const uint64_t *off, uint64_t n, uint64_t len0);

@@ -107,6 +107,12 @@ int dcn_filter_batch_packed(dcn_ctx *ctx, const uint32_t *codes, const uint16_t 
  * (the one byte of the ASCII form the packed form cannot tell from other non-ACGT bytes; src/filter_common.rs:229). */
 int dcn_newline_bits(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
                      uint32_t *nl_bits);
+/* dcn_pack_ascii over bases [0, rec_off[n_rec]) and dcn_newline_bits in ONE pass over the bytes (no GPU needed): what
+ * the library's own packer threads run per chunk, and what a parser that wants dcn_filter_batch_packed should call.
+ * The flags cost nothing extra: only records that end inside a 32-base block holding a non-ACGT byte are looked at.
+ * codes / inv: 2 * ceil(rec_off[n_rec] / 32) entries each; nl_bits: ceil(n_rec / 32) words. */
+int dcn_pack_records(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
+                     uint32_t *codes, uint16_t *inv, uint32_t *nl_bits);
 
 /* ---- B2: batch classify on pre-hashed records --------------------------------------------------
  * Replaces unpaired_should_keep / paired_should_keep (src/remote_filter.rs:230-301), i.e. the body of

@@ -72,6 +72,39 @@ def test_host_classification_matches_oracle():
     assert api.meets_filtering_criteria(0, 0, 2, 0.01, False) is False
 
 
+def test_pack_records_matches_the_two_separate_passes():
+    """dcn_pack_records (what the pipeline's packer threads run per chunk; no GPU needed) == dcn_pack_ascii +
+    dcn_newline_bits: the newline flags come from the packer's list of blocks with a non-ACGT byte, so every place a
+    flag can hide is exercised -- newline-terminated records of every length around k and the prefix, newlines in the
+    middle of records, runs of N, empty records, records ending on 32- and 64-base block edges."""
+    rng = np.random.default_rng(12)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    for n_rec, prefix in ((0, 0), (1, 0), (700, 0), (700, 40), (5000, 0), (5000, 100)):
+        lens = rng.integers(0, 130, n_rec).astype(np.uint64)
+        if n_rec > 100:
+            lens[::7] = 64                                              # block-edge endings
+            lens[3::11] = 0
+            lens[5::13] = rng.integers(28, 36, len(lens[5::13]))        # around k
+        off = np.zeros(n_rec + 1, np.uint64)
+        off[1:] = np.cumsum(lens)
+        nb = int(off[-1])
+        b = acgt[rng.integers(0, 4, nb)] if nb else np.zeros(0, np.uint8)
+        if nb:
+            b[rng.integers(0, nb, nb // 40)] = ord("N")
+            b[rng.integers(0, nb, nb // 60)] = 10                       # newlines anywhere
+            ends = off[1:][lens > 0] - np.uint64(1)
+            b[ends[rng.random(len(ends)) < 0.5].astype(np.int64)] = 10  # half of the records end in one
+            pre = (off[:-1] + np.uint64(prefix) - np.uint64(1))[lens > prefix] if prefix else np.zeros(0, np.uint64)
+            b[pre[rng.random(len(pre)) < 0.5].astype(np.int64)] = 10    # ... or their prefix does
+        codes, inv, nl = api.pack_records(b, off, 31, prefix)
+        want_c, want_i = api.pack_ascii(b)
+        want_nl = api.newline_bits(b, off, 31, prefix)
+        assert np.array_equal(codes, want_c) and np.array_equal(inv, want_i), (n_rec, prefix)
+        assert np.array_equal(nl, want_nl), (n_rec, prefix)
+        if n_rec >= 700:
+            assert int(np.unpackbits(nl.view(np.uint8)).sum()) > n_rec // 8
+
+
 def test_product_packer_matches_definition():
     """dcn_pack_ascii (the ingest stage of dcn_filter_batch; runs on the host, no GPU needed):
     code = (byte >> 1) & 3 (src/filter_common.rs:238), non-ACGT mask (:245-258)."""
