@@ -605,6 +605,24 @@ static int pack_threads_of(dcn_ctx *ctx) {   // -> host threads available for pa
         int hc = (int)std::thread::hardware_concurrency();
         cpu_set_t cs;   // a process bound to the CPUs next to its GPU (one rank per GPU) counts only those
         if (sched_getaffinity(0, sizeof(cs), &cs) == 0 && CPU_COUNT(&cs) > 0) hc = std::min(hc, (int)CPU_COUNT(&cs));
+        // ... and a container's CPU quota counts too (cgroup v2 cpu.max, v1 cfs quota / period)
+        auto quota_cpus = []() -> int {
+            long long q = -1, per = 100000;
+            if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+                char buf[64] = {0};
+                if (fscanf(f, "%63s %lld", buf, &per) >= 1 && strcmp(buf, "max") != 0) q = atoll(buf);
+                fclose(f);
+            } else if (FILE *f1 = fopen("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", "r")) {
+                if (fscanf(f1, "%lld", &q) != 1) q = -1;
+                fclose(f1);
+                if (FILE *f2 = fopen("/sys/fs/cgroup/cpu/cpu.cfs_period_us", "r")) {
+                    if (fscanf(f2, "%lld", &per) != 1) per = 100000;
+                    fclose(f2);
+                }
+            }
+            return (q > 0 && per > 0) ? (int)std::max<long long>(1, (q + per - 1) / per) : 0;
+        }();
+        if (quota_cpus > 0) hc = std::min(hc, quota_cpus);
         int n = e ? atoi(e) : std::min(std::max(hc - 4, 1), 16);
         ctx->pack_threads = std::max(0, std::min(n, 256));
     }
