@@ -109,14 +109,14 @@ struct dcn_ctx {
     DevBuf gx_bases, gx_off, gx_rc, gx_cc, gx_tmp, gx_h, gx_p, gx_oo, gx_entropy;
     static const int NSLOT = 4;
     Slot slot[NSLOT];
-    // host ingest (packing) pool; pack_threads = 0 ships ASCII over PCIe instead
-    int pack_threads = -1;   // -1: decide at first use (DCN_PACK_THREADS or min(hardware threads, 16))
-    std::vector<Slot> pslot;   // two stages per packer thread (filter_pipeline), created by the threads themselves
+    // host ingest (filter_pipeline): pack_threads = 0 ships everything as ASCII over PCIe
+    int pack_threads = -1;   // -1: decide at first use (DCN_PACK_THREADS, or the CPUs this process may use - 4, at most 16)
+    std::vector<Slot> pslot;   // the stages of the packer threads (four each), created by the threads themselves
     float t_pack = 0;
-    // Ingest: a chunk is either packed by the host pool (CPU reads 1 B/bp, PCIe carries 0.4 B/bp) or shipped
-    // as ASCII (PCIe carries 1 B/bp, no CPU work); `pack_fraction` of the chunks take the first route.
+    // A chunk is either packed by a host thread (the CPU reads 1 B/bp, PCIe carries 0.43 B/bp) or shipped as ASCII
+    // (PCIe carries 1 B/bp, no CPU work); `pack_fraction` caps the share of the batch the first route may take.
     double pack_gbps = 0;       // packing rate of the last call that packed (ASCII GB/s), for reporting
-    double pack_fraction = -1;  // < 0: automatic (pinned caller buffers: 0, pageable: 1); DCN_PACK_FRACTION overrides
+    double pack_fraction = -1;  // < 0: automatic (pinned caller buffers: dynamic split, pageable: 1); DCN_PACK_FRACTION overrides
     uint64_t n_packed_chunks = 0, n_ascii_chunks = 0, n_uniform_chunks = 0;
     std::atomic<uint64_t> launches{0};
     float t_h2d = 0, t_kernel = 0, t_d2h = 0;
