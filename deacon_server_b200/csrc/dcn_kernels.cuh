@@ -91,7 +91,7 @@ struct BatchStats {
     uint32_t n_chunks;       // chunk descriptors written
     uint32_t overflow;       // an internal table overflowed
     uint32_t n_long_listed;  // entries of the long-unit list
-    uint32_t pad;
+    uint32_t tile_claims;    // tiles claimed beyond the first wave (filter_fused_kernel)
     unsigned long long long_bases;  // bases in long units
 };
 
@@ -187,7 +187,7 @@ __global__ void prep_tiles_kernel(const uint64_t *__restrict__ rec_off, uint32_t
 }
 
 // ------------------------------------------------------------------ the fused filter kernel
-// Persistent CTAs; tile i -> CTA (i mod grid).  4 CTAs per SM (64 registers, ~53 KB shared memory each).
+// Persistent CTAs; the first wave takes tile = CTA index, later tiles are claimed from a counter.  4 CTAs per SM (64 registers, ~53 KB shared memory each).
 #ifndef DCN_CTAS_PER_SM
 #define DCN_CTAS_PER_SM (1024 / DCN_NT)
 #endif
@@ -201,6 +201,13 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     ex.wsum = s.wsum;
     init_tables<G>((int)threadIdx.x, s);
     init_required<G>((int)threadIdx.x, s, P.abs_thr, P.rel_thr);
+    // Tiles beyond the first wave are claimed from a counter (BatchStats::tile_claims, cleared with the plan) instead of
+    // dealt out round-robin: a CTA that drew cheap tiles takes more of them (static map: 185.3 Gbp/s, claims: 197.8).
+    // The claim for the tile after next is issued by thread 0 at the top of a tile and read by everyone at the top of
+    // the next one (the barriers of the tile in between order the two slots).
+    unsigned int *tile_ctr = const_cast<unsigned int *>(&st->tile_claims);
+    if (threadIdx.x == 0) s.next_tile[0] = gridDim.x + atomicAdd(tile_ctr, 1u);
+    uint32_t par = 0;
     __syncthreads();
     const PlanCfg cfg = plan_make_cfg<G>(st->max_short);
     const uint32_t n_tiles = plan_num_tiles(P.n_bases - P.base0, cfg);
@@ -211,7 +218,9 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     if (tile < n_tiles) { a = tile_first[tile]; b = tile_end[tile]; }
     ex.pf_off = P.rec_off;
     while (tile < n_tiles) {
-        const uint32_t nt = tile + gridDim.x;
+        const uint32_t nt = s.next_tile[par];
+        if (threadIdx.x == 0) s.next_tile[par ^ 1u] = nt < n_tiles ? gridDim.x + atomicAdd(tile_ctr, 1u) : 0xFFFFFFFFu;
+        par ^= 1u;
         uint32_t a2 = 0, b2 = 0;
         if (nt < n_tiles) {
             a2 = tile_first[nt]; b2 = tile_end[nt];
@@ -229,6 +238,7 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
         }
         ex.pf_lo = a2 * P.rpu; ex.pf_hi = b2 * P.rpu;   // a2 == b2 == 0: one harmless line
         if (a < b) filter_tile<G, PACKED, MODE_FILTER>(ex, s, P, cfg, n_long, a, b);
+        else __syncthreads();   // an empty tile has no barrier of its own to order the claim slots
         tile = nt; a = a2; b = b2;
     }
     if (n_long) {  // long units: chunks, spread over the CTAs in reverse so short and long work interleave

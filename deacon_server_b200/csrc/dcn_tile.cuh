@@ -69,6 +69,7 @@ struct alignas(16) TileSmem {
     uint16_t rec_eff[G::MAXR];        // end of the record's effective sequence (tile-local)
     uint32_t wsum[16];
     uint32_t npicks;
+    uint32_t next_tile[2];            // tile claims of filter_fused_kernel: next tile, tile after next
     uint16_t req[256];                // required_hits(total) for total < 256 (src/filter_common.rs:84-96), filled once per CTA
 };
 template <class G>
