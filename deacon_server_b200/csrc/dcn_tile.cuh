@@ -832,6 +832,7 @@ DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const Pla
         return;
     }
     uint32_t u = u_first;
+    bool any = false;
     while (u < u_end) {
         uint64_t len = P.rec_off[(uint64_t)(u + 1) * rpu] - P.rec_off[(uint64_t)u * rpu];
         if (len > cfg.max_short) { u++; continue; }
@@ -842,7 +843,10 @@ DCN_HD void filter_tile(Ex &ex, TileSmem<G> &s, const FilterParams &P, const Pla
         filter_short_run<G, PACKED, MODE>(ex, s, P, u, v);
         ex.barrier();  // a following pass rewrites the tables the last phase still reads
         u = v;
+        any = true;
     }
+    // a tile of long units only: the caller's tile-claim slots (filter_fused_kernel) rely on at least one barrier per tile
+    if (!any) ex.barrier();
 }
 
 // =====================================================================================
