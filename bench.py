@@ -366,7 +366,8 @@ def run_ours(args):
                          "random_sector_ceiling_gsectors_per_s": round(nprobe / (rms * 1e-3) / 1e9, 3),
                          "int_alu_pipe_pct_of_peak": traffic.get("alu_pipe_pct_of_peak") if traffic else None,
                          "issue_slots_pct": traffic.get("issue_active_pct") if traffic else None,
-                         "note": "integer-ALU bound, not HBM bound (ncu: profiles/r1_final_fused_ncu_summary.json); "
+                         "note": "integer-ALU bound, not HBM bound (ncu: profiles/r1_final_fused_ncu_summary.json, captured one "
+                                 "scheduling change earlier at 8.10 ms/launch: traffic and pipe percentages are that launch's); "
                                  "the lookup kernel alone (dcn_lookup_batch) runs at 89 % of the random-sector ceiling: DESIGN.md"},
             "cpu_baseline": cpu,
             "clocks": clk,
