@@ -93,6 +93,9 @@ struct BatchStats {
     uint32_t n_long_listed;  // entries of the long-unit list
     uint32_t tile_claims;    // tiles claimed beyond the first wave (filter_fused_kernel)
     unsigned long long long_bases;  // bases in long units
+#ifdef DCN_DYNAMIC_CHUNKS
+    uint32_t chunk_claims, pad2;    // long-path chunks claimed beyond the first wave (inside the plan's 64-byte header)
+#endif
 };
 
 // ------------------------------------------------------------------ prep: unit statistics
@@ -244,8 +247,26 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     if (n_long) {  // long units: chunks, spread over the CTAs in reverse so short and long work interleave
         __syncthreads();
         const uint32_t n_chunks = st->n_chunks;
+#ifdef DCN_DYNAMIC_CHUNKS
+        // UNMEASURED build variant (make EXTRA=-DDCN_DYNAMIC_CHUNKS): chunks beyond the first wave are
+        // claimed from a counter like the tiles above (a chunk's cost follows its hit density).  Every chunk passes
+        // barriers (the phases of chunk_picks), which order the two claim slots.
+        unsigned int *chunk_ctr = const_cast<unsigned int *>(&st->chunk_claims);
+        if (threadIdx.x == 0) s.next_tile[0] = gridDim.x + atomicAdd(chunk_ctr, 1u);
+        uint32_t cpar = 0;
+        __syncthreads();
+        uint32_t w = gridDim.x - 1 - blockIdx.x;
+        while (w < n_chunks) {
+            const uint32_t nw = s.next_tile[cpar];
+            if (threadIdx.x == 0) s.next_tile[cpar ^ 1u] = nw < n_chunks ? gridDim.x + atomicAdd(chunk_ctr, 1u) : 0xFFFFFFFFu;
+            cpar ^= 1u;
+            filter_long_chunk<G, PACKED>(ex, s, P, dd, desc[w]);
+            w = nw;
+        }
+#else
         for (uint32_t w = gridDim.x - 1 - blockIdx.x; w < n_chunks; w += gridDim.x)
             filter_long_chunk<G, PACKED>(ex, s, P, dd, desc[w]);
+#endif
     }
 }
 
