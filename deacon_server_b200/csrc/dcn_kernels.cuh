@@ -248,7 +248,8 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
         __syncthreads();
         const uint32_t n_chunks = st->n_chunks;
 #ifdef DCN_DYNAMIC_CHUNKS
-        // UNMEASURED build variant (make EXTRA=-DDCN_DYNAMIC_CHUNKS): chunks beyond the first wave are
+        // Build variant, off by default until its parity run exists (make EXTRA=-DDCN_DYNAMIC_CHUNKS; DESIGN.md 9:
+        // 127.7 -> 143.2 Gbp/s on the config-3 batch in one measurement): chunks beyond the first wave are
         // claimed from a counter like the tiles above (a chunk's cost follows its hit density).  Every chunk passes
         // barriers (the phases of chunk_picks), which order the two claim slots.
         unsigned int *chunk_ctr = const_cast<unsigned int *>(&st->chunk_claims);
