@@ -95,6 +95,7 @@ struct dcn_ctx {
     int has_empty = 0;
     uint8_t k = 0, w = 0;
     double load = 0.5;
+    int fused_impl = 0;   // 0: warp tiles (filter_warp_kernel + filter_tail_kernel); 1: CTA tiles (filter_fused_kernel), DCN_FUSED_IMPL=cta
     // scratch
     DevBuf plan;       // BatchStats + tile_first + tile_end (one memset clears all three)
     DevBuf counters;   // 6 x u64 ProcessingStats + 2 x u64 table-build counters
@@ -142,6 +143,16 @@ struct dcn_ctx {
     } while (0)
 
 using G31 = Geo<31, 15>;
+
+static size_t warp_kernel_smem() { return ((sizeof(WarpTables) + 15) & ~(size_t)15) + DCN_WARPS * (sizeof(WarpPipe) + sizeof(WarpSmem)); }
+
+// warp-tile plan: the 64-byte header + the tile list.  A tile ends because the next unit does not fit (it then spans
+// more than TB - 15 - DCN_MAX_SHORT bases), because it holds MAXR records, because a long unit follows, or at a
+// segment end.
+static uint64_t wplan_tile_cap(uint64_t n_rel, uint32_t n_rec) {
+    return n_rel / (uint64_t)(WG::TB - 15 - (int)DCN_MAX_SHORT) + (uint64_t)n_rec / (WG::MAXR / 2) + n_rel / DCN_MAX_SHORT + n_rel / DCN_WSEG + 16;
+}
+static uint64_t wplan_ovf_cap(uint64_t n_rel) { return n_rel / WG::PKCAP + 16; }   // a unit of more than PKCAP picks has more than PKCAP bases
 
 static size_t plan_bytes(uint64_t n_rel_bases) {
     // smallest stride the planner can choose -> most tiles
@@ -330,12 +341,18 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         return ctx->fail(DCN_ERR_ARG, "d_bases must be 16-byte aligned");
 
     const uint64_t n_rel = n_bases_abs - base0;
-    const size_t pbytes = plan_bytes(n_rel);
+    const bool warp_impl = ctx->fused_impl == 0;
+    // plan buffer: 64-byte header (BatchStats), then the tile plan.  CTA tiles: tile_first | tile_end (cleared per call);
+    // warp tiles: the tile list | the list of units handed to the CTA path (only the header is cleared).
+    const uint64_t wtile_cap = wplan_tile_cap(n_rel, n_rec), wovf_cap = wplan_ovf_cap(n_rel);
+    const size_t pbytes = warp_impl ? 64 + (size_t)wtile_cap * sizeof(WTile) + (size_t)wovf_cap * 4 : plan_bytes(n_rel);
     CK(plan.ensure(pbytes));
-    const uint64_t n_tiles_max = (pbytes - 64) / (2 * sizeof(uint32_t));
+    const uint64_t n_tiles_max = (plan_bytes(n_rel) - 64) / (2 * sizeof(uint32_t));
     BatchStats *d_stats = plan.as<BatchStats>();
     uint32_t *tile_first = reinterpret_cast<uint32_t *>(plan.as<uint8_t>() + 64);
     uint32_t *tile_end = tile_first + n_tiles_max;
+    WTile *wtiles = reinterpret_cast<WTile *>(plan.as<uint8_t>() + 64);
+    uint32_t *wovf = reinterpret_cast<uint32_t *>(plan.as<uint8_t>() + 64 + (size_t)wtile_cap * sizeof(WTile));
 
     FilterParams P;
     P.bases = d_bases; P.pk_codes = in.codes; P.pk_inv = in.inv; P.nl_bits = in.nl; P.nl_bit0 = in.nl_bit0; P.base0 = base0; P.n_bases = n_bases_abs;
@@ -349,14 +366,18 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     const size_t smem = sizeof(TileSmem<G31>);
     const uint64_t tiles_lb = n_rel / G31::BCAP + 1;
     const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * DCN_CTAS_PER_SM);
+    const int wgrid = (int)std::min<uint64_t>((n_rel / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count);
+    const uint64_t n_seg = (n_rel + DCN_WSEG - 1) / DCN_WSEG;
+    const int sg = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_seg + 63) / 64, (uint64_t)ctx->sm_count * 8));
 
     // A batch can only contain a long unit if it holds more than DCN_MAX_SHORT bases; otherwise the
     // stats readback (one small sync) is skipped.
     uint64_t dedup_cap = 0;
     for (int attempt = 0; attempt < 4; attempt++) {
-        CK(cudaMemsetAsync(plan.p, 0, pbytes, st));
+        CK(cudaMemsetAsync(plan.p, 0, warp_impl ? 64 : pbytes, st));
         prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_stats);
-        prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, rpu, n_units, base0, d_stats, tile_first, tile_end);
+        if (warp_impl) wplan_kernel<<<sg, 64, 0, st>>>(d_off, rpu, n_units, base0, n_rel, d_stats, wtiles, (uint32_t)std::min<uint64_t>(wtile_cap, 0xFFFFFFFFull));
+        else prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, rpu, n_units, base0, d_stats, tile_first, tile_end);
         ctx->launches += 2;
         BatchStats hs;
         memset(&hs, 0, sizeof(hs));
@@ -388,7 +409,17 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         }
         const uint32_t ke = ctx->kev_head % dcn_ctx::KEV;
         if (time_fused) CK(cudaEventRecord(ctx->kev0[ke], st));
-        if (in.codes) filter_fused_kernel<G31, true><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
+        if (warp_impl) {
+            // short units: warp tiles; then the CTA-tile tail (units of more than a warp pass's picks, long chunks).  With
+            // no long unit in the batch the tail only has work on pathological input, so a few CTAs are enough.
+            const uint32_t ocap = (uint32_t)std::min<uint64_t>(wovf_cap, 0xFFFFFFFFull);
+            if (in.codes) filter_warp_kernel<true><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap);
+            else filter_warp_kernel<false><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap);
+            const int tgrid = hs.n_long ? grid : std::min(grid, 16);
+            if (in.codes) filter_tail_kernel<G31, true><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc);
+            else filter_tail_kernel<G31, false><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc);
+            ctx->launches += 1;
+        } else if (in.codes) filter_fused_kernel<G31, true><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
         else filter_fused_kernel<G31, false><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
         if (time_fused) {
             CK(cudaEventRecord(ctx->kev1[ke], st));
@@ -459,6 +490,15 @@ dcn_ctx *dcn_ctx_create(int device) {
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)warp_kernel_smem()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)warp_kernel_smem()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_tail_kernel<G31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(TileSmem<G31>)) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_tail_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(TileSmem<G31>)) == cudaSuccess;
+    if (const char *fi = getenv("DCN_FUSED_IMPL")) ctx->fused_impl = strcmp(fi, "cta") == 0 ? 1 : 0;
     ok = ok && cudaFuncSetAttribute(extract_tiles_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(extract_index_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "dcn_tile.cuh"
+#include "dcn_warp.cuh"
 
 namespace dcn {
 
@@ -93,10 +94,12 @@ struct BatchStats {
     uint32_t n_long_listed;  // entries of the long-unit list
     uint32_t tile_claims;    // tiles claimed beyond the first wave (filter_fused_kernel)
     unsigned long long long_bases;  // bases in long units
-#ifdef DCN_DYNAMIC_CHUNKS
-    uint32_t chunk_claims, pad2;    // long-path chunks claimed beyond the first wave (inside the plan's 64-byte header)
-#endif
+    uint32_t chunk_claims;   // long-path chunks claimed beyond the first wave (filter_tail_kernel)
+    uint32_t n_wtiles;       // warp tiles written by the planner (filter_warp_kernel)
+    uint32_t n_ovf;          // units handed from the warp path to the CTA path (more picks than a warp pass holds)
+    uint32_t ovf_claims;
 };
+static_assert(sizeof(BatchStats) <= 64, "the plan header is 64 bytes");
 
 // ------------------------------------------------------------------ prep: unit statistics
 __global__ void prep_stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,
@@ -189,6 +192,29 @@ __global__ void prep_tiles_kernel(const uint64_t *__restrict__ rec_off, uint32_t
         plan_unit_tiles(rec_off, base0, rpu, n_units, u, cfg, tile_first, tile_end);
 }
 
+// ------------------------------------------------------------------ long path: chunks of long units
+// The first wave takes chunk = (last CTA first, so that short and long work interleave in the fused kernel); chunks
+// beyond it are claimed from a counter like the tiles: a chunk's cost follows its hit density (host-derived chunks hit
+// on every probe, random ones never).  Measured on the config-3 batch: 127.7 -> 143.2 Gbp/s against the static map.
+// Every chunk passes barriers (the phases of chunk_picks), which order the two claim slots.
+template <class G, bool PACKED>
+__device__ __forceinline__ void long_chunks_loop(DevExec<G> &ex, TileSmem<G> &s, const FilterParams &P, const DedupView &dd,
+                                                 const ChunkDesc *__restrict__ desc, const BatchStats *st) {
+    const uint32_t n_chunks = st->n_chunks;
+    unsigned int *chunk_ctr = const_cast<unsigned int *>(&st->chunk_claims);
+    if (threadIdx.x == 0) s.next_tile[0] = gridDim.x + atomicAdd(chunk_ctr, 1u);
+    uint32_t cpar = 0;
+    __syncthreads();
+    uint32_t w = gridDim.x - 1 - blockIdx.x;
+    while (w < n_chunks) {
+        const uint32_t nw = s.next_tile[cpar];
+        if (threadIdx.x == 0) s.next_tile[cpar ^ 1u] = nw < n_chunks ? gridDim.x + atomicAdd(chunk_ctr, 1u) : 0xFFFFFFFFu;
+        cpar ^= 1u;
+        filter_long_chunk<G, PACKED>(ex, s, P, dd, desc[w]);
+        w = nw;
+    }
+}
+
 // ------------------------------------------------------------------ the fused filter kernel
 // Persistent CTAs; the first wave takes tile = CTA index, later tiles are claimed from a counter.  4 CTAs per SM (64 registers, ~53 KB shared memory each).
 #ifndef DCN_CTAS_PER_SM
@@ -246,28 +272,224 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
     }
     if (n_long) {  // long units: chunks, spread over the CTAs in reverse so short and long work interleave
         __syncthreads();
-        const uint32_t n_chunks = st->n_chunks;
-#ifdef DCN_DYNAMIC_CHUNKS
-        // Build variant, off by default until its parity run exists (make EXTRA=-DDCN_DYNAMIC_CHUNKS; DESIGN.md 9:
-        // 127.7 -> 143.2 Gbp/s on the config-3 batch in one measurement): chunks beyond the first wave are
-        // claimed from a counter like the tiles above (a chunk's cost follows its hit density).  Every chunk passes
-        // barriers (the phases of chunk_picks), which order the two claim slots.
-        unsigned int *chunk_ctr = const_cast<unsigned int *>(&st->chunk_claims);
-        if (threadIdx.x == 0) s.next_tile[0] = gridDim.x + atomicAdd(chunk_ctr, 1u);
-        uint32_t cpar = 0;
-        __syncthreads();
-        uint32_t w = gridDim.x - 1 - blockIdx.x;
-        while (w < n_chunks) {
-            const uint32_t nw = s.next_tile[cpar];
-            if (threadIdx.x == 0) s.next_tile[cpar ^ 1u] = nw < n_chunks ? gridDim.x + atomicAdd(chunk_ctr, 1u) : 0xFFFFFFFFu;
-            cpar ^= 1u;
-            filter_long_chunk<G, PACKED>(ex, s, P, dd, desc[w]);
-            w = nw;
-        }
-#else
-        for (uint32_t w = gridDim.x - 1 - blockIdx.x; w < n_chunks; w += gridDim.x)
-            filter_long_chunk<G, PACKED>(ex, s, P, dd, desc[w]);
+        long_chunks_loop<G, PACKED>(ex, s, P, dd, desc, st);
+    }
+}
+
+// ------------------------------------------------------------------ warp-tile planner
+// One thread per 64 KB segment of the batch walks its units twice (count, reserve a block of the tile list with one
+// atomic, write).  The list order is irrelevant: tiles are claimed from a counter.
+__global__ void wplan_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units, uint64_t base0,
+                             uint64_t n_rel, BatchStats *st, WTile *tiles, uint32_t tile_cap) {
+    const uint64_t n_seg = (n_rel + DCN_WSEG - 1) / DCN_WSEG;
+    for (uint64_t seg = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; seg < n_seg; seg += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t n = wplan_segment(rec_off, base0, rpu, n_units, seg, [](uint64_t, uint32_t, uint32_t) {});
+        if (!n) continue;
+        uint32_t at = atomicAdd(&st->n_wtiles, n);
+        wplan_segment(rec_off, base0, rpu, n_units, seg, [&](uint64_t origin, uint32_t a, uint32_t b) {
+            if (at < tile_cap) { WTile t; t.origin = origin; t.a = a; t.b = b; tiles[at] = t; }
+            else st->overflow = 1;
+            at++;
+        });
+    }
+}
+
+// ------------------------------------------------------------------ the warp-tile filter kernel (short units)
+// One persistent CTA of 32 warps per SM; every warp runs tiles on its own (dcn_warp.cuh): the first wave takes tile =
+// global warp index, later tiles are claimed from a counter two tiles ahead.  The tile's bytes are brought into the
+// warp's stage by one bulk copy (cp.async.bulk -> mbarrier complete_tx) issued by lane 0 as soon as the previous
+// tile's convert phase has drained the stage, i.e. the copy of tile i + 1 runs under the hash / slice / probe / count
+// phases of tile i.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t phase) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+#ifndef DCN_WARPS
+#define DCN_WARPS 32            // warps per CTA of filter_warp_kernel (one CTA per SM): 32 x 64 registers
 #endif
+
+// Per-warp pipeline state that is only touched between tiles lives in shared memory, not in registers: the
+// descriptors of the next two tiles (brought in by cp.async, so that no register waits for them).
+struct WarpPipe {
+    WTile d1, d2;   // next tile, tile after next
+};
+
+struct WarpDevExec {
+    WarpPriv pv;
+    int lane;
+    // what after_scan() needs to start the next tile
+    const FilterParams *P;
+    WarpSmem *s;
+    WarpPipe *pipe;
+    const WTile *tiles;
+    unsigned int *tile_ctr;
+    uint32_t id1, id2, c3;  // ids of the next two tiles; c3: claim for the one after (lane 0)
+    uint32_t n_tiles, total_warps;
+    bool packed;
+
+    template <class F>
+    __device__ __forceinline__ void par(F f) { f(lane, pv); __syncwarp(); }
+    __device__ __forceinline__ uint32_t ballot(int, bool p) { return __ballot_sync(0xFFFFFFFFu, p); }
+    __device__ __forceinline__ uint64_t bcast64(int, uint64_t v, uint32_t src) {
+        return (uint64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)v, (int)src);
+    }
+    __device__ __forceinline__ uint32_t match64(int, uint64_t v, bool) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
+    template <class Get, class Put>
+    __device__ __forceinline__ void scan(Get get, Put put) {
+        const uint32_t v = get(lane, pv);
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
+        put(lane, pv, x - v, total);
+        __syncwarp();
+    }
+    // bytes of tile t that the bulk copy brings (multiple of 16); the up-to-15 bytes after them are copied by lanes
+    __device__ __forceinline__ uint32_t tile_need(uint64_t origin) const {
+        const uint64_t left = P->n_bases - P->base0 - origin;
+        return left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
+    }
+    __device__ __forceinline__ void issue_copy(const WTile &t) {
+        if (packed) {   // packed input is read straight from global memory: pull the next tile's words into L2
+            const uint64_t w0 = t.origin >> 4;
+            if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P->pk_codes + w0 + 32u * (uint32_t)lane));
+            else if (lane < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(P->pk_inv + w0 + 64u * (uint32_t)(lane - 4)));
+        } else if (lane == 0) {
+            const uint32_t bytes = tile_need(t.origin) & ~15u;
+            mbar_expect_tx(&s->mbar, bytes);
+            if (bytes) bulk_copy_g2s(s->stage, P->bases + t.origin, bytes, &s->mbar);
+        }
+        // the record offsets of the tile: one 128-byte line holds 16
+        const uint32_t r0 = t.a * P->rpu, r1 = t.b * P->rpu;
+        if (lane >= 8 && lane < 14 && r0 + 16u * (uint32_t)(lane - 8) <= r1)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(P->rec_off + r0 + 16u * (uint32_t)(lane - 8)));
+    }
+    __device__ __forceinline__ void fetch_desc(WTile *dst, uint32_t id) {   // lane 0: 16 bytes global -> shared, asynchronously
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(tiles + id) : "memory");
+    }
+    __device__ __forceinline__ void after_scan(bool go) {
+        if (!go) return;
+        if (id1 < n_tiles) issue_copy(pipe->d1);
+        c3 = 0xFFFFFFFFu;
+        if (lane == 0 && id2 < n_tiles) {
+            fetch_desc(&pipe->d2, id2);
+            c3 = total_warps + atomicAdd(tile_ctr, 1u);
+        }
+    }
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(DCN_WARPS * 32, 1)
+filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ tiles, uint32_t *ovf_list, uint32_t ovf_cap) {
+    extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
+    WarpTables &T = *reinterpret_cast<WarpTables *>(dcn_smem_raw);
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+    constexpr size_t OFF_PIPE = (sizeof(WarpTables) + 15) & ~(size_t)15, OFF_WARPS = OFF_PIPE + DCN_WARPS * sizeof(WarpPipe);
+    WarpPipe &pipe = reinterpret_cast<WarpPipe *>(dcn_smem_raw + OFF_PIPE)[warp];
+    WarpSmem &s = reinterpret_cast<WarpSmem *>(dcn_smem_raw + OFF_WARPS)[warp];
+    winit_tables((int)threadIdx.x, (int)blockDim.x, T, P.abs_thr, P.rel_thr);
+    if (lane == 0) mbar_init(&s.mbar, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();   // the only CTA barrier of the kernel
+
+    WarpDevExec ex;
+    ex.lane = lane; ex.P = &P; ex.s = &s; ex.pipe = &pipe; ex.tiles = tiles; ex.packed = PACKED;
+    ex.tile_ctr = &st->tile_claims;
+    ex.n_tiles = st->n_wtiles;
+    ex.total_warps = gridDim.x * DCN_WARPS;
+    const uint32_t n_tiles = ex.n_tiles;
+
+    // first wave: tile = global warp index; two more tiles claimed up front
+    uint32_t id0 = blockIdx.x * DCN_WARPS + (uint32_t)warp;
+    uint32_t claim = 0;
+    if (lane == 0 && id0 < n_tiles) claim = ex.total_warps + atomicAdd(ex.tile_ctr, 2u);
+    claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+    ex.id1 = id0 < n_tiles ? claim : 0xFFFFFFFFu;
+    ex.id2 = id0 < n_tiles ? claim + 1u : 0xFFFFFFFFu;
+    ex.c3 = 0xFFFFFFFFu;
+    WTile d0;
+    d0.origin = 0; d0.a = d0.b = 0;
+    if (id0 < n_tiles) { d0 = tiles[id0]; ex.issue_copy(d0); }
+    if (lane == 0 && ex.id1 < n_tiles) ex.fetch_desc(&pipe.d1, ex.id1);
+    bool have = id0 < n_tiles;
+    uint32_t phase = 0;
+    while (have) {
+        const uint32_t need = ex.tile_need(d0.origin);
+        asm volatile("cp.async.wait_all;" ::: "memory");   // the descriptors requested during the previous tile (lane 0)
+        __syncwarp();
+        if (!PACKED) {
+            mbar_wait(&s.mbar, phase);
+            phase ^= 1u;
+            const uint32_t bulk = need & ~15u;
+            if ((uint32_t)lane < need - bulk) s.stage[bulk + (uint32_t)lane] = P.bases[d0.origin + bulk + (uint32_t)lane];
+            __syncwarp();
+        }
+        warp_tile<PACKED>(ex, T, s, P, d0, need, [&](uint32_t u) {
+            if (lane == 0) {
+                const uint32_t at = atomicAdd(&st->n_ovf, 1u);
+                if (at < ovf_cap) ovf_list[at] = u; else st->overflow = 1;
+            }
+        });
+        // rotate the pipeline: d1 (in shared memory since the previous tile) becomes the current tile
+        have = ex.id1 < n_tiles;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        d0 = pipe.d1;
+        __syncwarp();
+        if (lane == 0) pipe.d1 = pipe.d2;
+        ex.id1 = ex.id2;
+        ex.id2 = __shfl_sync(0xFFFFFFFFu, ex.c3, 0);
+    }
+}
+
+// ------------------------------------------------------------------ the CTA-tile tail of the warp kernel
+// What a warp tile cannot hold: single units that emit more picks than a warp pass takes (filter_short_run holds
+// 1024 per unit: enough for any short unit) and the chunks of long units.  Launched after filter_warp_kernel on the
+// same stream; with nothing listed every CTA leaves at once.
+template <class G, bool PACKED>
+__global__ void __launch_bounds__(G::NT, DCN_CTAS_PER_SM)
+filter_tail_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ ovf_list, DedupView dd,
+                   const ChunkDesc *__restrict__ desc) {
+    const uint32_t n_ovf = st->n_ovf, n_long = st->n_long;
+    if (n_ovf == 0 && n_long == 0) return;
+    extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
+    TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);
+    DevExec<G> ex;
+    ex.wsum = s.wsum;
+    init_tables<G>((int)threadIdx.x, s);
+    init_required<G>((int)threadIdx.x, s, P.abs_thr, P.rel_thr);
+    __syncthreads();
+    ex.pf_off = P.rec_off;
+    for (uint32_t i = blockIdx.x; i < n_ovf; i += gridDim.x) {
+        const uint32_t u = ovf_list[i];
+        filter_short_run<G, PACKED, MODE_FILTER>(ex, s, P, u, u + 1u);
+        __syncthreads();
+    }
+    if (n_long) {
+        __syncthreads();
+        long_chunks_loop<G, PACKED>(ex, s, P, dd, desc, st);
     }
 }
 

@@ -13,15 +13,18 @@
 
 #include "../../deacon_server_b200/csrc/dcn_plan.cuh"
 #include "../../deacon_server_b200/csrc/dcn_tile.cuh"
+#include "../../deacon_server_b200/csrc/dcn_warp.cuh"
 #include "../../deacon_server_b200/csrc/dcn_generic.cuh"
 #include "../../deacon_server_b200/csrc/dcn_host_pack.h"
 
 using namespace dcn;
 
-template <class G>
+template <class G, class PrivT = TilePriv<G>>
 struct HostExec {
-    std::vector<TilePriv<G>> pv;
+    std::vector<PrivT> pv;
     HostExec() : pv(G::NT) {}
+    int after_scan_calls = 0;
+    void after_scan(bool go) { after_scan_calls += go ? 1 : 0; }
 
     // ---- warp votes.  A phase runs thread after thread here, so a vote cannot see the other
     // lanes' operands of the same pass.  The phase is therefore re-run from a snapshot until the
@@ -63,7 +66,7 @@ struct HostExec {
 
     template <class F>
     void par(F f) {
-        std::vector<TilePriv<G>> saved_pv = pv;
+        std::vector<PrivT> saved_pv = pv;
         std::vector<uint8_t> saved_smem;
         if (smem_ptr) saved_smem.assign((uint8_t *)smem_ptr, (uint8_t *)smem_ptr + smem_bytes);
         prev_v.clear();
@@ -107,10 +110,16 @@ struct HostExec {
 };
 
 static uint64_t dedup_cap_override = 0;
+static int emu_impl = 0;   // 0: warp tiles (filter_warp_kernel + filter_tail_kernel), 1: CTA tiles (filter_fused_kernel)
+static uint64_t emu_ovf_units = 0, emu_wtiles = 0;
+struct WEmuGeo { static constexpr int NT = 32; };
 
 extern "C" {
 
 void emu_set_dedup_cap(uint64_t cap) { dedup_cap_override = cap; }
+void emu_set_impl(int impl) { emu_impl = impl; }
+uint64_t emu_last_overflow_units() { return emu_ovf_units; }
+uint64_t emu_last_wtiles() { return emu_wtiles; }
 
 // bucketed table, same layout as the device table (dcn_core.cuh)
 int emu_table_build(const uint64_t *keys, uint64_t n, double load, uint64_t **slots_out, uint64_t *nb_out,
@@ -184,9 +193,45 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
     HostExec<G> ex;
     ex.smem_ptr = s; ex.smem_bytes = sizeof(*s);
     ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); init_required<G>(t, *s, abs_thr, rel_thr); });
-    for (uint32_t tile = 0; tile < n_tiles; tile++)
-        if (tile_first[tile] < tile_end[tile])
-            filter_tile<G, PACKED, MODE_FILTER>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
+    if (emu_impl == 1) {
+        for (uint32_t tile = 0; tile < n_tiles; tile++)
+            if (tile_first[tile] < tile_end[tile])
+                filter_tile<G, PACKED, MODE_FILTER>(ex, *s, P, cfg, n_long, tile_first[tile], tile_end[tile]);
+    } else {
+        // mirrors wplan_kernel + filter_warp_kernel (one "warp" runs every tile) + the overflow part of filter_tail_kernel
+        std::vector<WTile> wt;
+        const uint64_t n_seg = (n_bases + DCN_WSEG - 1) / DCN_WSEG;
+        for (uint64_t seg = 0; seg < n_seg; seg++) {
+            const uint32_t cnt = wplan_segment(rec_off, 0, P.rpu, P.n_units, seg, [](uint64_t, uint32_t, uint32_t) {});
+            const size_t before = wt.size();
+            wplan_segment(rec_off, 0, P.rpu, P.n_units, seg, [&](uint64_t o, uint32_t a, uint32_t b) { WTile t; t.origin = o; t.a = a; t.b = b; wt.push_back(t); });
+            if (wt.size() - before != cnt) abort();
+        }
+        if (wt.size() > n_bases / (uint64_t)(WG::TB - 15 - (int)DCN_MAX_SHORT) + (uint64_t)n_rec / (WG::MAXR / 2) + n_bases / DCN_MAX_SHORT + n_bases / DCN_WSEG + 16) abort();
+        emu_wtiles = wt.size();
+        auto *T = new WarpTables();
+        auto *ws = new WarpSmem();
+        memset(T, 0xA5, sizeof(*T));
+        memset(ws, 0xA5, sizeof(*ws));
+        HostExec<WEmuGeo, WarpPriv> wex;
+        wex.smem_ptr = ws; wex.smem_bytes = sizeof(*ws);
+        for (int t = 0; t < 1024; t++) winit_tables(t, 1024, *T, abs_thr, rel_thr);
+        std::vector<uint32_t> ovf;
+        for (size_t i = wt.size(); i-- > 0;) {   // any order
+            const WTile &t = wt[i];
+            const uint64_t left = n_bases - t.origin;
+            const uint32_t need = left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
+            if (!PACKED) memcpy(ws->stage, bases + t.origin, need);   // bulk copy + tail bytes; the rest of the stage keeps the previous tile
+            const int calls0 = wex.after_scan_calls;
+            warp_tile<PACKED>(wex, *T, *ws, P, t, need, [&](uint32_t u) { ovf.push_back(u); });
+            if (wex.after_scan_calls != calls0 + 1) abort();   // the device starts the next tile's copy exactly once per tile
+        }
+        emu_ovf_units = ovf.size();
+        if (ovf.size() > n_bases / WG::PKCAP + 16) abort();
+        for (uint32_t u : ovf) filter_short_run<G, PACKED, MODE_FILTER>(ex, *s, P, u, u + 1);
+        delete T;
+        delete ws;
+    }
     int rc = 0;
     if (n_long) {  // mirrors prep_long_kernel + the chunk loop of filter_fused_kernel + finalize_long_kernel
         std::vector<uint32_t> long_units;

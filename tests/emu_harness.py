@@ -14,7 +14,7 @@ u8p, u32p, u64p = C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uin
 
 def build():
     srcs = [os.path.join(_HERE, "dcn_emu.cpp")] + [os.path.join(_CSRC, f) for f in (
-        "dcn_host_pack.cpp", "dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh", "dcn_generic.cuh", "dcn_host_pack.h")]
+        "dcn_host_pack.cpp", "dcn_core.cuh", "dcn_plan.cuh", "dcn_tile.cuh", "dcn_warp.cuh", "dcn_generic.cuh", "dcn_host_pack.h")]
     if os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wno-unknown-pragmas", *_FLAGS, "-o", _SO, srcs[0], srcs[1]])
@@ -75,6 +75,16 @@ def index_extract(bases, off, entropy_bitmap=None):
     n = L.emu_index_extract(_p(b, u8p), _p(off, u64p), C.c_uint32(n_rec), eb, _p(out, u64p), C.c_uint64(cap))
     assert 0 <= n <= cap
     return out[:n]
+
+
+def set_impl(name):
+    """'warp' (default): warp tiles + CTA tail, as the product runs; 'cta': the CTA-tile fused kernel."""
+    lib().emu_set_impl(1 if name == "cta" else 0)
+
+
+def last_overflow_units():
+    lib().emu_last_overflow_units.restype = C.c_uint64
+    return int(lib().emu_last_overflow_units())
 
 
 def set_dedup_cap(cap):

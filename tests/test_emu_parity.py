@@ -17,14 +17,25 @@ def _index_for(case):
     return idx
 
 
+@pytest.fixture(params=["warp", "cta"])
+def impl(request):
+    """Both mappings of the short path: warp tiles (+ CTA tail), which is what the library runs, and the CTA-tile
+    fused kernel kept behind DCN_FUSED_IMPL=cta."""
+    E.set_impl(request.param)
+    yield request.param
+    E.set_impl("warp")
+
+
 @pytest.mark.parametrize("packed", [False, True], ids=["ascii", "packed"])
 @pytest.mark.parametrize("case", CASES.make_cases(), ids=lambda c: c["name"])
-def test_short_path_matches_oracle(case, packed):
+def test_short_path_matches_oracle(case, packed, impl):
     idx = _index_for(case)
     bases, off = H.concat(case["records"])
     rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"],
                                  packed=packed)
     assert rc == 0
+    if impl == "warp" and case["name"] == "dense_picks_polyA":
+        assert E.last_overflow_units() == 8   # the 1000-base poly-A units emit more picks than a warp pass holds: CTA tail
     ok, oh, ot = O.filter_batch(idx, bases, off, paired=case["paired"], prefix_len=case["prefix"], abs_thr=case["abs"],
                                 rel_thr=case["rel"], deplete=case["deplete"])
     assert np.array_equal(t, ot), "total minimizers differ"
@@ -45,7 +56,7 @@ def test_high_load_factor_table_probing():
 
 @pytest.mark.parametrize("packed", [False, True], ids=["ascii", "packed"])
 @pytest.mark.parametrize("case", CASES.make_long_cases(), ids=lambda c: c["name"])
-def test_long_path_matches_oracle(case, packed):
+def test_long_path_matches_oracle(case, packed, impl):
     idx = _index_for(case)
     bases, off = H.concat(case["records"])
     rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"],
