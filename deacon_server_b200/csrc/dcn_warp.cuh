@@ -29,7 +29,7 @@ struct WG {
     static constexpr int MAXR = 64;            // records per tile
     static constexpr int PKCAP = 320;          // picks per pass; a denser run of units is split, a denser single unit goes to the CTA path
     static constexpr int NBW = TB / 32;        // words of the per-position bit arrays
-    static constexpr int HXP = 12;             // pitch (words) of the rows that hand a lane's first hashes to its left neighbour
+    static constexpr int HXP = 8;              // pitch (words) of the rows that hand a lane's first hashes to its left neighbour
 };
 
 // tile descriptor written by the planner: units [a, b) live in [origin, origin + TB) (origin relative to base0)
@@ -41,32 +41,42 @@ struct WarpTables {                    // one per CTA
     uint16_t req[256];                 // required_hits(total), total < 256
 };
 
-struct alignas(16) WarpSmem {          // one per warp
-    union {
-        uint32_t hx[WG::NL * WG::HXP + WG::HXP];                                   // dead once the windows are sliced ...
-        struct { uint64_t hash[WG::PKCAP]; uint16_t pos[WG::PKCAP]; } pk;          // ... the pick list reuses it
-    };
+struct alignas(16) u32x4a { uint32_t x, y, z, w; };   // 16-byte aligned: one LDS.128 / STS.128
+
+// Shared memory of one warp.  The first region is used three ways in turn:
+//   hash / slice phases:  hx (each lane's first 14 hashes for its left neighbour) | per-block results rel4, em
+//   compaction:           pk_pos over hx (dead)                                    | rel4, em still read
+//   probe / count:        pk_pos | pk_hash over the rest (rel4 / em dead)
+struct alignas(16) WarpSmem {
+    static constexpr int HX_BYTES = (WG::NL + 1) * WG::HXP * 4;   // 1056
+    static constexpr int POS_BYTES = WG::PKCAP * 2;               // 640 <= HX_BYTES
+    static constexpr int REGION = POS_BYTES + WG::PKCAP * 8;      // 3200
+    alignas(16) unsigned char region[REGION];
     alignas(16) uint8_t stage[WG::TB + 16];   // ASCII bytes of the tile (bulk-copy destination)
     uint32_t codes[WG::NSLOT + 4];     // 16 bases x 2 bit per word
     uint32_t inv[WG::NBW + 2];         // non-ACGT bits
     uint32_t brk[WG::NBW + 2];         // position is a record start or lies outside every effective sequence
     uint32_t dead[WG::NBW + 2];        // no window may start here
-    uint16_t poff[WG::NSLOT];          // exclusive pick offset of each block
-    uint16_t emk[WG::NSLOT];           // emit mask of each block
     uint16_t ufirst[WG::MAXR + 2];     // first pick index of each unit
     uint16_t ustartpos[WG::MAXR + 2];
     uint16_t lastpick[WG::NL];         // last window's pick of each lane (0xFFFF: that window is invalid)
     uint32_t npicks, pad_;
     unsigned long long mbar;           // transaction barrier of the bulk copy
+
+    DCN_HD uint32_t *hx() { return reinterpret_cast<uint32_t *>(region); }
+    DCN_HD uint16_t *pk_pos() { return reinterpret_cast<uint16_t *>(region); }
+    DCN_HD const uint16_t *pk_pos() const { return reinterpret_cast<const uint16_t *>(region); }
+    DCN_HD uint64_t *pk_hash() { return reinterpret_cast<uint64_t *>(region + POS_BYTES); }
+    DCN_HD u32x4a *rel4() { return reinterpret_cast<u32x4a *>(region + HX_BYTES); }                       // per block: pick positions, 8 bits per window
+    DCN_HD uint32_t *em() { return reinterpret_cast<uint32_t *>(region + HX_BYTES + WG::NSLOT * 16); }    // per block: emit mask | exclusive pick offset << 16
 };
+static_assert(WarpSmem::POS_BYTES <= WarpSmem::HX_BYTES, "the pick positions replace the hash rows only");
+static_assert(WarpSmem::HX_BYTES + WG::NSLOT * 20 <= WarpSmem::REGION, "block results fit beside the hash rows");
 
 struct WarpPriv {
-    uint32_t c[3];            // own 48 codes
     uint32_t sL[2], eL[2], eff[2];   // up to two records of the tile per lane (tile-local start, end, effective end)
-    uint32_t fw, rc;          // rolling state: k-mer at the start of block 1 after the hash phase
+    uint32_t fw, rc;          // rolling state: k-mer at the start of block 1 after the seed phase
     uint32_t hp[8];           // block 0 hashes (upper 16 bits), two per word
-    uint32_t rel4[3][4];      // pick position relative to the block start, 8 bits per window
-    uint32_t emask[3];
     uint32_t vfirst;          // the lane's first window is valid
     uint32_t pickoff;
 };
@@ -279,9 +289,9 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
                 pv.eff[j] = sL + w_eff_len(P, src, r_begin + i, sL, eL - sL);
             }
         }
-        uint32_t inv48[3];
-#pragma unroll
-        for (int v = 0; v < 3; v++) {
+        uint16_t *ih = reinterpret_cast<uint16_t *>(s.inv);   // 48 non-ACGT bits of the lane: three halfwords of its own
+#pragma unroll 1
+        for (int v = 0; v < 3; v++) {   // a loop, not three copies: 32 warps in 32 different places share one instruction cache
             uint32_t codes = 0, inv16 = 0xFFFFu;
             if (PACKED) {
                 const uint64_t wi = 3ull * (uint64_t)l + (uint64_t)v;
@@ -289,7 +299,7 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
             } else {
                 const uint32_t off = 48u * (uint32_t)l + 16u * (uint32_t)v;
                 if (off + 16u <= src.stage_bytes) {
-                    const u32x4 qv = *reinterpret_cast<const u32x4 *>(src.stage + off);
+                    const u32x4a qv = *reinterpret_cast<const u32x4a *>(src.stage + off);
                     const uint32_t w[4] = {qv.x, qv.y, qv.z, qv.w};
                     inv16 = 0;
 #pragma unroll
@@ -301,12 +311,9 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
                     }
                 }
             }
-            pv.c[v] = codes; inv48[v] = inv16;
             s.codes[3 * l + v] = codes;
+            ih[3 * l + v] = (uint16_t)inv16;
         }
-        // 48 non-ACGT bits of the lane at bit 48 l: three halfwords (no two lanes share a halfword)
-        uint16_t *ih = reinterpret_cast<uint16_t *>(s.inv);
-        ih[3 * l] = (uint16_t)inv48[0]; ih[3 * l + 1] = (uint16_t)inv48[1]; ih[3 * l + 2] = (uint16_t)inv48[2];
         if (l < 4) s.codes[WG::NSLOT + l] = 0;
         if (l < 2) s.inv[WG::NBW + l] = 0;
     });
@@ -323,10 +330,11 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
             }
         }
         // k-mer at the lane's first base: bases 0..30 = own words 0 and 1 (less its last base)
+        const uint32_t c0 = s.codes[3 * l], c1 = s.codes[3 * l + 1], c2 = s.codes[3 * l + 2];
         uint32_t fw = 0, rc = 0;
 #pragma unroll
         for (int g = 0; g < 8; g++) {
-            uint32_t byte = ((g < 4 ? pv.c[0] : pv.c[1]) >> (8 * (g & 3))) & 0xFFu;
+            uint32_t byte = ((g < 4 ? c0 : c1) >> (8 * (g & 3))) & 0xFFu;
             if (g == 7) byte &= 0x3Fu;
             const u32x2 e = T.tb0[byte];
             fw ^= rotr32(e.x, 4 * g);
@@ -334,75 +342,87 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
         }
         fw ^= rotr32(nt_f(0u), 1);       // slot 31 of the table entry (code 0) is not part of the k-mer
         rc ^= rotl32(nt_f(2u), 31);
-        whash_block<true>(T, fw, rc, pv.c[0], pv.c[1], pv.c[2], pv.hp);
+        whash_block<true>(T, fw, rc, c0, c1, c2, pv.hp);
         pv.fw = fw; pv.rc = rc;
-        u32x4 *row = reinterpret_cast<u32x4 *>(&s.hx[l * WG::HXP]);
-        u32x4 a, b;
+        u32x4a *row = reinterpret_cast<u32x4a *>(&s.hx()[l * WG::HXP]);
+        u32x4a a, b;
         a.x = pv.hp[0]; a.y = pv.hp[1]; a.z = pv.hp[2]; a.w = pv.hp[3];
         b.x = pv.hp[4]; b.y = pv.hp[5]; b.z = pv.hp[6]; b.w = pv.hp[7];
         row[0] = a; row[1] = b;
     });
 
-    // ---- P3: blocks 1 and 2 hashed, all three blocks sliced
+    // ---- P3: the three blocks in turn: hashes of the next block (block 2: the right neighbour's first hashes), window
+    // minima, consecutive-duplicate rule against the block before; per-block results go to shared memory
     ex.par([&](int l, Priv &pv) {
-        const uint32_t n0 = s.codes[3 * l + 3], n1 = s.codes[3 * l + 4], n2 = s.codes[3 * l + 5];   // next lane's words
+        uint32_t W0 = s.codes[3 * l], W1 = s.codes[3 * l + 1], W2 = s.codes[3 * l + 2], W3 = s.codes[3 * l + 3];
         uint32_t fw = pv.fw, rc = pv.rc;
-        uint32_t q[15], hb[8], v16, r15, prev_last;
+        uint32_t q[15], prev_last = 0xFFFFu;   // last pick of the previous block, relative to ITS first base
 #pragma unroll
         for (int j = 0; j < 8; j++) q[j] = pv.hp[j];
-        whash_block<true>(T, fw, rc, pv.c[1], pv.c[2], n0, hb);
+#pragma unroll 1
+        for (int r = 0; r < 3; r++) {
+            const uint32_t W4 = s.codes[3 * l + r + 4];
+            uint32_t hb[8];
+            if (r < 2) {
+                whash_block<true>(T, fw, rc, W1, W2, W3, hb);   // (block 2's crossing step is one step too many: harmless)
+            } else {   // lane 31 reads the pad row: its last windows are dead
+                const u32x4a *row = reinterpret_cast<const u32x4a *>(&s.hx()[(l + 1) * WG::HXP]);
+                const u32x4a a = row[0], b = row[1];
+                hb[0] = a.x; hb[1] = a.y; hb[2] = a.z; hb[3] = a.w; hb[4] = b.x; hb[5] = b.y; hb[6] = b.z; hb[7] = b.w;
+            }
 #pragma unroll
-        for (int j = 0; j < 7; j++) q[8 + j] = hb[j];
-        wslide_block(q, pv.c[0], pv.c[1], pv.c[2], n0, s.brk, s.dead, 3 * l, pv.rel4[0], pv.emask[0], v16, r15);
-        pv.vfirst = v16 & 1u;
-        prev_last = (v16 & 0x8000u) ? r15 : 0xFFFFu;          // last pick of the block, relative to the lane's first base
+            for (int j = 0; j < 7; j++) q[8 + j] = hb[j];
+            u32x4a rel;
+            uint32_t rel4[4], emask, v16, r15;
+            wslide_block(q, W0, W1, W2, W3, s.brk, s.dead, 3 * l + r, rel4, emask, v16, r15);
+            // consecutive-duplicate rule across the lane's own block boundaries (A.3 step 5)
+            if ((v16 & 1u) && !(emask & 1u) && prev_last != 0xFFFFu && prev_last != 16u + (rel4[0] & 0xFFu)) emask |= 1u;
+            if (r == 0) pv.vfirst = v16 & 1u;
+            prev_last = (v16 & 0x8000u) ? r15 : 0xFFFFu;
+            rel.x = rel4[0]; rel.y = rel4[1]; rel.z = rel4[2]; rel.w = rel4[3];
+            s.rel4()[3 * l + r] = rel;
+            s.em()[3 * l + r] = emask;
+            W0 = W1; W1 = W2; W2 = W3; W3 = W4;
 #pragma unroll
-        for (int j = 0; j < 8; j++) q[j] = hb[j];
-        whash_block<false>(T, fw, rc, pv.c[2], n0, n1, hb);
-#pragma unroll
-        for (int j = 0; j < 7; j++) q[8 + j] = hb[j];
-        wslide_block(q, pv.c[1], pv.c[2], n0, n1, s.brk, s.dead, 3 * l + 1, pv.rel4[1], pv.emask[1], v16, r15);
-        // consecutive-duplicate rule across the lane's own block boundaries (A.3 step 5)
-        if ((v16 & 1u) && !(pv.emask[1] & 1u) && prev_last != 0xFFFFu && prev_last != 16u + (pv.rel4[1][0] & 0xFFu)) pv.emask[1] |= 1u;
-        prev_last = (v16 & 0x8000u) ? 16u + r15 : 0xFFFFu;
-#pragma unroll
-        for (int j = 0; j < 8; j++) q[j] = hb[j];
-        {   // the right neighbour's first hashes (lane 31: whatever the pad row holds; its last windows are dead)
-            const u32x4 *row = reinterpret_cast<const u32x4 *>(&s.hx[(l + 1) * WG::HXP]);
-            const u32x4 a = row[0], b = row[1];
-            q[8] = a.x; q[9] = a.y; q[10] = a.z; q[11] = a.w; q[12] = b.x; q[13] = b.y; q[14] = b.z;
+            for (int j = 0; j < 8; j++) q[j] = hb[j];
         }
-        wslide_block(q, pv.c[2], n0, n1, n2, s.brk, s.dead, 3 * l + 2, pv.rel4[2], pv.emask[2], v16, r15);
-        if ((v16 & 1u) && !(pv.emask[2] & 1u) && prev_last != 0xFFFFu && prev_last != 32u + (pv.rel4[2][0] & 0xFFu)) pv.emask[2] |= 1u;
-        s.lastpick[l] = (v16 & 0x8000u) ? (uint16_t)(48u * (uint32_t)l + 32u + r15) : (uint16_t)0xFFFFu;
+        s.lastpick[l] = prev_last != 0xFFFFu ? (uint16_t)(48u * (uint32_t)l + 32u + prev_last) : (uint16_t)0xFFFFu;
     });
 
-    // ---- P4 + scan: first window of each lane against the left neighbour's last pick; pick offsets
+    // ---- P4 + scan: first window of each lane against the left neighbour's last pick; pick offsets of every block
     ex.scan([&](int l, Priv &pv) {
-                if (pv.vfirst && !(pv.emask[0] & 1u)) {
+                uint32_t e0 = s.em()[3 * l];
+                if (pv.vfirst && !(e0 & 1u)) {
                     const uint32_t lp = l > 0 ? s.lastpick[l - 1] : 0xFFFFu;
-                    const uint32_t mine = 48u * (uint32_t)l + (pv.rel4[0][0] & 0xFFu);
-                    if (lp != 0xFFFFu && lp != mine) pv.emask[0] |= 1u;
+                    const uint32_t mine = 48u * (uint32_t)l + (s.rel4()[3 * l].x & 0xFFu);
+                    if (lp != 0xFFFFu && lp != mine) { e0 |= 1u; s.em()[3 * l] = e0; }
                 }
-                return popc32(pv.emask[0]) + popc32(pv.emask[1]) + popc32(pv.emask[2]);
+                return popc32(e0) + popc32(s.em()[3 * l + 1]) + popc32(s.em()[3 * l + 2]);
             },
             [&](int l, Priv &pv, uint32_t excl, uint32_t total) {
                 pv.pickoff = excl;
+                uint32_t off = excl;
+#pragma unroll
+                for (int r = 0; r < 3; r++) {
+                    const uint32_t e = s.em()[3 * l + r];
+                    s.em()[3 * l + r] = e | (off << 16);
+                    off += popc32(e);
+                }
                 if (l == 0) s.npicks = total;
             });
     const uint32_t npicks = s.npicks;
     if (npicks > (uint32_t)WG::PKCAP) { ex.after_scan(false); return false; }
     ex.after_scan(last_run);
 
-    // ---- P5: compact the picks (the list takes over the hx rows: every lane is past its last hx read)
-    ex.par([&](int l, Priv &pv) {
-        uint32_t idx = pv.pickoff;
-#pragma unroll
+    // ---- P5: compact the picks (the positions take over the hx rows: every lane is past its last hx read);
+    // unit -> pick range from the per-block offsets
+    ex.par([&](int l, Priv &) {
+#pragma unroll 1
         for (int r = 0; r < 3; r++) {
-            s.poff[3 * l + r] = (uint16_t)idx;
-            s.emk[3 * l + r] = (uint16_t)pv.emask[r];
-            uint32_t em = pv.emask[r];
-            const uint64_t relA = pv.rel4[r][0] | ((uint64_t)pv.rel4[r][1] << 32), relB = pv.rel4[r][2] | ((uint64_t)pv.rel4[r][3] << 32);
+            const u32x4a rel = s.rel4()[3 * l + r];
+            const uint32_t e = s.em()[3 * l + r];
+            uint32_t em = e & 0xFFFFu, idx = e >> 16;
+            const uint64_t relA = rel.x | ((uint64_t)rel.y << 32), relB = rel.z | ((uint64_t)rel.w << 32);
             const uint32_t base = 48u * (uint32_t)l + 16u * (uint32_t)r;
             while (em) {
 #ifdef __CUDA_ARCH__
@@ -411,25 +431,28 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
                 const int i = __builtin_ctz(em);
 #endif
                 em &= em - 1;
-                const uint32_t rel = (uint32_t)(((i & 8) ? relB : relA) >> (8 * (i & 7))) & 0xFFu;
-                s.pk.pos[idx++] = (uint16_t)(base + rel);
+                const uint32_t rl = (uint32_t)(((i & 8) ? relB : relA) >> (8 * (i & 7))) & 0xFFu;
+                s.pk_pos()[idx++] = (uint16_t)(base + rl);
             }
         }
-    });
-
-    // ---- P6: unit -> pick range; hash every pick and probe the table, two picks per lane in flight.
-    // pk.pos: position | valid << 14 | in-index << 15
-    ex.par([&](int l, Priv &) {
         for (uint32_t u = (uint32_t)l; u < n_units_t; u += WG::NL) {
             const uint32_t pos = s.ustartpos[u];
             const uint32_t tt = pos >> 4, ii = pos & 15u;
-            // an empty unit at the very end of the tile starts past the last block
-            s.ufirst[u] = (uint16_t)(tt >= (uint32_t)WG::NSLOT ? npicks : s.poff[tt] + popc32((uint32_t)s.emk[tt] & ((1u << ii) - 1u)));
+            uint32_t first = npicks;   // an empty unit at the very end of the tile starts past the last block
+            if (tt < (uint32_t)WG::NSLOT) { const uint32_t e = s.em()[tt]; first = (e >> 16) + popc32(e & ((1u << ii) - 1u)); }
+            s.ufirst[u] = (uint16_t)first;
             if (u == 0) s.ufirst[n_units_t] = (uint16_t)npicks;
         }
+    });
+
+    // ---- P6: hash every pick and probe the table, two picks per lane in flight (the hashes take over rel4 / em).
+    // pk_pos: position | valid << 14 | in-index << 15
+    ex.par([&](int l, Priv &) {
+        uint16_t *pk_pos = s.pk_pos();
+        uint64_t *pk_hash = s.pk_hash();
         for (uint32_t idx = (uint32_t)l; idx < npicks; idx += 2 * WG::NL) {
             const uint32_t idxB = idx + WG::NL;
-            const uint32_t ppA = s.pk.pos[idx], ppB = idxB < npicks ? s.pk.pos[idxB] : 0u;
+            const uint32_t ppA = pk_pos[idx], ppB = idxB < npicks ? pk_pos[idxB] : 0u;
             const bool vA = wpick_valid(s, ppA);
             const bool vB = idxB < npicks && wpick_valid(s, ppB);
             uint64_t hA = 0, hB = 0, bA = 0, bB = 0;
@@ -438,12 +461,12 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
             if (vA) { hA = wpick_hash(s, ppA); bA = table_bucket(hA, P.table.n_buckets); kA = load_bucket(P.table.slots, bA); }
             if (vB) { hB = wpick_hash(s, ppB); bB = table_bucket(hB, P.table.n_buckets); kB = load_bucket(P.table.slots, bB); }
             if (vA) {
-                s.pk.hash[idx] = hA;
-                s.pk.pos[idx] = (uint16_t)(ppA | 0x4000u | (table_contains_from(P.table, hA, bA, kA) ? 0x8000u : 0u));
+                pk_hash[idx] = hA;
+                pk_pos[idx] = (uint16_t)(ppA | 0x4000u | (table_contains_from(P.table, hA, bA, kA) ? 0x8000u : 0u));
             }
             if (vB) {
-                s.pk.hash[idxB] = hB;
-                s.pk.pos[idxB] = (uint16_t)(ppB | 0x4000u | (table_contains_from(P.table, hB, bB, kB) ? 0x8000u : 0u));
+                pk_hash[idxB] = hB;
+                pk_pos[idxB] = (uint16_t)(ppB | 0x4000u | (table_contains_from(P.table, hB, bB, kB) ? 0x8000u : 0u));
             }
         }
     });
@@ -452,6 +475,8 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
     // units; a unit's picks are consecutive list entries, 32 per pass (see filter_short_tile for the later-pass rules)
     ex.par([&](int l, Priv &) {
         const uint32_t lane = (uint32_t)l, lt = (1u << lane) - 1u;
+        const uint16_t *pk_pos = s.pk_pos();
+        const uint64_t *pk_hash = s.pk_hash();
         for (uint32_t u = 0; u < n_units_t; u++) {
             const uint32_t a = s.ufirst[u], b = s.ufirst[u + 1];
             uint32_t hits = 0, total = 0, vprev = 0;
@@ -461,10 +486,10 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
                 bool valid = false, found = false;
                 uint64_t h = 0;
                 if (idx < b) {
-                    const uint32_t pp = s.pk.pos[idx];
+                    const uint32_t pp = pk_pos[idx];
                     valid = (pp & 0x4000u) != 0;
                     found = (pp & 0x8000u) != 0;
-                    if (valid) h = s.pk.hash[idx];
+                    if (valid) h = pk_hash[idx];
                 }
                 const uint32_t vmask = ex.ballot(l, valid);
                 const uint32_t same = ex.match64(l, h, valid);
@@ -480,7 +505,7 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
                     }
                     if (fresh && base > a + 32u) {
                         for (uint32_t j = a; j < base - 32u && fresh; j++)
-                            if (s.pk.hash[j] == h && (s.pk.pos[j] & 0x4000u)) fresh = false;
+                            if (pk_hash[j] == h && (pk_pos[j] & 0x4000u)) fresh = false;
                     }
                 }
                 hits += popc32(ex.ballot(l, fresh));
