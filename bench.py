@@ -208,7 +208,7 @@ def run_ours(args):
 
     def step(i):
         gpu.filter_batch_device(batches[i % n_batches], off, NR, nb, keep, hits, tot, paired=True, abs_threshold=2,
-                                rel_threshold=0.01, deplete=True, stream=stream)
+                                rel_threshold=0.01, deplete=True, stream=stream, max_unit_len=2 * READ_LEN)
 
     def barrier():
         torch.cuda.synchronize()

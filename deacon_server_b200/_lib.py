@@ -33,6 +33,9 @@ SIGNATURES = {
     "dcn_filter_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_void_p]),
+    "dcn_filter_batch_device_hint": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint64, C.c_int,
+                                               C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_void_p, C.c_uint32]),
     "dcn_filter_batch_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_newline_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint32, C.c_void_p]),

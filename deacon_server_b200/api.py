@@ -215,12 +215,15 @@ class DeaconGpu:
                                                abs_threshold, rel_threshold, int(deplete), keep_ptr, hits_ptr, total_ptr))
 
     def filter_batch_device(self, d_bases, d_rec_off, n_rec, n_bases, d_keep, d_hits, d_total, paired=False,
-                            prefix_length=0, abs_threshold=2, rel_threshold=0.01, deplete=False, stream: int = 0):
-        """Inputs and outputs are CUDA tensors (anything with .data_ptr()); asynchronous on `stream`."""
-        self._check(self._lib.dcn_filter_batch_device(
+                            prefix_length=0, abs_threshold=2, rel_threshold=0.01, deplete=False, stream: int = 0,
+                            max_unit_len: int = 0):
+        """Inputs and outputs are CUDA tensors (anything with .data_ptr()); asynchronous on `stream`.
+        max_unit_len (<= 1024): the caller's promise that no record / pair is longer -- the call then only
+        enqueues (dcn_filter_batch_device_hint); 0 = unknown, the library asks the device (one small sync)."""
+        self._check(self._lib.dcn_filter_batch_device_hint(
             self._ctx, d_bases.data_ptr(), d_rec_off.data_ptr(), n_rec, n_bases, int(paired), prefix_length,
             abs_threshold, rel_threshold, int(deplete), d_keep.data_ptr(), d_hits.data_ptr(), d_total.data_ptr(),
-            stream))
+            stream, int(max_unit_len)))
 
     def filter_batch_packed(self, codes, inv, nl_bits, rec_off, paired=False, prefix_length=0, abs_threshold=2,
                             rel_threshold=0.01, deplete=False):

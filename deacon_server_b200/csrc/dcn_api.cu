@@ -95,6 +95,7 @@ struct dcn_ctx {
     int has_empty = 0;
     uint8_t k = 0, w = 0;
     double load = 0.5;
+    uint32_t *h_promise = nullptr;   // pinned: set by the device when a dcn_filter_batch_device_hint promise was broken
     int fused_impl = 0;   // 0: warp tiles (filter_warp_kernel + filter_tail_kernel); 1: CTA tiles (filter_fused_kernel), DCN_FUSED_IMPL=cta
     // scratch
     DevBuf plan;       // BatchStats + tile_first + tile_end (one memset clears all three)
@@ -325,7 +326,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
                           uint64_t base0, uint64_t n_bases_abs, const uint64_t *d_off, uint32_t n_rec, int paired,
                           uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep,
                           uint32_t *d_hits, uint32_t *d_total, cudaStream_t st, const BatchStats *host_stats = nullptr,
-                          bool time_fused = true) {   // false: no event pair around the fused kernel (the ring is not thread-safe)
+                          bool time_fused = true, bool promised_short = false) {   // false: no event pair around the fused kernel (the ring is not thread-safe)
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
     const uint32_t rpu = paired ? 2u : 1u;
     if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
@@ -345,14 +346,17 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     // plan buffer: 64-byte header (BatchStats), then the tile plan.  CTA tiles: tile_first | tile_end (cleared per call);
     // warp tiles: the tile list | the list of units handed to the CTA path (only the header is cleared).
     const uint64_t wtile_cap = wplan_tile_cap(n_rel, n_rec), wovf_cap = wplan_ovf_cap(n_rel);
-    const size_t pbytes = warp_impl ? 64 + (size_t)wtile_cap * sizeof(WTile) + (size_t)wovf_cap * 4 : plan_bytes(n_rel);
+    const size_t pbytes = warp_impl ? 128 + (size_t)wtile_cap * sizeof(WTile) + (size_t)wovf_cap * 4 : plan_bytes(n_rel);
     CK(plan.ensure(pbytes));
     const uint64_t n_tiles_max = (plan_bytes(n_rel) - 64) / (2 * sizeof(uint32_t));
     BatchStats *d_stats = plan.as<BatchStats>();
     uint32_t *tile_first = reinterpret_cast<uint32_t *>(plan.as<uint8_t>() + 64);
     uint32_t *tile_end = tile_first + n_tiles_max;
-    WTile *wtiles = reinterpret_cast<WTile *>(plan.as<uint8_t>() + 64);
-    uint32_t *wovf = reinterpret_cast<uint32_t *>(plan.as<uint8_t>() + 64 + (size_t)wtile_cap * sizeof(WTile));
+    // warp tiles: bytes 64..127 hold this call's share of the six summary counters; it is added to the ctx's counters
+    // when the call's last attempt is enqueued (a retry after a distinct-hit set overflow starts it from zero again)
+    unsigned long long *call_cnt = reinterpret_cast<unsigned long long *>(plan.as<uint8_t>() + 64);
+    WTile *wtiles = reinterpret_cast<WTile *>(plan.as<uint8_t>() + 128);
+    uint32_t *wovf = reinterpret_cast<uint32_t *>(plan.as<uint8_t>() + 128 + (size_t)wtile_cap * sizeof(WTile));
 
     FilterParams P;
     P.bases = d_bases; P.pk_codes = in.codes; P.pk_inv = in.inv; P.nl_bits = in.nl; P.nl_bit0 = in.nl_bit0; P.base0 = base0; P.n_bases = n_bases_abs;
@@ -368,21 +372,28 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * DCN_CTAS_PER_SM);
     const int wgrid = (int)std::min<uint64_t>((n_rel / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count);
     const uint64_t n_seg = (n_rel + DCN_WSEG - 1) / DCN_WSEG;
-    const int sg = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_seg + 63) / 64, (uint64_t)ctx->sm_count * 8));
+    const int sg = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_seg + 7) / 8, (uint64_t)ctx->sm_count * 8));   // 8 warps per CTA, one segment per warp
 
     // A batch can only contain a long unit if it holds more than DCN_MAX_SHORT bases; otherwise the
     // stats readback (one small sync) is skipped.
     uint64_t dedup_cap = 0;
     for (int attempt = 0; attempt < 4; attempt++) {
-        CK(cudaMemsetAsync(plan.p, 0, warp_impl ? 64 : pbytes, st));
-        prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_stats);
-        if (warp_impl) wplan_kernel<<<sg, 64, 0, st>>>(d_off, rpu, n_units, base0, n_rel, d_stats, wtiles, (uint32_t)std::min<uint64_t>(wtile_cap, 0xFFFFFFFFull));
-        else prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, rpu, n_units, base0, d_stats, tile_first, tile_end);
-        ctx->launches += 2;
+        CK(cudaMemsetAsync(plan.p, 0, warp_impl ? 128 : pbytes, st));
+        if (warp_impl) {   // the planner also counts the long units
+            wplan_kernel<<<sg, 256, 0, st>>>(d_off, rpu, n_units, base0, n_rel, d_stats, wtiles, (uint32_t)std::min<uint64_t>(wtile_cap, 0xFFFFFFFFull),
+                                             promised_short ? ctx->h_promise : nullptr);
+            ctx->launches += 1;
+        } else {
+            prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_stats);
+            prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, rpu, n_units, base0, d_stats, tile_first, tile_end);
+            ctx->launches += 2;
+        }
         BatchStats hs;
         memset(&hs, 0, sizeof(hs));
         if (host_stats) {
             hs = *host_stats;   // the host-pointer pipeline knows the unit lengths: no readback, no sync
+        } else if (promised_short && warp_impl) {
+            // the caller vouches for short units only: nothing to read back (the planner reports a broken promise)
         } else if (n_rel > DCN_MAX_SHORT) {
             CK(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -413,11 +424,12 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             // short units: warp tiles; then the CTA-tile tail (units of more than a warp pass's picks, long chunks).  With
             // no long unit in the batch the tail only has work on pathological input, so a few CTAs are enough.
             const uint32_t ocap = (uint32_t)std::min<uint64_t>(wovf_cap, 0xFFFFFFFFull);
-            if (in.codes) filter_warp_kernel<true><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap);
-            else filter_warp_kernel<false><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap);
+            unsigned long long *cnt = call_cnt;
+            if (in.codes) filter_warp_kernel<true><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt);
+            else filter_warp_kernel<false><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt);
             const int tgrid = hs.n_long ? grid : std::min(grid, 16);
-            if (in.codes) filter_tail_kernel<G31, true><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc);
-            else filter_tail_kernel<G31, false><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc);
+            if (in.codes) filter_tail_kernel<G31, true><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc, call_cnt);
+            else filter_tail_kernel<G31, false><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc, call_cnt);
             ctx->launches += 1;
         } else if (in.codes) filter_fused_kernel<G31, true><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
         else filter_fused_kernel<G31, false><<<grid, G31::NT, smem, st>>>(P, d_stats, tile_first, tile_end, dd, desc);
@@ -428,7 +440,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         }
         ctx->launches += 1;
         if (hs.n_long) {
-            finalize_long_kernel<<<std::max(1, (int)std::min<uint32_t>((hs.n_long + 255) / 256, 1024)), 256, 0, st>>>(P, d_stats, long_units);
+            finalize_long_kernel<<<std::max(1, (int)std::min<uint32_t>((hs.n_long + 255) / 256, 1024)), 256, 0, st>>>(P, d_stats, long_units, warp_impl ? call_cnt : nullptr);
             ctx->launches += 1;
             BatchStats after;
             CK(cudaMemcpyAsync(&after, d_stats, sizeof(after), cudaMemcpyDeviceToHost, st));
@@ -441,7 +453,8 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         }
         break;
     }
-    stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_keep, ctx->counters.as<unsigned long long>());
+    if (warp_impl) commit_counters_kernel<<<1, 32, 0, st>>>(call_cnt, ctx->counters.as<unsigned long long>());   // the warp-tile kernels counted on the way
+    else stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_keep, ctx->counters.as<unsigned long long>());
     ctx->launches += 1;
     CK(cudaGetLastError());
     return DCN_OK;
@@ -486,6 +499,8 @@ dcn_ctx *dcn_ctx_create(int device) {
         ok = ok && cudaEventCreate(&ctx->kev0[i]) == cudaSuccess && cudaEventCreate(&ctx->kev1[i]) == cudaSuccess;
     ok = ok && ctx->counters.ensure(8 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMemset(ctx->counters.p, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMallocHost(reinterpret_cast<void **>(&ctx->h_promise), 64) == cudaSuccess;
+    if (ok) *ctx->h_promise = 0;
     ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -537,6 +552,7 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
         if (ctx->kev1[i]) cudaEventDestroy(ctx->kev1[i]);
     }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_promise) cudaFreeHost(ctx->h_promise);
     delete ctx;
 }
 
@@ -623,16 +639,37 @@ int dcn_index_info(dcn_ctx *ctx, uint64_t *n_keys, uint8_t *k, uint8_t *w, uint6
 }
 
 // ---------------------------------------------------------------------------- B1 filter
-int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
-                            uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
-                            int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream) {
+// a promise given to dcn_filter_batch_device_hint that the device found broken: reported once, by the next call
+static int check_promise(dcn_ctx *ctx) {
+    if (ctx->h_promise && *reinterpret_cast<volatile uint32_t *>(ctx->h_promise)) {
+        *ctx->h_promise = 0;
+        return ctx->fail(DCN_ERR_ARG, "an earlier dcn_filter_batch_device_hint call held a unit longer than the promised max_unit_len: "
+                                      "its long units were not classified");
+    }
+    return DCN_OK;
+}
+
+int dcn_filter_batch_device_hint(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                                 uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
+                                 int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream,
+                                 uint32_t max_unit_len) {
     if (!ctx) return DCN_ERR_ARG;
+    int rc = check_promise(ctx);
+    if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;   // NULL = the legacy default stream, like any CUDA API
     FilterInput in;
     in.bases = d_bases;
+    const bool promised = max_unit_len > 0 && max_unit_len <= DCN_MAX_SHORT;
     return enqueue_filter(ctx, ctx->plan, ctx->longs, ctx->dedup, in, 0, n_bases, d_rec_off, n_rec, paired,
-                          prefix_len, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, st);
+                          prefix_len, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, st, nullptr, true, promised);
+}
+
+int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                            uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
+                            int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream) {
+    return dcn_filter_batch_device_hint(ctx, d_bases, d_rec_off, n_rec, n_bases, paired, prefix_len, abs_thr, rel_thr, deplete,
+                                        d_keep, d_hits, d_total, stream, 0);
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -1806,7 +1843,7 @@ int dcn_stats_get(dcn_ctx *ctx, uint64_t counters[6]) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(counters, ctx->counters.p, 6 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    return DCN_OK;
+    return check_promise(ctx);   // everything enqueued has run: a promise broken by any earlier call shows here
 }
 int dcn_stats_accumulate_device(dcn_ctx *ctx, const uint64_t *d_rec_off, uint32_t n_rec, int paired, const uint8_t *d_keep,
                                 void *stream) {

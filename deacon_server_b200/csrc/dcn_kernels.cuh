@@ -162,10 +162,20 @@ __global__ void prep_index_chunks_kernel(const uint64_t *__restrict__ rec_off, u
 }
 
 // keep flag of the long units once every chunk has added its counts
-__global__ void finalize_long_kernel(FilterParams P, const BatchStats *st, const uint32_t *long_units) {
+// `counters` (optional): the long units' share of the summary counters (warp-tile path; the CTA path runs stats_kernel)
+__global__ void finalize_long_kernel(FilterParams P, const BatchStats *st, const uint32_t *long_units, unsigned long long *counters) {
+    unsigned long long n_all = 0, n_kept = 0, bp_all = 0, bp_kept = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < st->n_long_listed; i += gridDim.x * blockDim.x) {
         uint32_t u = long_units[i];
-        P.keep[u] = meets_criteria(P.hits[u], P.total[u], P.abs_thr, P.rel_thr, P.deplete) ? 1 : 0;
+        const bool keep = meets_criteria(P.hits[u], P.total[u], P.abs_thr, P.rel_thr, P.deplete);
+        P.keep[u] = keep ? 1 : 0;
+        const unsigned long long len = P.rec_off[(uint64_t)(u + 1) * P.rpu] - P.rec_off[(uint64_t)u * P.rpu];
+        n_all += P.rpu; bp_all += len;
+        if (keep) { n_kept += P.rpu; bp_kept += len; }
+    }
+    if (counters && n_all) {
+        atomicAdd(&counters[0], n_all); atomicAdd(&counters[1], n_all - n_kept); atomicAdd(&counters[2], bp_all);
+        atomicAdd(&counters[3], bp_kept); atomicAdd(&counters[4], bp_all - bp_kept); atomicAdd(&counters[5], n_kept);
     }
 }
 
@@ -277,20 +287,58 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
 }
 
 // ------------------------------------------------------------------ warp-tile planner
-// One thread per 64 KB segment of the batch walks its units twice (count, reserve a block of the tile list with one
-// atomic, write).  The list order is irrelevant: tiles are claimed from a counter.
-__global__ void wplan_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units, uint64_t base0,
-                             uint64_t n_rel, BatchStats *st, WTile *tiles, uint32_t tile_cap) {
+// One warp per 64 KB segment of the batch (units whose first base lies in the segment).  The greedy walk of
+// wplan_segment, 32 units at a time: the lanes load the offsets of the 32 units from the current tile start
+// (coalesced), one ballot says how many of them the tile takes.  Tiles are staged in shared memory and appended to
+// the list 64 at a time (one atomic per flush); the list order is irrelevant, tiles are claimed from a counter.
+// Long units (skipped here, cut into chunks by prep_long_kernel) are counted on the way: n_long, long_bases.
+__global__ void __launch_bounds__(256)
+wplan_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units, uint64_t base0, uint64_t n_rel,
+             BatchStats *st, WTile *tiles, uint32_t tile_cap, uint32_t *promise_broken) {
+    __shared__ WTile buf[8][64];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint64_t n_seg = (n_rel + DCN_WSEG - 1) / DCN_WSEG;
-    for (uint64_t seg = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; seg < n_seg; seg += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t n = wplan_segment(rec_off, base0, rpu, n_units, seg, [](uint64_t, uint32_t, uint32_t) {});
-        if (!n) continue;
-        uint32_t at = atomicAdd(&st->n_wtiles, n);
-        wplan_segment(rec_off, base0, rpu, n_units, seg, [&](uint64_t origin, uint32_t a, uint32_t b) {
-            if (at < tile_cap) { WTile t; t.origin = origin; t.a = a; t.b = b; tiles[at] = t; }
-            else st->overflow = 1;
-            at++;
-        });
+    const uint64_t n_warps = (uint64_t)gridDim.x * 8u;
+    const uint32_t maxu = wplan_max_units(rpu);
+    const uint64_t HUGE = ~0ull >> 1;
+    for (uint64_t seg = (uint64_t)blockIdx.x * 8u + warp; seg < n_seg; seg += n_warps) {
+        const uint64_t hi_pos = (seg + 1) * DCN_WSEG;
+        uint32_t u = wplan_first_unit(rec_off, base0, rpu, n_units, seg * DCN_WSEG);
+        uint32_t nbuf = 0, n_long = 0;
+        unsigned long long long_bases = 0;
+        auto flush = [&]() {
+            uint32_t at = 0;
+            if (lane == 0) at = atomicAdd(&st->n_wtiles, nbuf);
+            at = __shfl_sync(0xFFFFFFFFu, at, 0);
+            for (uint32_t i = lane; i < nbuf; i += 32u) {
+                if (at + i < tile_cap) tiles[at + i] = buf[warp][i];
+                else st->overflow = 1;
+            }
+            __syncwarp();
+            nbuf = 0;
+        };
+        while (u < n_units) {
+            const uint64_t idx = (uint64_t)u + lane;
+            const uint64_t s_l = idx <= n_units ? rec_off[idx * rpu] - base0 : HUGE;
+            const uint64_t e_l = idx + 1 <= n_units ? rec_off[(idx + 1) * rpu] - base0 : HUGE;
+            const uint64_t s0 = __shfl_sync(0xFFFFFFFFu, s_l, 0), e0 = __shfl_sync(0xFFFFFFFFu, e_l, 0);
+            if (s0 >= hi_pos) break;
+            if (e0 - s0 > DCN_MAX_SHORT) { n_long++; long_bases += e0 - s0; u++; continue; }
+            const uint64_t origin = s0 & ~15ull;
+            const bool fit = idx < n_units && s_l < hi_pos && e_l - s_l <= DCN_MAX_SHORT && e_l - origin <= (uint64_t)WG::TB && lane < maxu;
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, fit);          // bit 0 is set: a short unit always fits a tile of its own
+            const uint32_t cnt = m == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
+            if (lane == 0) { WTile t; t.origin = origin; t.a = u; t.b = u + cnt; buf[warp][nbuf] = t; }
+            nbuf++;
+            u += cnt;
+            __syncwarp();
+            if (nbuf == 64u) flush();
+        }
+        if (nbuf) flush();
+        if (lane == 0 && n_long) {
+            atomicAdd(&st->n_long, n_long); atomicAdd(&st->long_bases, long_bases);
+            if (promise_broken) *reinterpret_cast<volatile uint32_t *>(promise_broken) = 1u;   // pinned host word (dcn_filter_batch_device_hint)
+        }
     }
 }
 
@@ -323,6 +371,17 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// src/local_filter.rs:347-371 (single) / 488-525 (pair): seqs and bp in / kept / filtered
+__device__ __forceinline__ void add_summary(unsigned long long *counters, unsigned long long n_all, unsigned long long n_kept,
+                                            unsigned long long bp_all, unsigned long long bp_kept) {
+    atomicAdd(&counters[0], n_all);                  // total_seqs
+    atomicAdd(&counters[1], n_all - n_kept);         // filtered_seqs
+    atomicAdd(&counters[2], bp_all);                 // total_bp
+    atomicAdd(&counters[3], bp_kept);                // output_bp
+    atomicAdd(&counters[4], bp_all - bp_kept);       // filtered_bp
+    atomicAdd(&counters[5], n_kept);                 // output_seq_counter
+}
+
 #ifndef DCN_WARPS
 #define DCN_WARPS 32            // warps per CTA of filter_warp_kernel (one CTA per SM): 32 x 64 registers
 #endif
@@ -331,6 +390,8 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
 // descriptors of the next two tiles (brought in by cp.async, so that no register waits for them).
 struct WarpPipe {
     WTile d1, d2;   // next tile, tile after next
+    unsigned long long bp_all, bp_kept;   // summary counters of the units this warp classified (lane 0 adds, flushed once at the end)
+    uint32_t n_all, n_kept, pad_[2];
 };
 
 struct WarpDevExec {
@@ -353,6 +414,10 @@ struct WarpDevExec {
         return (uint64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)v, (int)src);
     }
     __device__ __forceinline__ uint32_t match64(int, uint64_t v, bool) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
+    __device__ __forceinline__ void tally(uint32_t nrec, uint32_t len, bool keep) {   // lane 0 only
+        pipe->bp_all += len; pipe->n_all += nrec;
+        if (keep) { pipe->bp_kept += len; pipe->n_kept += nrec; }
+    }
     template <class Get, class Put>
     __device__ __forceinline__ void scan(Get get, Put put) {
         const uint32_t v = get(lane, pv);
@@ -402,7 +467,8 @@ struct WarpDevExec {
 
 template <bool PACKED>
 __global__ void __launch_bounds__(DCN_WARPS * 32, 1)
-filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ tiles, uint32_t *ovf_list, uint32_t ovf_cap) {
+filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ tiles, uint32_t *ovf_list, uint32_t ovf_cap,
+                   unsigned long long *counters) {
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
     WarpTables &T = *reinterpret_cast<WarpTables *>(dcn_smem_raw);
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
@@ -410,7 +476,10 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
     WarpPipe &pipe = reinterpret_cast<WarpPipe *>(dcn_smem_raw + OFF_PIPE)[warp];
     WarpSmem &s = reinterpret_cast<WarpSmem *>(dcn_smem_raw + OFF_WARPS)[warp];
     winit_tables((int)threadIdx.x, (int)blockDim.x, T, P.abs_thr, P.rel_thr);
-    if (lane == 0) mbar_init(&s.mbar, 1u);
+    if (lane == 0) {
+        mbar_init(&s.mbar, 1u);
+        pipe.bp_all = pipe.bp_kept = 0; pipe.n_all = pipe.n_kept = 0;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();   // the only CTA barrier of the kernel
 
@@ -462,6 +531,7 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
         ex.id1 = ex.id2;
         ex.id2 = __shfl_sync(0xFFFFFFFFu, ex.c3, 0);
     }
+    if (lane == 0 && pipe.n_all) add_summary(counters, pipe.n_all, pipe.n_kept, pipe.bp_all, pipe.bp_kept);
 }
 
 // ------------------------------------------------------------------ the CTA-tile tail of the warp kernel
@@ -471,7 +541,7 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
 template <class G, bool PACKED>
 __global__ void __launch_bounds__(G::NT, DCN_CTAS_PER_SM)
 filter_tail_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ ovf_list, DedupView dd,
-                   const ChunkDesc *__restrict__ desc) {
+                   const ChunkDesc *__restrict__ desc, unsigned long long *counters) {
     const uint32_t n_ovf = st->n_ovf, n_long = st->n_long;
     if (n_ovf == 0 && n_long == 0) return;
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
@@ -486,6 +556,11 @@ filter_tail_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restr
         const uint32_t u = ovf_list[i];
         filter_short_run<G, PACKED, MODE_FILTER>(ex, s, P, u, u + 1u);
         __syncthreads();
+        if (threadIdx.x == 0) {   // the unit's share of the summary counters (the warp kernel left it out)
+            const unsigned long long len = P.rec_off[(uint64_t)(u + 1) * P.rpu] - P.rec_off[(uint64_t)u * P.rpu];
+            const bool kept = P.keep[u] != 0;
+            add_summary(counters, P.rpu, kept ? P.rpu : 0u, len, kept ? len : 0ull);
+        }
     }
     if (n_long) {
         __syncthreads();
@@ -643,6 +718,11 @@ __global__ void stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu,
         atomicAdd(&counters[4], bp_all - bp_kept);       // filtered_bp
         atomicAdd(&counters[5], n_kept);                 // output_seq_counter
     }
+}
+
+// one call's share of the summary counters -> the ctx's counters
+__global__ void commit_counters_kernel(const unsigned long long *__restrict__ call_cnt, unsigned long long *counters) {
+    if (threadIdx.x < 6 && call_cnt[threadIdx.x]) atomicAdd(&counters[threadIdx.x], call_cnt[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------ table build (K4)

@@ -325,10 +325,11 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
             const uint32_t i = (uint32_t)l + 32u * (uint32_t)j;
             if (i < n_rec_t) {
                 set_bit(s.brk, pv.sL[j]);
-                if (i % P.rpu == 0) s.ustartpos[i / P.rpu] = (uint16_t)pv.sL[j];
+                if ((i & (P.rpu - 1u)) == 0) s.ustartpos[i >> (P.rpu - 1u)] = (uint16_t)pv.sL[j];   // rpu is 1 or 2
                 if (pv.eff[j] < pv.eL[j]) { set_bits(s.dead, pv.eff[j], pv.eL[j]); set_bits(s.brk, pv.eff[j], pv.eL[j]); }
             }
         }
+        if (l == 0) s.ustartpos[n_units_t] = (uint16_t)span_hi;   // P7 takes a unit's length from two consecutive starts
         // k-mer at the lane's first base: bases 0..30 = own words 0 and 1 (less its last base)
         const uint32_t c0 = s.codes[3 * l], c1 = s.codes[3 * l + 1], c2 = s.codes[3 * l + 2];
         uint32_t fw = 0, rc = 0;
@@ -520,6 +521,7 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
                 if (total < 256u) { const uint32_t req = T.req[total]; keep = P.deplete ? hits < req : hits >= req; }
                 else keep = meets_criteria(hits, total, P.abs_thr, P.rel_thr, P.deplete);
                 P.keep[gu] = keep ? 1 : 0;
+                ex.tally(P.rpu, (uint32_t)s.ustartpos[u + 1] - (uint32_t)s.ustartpos[u], keep);   // the six summary counters (a13)
             }
         }
     });
@@ -564,6 +566,9 @@ DCN_HD void warp_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterPara
 // One thread per segment of the batch (units whose first base lies in [seg * SEG, (seg + 1) * SEG)).
 static constexpr uint32_t DCN_WSEG = 1u << 16;
 
+// units a tile may hold: MAXR records, and at most the 32 the planner's warp looks at in one step
+DCN_HD uint32_t wplan_max_units(uint32_t rpu) { const uint32_t m = (uint32_t)WG::MAXR / rpu; return m < 32u ? m : 32u; }
+
 DCN_HD uint32_t wplan_first_unit(const uint64_t *rec_off, uint64_t base0, uint32_t rpu, uint32_t n_units, uint64_t pos) {
     uint32_t lo = 0, hi = n_units;   // first unit with start >= pos
     while (lo < hi) {
@@ -579,7 +584,7 @@ DCN_HD uint32_t wplan_segment(const uint64_t *rec_off, uint64_t base0, uint32_t 
                               Emit emit) {
     const uint64_t lo_pos = seg * DCN_WSEG, hi_pos = lo_pos + DCN_WSEG;
     uint32_t u = wplan_first_unit(rec_off, base0, rpu, n_units, lo_pos);
-    const uint32_t maxu = (uint32_t)WG::MAXR / rpu;
+    const uint32_t maxu = wplan_max_units(rpu);
     uint32_t n = 0;
     while (u < n_units) {
         const uint64_t start = rec_off[(uint64_t)u * rpu] - base0;

@@ -77,6 +77,16 @@ int dcn_filter_batch(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off
 int dcn_filter_batch_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
                             uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
                             int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream);
+/* The same with the caller's promise that no unit (a record, or a pair of mates) is longer than `max_unit_len`
+ * bases -- the reference's callers know this from the parser that produced rec_off.  With max_unit_len <= 1024 the
+ * call only enqueues work on `stream`: nothing is read back, no stream synchronisation (dcn_filter_batch_device has
+ * to learn from the device whether the batch holds long units, which costs one small synchronisation per call).
+ * A broken promise is detected on the device; the units that were too long are left unclassified and the NEXT
+ * filter / stats call on this ctx returns DCN_ERR_ARG.  max_unit_len = 0 or > 1024: same as dcn_filter_batch_device. */
+int dcn_filter_batch_device_hint(dcn_ctx *ctx, const uint8_t *d_bases, const uint64_t *d_rec_off, uint32_t n_rec,
+                                 uint64_t n_bases, int paired, uint32_t prefix_len, uint32_t abs_thr, double rel_thr,
+                                 int deplete, uint8_t *d_keep, uint32_t *d_hits, uint32_t *d_total, void *stream,
+                                 uint32_t max_unit_len);
 
 /* Host ingest of dcn_filter_batch.  For k=31, w=15 indexes part of the batch can be packed on
  * `n_threads` host threads (2-bit codes + non-ACGT bits: what PackedSeqVec::from_ascii and the mask loop of

@@ -25,6 +25,8 @@ struct HostExec {
     HostExec() : pv(G::NT) {}
     int after_scan_calls = 0;
     void after_scan(bool go) { after_scan_calls += go ? 1 : 0; }
+    uint64_t tally_n = 0, tally_bp = 0, tally_n_kept = 0, tally_bp_kept = 0;
+    void tally(uint32_t nrec, uint32_t len, bool keep) { tally_n += nrec; tally_bp += len; if (keep) { tally_n_kept += nrec; tally_bp_kept += len; } }
 
     // ---- warp votes.  A phase runs thread after thread here, so a vote cannot see the other
     // lanes' operands of the same pass.  The phase is therefore re-run from a snapshot until the

@@ -358,6 +358,62 @@ def test_device_pointer_api_matches_host_api(gpu):
     assert np.array_equal(d_t.cpu().numpy().view(np.uint32), t)
 
 
+def test_device_pointer_api_with_length_promise(gpu):
+    """dcn_filter_batch_device_hint: with the caller's promise that every unit is short the call only enqueues
+    (no readback); results and the six counters are the same; a broken promise is reported by the next call."""
+    import torch
+    from deacon_server_b200 import IndexHeader, DeaconCudaError
+    g = H.random_genome(300_000, 17)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    reads = H.sample_reads(g, 30_000, (60, 151), 18, n_rate=0.01)
+    bases, off = H.concat(reads)
+    ok, oh, ot = O.filter_batch(idx, bases, off, paired=True, deplete=True, threads=8)
+    dev = torch.device("cuda:0")
+    d_b = torch.from_numpy(bases).to(dev)
+    d_o = torch.from_numpy(off.view(np.int64)).to(dev)
+    nu = len(reads) // 2
+    st = torch.cuda.current_stream().cuda_stream
+    gpu.stats_reset()
+    outs = []
+    for hint in (0, 302, 1024):
+        d_k = torch.zeros(nu, dtype=torch.uint8, device=dev)
+        d_h = torch.zeros(nu, dtype=torch.int32, device=dev)
+        d_t = torch.zeros(nu, dtype=torch.int32, device=dev)
+        gpu.filter_batch_device(d_b, d_o, len(reads), len(bases), d_k, d_h, d_t, paired=True, deplete=True, stream=st,
+                                max_unit_len=hint)
+        outs.append((d_k, d_h, d_t))
+    torch.cuda.synchronize()
+    for d_k, d_h, d_t in outs:
+        assert np.array_equal(d_k.cpu().numpy(), ok)
+        assert np.array_equal(d_h.cpu().numpy().view(np.uint32), oh)
+        assert np.array_equal(d_t.cpu().numpy().view(np.uint32), ot)
+    c = gpu.stats()
+    assert c["total_seqs"] == 3 * len(reads) and c["total_bp"] == 3 * len(bases)
+    assert c["output_seq_counter"] == 3 * 2 * int(ok.sum())
+    # a batch with one long unit under a "short units only" promise: detected on the device, reported by the next call
+    long_reads = reads[:100] + [g[:5000].copy(), g[5000:5150].copy()] + reads[100:200]
+    b2, o2 = H.concat(long_reads)
+    d_b2 = torch.from_numpy(b2).to(dev)
+    d_o2 = torch.from_numpy(o2.view(np.int64)).to(dev)
+    n2 = len(long_reads) // 2
+    d_k = torch.zeros(n2, dtype=torch.uint8, device=dev)
+    d_h = torch.zeros(n2, dtype=torch.int32, device=dev)
+    d_t = torch.zeros(n2, dtype=torch.int32, device=dev)
+    gpu.filter_batch_device(d_b2, d_o2, len(long_reads), len(b2), d_k, d_h, d_t, paired=True, deplete=True, stream=st,
+                            max_unit_len=302)
+    torch.cuda.synchronize()
+    with pytest.raises(DeaconCudaError):
+        gpu.filter_batch_device(d_b2, d_o2, len(long_reads), len(b2), d_k, d_h, d_t, paired=True, deplete=True, stream=st)
+    # the error is reported once; without the promise the same batch is classified in full
+    gpu.filter_batch_device(d_b2, d_o2, len(long_reads), len(b2), d_k, d_h, d_t, paired=True, deplete=True, stream=st)
+    torch.cuda.synchronize()
+    k2, h2, t2 = O.filter_batch(idx, b2, o2, paired=True, deplete=True, threads=8)
+    assert np.array_equal(d_k.cpu().numpy(), k2) and np.array_equal(d_h.cpu().numpy().view(np.uint32), h2)
+    assert np.array_equal(d_t.cpu().numpy().view(np.uint32), t2)
+    gpu.stats_reset()
+
+
 @pytest.mark.parametrize("case", CASES.make_long_cases(), ids=lambda c: c["name"])
 def test_long_path_matches_oracle(gpu, case):
     """Units longer than 1024 bases: chunked kernel + global (hash, unit) distinct-hit set."""

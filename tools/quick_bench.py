@@ -22,8 +22,10 @@ ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--load", type=float, default=0.5)
 ap.add_argument("--check", type=int, default=20000)
 ap.add_argument("--no-e2e", action="store_true")
+ap.add_argument("--no-hint", action="store_true", help="do not promise the unit length (dcn_filter_batch_device: one small sync per call)")
 ap.add_argument("--sweep", default="", help="e2e ingest sweep: threads:fraction,threads:fraction,... (replaces the default three settings)")
 args = ap.parse_args()
+HINT = 0 if args.no_hint else 300
 
 dev = torch.device("cuda:0")
 torch.manual_seed(1)
@@ -70,7 +72,7 @@ st = torch.cuda.current_stream().cuda_stream
 nb = bases.numel()
 
 def step():
-    gpu.filter_batch_device(bases, off, NR, nb, keep, hits, tot, paired=True, deplete=True, stream=st)
+    gpu.filter_batch_device(bases, off, NR, nb, keep, hits, tot, paired=True, deplete=True, stream=st, max_unit_len=HINT)
 
 for _ in range(3):
     step()
