@@ -736,7 +736,21 @@ struct ChunkPlan {
     uint64_t a0, b1, nb;   // chunk origin (64-aligned), end, bases covered
     // blob layouts
     size_t n_words, o_inv, o_off_p, o_nl, in_packed, o_off_a, in_ascii, out_bytes;
+    // sparse packed form (what the packer threads ship): codes | newline flags | exceptions | offsets on the wire and on
+    // the device, where the dense non-ACGT bit array follows (cleared by a memset, the listed blocks written by a kernel)
+    size_t s_nl, s_exc, s_off, s_inv, in_sparse, dev_sparse;
+    uint32_t exc_cap;   // exception slots: 32-base blocks that hold a non-ACGT byte; a chunk with more goes dense
 };
+
+static void sparse_layout(ChunkPlan &c) {
+    c.s_nl = align_up(c.n_words * 4, 8);
+    c.s_exc = c.s_nl + align_up(((size_t)c.nr + 31) / 32 * 4 + 4, 8);
+    c.exc_cap = (uint32_t)std::min<uint64_t>(c.n_words / 64 + 4, 0x7FFFFFFFu);   // 1 block in 32: beyond that the dense mask is smaller
+    c.s_off = c.s_exc + (size_t)c.exc_cap * 8;
+    c.in_sparse = c.s_off + ((size_t)c.nr + 1) * 8;
+    c.s_inv = align_up(c.in_sparse, 16);
+    c.dev_sparse = c.s_inv + c.n_words * 2 + 16;
+}
 
 struct ChunkStats {
     BatchStats st;
@@ -839,6 +853,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         c.in_packed = c.o_off_p + ((size_t)c.nr + 1) * 8;
         c.o_off_a = align_up(c.nb + 16, 16); c.in_ascii = c.o_off_a + ((size_t)c.nr + 1) * 8;
         c.out_bytes = (size_t)c.nu * 9;
+        sparse_layout(c);
         return c;
     };
     // the largest chunks of the two routes, for sizing the stages once (records of >= 64 bases on average assumed;
@@ -855,6 +870,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         c.in_packed = c.o_off_p + ((size_t)c.nr + 1) * 8;
         c.o_off_a = align_up(c.nb + 16, 16); c.in_ascii = c.o_off_a + ((size_t)c.nr + 1) * 8;
         c.out_bytes = (size_t)c.nu * 9;
+        sparse_layout(c);
         return c;
     };
     const int packer_grab_max = std::max<int>(1, (int)atoms_per_chunk / 2);
@@ -921,12 +937,13 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
     // Enqueue one chunk on stage `s`: copies in, the kernels, results out.  `route`: 0 ASCII bytes, 1 the caller's packed
     // arrays, 2 the blob a packer thread has just written to s.h_in.  Called by the enqueueing thread (stages ctx->slot)
     // and by every packer thread (its own two stages): it touches nothing shared but atomics and the device.
-    auto ship = [&](Slot &s, const ChunkPlan &c, int route, const ChunkStats &cs, Acc &acc, bool time_fused) -> int {
+    // n_exc >= 0 (route 2 only): the blob is in the sparse form with that many exceptions; < 0: dense
+    auto ship = [&](Slot &s, const ChunkPlan &c, int route, const ChunkStats &cs, Acc &acc, bool time_fused, int64_t n_exc = -1) -> int {
         const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
         // sized for the largest chunk the stage is likely to see, not for this one: growing a buffer later costs a
         // cudaFree / cudaFreeHost (a device-wide sync) in the middle of some call
         const ChunkPlan &big = route == 2 ? big_packed : big_ascii;
-        if (s.in.ensure(std::max(route ? c.in_packed + 8 : c.in_ascii, route ? big.in_packed + 8 : big.in_ascii)) != cudaSuccess ||
+        if (s.in.ensure(std::max(route ? std::max(c.in_packed, c.dev_sparse) + 8 : c.in_ascii, route ? std::max(big.in_packed, big.dev_sparse) + 8 : big.in_ascii)) != cudaSuccess ||
             s.out.ensure(std::max(c.out_bytes, big.out_bytes)) != cudaSuccess || s.h_out.ensure(std::max(c.out_bytes, big.out_bytes)) != cudaSuccess)
             return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
         uint8_t *din = s.in.as<uint8_t>();
@@ -961,6 +978,25 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
             in.codes = reinterpret_cast<const uint32_t *>(din);
             in.inv = reinterpret_cast<const uint16_t *>(din + c.o_inv);
             d_off = reinterpret_cast<const uint64_t *>(din + c.o_off_p);
+        } else if (route == 2 && n_exc >= 0) {
+            // sparse form: codes, newline flags and the exception list in one copy (+ the offsets unless they are generated);
+            // the dense non-ACGT bits the kernel reads are rebuilt on the device: cleared, then the listed blocks written
+            const uint8_t *hin = s.h_in.as<uint8_t>();
+            const size_t wire = cs.uniform ? c.s_exc + (size_t)n_exc * 8 : c.in_sparse;
+            CK(cudaMemcpyAsync(din, hin, wire, cudaMemcpyHostToDevice, s.stream));
+            acc.h2d += wire;
+            if (cs.uniform) CK(ship_offsets(din + c.s_off, nullptr));
+            CK(cudaMemsetAsync(din + c.s_inv, 0, c.n_words * 2, s.stream));
+            if (n_exc) {
+                inv_scatter_kernel<<<grid_for(ctx, (uint64_t)n_exc, 128), 128, 0, s.stream>>>(
+                    reinterpret_cast<uint32_t *>(din + c.s_inv), reinterpret_cast<const uint2 *>(din + c.s_exc), (uint32_t)n_exc);
+                ctx->launches += 1;
+            }
+            acc.n_packed++;
+            in.codes = reinterpret_cast<const uint32_t *>(din);
+            in.inv = reinterpret_cast<const uint16_t *>(din + c.s_inv);
+            in.nl = reinterpret_cast<const uint32_t *>(din + c.s_nl);
+            d_off = reinterpret_cast<const uint64_t *>(din + c.s_off);
         } else if (route == 2) {
             const uint8_t *hin = s.h_in.as<uint8_t>();
             if (cs.uniform) {   // codes, non-ACGT bits and newline flags in one copy; the offsets are generated
@@ -1031,6 +1067,8 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         Acc acc;
         int rc = DCN_OK;
         std::vector<uint64_t> bad32;
+        std::vector<uint32_t> bad_mask;
+        static const bool sparse_wire = []() { const char *e = getenv("DCN_SPARSE_MASK"); return !e || atoi(e) != 0; }();
         auto body = [&]() -> int {
             CK(cudaSetDevice(ctx->device));
             for (int i = 0; i < PST; i++) {
@@ -1042,7 +1080,8 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
             }
             for (int i = 0; i < PST; i++) {   // all of the thread's staging in its first call (pinning memory is slow)
                 Slot &s = ctx->pslot[(size_t)(PST * t + i)];
-                if (s.h_in.ensure(big_packed.in_packed) != cudaSuccess || s.in.ensure(big_packed.in_packed + 8) != cudaSuccess ||
+                if (s.h_in.ensure(std::max(big_packed.in_packed, big_packed.in_sparse)) != cudaSuccess ||
+                    s.in.ensure(std::max(big_packed.in_packed, big_packed.dev_sparse) + 8) != cudaSuccess ||
                     s.out.ensure(big_packed.out_bytes) != cudaSuccess || s.h_out.ensure(big_packed.out_bytes) != cudaSuccess)
                     return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
             }
@@ -1060,19 +1099,40 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
                 int r = retire(s, acc);   // the blob's previous copy has left the host once its results are back
                 if (r) return r;
                 const double t0 = now_ms();
-                if (s.h_in.ensure(std::max(c.in_packed, big_packed.in_packed)) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed", cudaGetLastError());
+                if (s.h_in.ensure(std::max(std::max(c.in_packed, c.in_sparse), std::max(big_packed.in_packed, big_packed.in_sparse))) != cudaSuccess)
+                    return ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed", cudaGetLastError());
                 uint8_t *hin = s.h_in.as<uint8_t>();
                 const uint64_t *off0 = rec_off + (uint64_t)c.u0 * rpu;
                 const ChunkStats cs = chunk_stats(off0, c.nu, rpu);
-                if (!cs.uniform) memcpy(hin + c.o_off_p, off0, ((size_t)c.nr + 1) * 8);
                 uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
-                uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + c.o_inv);
-                uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + c.o_nl);
-                // codes, non-ACGT bits and newline flags in one pass over the atom (dcn_host_pack.h)
-                pack_records(bases, c.a0, c.nb, off0, c.nr, ctx->k, prefix_len, h_codes, h_inv, h_nl, bad32);
+                int64_t n_exc = -1;
+                if (sparse_wire) {
+                    // codes and newline flags into the blob; the non-ACGT bits only as (block, mask) pairs of the blocks that
+                    // have any (real reads: a handful per chunk): 0.25 B/bp cross PCIe instead of 0.375
+                    uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + c.s_nl);
+                    pack_records(bases, c.a0, c.nb, off0, c.nr, ctx->k, prefix_len, h_codes, nullptr, h_nl, bad32, &bad_mask);
+                    if (bad32.size() <= c.exc_cap) {
+                        n_exc = (int64_t)bad32.size();
+                        uint32_t *ex = reinterpret_cast<uint32_t *>(hin + c.s_exc);
+                        for (size_t i = 0; i < bad32.size(); i++) { ex[2 * i] = (uint32_t)bad32[i]; ex[2 * i + 1] = bad_mask[i]; }
+                        if (!cs.uniform) memcpy(hin + c.s_off, off0, ((size_t)c.nr + 1) * 8);
+                    } else {   // N-rich chunk: the dense form is smaller; rebuild it from the list, flags moved to their dense place
+                        uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + c.o_inv);
+                        memmove(hin + c.o_nl, h_nl, ((size_t)c.nr + 31) / 32 * 4);
+                        memset(h_inv, 0, c.n_words * 2);
+                        for (size_t i = 0; i < bad32.size(); i++) memcpy(h_inv + 2 * bad32[i], &bad_mask[i], 4);
+                        if (!cs.uniform) memcpy(hin + c.o_off_p, off0, ((size_t)c.nr + 1) * 8);
+                    }
+                } else {
+                    if (!cs.uniform) memcpy(hin + c.o_off_p, off0, ((size_t)c.nr + 1) * 8);
+                    uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + c.o_inv);
+                    uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + c.o_nl);
+                    // codes, non-ACGT bits and newline flags in one pass over the atom (dcn_host_pack.h)
+                    pack_records(bases, c.a0, c.nb, off0, c.nr, ctx->k, prefix_len, h_codes, h_inv, h_nl, bad32);
+                }
                 acc.pack_ms += now_ms() - t0;
                 acc.packed_bases += c.nb;
-                if ((r = ship(s, c, 2, cs, acc, false))) return r;
+                if ((r = ship(s, c, 2, cs, acc, false, n_exc))) return r;
             }
             for (int i = 0; i < PST; i++) {
                 const int r = retire(ctx->pslot[(size_t)(PST * t + i)], acc);

@@ -31,7 +31,8 @@ static inline void pack32_scalar(const uint8_t *p, uint32_t *codes, uint16_t *in
 
 #ifdef DCN_X86
 __attribute__((target("avx2,bmi2"))) static void pack_blocks_avx2(const uint8_t *p, uint64_t n_blocks, uint32_t *codes,
-                                                                  uint16_t *inv, std::vector<uint64_t> *bad32) {
+                                                                  uint16_t *inv, std::vector<uint64_t> *bad32,
+                                                                  std::vector<uint32_t> *bad_mask) {
     // letter expected for each low nibble of the byte: 1 -> 'A', 3 -> 'C', 4 -> 'T', 7 -> 'G'
     const __m256i lut = _mm256_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1,
                                          -1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1);
@@ -43,8 +44,8 @@ __attribute__((target("avx2,bmi2"))) static void pack_blocks_avx2(const uint8_t 
         __m256i want = _mm256_shuffle_epi8(lut, _mm256_and_si256(v, m0f));
         uint32_t ok = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(want, _mm256_and_si256(v, mdf)));
         uint32_t bad = ~ok;
-        memcpy(inv + 2 * i, &bad, 4);
-        if (bad && bad32) bad32->push_back(i);
+        if (inv) memcpy(inv + 2 * i, &bad, 4);
+        if (bad && bad32) { bad32->push_back(i); if (bad_mask) bad_mask->push_back(bad); }
         uint64_t x0, x1, x2, x3;
         memcpy(&x0, q, 8); memcpy(&x1, q + 8, 8); memcpy(&x2, q + 16, 8); memcpy(&x3, q + 24, 8);
         uint64_t c = _pext_u64(x0, M) | (_pext_u64(x1, M) << 16) | (_pext_u64(x2, M) << 32) | (_pext_u64(x3, M) << 48);
@@ -58,7 +59,8 @@ __attribute__((target("avx2,bmi2"))) static void pack_blocks_avx2(const uint8_t 
 // pinned staging buffer the GPU's copy engine reads next, so keep it out of the cores' caches.
 __attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_blocks_avx512(const uint8_t *p, uint64_t n_blocks64,
                                                                                    uint32_t *codes, uint16_t *inv, bool nt,
-                                                                                   std::vector<uint64_t> *bad32) {
+                                                                                   std::vector<uint64_t> *bad32,
+                                                                                   std::vector<uint32_t> *bad_mask) {
     const __m512i lut = _mm512_broadcast_i32x4(_mm_setr_epi8(-1, 0x41, -1, 0x43, 0x54, -1, -1, 0x47, -1, -1, -1, -1, -1, -1, -1, -1));
     const __m512i m0f = _mm512_set1_epi8(0x0F), mdf = _mm512_set1_epi8((char)0xDF), m03 = _mm512_set1_epi8(0x03);
     const __m512i mul8 = _mm512_set1_epi16(0x0401), mul16 = _mm512_set1_epi32(0x00100001);
@@ -70,8 +72,8 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_blocks_avx
         __m512i want = _mm512_shuffle_epi8(lut, _mm512_and_si512(v, m0f));
         uint64_t bad = ~_mm512_cmpeq_epi8_mask(want, _mm512_and_si512(v, mdf));
         if (bad && bad32) {   // rare: reads are almost all ACGT
-            if ((uint32_t)bad) bad32->push_back(2 * i);
-            if (bad >> 32) bad32->push_back(2 * i + 1);
+            if ((uint32_t)bad) { bad32->push_back(2 * i); if (bad_mask) bad_mask->push_back((uint32_t)bad); }
+            if (bad >> 32) { bad32->push_back(2 * i + 1); if (bad_mask) bad_mask->push_back((uint32_t)(bad >> 32)); }
         }
         __m512i c = _mm512_and_si512(_mm512_srli_epi16(v, 1), m03);
         __m512i c4 = _mm512_maddubs_epi16(c, mul8);          // c0 + 4 c1 per 16-bit lane
@@ -79,10 +81,10 @@ __attribute__((target("avx512f,avx512bw,avx512vl"))) static void pack_blocks_avx
         __m128i out = _mm512_cvtepi32_epi8(c8);              // 16 bytes = 64 bases
         if (nt) {
             _mm_stream_si128(reinterpret_cast<__m128i *>(codes + 4 * i), out);
-            _mm_stream_si64(reinterpret_cast<long long *>(inv + 4 * i), (long long)bad);
+            if (inv) _mm_stream_si64(reinterpret_cast<long long *>(inv + 4 * i), (long long)bad);
         } else {
             _mm_storeu_si128(reinterpret_cast<__m128i *>(codes + 4 * i), out);
-            memcpy(inv + 4 * i, &bad, 8);
+            if (inv) memcpy(inv + 4 * i, &bad, 8);
         }
     }
     if (nt) _mm_sfence();
@@ -100,9 +102,11 @@ static int simd_level() {   // 0 scalar, 1 AVX2 + BMI2, 2 AVX-512 BW
 
 // ------------------------------------------------------------------ packing + newline flags in one pass
 void pack_records(const uint8_t *bases, uint64_t a0, uint64_t nb, const uint64_t *off0, uint32_t nr, uint32_t k,
-                  uint32_t prefix_len, uint32_t *codes, uint16_t *inv, uint32_t *nl, std::vector<uint64_t> &bad32) {
+                  uint32_t prefix_len, uint32_t *codes, uint16_t *inv, uint32_t *nl, std::vector<uint64_t> &bad32,
+                  std::vector<uint32_t> *bad_mask) {
     bad32.clear();
-    pack_ascii(bases + a0, nb, codes, inv, 1, &bad32);
+    if (bad_mask) bad_mask->clear();
+    pack_ascii(bases + a0, nb, codes, inv, 1, &bad32, bad_mask);
     memset(nl, 0, ((size_t)nr + 31) / 32 * 4);
     auto rec_end = [&](uint32_t q) {   // one past the last byte the reference looks at
         const uint64_t len = off0[q + 1] - off0[q];
@@ -162,32 +166,36 @@ bool pack_has_simd() {
 #endif
 }
 
-void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd, std::vector<uint64_t> *bad32) {
+void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd, std::vector<uint64_t> *bad32,
+                std::vector<uint32_t> *bad_mask) {
     const uint64_t full = n / 32;
     uint64_t done = 0;
 #ifdef DCN_X86
     // simd: 1 = best available, 2 = force the AVX2 path (tests), 0 = scalar
     if (simd == 1 && simd_level() == 2) {
         const bool nt = ((reinterpret_cast<uintptr_t>(codes) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(inv) & 7u) == 0);
-        pack_blocks_avx512(bases, n / 64, codes, inv, nt, bad32);
+        pack_blocks_avx512(bases, n / 64, codes, inv, nt, bad32, bad_mask);
         done = (n / 64) * 2;
     } else if (simd && simd_level() >= 1) {
-        pack_blocks_avx2(bases, full, codes, inv, bad32);
+        pack_blocks_avx2(bases, full, codes, inv, bad32, bad_mask);
         done = full;
     }
 #else
     (void)simd;
 #endif
+    uint16_t m2[2];
     for (uint64_t i = done; i < full; i++) {
-        pack32_scalar(bases + 32 * i, codes + 2 * i, inv + 2 * i);
-        if (bad32 && (inv[2 * i] | inv[2 * i + 1])) bad32->push_back(i);
+        pack32_scalar(bases + 32 * i, codes + 2 * i, m2);
+        if (inv) { inv[2 * i] = m2[0]; inv[2 * i + 1] = m2[1]; }
+        if (bad32 && (m2[0] | m2[1])) { bad32->push_back(i); if (bad_mask) bad_mask->push_back((uint32_t)m2[0] | ((uint32_t)m2[1] << 16)); }
     }
     if (n % 32) {
         uint8_t tail[32];
         memset(tail, 0, sizeof(tail));   // byte 0: code 0, not ACGT
         memcpy(tail, bases + 32 * full, n % 32);
-        pack32_scalar(tail, codes + 2 * full, inv + 2 * full);
-        if (bad32) bad32->push_back(full);   // the padding is flagged non-ACGT: always listed
+        pack32_scalar(tail, codes + 2 * full, m2);
+        if (inv) { inv[2 * full] = m2[0]; inv[2 * full + 1] = m2[1]; }
+        if (bad32) { bad32->push_back(full); if (bad_mask) bad_mask->push_back((uint32_t)m2[0] | ((uint32_t)m2[1] << 16)); }   // the padding is flagged non-ACGT: always listed
     }
 }
 

@@ -16,8 +16,11 @@ namespace dcn {
 // non-ACGT 1.  simd = 0 forces the scalar loop (tests compare the two).  `bad32`, when given, receives
 // (appended, ascending) the index of every 32-base block that holds a non-ACGT byte or padding: the only
 // places a record-terminating newline can be, so the caller's newline-flag pass visits those and nothing else.
+// `inv` may be null (sparse form): then the non-ACGT bits exist only as `bad_mask` -- the 32-bit mask of every block
+// listed in `bad32`, in the same order (a batch of real reads has a handful: 4 bytes per listed block cross PCIe
+// instead of 1 bit per base).
 void pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd,
-                std::vector<uint64_t> *bad32 = nullptr);
+                std::vector<uint64_t> *bad32 = nullptr, std::vector<uint32_t> *bad_mask = nullptr);
 bool pack_has_simd();
 
 // One pass over a chunk: packs bases[a0 .. a0 + nb) (pack_ascii) and writes the newline flags of its `nr` records
@@ -26,7 +29,8 @@ bool pack_has_simd();
 // a 32-base block where the packer saw a non-ACGT byte, so only the records ending inside the listed blocks are
 // looked at (a per-record pass over the chunk costs 28 % of the packing time).  `bad32` is scratch.
 void pack_records(const uint8_t *bases, uint64_t a0, uint64_t nb, const uint64_t *off0, uint32_t nr, uint32_t k,
-                  uint32_t prefix_len, uint32_t *codes, uint16_t *inv, uint32_t *nl, std::vector<uint64_t> &bad32);
+                  uint32_t prefix_len, uint32_t *codes, uint16_t *inv, uint32_t *nl, std::vector<uint64_t> &bad32,
+                  std::vector<uint32_t> *bad_mask = nullptr);
 
 // true iff off[r + 1] - off[r] == len0 for every r < n (off holds n + 1 entries): a chunk whose records all have
 // one length gets its offsets written on the device instead of copied.  Memory-speed (AVX2) scan, early exit.

@@ -693,6 +693,13 @@ __global__ void uniform_offsets_kernel(uint64_t *__restrict__ off, uint32_t n, u
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) off[i] = first + (uint64_t)i * len;
 }
 
+// ------------------------------------------------------------------ sparse non-ACGT mask of the host-packed form
+// The packer threads ship (32-base block, 32-bit mask) pairs for the blocks that hold a non-ACGT byte; the dense bit
+// array the kernels read is a memset plus this.
+__global__ void inv_scatter_kernel(uint32_t *__restrict__ inv32, const uint2 *__restrict__ exc, uint32_t n) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) inv32[exc[i].x] = exc[i].y;
+}
+
 // ------------------------------------------------------------------ summary counters (a13)
 // src/local_filter.rs:347-371 (single) / 488-525 (pair): seqs and bp in / kept / filtered.
 __global__ void stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,

@@ -306,7 +306,7 @@ off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
 total = int(off[-1])
 start = rng.integers(0, len(g) - 300, total // 128 + 2)
 bases = g[(start[:, None] + np.arange(128)[None, :])].reshape(-1)[:total].copy()
-bases[rng.integers(0, total, total // 500)] = ord("N")
+bases[rng.integers(0, total, total // int(sys.argv[2]))] = ord("N")
 nl = rng.integers(0, n, n // 10); nl = nl[lens[nl] >= 1]
 bases[(off[nl + 1] - 1).astype(np.int64)] = 10         # every tenth record ends in a newline
 for paired, prefix in ((False, 0), (True, 0), (False, 120)):
@@ -320,17 +320,22 @@ print("small atoms ok")
 """
 
 
-def test_two_route_ingest_small_atoms(tmp_path):
+@pytest.mark.parametrize("n_every,sparse", [(500, "1"), (40000, "1"), (500, "0")],
+                         ids=["N-rich:dense-fallback", "N-rare:sparse-mask", "dense-wire"])
+def test_two_route_ingest_small_atoms(tmp_path, n_every, sparse):
     """The two-route ingest with 1 MB chunks (128 KB atoms; DCN_CHUNK_MB is read once per process, hence the
     subprocess): hundreds of atoms per call, every kind of record boundary inside them -- empty and sub-k records,
-    newline-terminated ones, N runs, long-path units, prefix trimming -- on pageable buffers, all splits."""
+    newline-terminated ones, N runs, long-path units, prefix trimming -- on pageable buffers, all splits.  The packer
+    threads ship the non-ACGT bits as a sparse exception list (an N every 40 000 bases: few blocks listed) and fall
+    back to the dense mask when more than one 32-base block in 32 is listed (an N every 500 bases);
+    DCN_SPARSE_MASK=0 keeps the dense wire form of round 1."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "small_atoms.py"
     script.write_text(_SMALL_ATOMS)
-    env = dict(os.environ, DCN_CHUNK_MB="1")
-    r = subprocess.run([sys.executable, str(script), root], env=env, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ, DCN_CHUNK_MB="1", DCN_SPARSE_MASK=sparse)
+    r = subprocess.run([sys.executable, str(script), root, str(n_every)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "small atoms ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
