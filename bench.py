@@ -400,9 +400,11 @@ def run_ours(args):
     genome = make_genome(torch, dev, G, args.seed)
     coff = torch.from_numpy(contig_offsets(G, args.seed)).to(dev)
     gpu = d.DeaconGpu(local)
-    pack_threads = None   # library default (hardware threads this process may use - 4, at most 16)
-    if world > 1 and not os.environ.get("DCN_PACK_THREADS"):
-        pack_threads = par.pack_threads_for_rank(int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    # host-ingest ceiling of this box with the ranks that are running (parallel.h2d_probe), and the packing policy it implies
+    ingest = par.h2d_probe(dev)
+    pack_threads = None   # library default (hardware threads this process may use - 4, at most 12)
+    if not os.environ.get("DCN_PACK_THREADS"):
+        pack_threads = par.pack_threads_for_rank(int(os.environ.get("LOCAL_WORLD_SIZE", world)), ingest)
         gpu.host_pack_threads(pack_threads)
     t0 = time.time()
     n_keys = gpu.index_build_device(genome, coff, CONTIGS, G, 31, 15, 0.0, True, stream=torch.cuda.current_stream().cuda_stream)
@@ -584,6 +586,12 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(e2e_d2h), "steps": e2e_steps, "host_buffers": "pinned",
                     "host_pack_threads": pack_threads if pack_threads is not None else os.environ.get("DCN_PACK_THREADS", "default"),
                     "caller_buffer_bytes_per_step": nb + (NR + 1) * 8,
+                    # what the host can feed: pinned H2D GB/s of a rank alone and of all ranks at once (one ASCII base = one
+                    # byte of it); packing on host threads is switched on while the ranks' own links are what binds
+                    "ingest_ceiling": dict(ingest, ascii_route_gbp_per_s=ingest["concurrent_sum_gbs"],
+                                           limiter=("each rank's PCIe link (packing on: fewer bytes per base)" if (pack_threads or 0) > 0
+                                                    else "host DRAM / PCIe root shared by the ranks (ASCII route only: a packed base costs 1.5 B of host DRAM traffic, a copied one 1.0 B)")),
+                    "frac_of_ascii_ceiling": round(e2e_value / max(ingest["concurrent_sum_gbs"], 1e-9), 3),
                     "api": "dcn_filter_batch (C ABI), ASCII records + u64 offsets in host memory; bytes as counted by the "
                            "library (dcn_last_transfer_bytes) for the last step: part of the batch crosses as ASCII, part is packed "
                            "by host threads inside the call (the split is dynamic), and the offsets of "

@@ -700,7 +700,7 @@ static int pack_threads_of(dcn_ctx *ctx) {   // -> host threads available for pa
             return (q > 0 && per > 0) ? (int)std::max<long long>(1, (q + per - 1) / per) : 0;
         }();
         if (quota_cpus > 0) hc = std::min(hc, quota_cpus);
-        int n = e ? atoi(e) : std::min(std::max(hc - 4, 1), 16);
+        int n = e ? atoi(e) : std::min(std::max(hc - 4, 1), 12);   // beyond ~12 the packers share out the host's DRAM bandwidth, not cores (measured: 12 = 16)
         ctx->pack_threads = std::max(0, std::min(n, 256));
     }
     return ctx->pack_threads;
@@ -1179,7 +1179,9 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         {
             std::lock_guard<std::mutex> g(m);
             if (first_rc || head >= tail) break;
-            const int grab = n_packers > 0 ? std::max(1, std::min<int>((int)atoms_per_chunk, (tail - head) / 6)) : (int)atoms_per_chunk;
+            // beside packers an ASCII chunk is a few atoms only: the packed chunks' small copies queue behind it on the copy engine
+            static const int ascii_atoms = []() { const char *e = getenv("DCN_ASCII_ATOMS"); return e ? std::max(1, atoi(e)) : 2; }();   // measured: 8 atoms 89.5, 2 atoms 97.7 Gbp/s
+            const int grab = n_packers > 0 ? std::max(1, std::min<int>(std::min<int>((int)atoms_per_chunk, ascii_atoms), (tail - head) / 6)) : (int)atoms_per_chunk;
             a_lo = head;
             a_hi = head = std::min<int>(tail, head + grab);
         }

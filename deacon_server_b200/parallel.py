@@ -37,15 +37,65 @@ def bind_to_gpu(local_rank: int) -> list[int]:
     return []
 
 
-def pack_threads_for_rank(local_world: int) -> int:
-    """Host packing threads for one rank of `local_world` on this box (dcn_host_pack_threads): the CPUs this process
-    may run on, shared with the other ranks when it is not bound to a GPU-local subset of its own, minus four for the
-    caller, the enqueueing thread and the driver's threads; at most 16, and 0 (ASCII route only: the copy engine
-    needs no CPU) when fewer than two would be left or when four or more ranks share the host."""
+def h2d_probe(device, nbytes: int = 1 << 30, reps: int = 3) -> dict:
+    """The host-ingest ceiling of this box for the ranks that are running: pinned host -> device copy bandwidth of
+    this rank ALONE (ranks take turns) and with every rank copying AT THE SAME TIME.  An ASCII base costs one byte of
+    this, so the concurrent sum in GB/s is the Gbp/s the ASCII route can reach at best; when `concurrent` falls well
+    below `solo` the ranks are held back by what they share (the host's DRAM and PCIe root), not by their own links.
+    Works with or without an initialised process group.  -> {"solo_gbs", "concurrent_gbs", "concurrent_sum_gbs", "world"}"""
+    import torch
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    world = dist.get_world_size() if multi else 1
+    rank = dist.get_rank() if multi else 0
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    h.fill_(65)
+    d = torch.empty(nbytes, dtype=torch.uint8, device=device)
+
+    def once():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        d.copy_(h, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return nbytes / e0.elapsed_time(e1) / 1e6
+
+    def barrier():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+
+    once()
+    solo = 0.0
+    for r in range(world):          # one rank at a time
+        barrier()
+        if r == rank:
+            solo = max(once() for _ in range(reps))
+    barrier()
+    conc = min(once() for _ in range(reps))      # everybody at once (the slowest repetition: the contended one)
+    barrier()
+    vec = torch.tensor([conc], dtype=torch.float64, device=device)
+    if multi:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    del h, d
+    return {"solo_gbs": round(solo, 2), "concurrent_gbs": round(conc, 2), "concurrent_sum_gbs": round(float(vec.item()), 2), "world": world}
+
+
+def pack_threads_for_rank(local_world: int, probe: dict | None = None) -> int:
+    """Host packing threads for one rank of `local_world` on this box (dcn_host_pack_threads).
+
+    Packing trades host work for PCIe bytes: a packed base costs ~1.5 B of host DRAM traffic (read, write, DMA read)
+    and 0.25 B of the link, a copied one 1.0 B of each.  It pays while a rank's own link is what holds it back and
+    costs when the ranks are already held back by the DRAM they share.  `probe` (h2d_probe) tells which: with every
+    rank copying at once, a rank that still gets >= 80 % of its solo rate is link-bound -> pack with the CPUs this
+    process may use, shared with the other ranks, minus four (caller, enqueueing thread, driver), at most 12;
+    otherwise 0 (ASCII route only: the copy engine needs no CPU).  Without a probe the round-1 rule applies
+    (no packing from four ranks per host: measured host-DRAM-bound on the 8-GPU boxes of this pool)."""
     import os
-    if local_world >= 4:
-        # measured (DESIGN.md 6): with 8 ranks the host's DRAM (~160 GB/s) bounds the ingest, and a packed base costs
-        # 1.86 B of DRAM traffic against 1.0 for a copied one
+    if probe is not None and probe.get("solo_gbs"):
+        if probe["concurrent_gbs"] < 0.8 * probe["solo_gbs"]:
+            return 0
+    elif local_world >= 4:
         return 0
     allowed = len(os.sched_getaffinity(0))
     total = os.cpu_count() or allowed
@@ -54,7 +104,7 @@ def pack_threads_for_rank(local_world: int) -> int:
         # bound to one NUMA node: the node's ranks share it (ranks are dealt out evenly over the nodes)
         nodes = max(1, round(total / allowed)) if allowed < total else 1
         share = allowed // max(1, -(-local_world // nodes))
-    n = min(16, share - 4)
+    n = min(12, share - 4)
     return n if n >= 2 else 0
 
 

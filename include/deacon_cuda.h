@@ -93,7 +93,7 @@ int dcn_filter_batch_device_hint(dcn_ctx *ctx, const uint8_t *d_bases, const uin
  * src/filter_common.rs:238-258 compute per record on the CPU) into pinned staging, so 0.4 B/bp cross PCIe instead
  * of 1 B/bp; the rest is copied as ASCII and converted on the GPU.  Results are identical.
  * Default threads: DCN_PACK_THREADS, else the CPUs this process may use (affinity mask, cgroup quota) - 4, at least 1
- * and at most 16; 0 = never pack. */
+ * and at most 12; 0 = never pack. */
 int dcn_host_pack_threads(dcn_ctx *ctx, int n_threads);
 /* Share of the batch the packing route may take.  Negative (default) = automatic.  Pinned caller buffers: the two
  * routes split the batch dynamically -- the copy engine ships ASCII chunks from the front of the batch while the

@@ -92,8 +92,9 @@ def test_counters_match_reference_semantics():
 
 
 def test_pack_threads_for_rank(monkeypatch):
-    """Host packing threads a rank gets (parallel.pack_threads_for_rank): its share of the CPUs minus four, none when
-    that leaves fewer than two or when four or more ranks share the host's DRAM."""
+    """Host packing threads a rank gets (parallel.pack_threads_for_rank): its share of the CPUs minus four (at most 12),
+    none when that leaves fewer than two; whether packing pays at all is read off the ingest probe (a rank that keeps
+    >= 80 % of its solo H2D rate while all ranks copy is link-bound), and without a probe from the rank count."""
     import os
     from deacon_server_b200 import parallel as P
     monkeypatch.setattr(os, "cpu_count", lambda: 16)
@@ -103,8 +104,16 @@ def test_pack_threads_for_rank(monkeypatch):
     assert P.pack_threads_for_rank(8) == 0
     monkeypatch.setattr(os, "cpu_count", lambda: 224)
     monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(224)))
-    assert P.pack_threads_for_rank(1) == 16
-    assert P.pack_threads_for_rank(2) == 16
+    assert P.pack_threads_for_rank(1) == 12
+    assert P.pack_threads_for_rank(2) == 12
     assert P.pack_threads_for_rank(4) == 0
     monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(112)))     # bound to one of two sockets
-    assert P.pack_threads_for_rank(2) == 16
+    assert P.pack_threads_for_rank(2) == 12
+    # with a probe the decision follows the measurement, not the rank count
+    monkeypatch.setattr(os, "cpu_count", lambda: 64)
+    monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(64)))
+    link_bound = {"solo_gbs": 54.0, "concurrent_gbs": 52.0, "concurrent_sum_gbs": 208.0, "world": 4}
+    host_bound = {"solo_gbs": 54.0, "concurrent_gbs": 21.5, "concurrent_sum_gbs": 172.0, "world": 8}
+    assert P.pack_threads_for_rank(4, link_bound) == 12
+    assert P.pack_threads_for_rank(8, host_bound) == 0
+    assert P.pack_threads_for_rank(8, dict(host_bound, concurrent_gbs=50.0)) == 4      # 64 / 8 - 4

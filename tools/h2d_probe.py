@@ -1,23 +1,28 @@
-import torch, time
-n = 1_580_000_000
-h = torch.empty(n, dtype=torch.uint8).pin_memory()
-d = torch.empty(n, dtype=torch.uint8, device="cuda")
-out = torch.empty(45_000_000, dtype=torch.uint8, device="cuda"); ho = torch.empty(45_000_000, dtype=torch.uint8).pin_memory()
-for chunk in (n, 32 << 20, 8 << 20):
-    for rep in range(3):
-        torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for a in range(0, n, chunk):
-            d[a:a + chunk].copy_(h[a:a + chunk], non_blocking=True)
-        e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    print(f"H2D pinned, chunks of {chunk >> 20} MB: {n / ms / 1e6:.1f} GB/s ({ms:.2f} ms)")
-# H2D with concurrent D2H on another stream
-s2 = torch.cuda.Stream()
-torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-e0.record()
-with torch.cuda.stream(s2):
-    for _ in range(8): ho.copy_(out, non_blocking=True)
-d.copy_(h, non_blocking=True)
-e1.record(); torch.cuda.synchronize()
-print(f"H2D beside D2H: {n / e0.elapsed_time(e1) / 1e6:.1f} GB/s")
+#!/usr/bin/env python
+"""Host-ingest ceiling of a box: pinned host -> device bandwidth per rank, alone and with all ranks at once.
+  python tools/h2d_probe.py                                                       (one GPU)
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/h2d_probe.py   (N ranks of one host)
+Prints one JSON line per rank 0; the same probe runs inside bench.py (key "e2e.ingest_ceiling")."""
+import json
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from deacon_server_b200 import parallel as par  # noqa: E402
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+world = int(os.environ.get("WORLD_SIZE", "1"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+p = par.h2d_probe(dev)
+p["pack_threads_policy"] = par.pack_threads_for_rank(int(os.environ.get("LOCAL_WORLD_SIZE", world)), p)
+p["cpus"] = os.cpu_count()
+if int(os.environ.get("RANK", "0")) == 0:
+    print(json.dumps(p))
+if world > 1:
+    dist.destroy_process_group()
