@@ -64,6 +64,7 @@ SIGNATURES = {
     "dcn_index_diff_sequences": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, u64p]),
     "dcn_idx_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, u64p]),
     "dcn_working_set_info": (C.c_int, [C.c_void_p, u64p, u8p, u8p]),
+    "dcn_working_set_release": (C.c_int, [C.c_void_p]),
     "dcn_index_make_resident": (C.c_int, [C.c_void_p]),
     "dcn_stats_get": (C.c_int, [C.c_void_p, u64p]),
     "dcn_stats_reset": (C.c_int, [C.c_void_p]),

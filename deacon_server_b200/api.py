@@ -425,6 +425,10 @@ class DeaconGpu:
         self._check(self._lib.dcn_working_set_info(self._ctx, C.byref(n), C.byref(k), C.byref(w)))
         return {"n_keys": n.value, "kmer_length": k.value, "window_size": w.value}
 
+    def working_set_release(self):
+        """Free the working key set and all build / decode scratch (the resident table stays)."""
+        self._check(self._lib.dcn_working_set_release(self._ctx))
+
     def working_keys(self) -> np.ndarray:
         """Sorted unique keys of the working set."""
         n = self.working_set_info()["n_keys"]

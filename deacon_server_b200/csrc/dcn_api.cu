@@ -1511,7 +1511,7 @@ int dcn_extract(dcn_ctx *ctx, int flavour, const uint8_t *bases, const uint64_t 
                                     st, &m, &written);
     if (rc) return rc;
     CK(cudaMemcpyAsync(out_off, ctx->gx_oo.p, ((size_t)n_rec + 1) * 8, cudaMemcpyDeviceToHost, st));
-    if (written && m) {
+    if (written && m && m <= out_cap) {   // (a size query passes out_cap = 0 and no output arrays: nothing to copy then)
         CK(cudaMemcpyAsync(out_hashes, ctx->gx_h.p, m * 8, cudaMemcpyDeviceToHost, st));
         if (out_pos) CK(cudaMemcpyAsync(out_pos, ctx->gx_p.p, m * 4, cudaMemcpyDeviceToHost, st));
     }
@@ -1802,7 +1802,24 @@ int dcn_idx_decode(dcn_ctx *ctx, const uint8_t *file, uint64_t len, int mode, in
     }
     if (rc) return rc;
     if (n_set) *n_set = ctx->ib_n;
-    if (make_resident) return dcn_index_upload_device(ctx, ctx->ib_keys.as<uint64_t>(), ctx->ib_n, ctx->ws_k, ctx->ws_w, st);
+    if (make_resident) {
+        if ((rc = dcn_index_upload_device(ctx, ctx->ib_keys.as<uint64_t>(), ctx->ib_n, ctx->ws_k, ctx->ws_w, st))) return rc;
+        // a load for filtering: the decode / sort scratch (file bytes, two key-sized buffers: ~25 B per key beside the
+        // 16 B per key of the table) is dead weight from here on; the sorted key set itself stays for `index info`,
+        // union / diff and dcn_idx_encode until the caller releases it (dcn_working_set_release)
+        CK(cudaStreamSynchronize(st));
+        ctx->gx_bases.release(); ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->gx_h.release();
+    }
+    return DCN_OK;
+}
+
+int dcn_working_set_release(dcn_ctx *ctx) {
+    if (!ctx) return DCN_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    ctx->ib_keys.release(); ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->ib_bases.release(); ctx->ib_off.release();
+    ctx->ib_desc.release(); ctx->gx_bases.release(); ctx->gx_h.release(); ctx->ws_table.release(); ctx->ws_flags.release();
+    ctx->ib_n = 0;
     return DCN_OK;
 }
 

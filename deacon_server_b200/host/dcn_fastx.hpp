@@ -631,9 +631,11 @@ class FastxReader {
             std::vector<std::vector<Rec>> parts((size_t)T);
             std::vector<const char *> reached((size_t)T);
             pool_->run((size_t)T, [&](size_t i) {
-                // the last range may end in an incomplete record; the others end at a record start
+                // the last range may end in an incomplete record; the others end at a synced record start, which closes
+                // their final record the way the end of the file would (a FASTA record needs the next '>' or the end to
+                // know where it stops: without this every non-last range lost its last record and the block was parsed twice)
                 const bool last = start[i + 1] == e;
-                reached[i] = start[i] < start[i + 1] ? parse_range(start[i], start[i + 1], last ? e : start[i + 1], last && eof_, parts[i]) : start[i];
+                reached[i] = start[i] < start[i + 1] ? parse_range(start[i], start[i + 1], last ? e : start[i + 1], last ? eof_ : true, parts[i]) : start[i];
             });
             bool ok = true;
             const char *consumed = p;

@@ -194,6 +194,9 @@ int dcn_index_diff_sequences(dcn_ctx *ctx, const uint8_t *bases, const uint64_t 
 int dcn_idx_encode(dcn_ctx *ctx, uint8_t *out, uint64_t cap, uint64_t *len);
 /* `deacon index info` (src/index.rs:539-560): size and header of the working key set. */
 int dcn_working_set_info(dcn_ctx *ctx, uint64_t *n_keys, uint8_t *k, uint8_t *w);
+/* Frees the working key set and every build / decode scratch buffer (a ctx that only filters from here on keeps
+ * the resident table alone).  dcn_idx_decode(make_resident = 1) already drops its decode and sort scratch itself. */
+int dcn_working_set_release(dcn_ctx *ctx);
 /* Make the working key set the resident (probed) index. */
 int dcn_index_make_resident(dcn_ctx *ctx);
 

@@ -867,3 +867,31 @@ def test_debug_hit_kmers_match_reference_semantics(gpu):
     k, h, t, fl = gpu.lookup_batch_flags(np.concatenate(lists), off)
     ok, oh, ot = O.lookup_batch(idx, np.concatenate(lists), off)
     assert np.array_equal(h, oh) and np.array_equal(np.add.reduceat(fl.astype(np.uint32), off[:-1].astype(np.int64))[oh > 0], oh[oh > 0])
+
+
+def test_extract_size_query_and_working_set_release(gpu):
+    """dcn_extract with out_cap = 0 and no output arrays is the documented size query: DCN_ERR_OVERFLOW with the need in
+    out_off[n_rec] -- also when exactly one minimizer comes out (the copy to a null array used to be attempted).
+    dcn_working_set_release drops the key set and scratch; the resident table keeps answering."""
+    import ctypes as C
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(5_000, 91)
+    one = g[:45].copy()                      # one window -> exactly one minimizer
+    bases, off = H.concat([one])
+    out_off = np.zeros(2, np.uint64)
+    rc = gpu._lib.dcn_extract(gpu._ctx, 0, bases.ctypes.data, off.ctypes.data, 1, 31, 15, 0, C.c_float(0.0), None, None,
+                              out_off.ctypes.data, 0)
+    assert rc == -6 and int(out_off[1]) == 1          # DCN_ERR_OVERFLOW, need = 1
+    h, p, oo = gpu.extract(bases, off, 0, 31, 15, 0)
+    assert len(h) == 1 and np.array_equal(h, O.extract_filter(one, 31, 15, 0)[0])
+    idx = O.index_build([g], 31, 15)
+    blob = O.idx_encode(idx.keys(), 31, 15)
+    gpu.idx_decode(blob, mode=0, make_resident=True)
+    assert gpu.working_set_info()["n_keys"] == len(idx)
+    gpu.working_set_release()
+    assert gpu.working_set_info()["n_keys"] == 0
+    reads = H.sample_reads(g, 200, 150, 92)
+    b2, o2 = H.concat(reads)
+    k, hh, t = gpu.filter_batch(b2, o2)
+    ok, oh, ot = O.filter_batch(idx, b2, o2)
+    assert np.array_equal(k, ok) and np.array_equal(hh, oh) and np.array_equal(t, ot)
