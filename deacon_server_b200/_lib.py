@@ -72,6 +72,7 @@ SIGNATURES = {
     "dcn_last_timing": (C.c_int, [C.c_void_p, f32p, f32p, f32p]),
     "dcn_last_transfer_bytes": (C.c_int, [C.c_void_p, u64p, u64p]),
     "dcn_measure_random_access": (C.c_int, [C.c_void_p, u64p, f32p]),
+    "dcn_measure_random_access_wide": (C.c_int, [C.c_void_p, C.c_int, u64p, f32p]),
     "dcn_launch_count": (C.c_uint64, [C.c_void_p]),
     "dcn_fused_time_take": (C.c_int, [C.c_void_p, f32p, u32p]),
 }

@@ -497,6 +497,11 @@ class DeaconGpu:
         self._check(self._lib.dcn_measure_random_access(self._ctx, C.byref(n), C.byref(ms)))
         return n.value, ms.value
 
+    def measure_random_access_wide(self, sectors: int, n_probes: int):
+        n, ms = C.c_uint64(n_probes), C.c_float()
+        self._check(self._lib.dcn_measure_random_access_wide(self._ctx, int(sectors), C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
     def fused_time_take(self):
         """(total ms, launches) of the fused kernel since the last call (CUDA events, launching stream)."""
         ms, n = C.c_float(), C.c_uint32()

@@ -1964,19 +1964,23 @@ int dcn_last_transfer_bytes(dcn_ctx *ctx, uint64_t *h2d_bytes, uint64_t *d2h_byt
     return DCN_OK;
 }
 
-int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms) {
+int dcn_measure_random_access_wide(dcn_ctx *ctx, int sectors, uint64_t *n_probes, float *ms) {
     if (!ctx || !ms || !n_probes) return DCN_ERR_ARG;
+    if (sectors != 1 && sectors != 2 && sectors != 4 && sectors != -4) return ctx->fail(DCN_ERR_ARG, "sectors per probe: 1, 2, 4, or -4 (four lanes share a 128-byte line)");
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident");
     CK(cudaSetDevice(ctx->device));
     const int threads = 256, grid = ctx->sm_count * 8;
     uint64_t per_thread = *n_probes / ((uint64_t)threads * grid);
     per_thread = std::max<uint64_t>(4, (per_thread + 3) / 4 * 4);
-    *n_probes = per_thread * threads * grid;
+    *n_probes = per_thread * threads * grid / (sectors == -4 ? 4 : 1);
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     CK(cudaEventRecord(a, ctx->stream));
-    random_access_kernel<<<grid, threads, 0, ctx->stream>>>(ctx->table.as<uint64_t>(), ctx->n_buckets, (uint32_t)per_thread,
-                                                            ctx->counters.as<unsigned long long>() + 7);
+    unsigned long long *sink = ctx->counters.as<unsigned long long>() + 7;
+    if (sectors == -4) random_access_line_kernel<<<grid, threads, 0, ctx->stream>>>(ctx->table.as<uint64_t>(), ctx->n_buckets, (uint32_t)per_thread, sink);
+    else if (sectors == 1) random_access_kernel<1><<<grid, threads, 0, ctx->stream>>>(ctx->table.as<uint64_t>(), ctx->n_buckets, (uint32_t)per_thread, sink);
+    else if (sectors == 2) random_access_kernel<2><<<grid, threads, 0, ctx->stream>>>(ctx->table.as<uint64_t>(), ctx->n_buckets, (uint32_t)per_thread, sink);
+    else random_access_kernel<4><<<grid, threads, 0, ctx->stream>>>(ctx->table.as<uint64_t>(), ctx->n_buckets, (uint32_t)per_thread, sink);
     CK(cudaEventRecord(b, ctx->stream));
     CK(cudaEventSynchronize(b));
     CK(cudaEventElapsedTime(ms, a, b));
@@ -1984,6 +1988,8 @@ int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms) {
     ctx->launches += 1;
     return DCN_OK;
 }
+
+int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms) { return dcn_measure_random_access_wide(ctx, 1, n_probes, ms); }
 
 int dcn_last_pack_ms(dcn_ctx *ctx, float *pack_ms) {
     if (!ctx || !pack_ms) return DCN_ERR_ARG;

@@ -768,17 +768,47 @@ __global__ void table_insert_kernel(uint64_t *slots, uint64_t n_buckets, const u
 }
 
 // ------------------------------------------------------------------ random-access ceiling probe
-// Every thread issues `per_thread` independent 32-byte loads at pseudo-random buckets.
+// Every thread issues `per_thread` independent probes at pseudo-random buckets; a probe reads SECTORS consecutive
+// 32-byte sectors of a SECTORS * 32-byte aligned bucket (1 = the table's layout: 4 keys; 4 = what a 128-byte / 16-key
+// bucket would cost).  Four probes in flight per thread.
+template <int SECTORS>
 __global__ void random_access_kernel(const uint64_t *__restrict__ slots, uint64_t n_buckets, uint32_t per_thread,
                                      unsigned long long *sink) {
     uint64_t x = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
     unsigned long long acc = 0;
+    const uint64_t n_wide = n_buckets / SECTORS;
     for (uint32_t i = 0; i < per_thread; i += 4) {
+        Bucket bk[4][SECTORS];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            x = xxh3_u64(x + i + j);
+            const uint64_t b0 = table_bucket(x, n_wide) * SECTORS;
+#pragma unroll
+            for (int q = 0; q < SECTORS; q++) bk[j][q] = load_bucket(slots, b0 + q);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int q = 0; q < SECTORS; q++) acc += bk[j][q].k0 ^ bk[j][q].k1 ^ bk[j][q].k2 ^ bk[j][q].k3;
+    }
+    if (acc == 0x0123456789ABCDEFULL) *sink = acc;
+}
+
+// The 128-byte bucket read the way a cooperative probe would do it: four adjacent lanes take the four sectors of one
+// line in the same instruction (one line request per probe instead of four sector requests).
+__global__ void random_access_line_kernel(const uint64_t *__restrict__ slots, uint64_t n_buckets, uint32_t per_group,
+                                          unsigned long long *sink) {
+    const uint64_t group = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 2;
+    const uint32_t q = threadIdx.x & 3u;
+    uint64_t x = group * 0x9E3779B97F4A7C15ULL + 0x1234567ULL;
+    unsigned long long acc = 0;
+    const uint64_t n_wide = n_buckets / 4;
+    for (uint32_t i = 0; i < per_group; i += 4) {
         Bucket bk[4];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             x = xxh3_u64(x + i + j);
-            bk[j] = load_bucket(slots, table_bucket(x, n_buckets));
+            bk[j] = load_bucket(slots, table_bucket(x, n_wide) * 4 + q);
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) acc += bk[j].k0 ^ bk[j].k1 ^ bk[j].k2 ^ bk[j].k3;

@@ -223,6 +223,9 @@ int dcn_last_pack_ms(dcn_ctx *ctx, float *pack_ms);
 /* Random 32-byte-sector read ceiling over the resident table: about *n_probes independent loads;
  * on return *n_probes is the exact number issued and *ms the kernel time. */
 int dcn_measure_random_access(dcn_ctx *ctx, uint64_t *n_probes, float *ms);
+/* The same with `sectors` (1, 2 or 4) consecutive 32-byte sectors read per probe from a sectors * 32-byte aligned
+ * bucket: what a 64- or 128-byte (8- / 16-key) bucket layout would pay per probe (bucket-width A/B). */
+int dcn_measure_random_access_wide(dcn_ctx *ctx, int sectors, uint64_t *n_probes, float *ms);
 /* Number of kernel launches issued by this ctx so far. */
 uint64_t dcn_launch_count(dcn_ctx *ctx);
 /* Sum of the CUDA-event durations of the fused filter kernel's launches since the last take (at most
