@@ -19,6 +19,10 @@
 
 namespace dcn {
 
+#ifndef DCN_PICKS_IN_FLIGHT
+#define DCN_PICKS_IN_FLIGHT 2   // probes a lane has outstanding in P6
+#endif
+
 struct WG {
     static constexpr int K = 31, W = 15, L = 45;
     static constexpr int NL = 32;              // lanes
@@ -446,28 +450,33 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
         }
     });
 
-    // ---- P6: hash every pick and probe the table, two picks per lane in flight (the hashes take over rel4 / em).
-    // pk_pos: position | valid << 14 | in-index << 15
+    // ---- P6: hash every pick and probe the table, DCN_PICKS_IN_FLIGHT picks per lane in flight: hash + request all
+    // of them, then test (the hashes take over rel4 / em).  pk_pos: position | valid << 14 | in-index << 15
     ex.par([&](int l, Priv &) {
         uint16_t *pk_pos = s.pk_pos();
         uint64_t *pk_hash = s.pk_hash();
-        for (uint32_t idx = (uint32_t)l; idx < npicks; idx += 2 * WG::NL) {
-            const uint32_t idxB = idx + WG::NL;
-            const uint32_t ppA = pk_pos[idx], ppB = idxB < npicks ? pk_pos[idxB] : 0u;
-            const bool vA = wpick_valid(s, ppA);
-            const bool vB = idxB < npicks && wpick_valid(s, ppB);
-            uint64_t hA = 0, hB = 0, bA = 0, bB = 0;
-            Bucket kA, kB;
-            kA.k0 = kA.k1 = kA.k2 = kA.k3 = 0; kB = kA;
-            if (vA) { hA = wpick_hash(s, ppA); bA = table_bucket(hA, P.table.n_buckets); kA = load_bucket(P.table.slots, bA); }
-            if (vB) { hB = wpick_hash(s, ppB); bB = table_bucket(hB, P.table.n_buckets); kB = load_bucket(P.table.slots, bB); }
-            if (vA) {
-                pk_hash[idx] = hA;
-                pk_pos[idx] = (uint16_t)(ppA | 0x4000u | (table_contains_from(P.table, hA, bA, kA) ? 0x8000u : 0u));
+        constexpr int NF = DCN_PICKS_IN_FLIGHT;
+        for (uint32_t idx0 = (uint32_t)l; idx0 < npicks; idx0 += NF * WG::NL) {
+            uint32_t pp[NF];
+            bool v[NF];
+            uint64_t h[NF], bk[NF];
+            Bucket k[NF];
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
+                pp[f] = idx < npicks ? pk_pos[idx] : 0u;
+                v[f] = idx < npicks && wpick_valid(s, pp[f]);
+                h[f] = 0; bk[f] = 0;
+                k[f].k0 = k[f].k1 = k[f].k2 = k[f].k3 = 0;
+                if (v[f]) { h[f] = wpick_hash(s, pp[f]); bk[f] = table_bucket(h[f], P.table.n_buckets); k[f] = load_bucket(P.table.slots, bk[f]); }
             }
-            if (vB) {
-                pk_hash[idxB] = hB;
-                pk_pos[idxB] = (uint16_t)(ppB | 0x4000u | (table_contains_from(P.table, hB, bB, kB) ? 0x8000u : 0u));
+#pragma unroll
+            for (int f = 0; f < NF; f++) {
+                const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
+                if (v[f]) {
+                    pk_hash[idx] = h[f];
+                    pk_pos[idx] = (uint16_t)(pp[f] | 0x4000u | (table_contains_from(P.table, h[f], bk[f], k[f]) ? 0x8000u : 0u));
+                }
             }
         }
     });
