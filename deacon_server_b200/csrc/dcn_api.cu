@@ -151,7 +151,8 @@ static size_t warp_kernel_smem() { return ((sizeof(WarpTables) + 15) & ~(size_t)
 // more than TB - 15 - DCN_MAX_SHORT bases), because it holds MAXR records, because a long unit follows, or at a
 // segment end.
 static uint64_t wplan_tile_cap(uint64_t n_rel, uint32_t n_rec) {
-    return n_rel / (uint64_t)(WG::TB - 15 - (int)DCN_MAX_SHORT) + (uint64_t)n_rec / (WG::MAXR / 2) + n_rel / DCN_MAX_SHORT + n_rel / DCN_WSEG + 16;
+    return n_rel / (uint64_t)(WG::TB - 15 - (int)DCN_MAX_SHORT) + (uint64_t)n_rec / (WG::MAXR / 2) + n_rel / DCN_MAX_SHORT + n_rel / DCN_WSEG + 16 +
+           n_rel / DCN_WCS + n_rel / DCN_MAX_SHORT;   // + the chunks of long units: one per DCN_WCS windows and one partial per record
 }
 static uint64_t wplan_ovf_cap(uint64_t n_rel) { return n_rel / WG::PKCAP + 16; }   // a unit of more than PKCAP picks has more than PKCAP bases
 
@@ -415,7 +416,8 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             dd.slots = dedup.as<unsigned __int128>(); dd.cap = dedup_cap;
             long_units = longs.as<uint32_t>();
             desc = reinterpret_cast<ChunkDesc *>(longs.as<uint8_t>() + (((size_t)hs.n_long * 4 + 63) & ~(size_t)63));
-            prep_long_kernel<G31><<<pg, pb, 0, st>>>(P, d_stats, long_units, desc, desc_cap);
+            if (warp_impl) prep_long_warp_kernel<G31><<<pg, pb, 0, st>>>(P, d_stats, long_units, wtiles, (uint32_t)std::min<uint64_t>(wtile_cap, 0xFFFFFFFFull));
+            else prep_long_kernel<G31><<<pg, pb, 0, st>>>(P, d_stats, long_units, desc, desc_cap);
             ctx->launches += 1;
         }
         const uint32_t ke = ctx->kev_head % dcn_ctx::KEV;
@@ -425,9 +427,9 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             // no long unit in the batch the tail only has work on pathological input, so a few CTAs are enough.
             const uint32_t ocap = (uint32_t)std::min<uint64_t>(wovf_cap, 0xFFFFFFFFull);
             unsigned long long *cnt = call_cnt;
-            if (in.codes) filter_warp_kernel<true><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt);
-            else filter_warp_kernel<false><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt);
-            const int tgrid = hs.n_long ? grid : std::min(grid, 16);
+            if (in.codes) filter_warp_kernel<true><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
+            else filter_warp_kernel<false><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
+            const int tgrid = std::min(grid, 16);   // overflow units only (pathological input): the long chunks are warp tiles
             if (in.codes) filter_tail_kernel<G31, true><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc, call_cnt);
             else filter_tail_kernel<G31, false><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc, call_cnt);
             ctx->launches += 1;

@@ -146,6 +146,28 @@ __global__ void prep_long_kernel(FilterParams P, BatchStats *st, uint32_t *long_
     }
 }
 
+// Warp-tile form of the same: long units are listed and zeroed, every record of theirs is cut into chunks of
+// DCN_WCS windows, appended to the warp-tile list behind the short tiles (the planner ran before).
+template <class G>
+__global__ void prep_long_warp_kernel(FilterParams P, BatchStats *st, uint32_t *long_units, WTile *tiles, uint32_t tile_cap) {
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < P.n_units; u += gridDim.x * blockDim.x) {
+        uint64_t len = P.rec_off[(uint64_t)(u + 1) * P.rpu] - P.rec_off[(uint64_t)u * P.rpu];
+        if (len <= DCN_MAX_SHORT) continue;
+        long_units[atomicAdd(&st->n_long_listed, 1u)] = u;
+        P.hits[u] = 0; P.total[u] = 0;
+        for (uint32_t r = u * P.rpu; r < (u + 1) * P.rpu; r++) {
+            const uint64_t gs = P.rec_off[r] - P.base0, rl = P.rec_off[r + 1] - P.base0 - gs;
+            const uint64_t eff = filter_eff_len<G>(P, r, gs, rl);
+            const uint32_t nc = wplan_long_chunks_of(eff);
+            if (!nc) continue;
+            const uint32_t at = atomicAdd(&st->n_wtiles, nc);
+            wplan_long_record(r, gs, eff, [&](uint32_t c, const WTile &t) {
+                if (at + c < tile_cap) tiles[at + c] = t; else st->overflow = 1;
+            });
+        }
+    }
+}
+
 // Index build: every record is cut into chunks.
 template <class G>
 __global__ void prep_index_chunks_kernel(const uint64_t *__restrict__ rec_off, uint32_t n_rec, BatchStats *st,
@@ -414,6 +436,7 @@ struct WarpDevExec {
         return (uint64_t)__shfl_sync(0xFFFFFFFFu, (unsigned long long)v, (int)src);
     }
     __device__ __forceinline__ uint32_t match64(int, uint64_t v, bool) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
+    __device__ __forceinline__ void global_add(uint32_t *p, uint32_t v) { if (v) atomicAdd(p, v); }
     __device__ __forceinline__ void tally(uint32_t nrec, uint32_t len, bool keep) {   // lane 0 only
         pipe->bp_all += len; pipe->n_all += nrec;
         if (keep) { pipe->bp_kept += len; pipe->n_kept += nrec; }
@@ -434,21 +457,24 @@ struct WarpDevExec {
     // bytes of tile t that the bulk copy brings (multiple of 16); the up-to-15 bytes after them are copied by lanes
     __device__ __forceinline__ uint32_t tile_need(uint64_t origin) const {
         const uint64_t left = P->n_bases - P->base0 - origin;
-        return left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
+        return left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;   // (origin without the WTILE_LONG bit)
     }
-    __device__ __forceinline__ void issue_copy(const WTile &t) {
+    __device__ __forceinline__ void issue_copy(const WTile &tt) {
+        WTile t = tt;
+        const bool is_long = (t.origin & WTILE_LONG) != 0;
+        t.origin &= ~WTILE_LONG;
         if (packed) {   // packed input is read straight from global memory: pull the next tile's words into L2
             const uint64_t w0 = t.origin >> 4;
             if (lane < 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(P->pk_codes + w0 + 32u * (uint32_t)lane));
             else if (lane < 6) asm volatile("prefetch.global.L2 [%0];" ::"l"(P->pk_inv + w0 + 64u * (uint32_t)(lane - 4)));
         } else if (lane == 0) {
-            const uint32_t bytes = tile_need(t.origin) & ~15u;
+            const uint32_t bytes = tile_need(t.origin) & ~15u;   // t.origin: flag bit already cleared
             mbar_expect_tx(&s->mbar, bytes);
             if (bytes) bulk_copy_g2s(s->stage, P->bases + t.origin, bytes, &s->mbar);
         }
-        // the record offsets of the tile: one 128-byte line holds 16
+        // the record offsets of the tile: one 128-byte line holds 16 (a chunk of a long unit needs none)
         const uint32_t r0 = t.a * P->rpu, r1 = t.b * P->rpu;
-        if (lane >= 8 && lane < 14 && r0 + 16u * (uint32_t)(lane - 8) <= r1)
+        if (!is_long && lane >= 8 && lane < 14 && r0 + 16u * (uint32_t)(lane - 8) <= r1)
             asm volatile("prefetch.global.L2 [%0];" ::"l"(P->rec_off + r0 + 16u * (uint32_t)(lane - 8)));
     }
     __device__ __forceinline__ void fetch_desc(WTile *dst, uint32_t id) {   // lane 0: 16 bytes global -> shared, asynchronously
@@ -468,7 +494,7 @@ struct WarpDevExec {
 template <bool PACKED>
 __global__ void __launch_bounds__(DCN_WARPS * 32, 1)
 filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ tiles, uint32_t *ovf_list, uint32_t ovf_cap,
-                   unsigned long long *counters) {
+                   unsigned long long *counters, DedupView dd) {
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
     WarpTables &T = *reinterpret_cast<WarpTables *>(dcn_smem_raw);
     const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
@@ -505,22 +531,28 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
     bool have = id0 < n_tiles;
     uint32_t phase = 0;
     while (have) {
-        const uint32_t need = ex.tile_need(d0.origin);
+        const bool is_long = (d0.origin & WTILE_LONG) != 0;
+        const uint64_t origin0 = d0.origin & ~WTILE_LONG;
+        const uint32_t need = ex.tile_need(origin0);
         asm volatile("cp.async.wait_all;" ::: "memory");   // the descriptors requested during the previous tile (lane 0)
         __syncwarp();
         if (!PACKED) {
             mbar_wait(&s.mbar, phase);
             phase ^= 1u;
             const uint32_t bulk = need & ~15u;
-            if ((uint32_t)lane < need - bulk) s.stage[bulk + (uint32_t)lane] = P.bases[d0.origin + bulk + (uint32_t)lane];
+            if ((uint32_t)lane < need - bulk) s.stage[bulk + (uint32_t)lane] = P.bases[origin0 + bulk + (uint32_t)lane];
             __syncwarp();
         }
-        warp_tile<PACKED>(ex, T, s, P, d0, need, [&](uint32_t u) {
-            if (lane == 0) {
-                const uint32_t at = atomicAdd(&st->n_ovf, 1u);
-                if (at < ovf_cap) ovf_list[at] = u; else st->overflow = 1;
-            }
-        });
+        if (is_long) {   // a chunk of a long unit (listed behind the short tiles by prep_long_warp_kernel)
+            warp_long_tile<PACKED>(ex, T, s, P, dd, d0, need);
+        } else {
+            warp_tile<PACKED>(ex, T, s, P, d0, need, [&](uint32_t u) {
+                if (lane == 0) {
+                    const uint32_t at = atomicAdd(&st->n_ovf, 1u);
+                    if (at < ovf_cap) ovf_list[at] = u; else st->overflow = 1;
+                }
+            });
+        }
         // rotate the pipeline: d1 (in shared memory since the previous tile) becomes the current tile
         have = ex.id1 < n_tiles;
         asm volatile("cp.async.wait_all;" ::: "memory");
@@ -542,7 +574,7 @@ template <class G, bool PACKED>
 __global__ void __launch_bounds__(G::NT, DCN_CTAS_PER_SM)
 filter_tail_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ ovf_list, DedupView dd,
                    const ChunkDesc *__restrict__ desc, unsigned long long *counters) {
-    const uint32_t n_ovf = st->n_ovf, n_long = st->n_long;
+    const uint32_t n_ovf = st->n_ovf, n_long = desc ? st->n_long : 0u;   // no chunk list: the long units went through warp tiles
     if (n_ovf == 0 && n_long == 0) return;
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
     TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);

@@ -36,8 +36,13 @@ struct WG {
     static constexpr int HXP = 8;              // pitch (words) of the rows that hand a lane's first hashes to its left neighbour
 };
 
-// tile descriptor written by the planner: units [a, b) live in [origin, origin + TB) (origin relative to base0)
+// tile descriptor written by the planner: units [a, b) live in [origin, origin + TB) (origin relative to base0).
+// A chunk of a LONG unit (more than DCN_MAX_SHORT bases) is a tile too: bit 63 of origin set, a = record,
+// b = la | carry << 4 | nw << 5 (first computed window, tile-local; carry window present; own windows).
 struct alignas(16) WTile { uint64_t origin; uint32_t a, b; };
+static constexpr uint64_t WTILE_LONG = 1ull << 63;
+// own windows of a long-unit chunk: 15 (alignment) + 1 (carry window) + WCS + L - 1 <= TB
+static constexpr uint32_t DCN_WCS = 1472;
 
 struct WarpTables {                    // one per CTA
     u32x2 tb0[256];                    // 4-base ntHash aggregates (fw, rc), as TileSmem::tb0
@@ -83,6 +88,8 @@ struct WarpPriv {
     uint32_t hp[8];           // block 0 hashes (upper 16 bits), two per word
     uint32_t vfirst;          // the lane's first window is valid
     uint32_t pickoff;
+    u32x4a lrel[3];           // long chunks only: the lane's block results, read before the pick list overwrites them
+    uint32_t lem[3];
 };
 
 // ------------------------------------------------------------------ tables
@@ -266,27 +273,35 @@ DCN_HD uint32_t w_eff_len(const FilterParams &P, const WSrc &src, uint32_t r, ui
 // ballot / match64 / bcast64 = warp votes; after_scan(ok) is called once the picks are counted (the device uses
 // it to start the next tile's bulk copy into the stage the convert phase has drained).
 // Returns false, nothing written, if the run emits more than PKCAP picks.
-template <bool PACKED, class Ex>
-DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParams &P, const WSrc &src,
-                           uint64_t origin, uint32_t u_begin, uint32_t u_end, bool last_run) {
+// With LONG the run is one chunk of a long unit instead: windows [la, la + carry + nw) of the tile are its own (the
+// first one only carries the previous chunk's last pick for the consecutive-duplicate rule), no record table, every
+// window may emit (the pick list keeps positions only: 1600 fit), and the picks go through the global (hash, unit)
+// set `dd` and per-unit atomics instead of the per-unit count (filter_long_chunk is the CTA-tile form of the same).
+struct WLong { uint32_t unit, la, carry, nw; const DedupView *dd; };
+
+template <bool PACKED, bool LONG, class Ex>
+DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParams &P, const WSrc &src,
+                     uint64_t origin, uint32_t u_begin, uint32_t u_end, bool last_run, const WLong &lg) {
     using Priv = WarpPriv;
     const uint32_t r_begin = u_begin * P.rpu;
-    const uint32_t n_rec_t = (u_end - u_begin) * P.rpu;
-    const uint32_t n_units_t = u_end - u_begin;
-    const uint32_t span_lo = (uint32_t)(P.rec_off[r_begin] - P.base0 - origin);
-    const uint32_t span_hi = (uint32_t)(P.rec_off[r_begin + n_rec_t] - P.base0 - origin);
+    const uint32_t n_rec_t = LONG ? 0u : (u_end - u_begin) * P.rpu;
+    const uint32_t n_units_t = LONG ? 0u : u_end - u_begin;
+    // windows may start in [dead_lo, dead_hi); sequence exists in [span_lo, span_hi)
+    const uint32_t span_lo = LONG ? lg.la : (uint32_t)(P.rec_off[r_begin] - P.base0 - origin);
+    const uint32_t span_hi = LONG ? lg.la + lg.carry + lg.nw + (uint32_t)WG::L - 1u : (uint32_t)(P.rec_off[r_begin + n_rec_t] - P.base0 - origin);
+    const uint32_t dead_lo = span_lo, dead_hi = LONG ? lg.la + lg.carry + lg.nw : span_hi;
 
     // ---- P1: record boundaries (registers), start state of the bit arrays, convert
     ex.par([&](int l, Priv &pv) {
         for (int i = l; i < WG::NBW + 2; i += WG::NL) {
-            s.dead[i] = outside_mask(32u * (uint32_t)i, span_lo, span_hi);
+            s.dead[i] = outside_mask(32u * (uint32_t)i, dead_lo, dead_hi);
             s.brk[i] = outside_mask(32u * (uint32_t)i, span_lo, span_hi);
         }
 #pragma unroll
         for (int j = 0; j < 2; j++) {
             const uint32_t i = (uint32_t)l + 32u * (uint32_t)j;
             pv.sL[j] = pv.eL[j] = pv.eff[j] = 0;
-            if (i < n_rec_t) {
+            if (!LONG && i < n_rec_t) {
                 const uint32_t sL = (uint32_t)(P.rec_off[r_begin + i] - P.base0 - origin);
                 const uint32_t eL = (uint32_t)(P.rec_off[r_begin + i + 1] - P.base0 - origin);
                 pv.sL[j] = sL; pv.eL[j] = eL;
@@ -334,6 +349,7 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
             }
         }
         if (l == 0) s.ustartpos[n_units_t] = (uint16_t)span_hi;   // P7 takes a unit's length from two consecutive starts
+        if (LONG && l == 0 && !lg.carry) set_bit(s.brk, lg.la);   // record start: its first window always emits
         // k-mer at the lane's first base: bases 0..30 = own words 0 and 1 (less its last base)
         const uint32_t c0 = s.codes[3 * l], c1 = s.codes[3 * l + 1], c2 = s.codes[3 * l + 2];
         uint32_t fw = 0, rc = 0;
@@ -416,8 +432,65 @@ DCN_HD bool warp_short_run(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
                 if (l == 0) s.npicks = total;
             });
     const uint32_t npicks = s.npicks;
-    if (npicks > (uint32_t)WG::PKCAP) { ex.after_scan(false); return false; }
+    if (!LONG && npicks > (uint32_t)WG::PKCAP) { ex.after_scan(false); return false; }
     ex.after_scan(last_run);
+
+    if (LONG) {
+        // ---- P5 (long): block results into registers first: up to 1477 pick positions overwrite them
+        ex.par([&](int l, Priv &pv) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) { pv.lrel[r] = s.rel4()[3 * l + r]; pv.lem[r] = s.em()[3 * l + r]; }
+        });
+        ex.par([&](int l, Priv &pv) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const u32x4a rel = pv.lrel[r];
+                uint32_t em = pv.lem[r] & 0xFFFFu, idx = pv.lem[r] >> 16;
+                const uint64_t relA = rel.x | ((uint64_t)rel.y << 32), relB = rel.z | ((uint64_t)rel.w << 32);
+                const uint32_t base = 48u * (uint32_t)l + 16u * (uint32_t)r;
+                while (em) {
+#ifdef __CUDA_ARCH__
+                    const int i = __ffs((int)em) - 1;
+#else
+                    const int i = __builtin_ctz(em);
+#endif
+                    em &= em - 1;
+                    const uint32_t rl = (uint32_t)(((i & 8) ? relB : relA) >> (8 * (i & 7))) & 0xFFu;
+                    s.pk_pos()[idx++] = (uint16_t)(base + rl);
+                }
+            }
+        });
+        // ---- P6 (long): probe, distinct hits through the global (hash, unit) set, per-unit atomics
+        ex.par([&](int l, Priv &) {
+            const uint16_t *pk_pos = s.pk_pos();
+            uint32_t n_valid = 0, n_fresh = 0;   // this lane's picks
+            for (uint32_t idx0 = (uint32_t)l; idx0 < npicks; idx0 += 2 * WG::NL) {
+                const uint32_t idxB = idx0 + WG::NL;
+                const uint32_t ppA = pk_pos[idx0], ppB = idxB < npicks ? pk_pos[idxB] : 0u;
+                const bool vA = wpick_valid(s, ppA), vB = idxB < npicks && wpick_valid(s, ppB);
+                uint64_t hA = 0, hB = 0, bA = 0, bB = 0;
+                Bucket kA, kB;
+                kA.k0 = kA.k1 = kA.k2 = kA.k3 = 0; kB = kA;
+                if (vA) { hA = wpick_hash(s, ppA); bA = table_bucket(hA, P.table.n_buckets); kA = load_bucket(P.table.slots, bA); }
+                if (vB) { hB = wpick_hash(s, ppB); bB = table_bucket(hB, P.table.n_buckets); kB = load_bucket(P.table.slots, bB); }
+                const bool fA = vA && table_contains_from(P.table, hA, bA, kA) && dedup_insert(*lg.dd, hA, lg.unit);
+                const bool fB = vB && table_contains_from(P.table, hB, bB, kB) && dedup_insert(*lg.dd, hB, lg.unit);
+                n_valid += (uint32_t)vA + (uint32_t)vB;
+                n_fresh += (uint32_t)fA + (uint32_t)fB;
+            }
+            s.ufirst[l] = (uint16_t)n_valid;      // (<= 47 per lane; the unit tables are free in a long chunk)
+            s.ustartpos[l] = (uint16_t)n_fresh;
+        });
+        ex.par([&](int l, Priv &) {
+            if (l == 0) {
+                uint32_t nv = 0, nf = 0;
+                for (int i = 0; i < WG::NL; i++) { nv += s.ufirst[i]; nf += s.ustartpos[i]; }
+                ex.global_add(&P.total[lg.unit], nv);
+                ex.global_add(&P.hits[lg.unit], nf);
+            }
+        });
+        return true;
+    }
 
     // ---- P5: compact the picks (the positions take over the hx rows: every lane is past its last hx read);
     // unit -> pick range from the per-block offsets
@@ -558,7 +631,9 @@ DCN_HD void warp_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterPara
         src.inv = PACKED ? P.pk_inv + (origin >> 4) : nullptr;
         const uint64_t n_rel = P.n_bases - P.base0;
         src.words = PACKED ? ((n_rel + 15) >> 4) - (origin >> 4) : 0;
-        if (warp_short_run<PACKED>(ex, T, s, P, src, origin, lo, hi, hi == tile.b)) {
+        WLong none;
+        none.unit = none.la = none.carry = none.nw = 0; none.dd = nullptr;
+        if (warp_run<PACKED, false>(ex, T, s, P, src, origin, lo, hi, hi == tile.b, none)) {
             lo = hi;
         } else if (hi - lo == 1) {
             overflow(lo);
@@ -568,6 +643,44 @@ DCN_HD void warp_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterPara
             span = (hi - lo + 1) / 2;
         }
     }
+}
+
+// One chunk of a long unit (descriptor: WTILE_LONG set): see WLong.
+template <bool PACKED, class Ex>
+DCN_HD void warp_long_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParams &P, const DedupView &dd,
+                           const WTile &tile, uint32_t stage_bytes) {
+    const uint64_t origin = tile.origin & ~WTILE_LONG;
+    WLong lg;
+    lg.unit = tile.a / P.rpu; lg.la = tile.b & 15u; lg.carry = (tile.b >> 4) & 1u; lg.nw = tile.b >> 5; lg.dd = &dd;
+    WSrc src;
+    src.stage = PACKED ? nullptr : s.stage;
+    src.stage_bytes = (stage_bytes + 15u) & ~15u;
+    src.codes = PACKED ? P.pk_codes + (origin >> 4) : nullptr;
+    src.inv = PACKED ? P.pk_inv + (origin >> 4) : nullptr;
+    const uint64_t n_rel = P.n_bases - P.base0;
+    src.words = PACKED ? ((n_rel + 15) >> 4) - (origin >> 4) : 0;
+    warp_run<PACKED, true>(ex, T, s, P, src, origin, 0u, 0u, true, lg);
+}
+
+// chunk descriptors of one long record with `eff_len` effective bases starting at gs (relative to base0)
+template <class Emit>
+DCN_HD uint32_t wplan_long_record(uint32_t rec, uint64_t gs, uint64_t eff_len, Emit emit) {
+    if (eff_len < (uint64_t)WG::L) return 0;
+    const uint64_t nwin = eff_len - (uint64_t)WG::L + 1;
+    const uint32_t nc = (uint32_t)((nwin + DCN_WCS - 1) / DCN_WCS);
+    for (uint32_t c = 0; c < nc; c++) {
+        const uint64_t w0 = (uint64_t)c * DCN_WCS;
+        const uint32_t nw = (uint32_t)(nwin - w0 < DCN_WCS ? nwin - w0 : DCN_WCS), carry = c > 0 ? 1u : 0u;
+        const uint64_t a = gs + w0 - carry, origin = a & ~15ull;
+        WTile t;
+        t.origin = origin | WTILE_LONG; t.a = rec; t.b = (uint32_t)(a - origin) | (carry << 4) | (nw << 5);
+        emit(c, t);
+    }
+    return nc;
+}
+DCN_HD uint32_t wplan_long_chunks_of(uint64_t eff_len) {
+    if (eff_len < (uint64_t)WG::L) return 0;
+    return (uint32_t)((eff_len - (uint64_t)WG::L + 1 + DCN_WCS - 1) / DCN_WCS);
 }
 
 // ------------------------------------------------------------------ planner

@@ -235,9 +235,10 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
         delete ws;
     }
     int rc = 0;
-    if (n_long) {  // mirrors prep_long_kernel + the chunk loop of filter_fused_kernel + finalize_long_kernel
+    if (n_long) {  // mirrors prep_long[_warp]_kernel + the chunk loop (CTA tiles: filter_fused_kernel; warp tiles: filter_warp_kernel) + finalize_long_kernel
         std::vector<uint32_t> long_units;
         std::vector<ChunkDesc> desc;
+        std::vector<WTile> ltiles;
         uint64_t long_bases = 0;
         for (uint32_t u = 0; u < P.n_units; u++) {
             uint64_t len = rec_off[(uint64_t)(u + 1) * P.rpu] - rec_off[(uint64_t)u * P.rpu];
@@ -247,8 +248,11 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
             hits[u] = 0; total[u] = 0;
             for (uint32_t r = u * P.rpu; r < (u + 1) * P.rpu; r++) {
                 uint64_t gs = rec_off[r], rl = rec_off[r + 1] - gs;
-                uint32_t nc = chunks_of<G>(filter_eff_len<G>(P, r, gs, rl));
+                const uint64_t eff = filter_eff_len<G>(P, r, gs, rl);
+                uint32_t nc = chunks_of<G>(eff);
                 for (uint32_t c = 0; c < nc; c++) desc.push_back(ChunkDesc{r, c});
+                const uint32_t nw = wplan_long_record(r, gs, eff, [&](uint32_t, const WTile &t) { ltiles.push_back(t); });
+                if (nw != wplan_long_chunks_of(eff)) abort();
             }
         }
         uint64_t cap = std::max<uint64_t>(4096, long_bases / 4);
@@ -256,7 +260,25 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
         std::vector<unsigned __int128> slots(cap, 0);
         uint32_t overflow = 0;
         DedupView dd{slots.data(), cap, &overflow};
-        for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G, PACKED>(ex, *s, P, dd, desc[i]);
+        if (emu_impl == 1) {
+            for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G, PACKED>(ex, *s, P, dd, desc[i]);
+        } else {
+            auto *T = new WarpTables();
+            auto *ws = new WarpSmem();
+            memset(ws, 0xA5, sizeof(*ws));
+            HostExec<WEmuGeo, WarpPriv> wex;
+            wex.smem_ptr = ws; wex.smem_bytes = sizeof(*ws);
+            for (int t = 0; t < 1024; t++) winit_tables(t, 1024, *T, abs_thr, rel_thr);
+            for (size_t i = ltiles.size(); i-- > 0;) {   // any order
+                const uint64_t origin = ltiles[i].origin & ~WTILE_LONG;
+                const uint64_t left = n_bases - origin;
+                const uint32_t need = left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
+                if (!PACKED) memcpy(ws->stage, bases + origin, need);
+                warp_long_tile<PACKED>(wex, *T, *ws, P, dd, ltiles[i], need);
+            }
+            delete T;
+            delete ws;
+        }
         for (uint32_t u : long_units)
             keep[u] = meets_criteria(hits[u], total[u], abs_thr, rel_thr, deplete) ? 1 : 0;
         if (overflow) rc = -6;
