@@ -37,8 +37,12 @@ thread_local std::string g_create_error;
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    // only used when the buffer holds a distinct-hit set (DedupView): bytes cleared once, epoch of the last call
+    size_t set_cleared = 0;
+    uint32_t set_epoch = 0;
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
+        set_cleared = 0; set_epoch = 0;
         if (p) { cudaError_t e = cudaFree(p); p = nullptr; cap = 0; if (e != cudaSuccess) return e; }
         size_t want = bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
@@ -144,6 +148,20 @@ struct dcn_ctx {
     } while (0)
 
 using G31 = Geo<31, 15>;
+
+// A distinct-hit set of `entries` 16-byte slots in `buf` for one call: cleared only the first time the bytes are used
+// (and when the 32-bit epoch wraps); after that a new epoch makes every older entry count as free.
+static cudaError_t open_dedup_set(DevBuf &buf, uint64_t entries, cudaStream_t st, DedupView &dd, uint32_t *overflow_flag) {
+    cudaError_t e = buf.ensure(entries * 16);
+    if (e != cudaSuccess) return e;
+    if (buf.set_cleared < entries * 16 || buf.set_epoch == 0xFFFFFFFFu) {
+        if ((e = cudaMemsetAsync(buf.p, 0, buf.cap, st)) != cudaSuccess) return e;
+        buf.set_cleared = buf.cap;
+        buf.set_epoch = 0;
+    }
+    dd.slots = buf.as<unsigned __int128>(); dd.cap = entries; dd.overflow = overflow_flag; dd.epoch = ++buf.set_epoch;
+    return cudaSuccess;
+}
 
 static size_t warp_kernel_smem() { return ((sizeof(WarpTables) + 15) & ~(size_t)15) + DCN_WARPS * (sizeof(WarpPipe) + sizeof(WarpSmem)); }
 
@@ -298,10 +316,8 @@ static int enqueue_filter_generic(dcn_ctx *ctx, DevBuf &plan, DevBuf &tmp, DevBu
         CK(cudaMemsetAsync(d_stats, 0, sizeof(BatchStats), st));
         CK(cudaMemsetAsync(d_hits, 0, (size_t)n_units * 4, st));
         CK(cudaMemsetAsync(d_total, 0, (size_t)n_units * 4, st));
-        CK(dedup.ensure(dedup_cap * 16));
-        CK(cudaMemsetAsync(dedup.p, 0, dedup_cap * 16, st));
         DedupView dd;
-        dd.slots = dedup.as<unsigned __int128>(); dd.cap = dedup_cap; dd.overflow = &d_stats->overflow;
+        CK(open_dedup_set(dedup, dedup_cap, st, dd, &d_stats->overflow));
         if (n_chunks) {
             generic_filter_kernel<<<grid_for(ctx, n_chunks, 128), 128, 0, st>>>(B, n_chunks, rpu, tv, dd, d_hits, d_total);
             ctx->launches += 1;
@@ -400,7 +416,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             CK(cudaStreamSynchronize(st));
         }
         DedupView dd;
-        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow;
+        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow; dd.epoch = 1;
         uint32_t *long_units = nullptr;
         ChunkDesc *desc = nullptr;
         if (hs.n_long) {
@@ -410,10 +426,8 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             // its size is what the long path pays up front (4 bytes per long base).
             if (!dedup_cap) dedup_cap = std::max<uint64_t>(4096, hs.long_bases / 4);
             const uint32_t desc_cap = (uint32_t)(hs.long_bases / ChunkGeo<G31>::CSTRIDE + (uint64_t)hs.n_long * rpu + 16);
-            CK(dedup.ensure(dedup_cap * 16));
+            CK(open_dedup_set(dedup, dedup_cap, st, dd, &d_stats->overflow));
             CK(longs.ensure((size_t)hs.n_long * 4 + 64 + (size_t)desc_cap * sizeof(ChunkDesc)));
-            CK(cudaMemsetAsync(dedup.p, 0, dedup_cap * 16, st));
-            dd.slots = dedup.as<unsigned __int128>(); dd.cap = dedup_cap;
             long_units = longs.as<uint32_t>();
             desc = reinterpret_cast<ChunkDesc *>(longs.as<uint8_t>() + (((size_t)hs.n_long * 4 + 63) & ~(size_t)63));
             if (warp_impl) prep_long_warp_kernel<G31><<<pg, pb, 0, st>>>(P, d_stats, long_units, wtiles, (uint32_t)std::min<uint64_t>(wtile_cap, 0xFFFFFFFFull));
@@ -1312,12 +1326,10 @@ static int lookup_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t 
         CK(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         DedupView dd;
-        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow;
+        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow; dd.epoch = 1;
         if (hs.n_long) {
             if (!dedup_cap) dedup_cap = std::max<uint64_t>(4096, hs.long_bases * 2);
-            CK(ctx->dedup.ensure(dedup_cap * 16));
-            CK(cudaMemsetAsync(ctx->dedup.p, 0, dedup_cap * 16, st));
-            dd.slots = ctx->dedup.as<unsigned __int128>(); dd.cap = dedup_cap;
+            CK(open_dedup_set(ctx->dedup, dedup_cap, st, dd, &d_stats->overflow));
         }
         const int grid = (int)std::min<uint64_t>(((uint64_t)n_rec * 32 + 255) / 256, (uint64_t)ctx->sm_count * 8);
         lookup_kernel<<<grid, 256, 0, st>>>(d_hashes, d_rec_off, n_rec, tv, dd, abs_thr, rel_thr, deplete, d_keep, d_hits, d_total, d_flags);

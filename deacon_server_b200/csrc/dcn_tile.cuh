@@ -912,15 +912,18 @@ DCN_HD uint32_t chunk_picks(Ex &ex, TileSmem<G> &s, const TileSrc &src, uint64_t
 }
 
 // ------------------------------------------------------------------ global (hash, unit) set
-// 16-byte entries {hash, unit + 1}; all-zero = empty.  Exact: the full key is stored.
+// 16-byte entries {hash, epoch << 32 | unit + 1}; all-zero = empty.  Exact: the full key is stored.  The set is never
+// cleared between calls: every call inserts under a new EPOCH and an entry of another epoch counts as free (it is
+// replaced by a second compare-and-swap), so the long path no longer pays a memset of 4 bytes per long base per call.
 struct DedupView {
     unsigned __int128 *slots;
     uint64_t cap;         // entries (any size: the start slot is mulhi(mix, cap))
     uint32_t *overflow;   // set when an insert gives up
+    uint32_t epoch;       // >= 1
 };
 
 DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
-    const unsigned __int128 val = ((unsigned __int128)((uint64_t)unit + 1) << 64) | h;
+    const unsigned __int128 val = ((unsigned __int128)(((uint64_t)d.epoch << 32) | ((uint64_t)unit + 1)) << 64) | h;
     uint64_t slot = mulhi64(h ^ ((uint64_t)unit * 0x9E3779B97F4A7C15ULL), d.cap);
     for (uint32_t probes = 0; probes < 4096; probes++) {
 #ifdef __CUDA_ARCH__
@@ -931,6 +934,17 @@ DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
 #endif
         if (old == 0) return true;
         if (old == val) return false;
+        if ((uint32_t)(old >> 96) != d.epoch) {   // left by an earlier call: free
+#ifdef __CUDA_ARCH__
+            const unsigned __int128 old2 = atomicCAS(&d.slots[slot], old, val);
+#else
+            const unsigned __int128 old2 = d.slots[slot];
+            if (old2 == old) d.slots[slot] = val;
+#endif
+            if (old2 == old) return true;
+            if (old2 == val) return false;   // the same (hash, unit) got there first
+            // somebody else's entry of this call took the slot meanwhile: occupied
+        }
         if (++slot == d.cap) slot = 0;
     }
     *d.overflow = 1;

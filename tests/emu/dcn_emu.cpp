@@ -259,25 +259,32 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
         if (dedup_cap_override) cap = dedup_cap_override;
         std::vector<unsigned __int128> slots(cap, 0);
         uint32_t overflow = 0;
-        DedupView dd{slots.data(), cap, &overflow};
-        if (emu_impl == 1) {
-            for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G, PACKED>(ex, *s, P, dd, desc[i]);
-        } else {
-            auto *T = new WarpTables();
-            auto *ws = new WarpSmem();
-            memset(ws, 0xA5, sizeof(*ws));
-            HostExec<WEmuGeo, WarpPriv> wex;
-            wex.smem_ptr = ws; wex.smem_bytes = sizeof(*ws);
-            for (int t = 0; t < 1024; t++) winit_tables(t, 1024, *T, abs_thr, rel_thr);
-            for (size_t i = ltiles.size(); i-- > 0;) {   // any order
-                const uint64_t origin = ltiles[i].origin & ~WTILE_LONG;
-                const uint64_t left = n_bases - origin;
-                const uint32_t need = left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
-                if (!PACKED) memcpy(ws->stage, bases + origin, need);
-                warp_long_tile<PACKED>(wex, *T, *ws, P, dd, ltiles[i], need);
+        DedupView dd{slots.data(), cap, &overflow, 7u};
+        // the set is never cleared between calls (epoch tags): run the whole long path twice over the same slots, the
+        // first time under another epoch, so that the pass that counts finds every slot it wants taken by a stale entry
+        for (uint32_t epoch = 6; epoch <= 7; epoch++) {
+            dd.epoch = epoch;
+            for (uint32_t u : long_units) { hits[u] = 0; total[u] = 0; }
+            if (emu_impl == 1) {
+                for (size_t i = desc.size(); i-- > 0;) filter_long_chunk<G, PACKED>(ex, *s, P, dd, desc[i]);
+            } else {
+                auto *T = new WarpTables();
+                auto *ws = new WarpSmem();
+                memset(ws, 0xA5, sizeof(*ws));
+                HostExec<WEmuGeo, WarpPriv> wex;
+                wex.smem_ptr = ws; wex.smem_bytes = sizeof(*ws);
+                for (int t = 0; t < 1024; t++) winit_tables(t, 1024, *T, abs_thr, rel_thr);
+                for (size_t i = ltiles.size(); i-- > 0;) {   // any order
+                    const uint64_t origin = ltiles[i].origin & ~WTILE_LONG;
+                    const uint64_t left = n_bases - origin;
+                    const uint32_t need = left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
+                    if (!PACKED) memcpy(ws->stage, bases + origin, need);
+                    warp_long_tile<PACKED>(wex, *T, *ws, P, dd, ltiles[i], need);
+                }
+                delete T;
+                delete ws;
             }
-            delete T;
-            delete ws;
+            if (overflow) break;
         }
         for (uint32_t u : long_units)
             keep[u] = meets_criteria(hits[u], total[u], abs_thr, rel_thr, deplete) ? 1 : 0;
@@ -390,7 +397,7 @@ extern "C" int emu_generic_filter(const uint64_t *slots, uint64_t nb, int has_em
     while (cap < 4 * rec_off[n_rec] / ((uint64_t)w + 1)) cap <<= 1;
     std::vector<unsigned __int128> set(cap, 0);
     uint32_t overflow = 0;
-    DedupView dd{set.data(), cap, &overflow};
+    DedupView dd{set.data(), cap, &overflow, 7u};
     for (uint32_t u = 0; u < n_units; u++) hits[u] = total[u] = 0;
     for (uint64_t g = rco[n_rec]; g-- > 0;) {
         uint32_t r = 0, nt = 0, nh = 0;
