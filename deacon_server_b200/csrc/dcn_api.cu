@@ -530,6 +530,9 @@ dcn_ctx *dcn_ctx_create(int device) {
     ok = ok && cudaFuncSetAttribute(filter_tail_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     if (const char *fi = getenv("DCN_FUSED_IMPL")) ctx->fused_impl = strcmp(fi, "cta") == 0 ? 1 : 0;
+    ok = ok && cudaFuncSetAttribute(extract_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_kernel_smem()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(extract_tail_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(extract_tiles_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(extract_index_kernel<G31>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1394,15 +1397,19 @@ static int tile_extract_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint6
                                uint32_t prefix_len, bool want_pos, uint64_t cap_limit, cudaStream_t st, uint64_t *n_out,
                                bool *written) {
     *n_out = 0; *written = false;
-    const size_t pbytes = plan_bytes(n_bases);
+    const bool warp_impl = ctx->fused_impl == 0;
+    const uint64_t wtile_cap = wplan_tile_cap(n_bases, n_rec), wovf_cap = wplan_ovf_cap(n_bases);
+    const size_t pbytes = warp_impl ? 128 + (size_t)wtile_cap * sizeof(WTile) + (size_t)wovf_cap * 4 : plan_bytes(n_bases);
     CK(ctx->plan.ensure(pbytes));
-    const uint64_t n_tiles_max = (pbytes - 64) / (2 * sizeof(uint32_t));
+    const uint64_t n_tiles_max = (plan_bytes(n_bases) - 64) / (2 * sizeof(uint32_t));
     BatchStats *d_stats = ctx->plan.as<BatchStats>();
     uint32_t *tile_first = reinterpret_cast<uint32_t *>(ctx->plan.as<uint8_t>() + 64);
     uint32_t *tile_end = tile_first + n_tiles_max;
-    CK(ctx->gx_rc.ensure(((size_t)n_rec + 1) * 8));   // rec_cnt (scanned in place into the CSR offsets)
-    CK(ctx->gx_oo.ensure(((size_t)n_rec + 1) * 8));
-    CK(ctx->gx_cc.ensure(((size_t)n_rec + 1) * 8 + 64));   // rec_tmp + cursor
+    WTile *wtiles = reinterpret_cast<WTile *>(ctx->plan.as<uint8_t>() + 128);
+    uint32_t *wovf = reinterpret_cast<uint32_t *>(ctx->plan.as<uint8_t>() + 128 + (size_t)wtile_cap * sizeof(WTile));
+    CK(ctx->gx_rc.ensure(((size_t)n_rec + 1) * 8));     // valid picks per record, then (after the scan) unused
+    CK(ctx->gx_oo.ensure(((size_t)n_rec + 1) * 8));     // CSR offsets
+    CK(ctx->gx_cc.ensure(((size_t)n_rec + 1) * 8 + 64)); // temp start | pick count per record (+ the cursor)
     FilterParams P;
     memset(&P, 0, sizeof(P));
     P.bases = d_bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = d_off; P.n_rec = n_rec; P.rpu = 1; P.n_units = n_rec;
@@ -1411,26 +1418,36 @@ static int tile_extract_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint6
     const int pb = 256;
     const int pg = (int)std::min<uint64_t>(((uint64_t)n_rec + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
     const int grid = (int)std::min<uint64_t>(n_bases / G31::BCAP + 1, (uint64_t)ctx->sm_count * (1024 / G31::NT));
-    uint64_t cap = (uint64_t)((double)n_bases * 0.13) + 4096;   // ~0.095 picks per base for 150-base records
+    const int wgrid = (int)std::min<uint64_t>((n_bases / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count);
+    const uint64_t n_seg = (n_bases + DCN_WSEG - 1) / DCN_WSEG;
+    const int sg = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_seg + 7) / 8, (uint64_t)ctx->sm_count * 8));
+    // ~0.095 picks per base for 150-base records; the warp kernel's warps take the temp arrays in blocks of DCN_XBLK
+    uint64_t cap = (uint64_t)((double)n_bases * 0.13) + 4096 + (warp_impl ? (uint64_t)wgrid * DCN_WARPS * DCN_XBLK : 0);
     unsigned long long used = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
         CK(ctx->ib_alt.ensure(cap * 8));     // temp hashes
         CK(ctx->ib_tmp.ensure(cap * 4));     // temp positions
-        CK(cudaMemsetAsync(ctx->plan.p, 0, pbytes, st));
+        CK(cudaMemsetAsync(ctx->plan.p, 0, warp_impl ? 128 : pbytes, st));
         CK(cudaMemsetAsync(d_cursor, 0, 8, st));
         CK(cudaMemsetAsync(ctx->gx_rc.p, 0, ((size_t)n_rec + 1) * 8, st));
         P.xo.tmp_h = ctx->ib_alt.as<uint64_t>(); P.xo.tmp_p = ctx->ib_tmp.as<uint32_t>(); P.xo.tmp_cap = cap;
         P.xo.cursor = d_cursor; P.xo.rec_cnt = ctx->gx_rc.as<uint64_t>(); P.xo.rec_tmp = ctx->gx_cc.as<uint64_t>();
-        prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, 1, n_rec, d_stats);
-        prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, 1, n_rec, 0, d_stats, tile_first, tile_end);
-        extract_tiles_kernel<G31><<<grid, G31::NT, sizeof(TileSmem<G31>), st>>>(P, d_stats, tile_first, tile_end);
+        if (warp_impl) {
+            wplan_kernel<<<sg, 256, 0, st>>>(d_off, 1, n_rec, 0, n_bases, d_stats, wtiles, (uint32_t)std::min<uint64_t>(wtile_cap, 0xFFFFFFFFull), nullptr);
+            extract_warp_kernel<<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, (uint32_t)std::min<uint64_t>(wovf_cap, 0xFFFFFFFFull));
+            extract_tail_kernel<G31><<<std::min(grid, 16), G31::NT, sizeof(TileSmem<G31>), st>>>(P, d_stats, wovf);
+        } else {
+            prep_stats_kernel<<<pg, pb, 0, st>>>(d_off, 1, n_rec, d_stats);
+            prep_tiles_kernel<G31><<<pg, pb, 0, st>>>(d_off, 1, n_rec, 0, d_stats, tile_first, tile_end);
+            extract_tiles_kernel<G31><<<grid, G31::NT, sizeof(TileSmem<G31>), st>>>(P, d_stats, tile_first, tile_end);
+        }
         ctx->launches += 3;
         CK(cudaMemcpyAsync(&used, d_cursor, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
         if (used <= cap) break;
         if (attempt == 1) return ctx->fail(DCN_ERR_OVERFLOW, "pick buffer overflowed twice");
-        cap = used + 1024;
+        cap = used + 1024 + (warp_impl ? (uint64_t)wgrid * DCN_WARPS * DCN_XBLK : 0);
     }
     // records that own no window keep count 0 (memset); exclusive scan -> CSR offsets
     size_t tb = 0;

@@ -413,8 +413,10 @@ __device__ __forceinline__ void add_summary(unsigned long long *counters, unsign
 struct WarpPipe {
     WTile d1, d2;   // next tile, tile after next
     unsigned long long bp_all, bp_kept;   // summary counters of the units this warp classified (lane 0 adds, flushed once at the end)
-    uint32_t n_all, n_kept, pad_[2];
+    uint32_t n_all, n_kept, xleft, pad_;
+    unsigned long long xbase;             // extraction: the warp's current block of the temp arrays, entries left in it
 };
+static constexpr uint32_t DCN_XBLK = 4096;   // temp entries a warp reserves with one atomic (extract_warp_kernel)
 
 struct WarpDevExec {
     WarpPriv pv;
@@ -437,6 +439,22 @@ struct WarpDevExec {
     }
     __device__ __forceinline__ uint32_t match64(int, uint64_t v, bool) { return __match_any_sync(0xFFFFFFFFu, (unsigned long long)v); }
     __device__ __forceinline__ void global_add(uint32_t *p, uint32_t v) { if (v) atomicAdd(p, v); }
+    // extraction: room for n picks in the temp arrays, from the warp's own block (a new block when it does not fit)
+    __device__ __forceinline__ uint64_t xalloc(uint32_t n) {
+        if (lane == 0) {
+            if (n > pipe->xleft) {
+                const uint32_t blk = n > DCN_XBLK ? n : DCN_XBLK;
+                pipe->xbase = atomicAdd(P->xo.cursor, (unsigned long long)blk);
+                pipe->xleft = blk;
+            }
+            pipe->xleft -= n;
+            pipe->xbase += n;
+        }
+        __syncwarp();
+        const uint64_t at = pipe->xbase - n;
+        __syncwarp();
+        return at;
+    }
     __device__ __forceinline__ void tally(uint32_t nrec, uint32_t len, bool keep) {   // lane 0 only
         pipe->bp_all += len; pipe->n_all += nrec;
         if (keep) { pipe->bp_kept += len; pipe->n_kept += nrec; }
@@ -504,7 +522,7 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
     winit_tables((int)threadIdx.x, (int)blockDim.x, T, P.abs_thr, P.rel_thr);
     if (lane == 0) {
         mbar_init(&s.mbar, 1u);
-        pipe.bp_all = pipe.bp_kept = 0; pipe.n_all = pipe.n_kept = 0;
+        pipe.bp_all = pipe.bp_kept = 0; pipe.n_all = pipe.n_kept = 0; pipe.xleft = 0; pipe.xbase = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();   // the only CTA barrier of the kernel
@@ -546,7 +564,7 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
         if (is_long) {   // a chunk of a long unit (listed behind the short tiles by prep_long_warp_kernel)
             warp_long_tile<PACKED>(ex, T, s, P, dd, d0, need);
         } else {
-            warp_tile<PACKED>(ex, T, s, P, d0, need, [&](uint32_t u) {
+            warp_tile<PACKED, false>(ex, T, s, P, d0, need, [&](uint32_t u) {
                 if (lane == 0) {
                     const uint32_t at = atomicAdd(&st->n_ovf, 1u);
                     if (at < ovf_cap) ovf_list[at] = u; else st->overflow = 1;
@@ -564,6 +582,100 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
         ex.id2 = __shfl_sync(0xFFFFFFFFu, ex.c3, 0);
     }
     if (lane == 0 && pipe.n_all) add_summary(counters, pipe.n_all, pipe.n_kept, pipe.bp_all, pipe.bp_kept);
+}
+
+// B3 on warp tiles: the same skeleton, ASCII input, no long units (dcn_extract sends batches with a record above
+// DCN_MAX_SHORT bases through the generic kernels); records of more than a warp pass's picks are listed for
+// extract_tail_kernel.
+__global__ void __launch_bounds__(DCN_WARPS * 32, 1)
+extract_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ tiles, uint32_t *ovf_list, uint32_t ovf_cap) {
+    constexpr bool PACKED = false;
+    extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
+    WarpTables &T = *reinterpret_cast<WarpTables *>(dcn_smem_raw);
+    const int warp = (int)(threadIdx.x >> 5), lane = (int)(threadIdx.x & 31u);
+    constexpr size_t OFF_PIPE = (sizeof(WarpTables) + 15) & ~(size_t)15, OFF_WARPS = OFF_PIPE + DCN_WARPS * sizeof(WarpPipe);
+    WarpPipe &pipe = reinterpret_cast<WarpPipe *>(dcn_smem_raw + OFF_PIPE)[warp];
+    WarpSmem &s = reinterpret_cast<WarpSmem *>(dcn_smem_raw + OFF_WARPS)[warp];
+    winit_tables((int)threadIdx.x, (int)blockDim.x, T, P.abs_thr, P.rel_thr);
+    if (lane == 0) {
+        mbar_init(&s.mbar, 1u);
+        pipe.bp_all = pipe.bp_kept = 0; pipe.n_all = pipe.n_kept = 0; pipe.xleft = 0; pipe.xbase = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();   // the only CTA barrier of the kernel
+
+    WarpDevExec ex;
+    ex.lane = lane; ex.P = &P; ex.s = &s; ex.pipe = &pipe; ex.tiles = tiles; ex.packed = PACKED;
+    ex.tile_ctr = &st->tile_claims;
+    ex.n_tiles = st->n_wtiles;
+    ex.total_warps = gridDim.x * DCN_WARPS;
+    const uint32_t n_tiles = ex.n_tiles;
+
+    // first wave: tile = global warp index; two more tiles claimed up front
+    uint32_t id0 = blockIdx.x * DCN_WARPS + (uint32_t)warp;
+    uint32_t claim = 0;
+    if (lane == 0 && id0 < n_tiles) claim = ex.total_warps + atomicAdd(ex.tile_ctr, 2u);
+    claim = __shfl_sync(0xFFFFFFFFu, claim, 0);
+    ex.id1 = id0 < n_tiles ? claim : 0xFFFFFFFFu;
+    ex.id2 = id0 < n_tiles ? claim + 1u : 0xFFFFFFFFu;
+    ex.c3 = 0xFFFFFFFFu;
+    WTile d0;
+    d0.origin = 0; d0.a = d0.b = 0;
+    if (id0 < n_tiles) { d0 = tiles[id0]; ex.issue_copy(d0); }
+    if (lane == 0 && ex.id1 < n_tiles) ex.fetch_desc(&pipe.d1, ex.id1);
+    bool have = id0 < n_tiles;
+    uint32_t phase = 0;
+    while (have) {
+        const bool is_long = (d0.origin & WTILE_LONG) != 0;
+        const uint64_t origin0 = d0.origin & ~WTILE_LONG;
+        const uint32_t need = ex.tile_need(origin0);
+        asm volatile("cp.async.wait_all;" ::: "memory");   // the descriptors requested during the previous tile (lane 0)
+        __syncwarp();
+        if (!PACKED) {
+            mbar_wait(&s.mbar, phase);
+            phase ^= 1u;
+            const uint32_t bulk = need & ~15u;
+            if ((uint32_t)lane < need - bulk) s.stage[bulk + (uint32_t)lane] = P.bases[origin0 + bulk + (uint32_t)lane];
+            __syncwarp();
+        }
+        if (!is_long) {
+            warp_tile<PACKED, true>(ex, T, s, P, d0, need, [&](uint32_t u) {
+                if (lane == 0) {
+                    const uint32_t at = atomicAdd(&st->n_ovf, 1u);
+                    if (at < ovf_cap) ovf_list[at] = u; else st->overflow = 1;
+                }
+            });
+        }
+        // rotate the pipeline: d1 (in shared memory since the previous tile) becomes the current tile
+        have = ex.id1 < n_tiles;
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncwarp();
+        d0 = pipe.d1;
+        __syncwarp();
+        if (lane == 0) pipe.d1 = pipe.d2;
+        ex.id1 = ex.id2;
+        ex.id2 = __shfl_sync(0xFFFFFFFFu, ex.c3, 0);
+    }
+}
+
+// records the warp extraction could not hold (more than a warp pass's picks): the CTA-tile extraction, one record at a time
+template <class G>
+__global__ void __launch_bounds__(G::NT, 1024 / G::NT)
+extract_tail_kernel(FilterParams P, const BatchStats *st, const uint32_t *__restrict__ ovf_list) {
+    const uint32_t n_ovf = st->n_ovf;
+    if (n_ovf == 0) return;
+    extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
+    TileSmem<G> &s = *reinterpret_cast<TileSmem<G> *>(dcn_smem_raw);
+    DevExec<G> ex;
+    ex.wsum = s.wsum;
+    init_tables<G>((int)threadIdx.x, s);
+    __syncthreads();
+    ex.pf_off = P.rec_off;
+    for (uint32_t i = blockIdx.x; i < n_ovf; i += gridDim.x) {
+        const uint32_t u = ovf_list[i];
+        filter_short_run<G, false, MODE_EXTRACT>(ex, s, P, u, u + 1u);
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------ the CTA-tile tail of the warp kernel

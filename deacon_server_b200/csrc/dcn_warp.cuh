@@ -279,7 +279,10 @@ DCN_HD uint32_t w_eff_len(const FilterParams &P, const WSrc &src, uint32_t r, ui
 // set `dd` and per-unit atomics instead of the per-unit count (filter_long_chunk is the CTA-tile form of the same).
 struct WLong { uint32_t unit, la, carry, nw; const DedupView *dd; };
 
-template <bool PACKED, bool LONG, class Ex>
+// With EXTRACT (B3, get_minimizer_hashes_and_positions src/filter_common.rs:211-310; rpu = 1) nothing is probed: the
+// picks' hashes and record-relative positions go to a block of the temp arrays (ex.xalloc), per-record valid counts
+// feed the CSR offsets (ExtractOut, as extract_tiles_kernel).
+template <bool PACKED, bool LONG, bool EXTRACT, class Ex>
 DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParams &P, const WSrc &src,
                      uint64_t origin, uint32_t u_begin, uint32_t u_end, bool last_run, const WLong &lg) {
     using Priv = WarpPriv;
@@ -541,18 +544,55 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
                 v[f] = idx < npicks && wpick_valid(s, pp[f]);
                 h[f] = 0; bk[f] = 0;
                 k[f].k0 = k[f].k1 = k[f].k2 = k[f].k3 = 0;
-                if (v[f]) { h[f] = wpick_hash(s, pp[f]); bk[f] = table_bucket(h[f], P.table.n_buckets); k[f] = load_bucket(P.table.slots, bk[f]); }
+                if (v[f]) {
+                    h[f] = wpick_hash(s, pp[f]);
+                    if (!EXTRACT) { bk[f] = table_bucket(h[f], P.table.n_buckets); k[f] = load_bucket(P.table.slots, bk[f]); }
+                }
             }
 #pragma unroll
             for (int f = 0; f < NF; f++) {
                 const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
                 if (v[f]) {
                     pk_hash[idx] = h[f];
-                    pk_pos[idx] = (uint16_t)(pp[f] | 0x4000u | (table_contains_from(P.table, h[f], bk[f], k[f]) ? 0x8000u : 0u));
+                    pk_pos[idx] = (uint16_t)(pp[f] | 0x4000u | (!EXTRACT && table_contains_from(P.table, h[f], bk[f], k[f]) ? 0x8000u : 0u));
                 }
             }
         }
     });
+
+    if (EXTRACT) {
+        // ---- P7 (extract): the warp walks its records; a record's picks (list order = position order) go to the
+        // tile's block of the temp arrays with the position made relative to the record
+        const uint64_t tbase = ex.xalloc(npicks);
+        ex.par([&](int l, Priv &) {
+            const uint32_t lane = (uint32_t)l;
+            const uint16_t *pk_pos = s.pk_pos();
+            const uint64_t *pk_hash = s.pk_hash();
+            for (uint32_t u = 0; u < n_units_t; u++) {
+                const uint32_t a = s.ufirst[u], b = s.ufirst[u + 1], sL = s.ustartpos[u];
+                uint32_t cnt = 0;
+                for (uint32_t base = a; base < b; base += 32u) {
+                    const uint32_t idx = base + lane;
+                    bool valid = false;
+                    if (idx < b) {
+                        const uint32_t pp = pk_pos[idx];
+                        valid = (pp & 0x4000u) != 0;
+                        const uint64_t at = tbase + idx;
+                        if (at < P.xo.tmp_cap) {
+                            P.xo.tmp_p[at] = ((pp & 0x3FFFu) - sL) | (valid ? 0x80000000u : 0u);
+                            if (valid) P.xo.tmp_h[at] = pk_hash[idx];
+                        }
+                    }
+                    cnt += popc32(ex.ballot(l, valid));
+                }
+                if (lane == 0) {
+                    P.xo.rec_cnt[u_begin + u] = cnt;
+                    P.xo.rec_tmp[u_begin + u] = ((tbase + a) << 16) | (uint64_t)(b - a);
+                }
+            }
+        });
+        return true;
+    }
 
     // ---- P7: distinct hits per unit (src/filter_common.rs:143-145) and the threshold test: the warp walks its
     // units; a unit's picks are consecutive list entries, 32 per pass (see filter_short_tile for the later-pass rules)
@@ -613,7 +653,7 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
 // A tile: its units as one run, split in halves while a run emits more picks than one pass can hold.  A single
 // unit that still does not fit is handed to `overflow(u)` (the CTA-tile path holds 1024 picks per unit).
 // `stage0` = staged ASCII of the tile (position 0 = tile origin), `stage_bytes` = valid bytes in it.
-template <bool PACKED, class Ex, class Ovf>
+template <bool PACKED, bool EXTRACT, class Ex, class Ovf>
 DCN_HD void warp_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParams &P, const WTile &tile,
                       uint32_t stage_bytes, Ovf overflow) {
     uint32_t lo = tile.a, span = tile.b - tile.a;
@@ -633,7 +673,7 @@ DCN_HD void warp_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterPara
         src.words = PACKED ? ((n_rel + 15) >> 4) - (origin >> 4) : 0;
         WLong none;
         none.unit = none.la = none.carry = none.nw = 0; none.dd = nullptr;
-        if (warp_run<PACKED, false>(ex, T, s, P, src, origin, lo, hi, hi == tile.b, none)) {
+        if (warp_run<PACKED, false, EXTRACT>(ex, T, s, P, src, origin, lo, hi, hi == tile.b, none)) {
             lo = hi;
         } else if (hi - lo == 1) {
             overflow(lo);
@@ -659,7 +699,7 @@ DCN_HD void warp_long_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
     src.inv = PACKED ? P.pk_inv + (origin >> 4) : nullptr;
     const uint64_t n_rel = P.n_bases - P.base0;
     src.words = PACKED ? ((n_rel + 15) >> 4) - (origin >> 4) : 0;
-    warp_run<PACKED, true>(ex, T, s, P, src, origin, 0u, 0u, true, lg);
+    warp_run<PACKED, true, false>(ex, T, s, P, src, origin, 0u, 0u, true, lg);
 }
 
 // chunk descriptors of one long record with `eff_len` effective bases starting at gs (relative to base0)

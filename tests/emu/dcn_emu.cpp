@@ -25,6 +25,8 @@ struct HostExec {
     HostExec() : pv(G::NT) {}
     int after_scan_calls = 0;
     void after_scan(bool go) { after_scan_calls += go ? 1 : 0; }
+    unsigned long long *xcursor = nullptr;
+    uint64_t xalloc(uint32_t n) { uint64_t at = *xcursor; *xcursor += n; return at; }
     uint64_t tally_n = 0, tally_bp = 0, tally_n_kept = 0, tally_bp_kept = 0;
     void tally(uint32_t nrec, uint32_t len, bool keep) { tally_n += nrec; tally_bp += len; if (keep) { tally_n_kept += nrec; tally_bp_kept += len; } }
 
@@ -225,7 +227,7 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
             const uint32_t need = left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
             if (!PACKED) memcpy(ws->stage, bases + t.origin, need);   // bulk copy + tail bytes; the rest of the stage keeps the previous tile
             const int calls0 = wex.after_scan_calls;
-            warp_tile<PACKED>(wex, *T, *ws, P, t, need, [&](uint32_t u) { ovf.push_back(u); });
+            warp_tile<PACKED, false>(wex, *T, *ws, P, t, need, [&](uint32_t u) { ovf.push_back(u); });
             if (wex.after_scan_calls != calls0 + 1) abort();   // the device starts the next tile's copy exactly once per tile
         }
         emu_ovf_units = ovf.size();
@@ -305,6 +307,68 @@ int emu_filter_batch(const uint64_t *slots, uint64_t nb, int has_empty, const ui
                                         deplete, keep, hits, total);
     return emu_filter_batch_t<false>(slots, nb, has_empty, bases_in, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr,
                                      deplete, keep, hits, total);
+}
+
+// mirrors tile_extract_device (B3, k=31, w=15, every record <= DCN_MAX_SHORT): wplan + extract_warp_kernel +
+// extract_tail_kernel + scan + extract_compact_kernel.  -> number of minimizers, or -6 when out_cap is too small
+long long emu_tile_extract(const uint8_t *bases_in, const uint64_t *rec_off, uint32_t n_rec, uint32_t prefix_len, uint64_t *out_h,
+                           uint32_t *out_p, uint64_t *out_off, uint64_t out_cap) {
+    using G = Geo<31, 15>;
+    const uint64_t n_bases = rec_off[n_rec];
+    uint8_t *bases = (uint8_t *)aligned_alloc(16, ((n_bases + 15) / 16 + 1) * 16);
+    memcpy(bases, bases_in, n_bases);
+    FilterParams P;
+    memset(&P, 0, sizeof(P));
+    P.bases = bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = rec_off; P.n_rec = n_rec; P.rpu = 1; P.n_units = n_rec;
+    P.prefix_len = prefix_len;
+    const uint64_t cap = n_bases + 64 * 1024;
+    std::vector<uint64_t> tmp_h(cap), rec_cnt(n_rec + 1, 0), rec_tmp(n_rec + 1, 0);
+    std::vector<uint32_t> tmp_p(cap);
+    unsigned long long cursor = 0;
+    P.xo.tmp_h = tmp_h.data(); P.xo.tmp_p = tmp_p.data(); P.xo.tmp_cap = cap; P.xo.cursor = &cursor;
+    P.xo.rec_cnt = rec_cnt.data(); P.xo.rec_tmp = rec_tmp.data();
+    auto *T = new WarpTables();
+    auto *ws = new WarpSmem();
+    memset(ws, 0xA5, sizeof(*ws));
+    HostExec<WEmuGeo, WarpPriv> wex;
+    wex.smem_ptr = ws; wex.smem_bytes = sizeof(*ws); wex.xcursor = &cursor;
+    for (int t = 0; t < 1024; t++) winit_tables(t, 1024, *T, 2, 0.01);
+    std::vector<uint32_t> ovf;
+    const uint64_t n_seg = (n_bases + DCN_WSEG - 1) / DCN_WSEG;
+    for (uint64_t seg = 0; seg < n_seg; seg++)
+        wplan_segment(rec_off, 0, 1, n_rec, seg, [&](uint64_t o, uint32_t a, uint32_t b) {
+            WTile t; t.origin = o; t.a = a; t.b = b;
+            const uint64_t left = n_bases - o;
+            const uint32_t need = left < (uint64_t)WG::TB ? (uint32_t)left : (uint32_t)WG::TB;
+            memcpy(ws->stage, bases + o, need);
+            warp_tile<false, true>(wex, *T, *ws, P, t, need, [&](uint32_t u) { ovf.push_back(u); });
+        });
+    if (!ovf.empty()) {
+        auto *s = new TileSmem<G>();
+        memset(s, 0xA5, sizeof(*s));
+        HostExec<G> ex;
+        ex.smem_ptr = s; ex.smem_bytes = sizeof(*s);
+        ex.par([&](int t, TilePriv<G> &) { init_tables<G>(t, *s); });
+        for (uint32_t u : ovf) filter_short_run<G, false, MODE_EXTRACT>(ex, *s, P, u, u + 1);
+        delete s;
+    }
+    emu_ovf_units = ovf.size();
+    uint64_t m = 0;
+    for (uint32_t r = 0; r < n_rec; r++) { out_off[r] = m; m += rec_cnt[r]; }
+    out_off[n_rec] = m;
+    long long rc = (long long)m;
+    if (m > out_cap) rc = -6;
+    else
+        for (uint32_t r = 0; r < n_rec; r++) {
+            const uint64_t start = rec_tmp[r] >> 16, n = rec_tmp[r] & 0xFFFFu;
+            uint64_t at = out_off[r];
+            for (uint64_t i = 0; i < n; i++)
+                if (tmp_p[start + i] & 0x80000000u) { out_h[at] = tmp_h[start + i]; out_p[at] = tmp_p[start + i] & 0x7FFFFFFFu; at++; }
+            if (at != out_off[r + 1]) rc = -100;
+        }
+    delete T; delete ws;
+    free(bases);
+    return rc;
 }
 
 void emu_pack_ascii(const uint8_t *bases, uint64_t n, uint32_t *codes, uint16_t *inv, int simd) { pack_ascii(bases, n, codes, inv, simd); }

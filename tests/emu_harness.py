@@ -87,6 +87,21 @@ def last_overflow_units():
     return int(lib().emu_last_overflow_units())
 
 
+def tile_extract(bases, off, prefix=0, cap=None):
+    """B3 through the warp-tile extraction (k = 31, w = 15, short records) -> (hashes, positions, out_off) or (rc, None, off)."""
+    L = lib()
+    L.emu_tile_extract.restype = C.c_longlong
+    n_rec = len(off) - 1
+    cap = max(16, len(bases)) if cap is None else cap
+    oh, op, oo = np.zeros(cap, np.uint64), np.zeros(cap, np.uint32), np.zeros(n_rec + 1, np.uint64)
+    b = bases if len(bases) else np.zeros(1, np.uint8)
+    n = L.emu_tile_extract(_p(b, u8p), _p(off, u64p), C.c_uint32(n_rec), C.c_uint32(prefix), _p(oh, u64p), _p(op, u32p), _p(oo, u64p),
+                           C.c_uint64(cap))
+    if n < 0:
+        return int(n), None, oo
+    return oh[:n], op[:n], oo
+
+
 def set_dedup_cap(cap):
     lib().emu_set_dedup_cap(C.c_uint64(cap))
 

@@ -111,3 +111,20 @@ def test_host_packer_simd_matches_scalar_and_definition():
         bad = ~np.isin(pad & 0xDF, np.frombuffer(b"ACGT", np.uint8))
         want_i = (bad.reshape(-1, 16).astype(np.uint32) << np.arange(16, dtype=np.uint32)).sum(axis=1).astype(np.uint16)
         assert np.array_equal(c0, want_c) and np.array_equal(i0, want_i), n
+
+
+@pytest.mark.parametrize("prefix", [0, 100])
+def test_warp_tile_extraction_matches_oracle(prefix):
+    """B3 through the warp tiles (extract_warp_kernel + extract_tail_kernel for records of more than a warp pass's
+    picks): per record the hashes AND positions of get_minimizer_hashes_and_positions (src/filter_common.rs:211-310)."""
+    g = H.random_genome(80_000, 77)
+    recs = H.sample_reads(g, 700, (0, 420), 78, n_rate=0.02, lower_rate=0.1)
+    recs += [np.frombuffer(b"A" * 1000, np.uint8).copy()] * 3 + [np.frombuffer(b"ACGT" * 60, np.uint8).copy()] * 5   # dense picks
+    recs += [np.concatenate([r, np.frombuffer(b"\n", np.uint8)]) for r in recs[:50]]
+    bases, off = H.concat(recs)
+    h, p, oo = E.tile_extract(bases, off, prefix)
+    assert E.last_overflow_units() == (3 if prefix == 0 else 0)   # the untrimmed poly-A records go through the CTA-tile extraction
+    for r, rec in enumerate(recs):
+        wh, wp = O.extract_filter(rec, 31, 15, prefix)
+        a, b = int(oo[r]), int(oo[r + 1])
+        assert np.array_equal(h[a:b], wh) and np.array_equal(p[a:b], wp), r
