@@ -441,8 +441,14 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             // no long unit in the batch the tail only has work on pathological input, so a few CTAs are enough.
             const uint32_t ocap = (uint32_t)std::min<uint64_t>(wovf_cap, 0xFFFFFFFFull);
             unsigned long long *cnt = call_cnt;
-            if (in.codes) filter_warp_kernel<true><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
-            else filter_warp_kernel<false><<<wgrid, DCN_WARPS * 32, warp_kernel_smem(), st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
+            const size_t wsm = warp_kernel_smem();
+            if (hs.n_long) {
+                if (in.codes) filter_warp_kernel<true, true><<<wgrid, DCN_WARPS * 32, wsm, st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
+                else filter_warp_kernel<false, true><<<wgrid, DCN_WARPS * 32, wsm, st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
+            } else {
+                if (in.codes) filter_warp_kernel<true, false><<<wgrid, DCN_WARPS * 32, wsm, st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
+                else filter_warp_kernel<false, false><<<wgrid, DCN_WARPS * 32, wsm, st>>>(P, d_stats, wtiles, wovf, ocap, cnt, dd);
+            }
             const int tgrid = std::min(grid, 16);   // overflow units only (pathological input): the long chunks are warp tiles
             if (in.codes) filter_tail_kernel<G31, true><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc, call_cnt);
             else filter_tail_kernel<G31, false><<<tgrid, G31::NT, smem, st>>>(P, d_stats, wovf, dd, desc, call_cnt);
@@ -521,10 +527,10 @@ dcn_ctx *dcn_ctx_create(int device) {
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(filter_fused_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)warp_kernel_smem()) == cudaSuccess;
-    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)warp_kernel_smem()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_kernel_smem()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_kernel_smem()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_kernel_smem()) == cudaSuccess;
+    ok = ok && cudaFuncSetAttribute(filter_warp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_kernel_smem()) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(filter_tail_kernel<G31, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(TileSmem<G31>)) == cudaSuccess;
     ok = ok && cudaFuncSetAttribute(filter_tail_kernel<G31, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

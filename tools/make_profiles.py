@@ -17,7 +17,7 @@ summ = os.path.join(P, f"{tag}_warp_ncu_summary.json")
 subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_summary.py"), rep, summ,
                        f"ncu --set full --clock-control none, one launch of filter_warp_kernel inside: {cmd}"], stdout=subprocess.DEVNULL)
 with open(os.path.join(P, f"{tag}_warp_by_line.txt"), "w") as f:
-    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), rep, "filter_warp_kernelILb0", "70"], stdout=f)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tools", "ncu_by_line.py"), rep, "filter_warp_kernelILb0ELb0", "70"], stdout=f)
 shutil.copy(launches, os.path.join(P, f"{tag}_launches_bench.csv"))
 m = json.load(open(summ))["metrics"]
 
