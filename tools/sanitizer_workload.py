@@ -10,6 +10,7 @@ idx = O.index_build([g], 31, 15, threads=4)
 gpu = d.DeaconGpu(0)
 gpu.index_upload(idx.keys(), d.IndexHeader(2, 31, 15))
 reads = H.sample_reads(g, 1500, (1, 500), 2) + [g[:6000], g[10000:13000]] + H.sample_reads(g, 300, 150, 3)
+reads += [np.frombuffer(b"A" * 900, np.uint8).copy()] * 4          # more picks than a warp pass holds: CTA tail
 for paired in (False, True):
     recs = reads[: len(reads) // 2 * 2]
     bases, off = H.concat(recs)
