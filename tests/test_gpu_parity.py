@@ -408,8 +408,9 @@ def test_device_pointer_api_with_length_promise(gpu):
     gpu.filter_batch_device(d_b2, d_o2, len(long_reads), len(b2), d_k, d_h, d_t, paired=True, deplete=True, stream=st,
                             max_unit_len=302)
     torch.cuda.synchronize()
-    with pytest.raises(DeaconCudaError):
-        gpu.filter_batch_device(d_b2, d_o2, len(long_reads), len(b2), d_k, d_h, d_t, paired=True, deplete=True, stream=st)
+    if os.environ.get("DCN_FUSED_IMPL") != "cta":     # (the CTA-tile A/B path ignores the promise: it always asks the device)
+        with pytest.raises(DeaconCudaError):
+            gpu.filter_batch_device(d_b2, d_o2, len(long_reads), len(b2), d_k, d_h, d_t, paired=True, deplete=True, stream=st)
     # the error is reported once; without the promise the same batch is classified in full
     gpu.filter_batch_device(d_b2, d_o2, len(long_reads), len(b2), d_k, d_h, d_t, paired=True, deplete=True, stream=st)
     torch.cuda.synchronize()
