@@ -86,9 +86,23 @@ struct FilterInput {
     uint32_t nl_bit0 = 0;
 };
 
+// Device arena of the two-route host-pointer pipeline (filter_pipeline_arena): the whole batch in ONE coordinate system
+// (ASCII bytes, packed codes / non-ACGT bits / newline flags, record offsets, results), so that a kernel launch can
+// cover any contiguous range of units that has arrived, however many copies brought it.
+struct ArenaState {
+    DevBuf ascii, codes, inv, nl, off, out;
+    static const int NL = 16;
+    Slot launch[NL];              // plan / longs / dedup / h_out / stream / events of one kernel launch
+    std::mutex launch_m[NL];
+    cudaStream_t copy_stream = nullptr;   // the ASCII route's copies, in order
+    cudaEvent_t ev_sub[4] = {nullptr, nullptr, nullptr, nullptr};   // pacing of the ASCII copies
+    cudaEvent_t ev_front[NL] = {};        // "ASCII copied up to here", one per launch slot
+};
+
 }  // namespace
 
 struct dcn_ctx {
+    ArenaState *arena = nullptr;
     int device = 0;
     int sm_count = 148;
     std::string err;
@@ -118,6 +132,7 @@ struct dcn_ctx {
     // host ingest (filter_pipeline): pack_threads = 0 ships everything as ASCII over PCIe
     int pack_threads = -1;   // -1: decide at first use (DCN_PACK_THREADS, or the CPUs this process may use - 4, at most 16)
     std::vector<Slot> pslot;   // the stages of the packer threads (four each), created by the threads themselves
+    std::vector<Slot> aslot;   // arena form: the packer threads' blobs (h_in), exception lists (in), copy streams and events
     float t_pack = 0;
     // A chunk is either packed by a host thread (the CPU reads 1 B/bp, PCIe carries 0.43 B/bp) or shipped as ASCII
     // (PCIe carries 1 B/bp, no CPU work); `pack_fraction` caps the share of the batch the first route may take.
@@ -387,7 +402,13 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     const size_t smem = sizeof(TileSmem<G31>);
     const uint64_t tiles_lb = n_rel / G31::BCAP + 1;
     const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * DCN_CTAS_PER_SM);
-    const int wgrid = (int)std::min<uint64_t>((n_rel / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count);
+    // Warp-tile grid: one CTA per SM for a big batch.  A small one (a chunk of the host-pointer pipeline) gets only as many
+    // CTAs as give every warp DCN_TILES_PER_WARP tiles: a warp holds claims on the next two or three tiles, so with two
+    // tiles per warp the "dynamic" schedule is a static, lopsided one, and the SMs a small kernel leaves alone run the
+    // kernels of the chunks on the other streams.
+    static const uint64_t tiles_per_warp = []() { const char *e = getenv("DCN_TILES_PER_WARP"); return e ? (uint64_t)std::max(0, atoi(e)) : 8ull; }();
+    int wgrid = (int)std::min<uint64_t>((n_rel / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count * DCN_WCTAS);
+    if (tiles_per_warp) wgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)wgrid, (n_rel / WG::TB + 1 + DCN_WARPS * tiles_per_warp - 1) / (DCN_WARPS * tiles_per_warp)));
     const uint64_t n_seg = (n_rel + DCN_WSEG - 1) / DCN_WSEG;
     const int sg = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_seg + 7) / 8, (uint64_t)ctx->sm_count * 8));   // 8 warps per CTA, one segment per warp
 
@@ -562,8 +583,8 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     ctx->gx_bases.release(); ctx->gx_off.release(); ctx->gx_rc.release(); ctx->gx_cc.release(); ctx->gx_tmp.release();
     ctx->gx_h.release(); ctx->gx_p.release(); ctx->gx_oo.release(); ctx->gx_entropy.release();
     ctx->ws_table.release(); ctx->ws_flags.release();
-    for (size_t i = 0; i < dcn_ctx::NSLOT + ctx->pslot.size(); i++) {
-        Slot &s = i < dcn_ctx::NSLOT ? ctx->slot[i] : ctx->pslot[i - dcn_ctx::NSLOT];
+    for (size_t i = 0; i < dcn_ctx::NSLOT + ctx->pslot.size() + ctx->aslot.size(); i++) {
+        Slot &s = i < dcn_ctx::NSLOT ? ctx->slot[i] : i < dcn_ctx::NSLOT + ctx->pslot.size() ? ctx->pslot[i - dcn_ctx::NSLOT] : ctx->aslot[i - dcn_ctx::NSLOT - ctx->pslot.size()];
         s.in.release(); s.out.release(); s.plan.release(); s.longs.release(); s.dedup.release();
         s.h_in.release(); s.h_out.release();
         if (s.stream) cudaStreamDestroy(s.stream);
@@ -571,6 +592,21 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
+    if (ArenaState *ar = ctx->arena) {
+        ar->ascii.release(); ar->codes.release(); ar->inv.release(); ar->nl.release(); ar->off.release(); ar->out.release();
+        for (int i = 0; i < ArenaState::NL; i++) {
+            Slot &s = ar->launch[i];
+            s.plan.release(); s.longs.release(); s.dedup.release(); s.h_out.release();
+            if (s.stream) cudaStreamDestroy(s.stream);
+            if (s.ev_start) cudaEventDestroy(s.ev_start);
+            if (s.ev_kernel) cudaEventDestroy(s.ev_kernel);
+            if (s.ev_done) cudaEventDestroy(s.ev_done);
+            if (ar->ev_front[i]) cudaEventDestroy(ar->ev_front[i]);
+        }
+        for (int i = 0; i < 4; i++) if (ar->ev_sub[i]) cudaEventDestroy(ar->ev_sub[i]);
+        if (ar->copy_stream) cudaStreamDestroy(ar->copy_stream);
+        delete ar;
     }
     for (int i = 0; i < dcn_ctx::KEV; i++) {
         if (ctx->kev0[i]) cudaEventDestroy(ctx->kev0[i]);
@@ -806,6 +842,499 @@ static ChunkStats chunk_stats(const uint64_t *off0, uint32_t nu, uint32_t rpu) {
 
 }  // namespace
 
+// ---------------------------------------------------------------------------- two-route pipeline, arena form
+// What the chunk pipeline below could not do: the GPU side of a 16 MB chunk is a kernel of two or three tiles per
+// warp, which runs at a third of the big-launch rate (every warp of the SM is in the same phase, so the probe
+// phase and the ALU phases do not overlap, and three waves are paid for 2.3), and a 1.5 Gbp batch was 120 such
+// launches: 16 ms of SM time for 5.4 ms of work -- the limiter of the whole call (tools/e2e_timeline.py).  Here the
+// copies keep their granularity (the link and the packers are fed as before) but land in ONE device arena that
+// mirrors the batch, and kernels are launched over whatever contiguous range of units has arrived: 32 MB runs of the
+// ASCII front, 64 MB or more of the packed back.  A launch waits for its copies through events, never on the host.
+//   ASCII route   the calling thread copies atoms [head, ..) in order on one stream, two copies ahead of the link;
+//   packed route  packer threads claim atoms from the back, pack [p0, p1) -- the 64-byte-aligned cuts just below
+//                 the claim's first unit and below its upper neighbour's first unit, so the claims' words tile the
+//                 arena exactly and only the batch's last claim is padded -- and copy codes, newline flags and the
+//                 exception list (or the dense mask) to their places; the thread that completes a run of
+//                 DCN_LAUNCH_ATOMS copied atoms below the last launch launches it.
+// Atoms start at multiples of 32 units, so every claim owns whole words of the newline-flag array.
+static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, int paired,
+                                 uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
+                                 uint8_t *keep, uint32_t *hits, uint32_t *total,
+                                 int n_packers, bool ascii_route, double pack_share, uint64_t chunk_bases) {
+    const uint32_t rpu = paired ? 2u : 1u;
+    const uint32_t n_units = n_rec / rpu;
+    const uint64_t A0 = rec_off[0] & ~63ull, B1 = rec_off[(uint64_t)n_units * rpu];
+    const uint64_t nb_total = B1 - A0;
+    static const int trace_level = []() { const char *e = getenv("DCN_HOST_TRACE"); return e ? atoi(e) : 0; }();
+    static const int launch_atoms = []() { const char *e = getenv("DCN_LAUNCH_ATOMS"); return e ? std::max(1, atoi(e)) : 16; }();
+    static const int launch_atoms_ascii = []() { const char *e = getenv("DCN_LAUNCH_ATOMS_ASCII"); return e ? std::max(1, atoi(e)) : 8; }();
+    static const int ascii_atoms = []() { const char *e = getenv("DCN_ASCII_ATOMS"); return e ? std::max(1, atoi(e)) : 2; }();
+    static const bool sparse_wire = []() { const char *e = getenv("DCN_SPARSE_MASK"); return !e || atoi(e) != 0; }();
+    static const int PST = []() { const char *e = getenv("DCN_PACKER_STAGES"); return e ? std::max(1, std::min(8, atoi(e))) : 3; }();
+    static const int ascii_ahead = []() { const char *e = getenv("DCN_ASCII_AHEAD"); return e ? std::max(1, std::min(4, atoi(e))) : 2; }();
+    auto now_ms = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_call0 = now_ms();
+
+    // ---- atoms: ~4 MB of whole units, starting at multiples of 32 units
+    const uint64_t atom_bases = std::max<uint64_t>(chunk_bases / 8, 1);
+    std::vector<uint32_t> atom_u;
+    atom_u.push_back(0);
+    for (uint32_t u0 = 0; u0 < n_units;) {
+        const uint64_t b0 = rec_off[(uint64_t)u0 * rpu];
+        uint32_t lo = u0 + 1, hi = n_units;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo + 1) / 2;
+            if (rec_off[(uint64_t)mid * rpu] - b0 <= atom_bases) lo = mid; else hi = mid - 1;
+        }
+        if (lo < n_units) {
+            lo = std::max(u0 + 32u, lo & ~31u);
+            if (lo > n_units || n_units - lo < 32u) lo = n_units;
+        }
+        atom_u.push_back(lo);
+        u0 = lo;
+    }
+    const int n_atoms = (int)atom_u.size() - 1;
+    const int pack_budget = (int)std::min<double>(n_atoms, pack_share * n_atoms + 0.5);
+    n_packers = std::min(n_packers, pack_budget);
+    if (n_packers <= 0) return 1;   // not handled: the caller falls back to the chunk pipeline
+    const int packer_grab_max = 4;
+
+    // ---- the arena
+    if (!ctx->arena) ctx->arena = new ArenaState();
+    ArenaState &ar = *ctx->arena;
+    const uint64_t n_words_total = 2 * ((nb_total + 64 + 31) / 32);
+    if ((ascii_route && ar.ascii.ensure(nb_total + 256) != cudaSuccess) || ar.codes.ensure(n_words_total * 4 + 64) != cudaSuccess ||
+        ar.inv.ensure(n_words_total * 2 + 64) != cudaSuccess || ar.nl.ensure(((size_t)n_rec / 32 + 4) * 4) != cudaSuccess ||
+        ar.off.ensure(((size_t)n_rec + 1) * 8) != cudaSuccess || ar.out.ensure((size_t)n_units * 9 + 64) != cudaSuccess)
+        return ctx->fail(DCN_ERR_NOMEM, "arena allocation failed", cudaGetLastError());
+    if (!ar.copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ar.copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&ar.ev_sub[i], cudaEventDisableTiming));
+        for (int i = 0; i < ArenaState::NL; i++) {
+            Slot &s = ar.launch[i];
+            CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreate(&s.ev_start)); CK(cudaEventCreate(&s.ev_kernel)); CK(cudaEventCreate(&s.ev_done));
+            CK(cudaEventCreateWithFlags(&ar.ev_front[i], cudaEventDisableTiming));
+        }
+    }
+    // launch slots: plan buffers for the largest range a launch takes (a launch that needs more grows its buffer: a
+    // cudaFree in the middle of a call stalls everything, so it must not happen in the steady state)
+    static const uint64_t range_cap = []() { const char *e = getenv("DCN_LAUNCH_CAP_MB"); return (e ? strtoull(e, nullptr, 10) : 160ull) << 20; }();
+    {
+        const uint64_t cap_rel = std::min<uint64_t>(nb_total, range_cap + (uint64_t)atom_bases) + 4096;
+        const uint32_t cap_rec = (uint32_t)std::min<uint64_t>(n_rec, (uint64_t)((double)n_rec * 2.0 * (double)cap_rel / (double)std::max<uint64_t>(nb_total, 1)) + 64);
+        const size_t pbytes = 128 + (size_t)wplan_tile_cap(cap_rel, cap_rec) * sizeof(WTile) + (size_t)wplan_ovf_cap(cap_rel) * 4;
+        for (int i = 0; i < ArenaState::NL; i++)
+            if (ar.launch[i].plan.ensure(pbytes) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "plan allocation failed", cudaGetLastError());
+    }
+    uint8_t *const d_ascii = ar.ascii.as<uint8_t>();
+    uint32_t *const d_codes = ar.codes.as<uint32_t>();
+    uint16_t *const d_inv = ar.inv.as<uint16_t>();
+    uint32_t *const d_nl = ar.nl.as<uint32_t>();
+    uint64_t *const d_off = ar.off.as<uint64_t>();
+    uint32_t *const d_hits = ar.out.as<uint32_t>();
+    uint32_t *const d_total = d_hits + n_units;
+    uint8_t *const d_keep = reinterpret_cast<uint8_t *>(d_total + n_units);
+
+    const bool out_pinned = [&] {
+        const void *outs[3] = {keep, hits, total};
+        for (const void *o : outs) {
+            cudaPointerAttributes pa;
+            const bool pinned = cudaPointerGetAttributes(&pa, o) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+            cudaGetLastError();
+            if (!pinned) return false;
+        }
+        return true;
+    }();
+
+    ctx->t_h2d = ctx->t_kernel = ctx->t_d2h = ctx->t_pack = 0;
+    ctx->bytes_h2d = ctx->bytes_d2h = 0;
+    cudaEvent_t ev_call = nullptr;
+    if (trace_level >= 2) {
+        cudaEventCreate(&ev_call);
+        cudaEventRecord(ev_call, ar.copy_stream);
+    }
+
+    // ---- shared state
+    std::mutex m;
+    int head = 0, tail = n_atoms, taken_by_packers = 0, in_flight = 0;
+    int back_launched = n_atoms;          // packed atoms [back_launched, n_atoms) are launched
+    int first_rc = DCN_OK;
+    unsigned launch_seq = 0;
+    std::vector<uint8_t> astate((size_t)n_atoms, 0);            // 0 unclaimed (or ASCII), 1 being packed, 2 copied
+    std::vector<cudaEvent_t> aev((size_t)n_atoms, nullptr);     // the event after the atom's claim was copied
+    std::vector<int> claim_end((size_t)n_atoms, 0);             // at a claim's first atom: one past its last
+    std::vector<BatchStats> cstat((size_t)n_atoms);             // at a claim's first atom: unit statistics
+    std::atomic<uint64_t> n_h2d{0}, n_d2h{0}, n_launch_p{0}, n_launch_a{0}, n_packed_claims{0}, n_ascii_copies{0}, n_uniform{0}, packed_bases{0};
+    double kernel_ms_sum = 0, d2h_ms_sum = 0;   // under m
+    double pack_busy_ms = 0, pack_wait_ms = 0;
+    auto set_rc = [&](int rc) { std::lock_guard<std::mutex> g(m); if (rc && !first_rc) first_rc = rc; };
+
+    auto retire = [&](Slot &s) -> int {   // (the slot's mutex is held)
+        if (!s.busy) return DCN_OK;
+        CK(cudaEventSynchronize(s.ev_done));
+        const uint32_t nu = s.u1 - s.u0;
+        if (!out_pinned) {
+            const uint8_t *o = s.h_out.as<uint8_t>();
+            memcpy(hits + s.u0, o, (size_t)nu * 4);
+            memcpy(total + s.u0, o + (size_t)nu * 4, (size_t)nu * 4);
+            memcpy(keep + s.u0, o + (size_t)nu * 8, nu);
+        }
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, s.ev_start, s.ev_kernel);
+        cudaEventElapsedTime(&b, s.ev_kernel, s.ev_done);
+        { std::lock_guard<std::mutex> g(m); kernel_ms_sum += a; d2h_ms_sum += b; }
+        if (trace_level >= 2 && ev_call) {   // device timeline of the launch, ms since the call's first enqueue
+            float t0 = 0;
+            cudaEventElapsedTime(&t0, ev_call, s.ev_start);
+            fprintf(stderr, "[dcn launch done] units %u..%u %s: kernels %.3f .. %.3f, results back %.3f\n", s.u0, s.u1, s.packed ? "packed" : "ascii", t0, t0 + a, t0 + a + b);
+        }
+        s.busy = false;
+        return DCN_OK;
+    };
+
+    // one launch over atoms [a_lo, a_hi) of one representation, after `waits`
+    auto launch_range = [&](unsigned seq, int a_lo, int a_hi, bool packed, const BatchStats &hs, const std::vector<cudaEvent_t> &waits) -> int {
+        const int idx = (int)(seq % ArenaState::NL);
+        std::lock_guard<std::mutex> lg(ar.launch_m[idx]);
+        Slot &s = ar.launch[idx];
+        int rc = retire(s);
+        if (rc) return rc;
+        const uint32_t u_lo = atom_u[(size_t)a_lo], u_hi = atom_u[(size_t)a_hi], nu = u_hi - u_lo, nr = nu * rpu;
+        if (nu == 0) return DCN_OK;
+        const uint64_t r0 = (uint64_t)u_lo * rpu;
+        const uint64_t base0 = rec_off[r0] & ~63ull, n_abs = rec_off[(uint64_t)u_hi * rpu];
+        if (!out_pinned && s.h_out.ensure((size_t)nu * 9) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
+        for (cudaEvent_t e : waits) if (e) CK(cudaStreamWaitEvent(s.stream, e, 0));
+        FilterInput in;
+        if (packed) {
+            in.codes = d_codes + (base0 - A0) / 16;
+            in.inv = d_inv + (base0 - A0) / 16;
+            in.nl = d_nl + r0 / 32;
+            in.nl_bit0 = (uint32_t)(r0 % 32);
+        } else {
+            in.bases = d_ascii + (base0 - A0);
+        }
+        CK(cudaEventRecord(s.ev_start, s.stream));
+        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, base0, n_abs, d_off + r0, nr, paired, prefix_len, abs_thr, rel_thr, deplete,
+                            d_keep + u_lo, d_hits + u_lo, d_total + u_lo, s.stream, &hs, false);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.ev_kernel, s.stream));
+        if (out_pinned) {
+            CK(cudaMemcpyAsync(hits + u_lo, d_hits + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(total + u_lo, d_total + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(keep + u_lo, d_keep + u_lo, nu, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            uint8_t *o = s.h_out.as<uint8_t>();
+            CK(cudaMemcpyAsync(o, d_hits + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(o + (size_t)nu * 4, d_total + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(o + (size_t)nu * 8, d_keep + u_lo, nu, cudaMemcpyDeviceToHost, s.stream));
+        }
+        n_d2h += (uint64_t)nu * 9;
+        CK(cudaEventRecord(s.ev_done, s.stream));
+        s.busy = true; s.u0 = u_lo; s.u1 = u_hi; s.packed = packed;
+        (packed ? n_launch_p : n_launch_a)++;
+        if (trace_level >= 2)
+            fprintf(stderr, "[dcn launch] %.2f ms: %s atoms %d..%d units %u..%u (%.1f MB)\n", now_ms() - t_call0, packed ? "packed" : "ascii", a_lo, a_hi,
+                    u_lo, u_hi, (n_abs - base0) / 1e6);
+        return DCN_OK;
+    };
+
+    // no launch of this call is still running (racy reads of `busy` are harmless: the answer only tunes the batching)
+    auto gpu_idle = [&]() -> bool {
+        for (int i = 0; i < ArenaState::NL; i++)
+            if (ar.launch[i].busy && cudaEventQuery(ar.launch[i].ev_done) == cudaErrorNotReady) return false;
+        cudaGetLastError();
+        return true;
+    };
+    static const int launch_atoms_idle = []() { const char *e = getenv("DCN_LAUNCH_ATOMS_IDLE"); return e ? std::max(1, atoi(e)) : 4; }();
+
+    // (m held) the copied run of packed atoms just below the last launch; taken when it is long enough (DCN_LAUNCH_ATOMS; a
+    // few atoms are enough while the GPU has nothing to do: batching only pays when launches queue up), or when it is all
+    // there will be
+    struct Range { int a_lo = 0, a_hi = 0; unsigned seq = 0; BatchStats hs; std::vector<cudaEvent_t> waits; };
+    auto take_packed_range = [&](bool final_call, Range &r) -> bool {
+        int a = back_launched;
+        while (a > 0 && astate[(size_t)a - 1] == 2) a--;
+        const int pending = back_launched - a;
+        const bool all_in = final_call || (head >= tail && in_flight == 0) || (taken_by_packers >= pack_budget && in_flight == 0);
+        if (pending <= 0) return false;
+        if (pending < launch_atoms && !(all_in && (a == 0 || astate[(size_t)a - 1] == 0)) && !(pending >= launch_atoms_idle && gpu_idle())) return false;
+        // at most range_cap bases per launch (whole claims, from the top): the launch slots' plan buffers are sized for that
+        const uint64_t top = rec_off[(uint64_t)atom_u[(size_t)back_launched] * rpu];
+        int lowest = -1;
+        for (int i = a; i < back_launched; i = claim_end[(size_t)i])
+            if (lowest < 0 && top - rec_off[(uint64_t)atom_u[(size_t)i] * rpu] <= range_cap) lowest = i;
+        if (lowest < 0) {   // the top claim alone is larger (a record longer than the cap): it goes by itself
+            for (int i = a; i < back_launched; i = claim_end[(size_t)i]) lowest = i;
+        }
+        a = lowest;
+        r.a_lo = a; r.a_hi = back_launched; r.seq = launch_seq++;
+        memset(&r.hs, 0, sizeof(r.hs));
+        r.waits.clear();
+        for (int i = a; i < back_launched; i = claim_end[(size_t)i]) {
+            const BatchStats &c = cstat[(size_t)i];
+            r.hs.n_long += c.n_long; r.hs.long_bases += c.long_bases; r.hs.max_short = std::max(r.hs.max_short, c.max_short);
+            if (r.waits.empty() || r.waits.back() != aev[(size_t)i]) r.waits.push_back(aev[(size_t)i]);
+        }
+        if (back_launched < n_atoms) r.waits.push_back(aev[(size_t)back_launched]);   // the upper neighbour packed the last bases of this run's last unit
+        back_launched = a;
+        return true;
+    };
+
+    if ((int)ctx->aslot.size() < 8 * n_packers) ctx->aslot.resize((size_t)8 * n_packers);   // (8: room for any DCN_PACKER_STAGES)
+
+    auto packer = [&](int t) {
+        double pack_ms = 0, wait_ms = 0, ship_ms = 0, t_begin = now_ms() - t_call0, t_first = 0, t_last = 0;
+        uint64_t my_bases = 0;
+        std::vector<uint64_t> bad32;
+        std::vector<uint32_t> bad_mask;
+        auto body = [&]() -> int {
+            CK(cudaSetDevice(ctx->device));
+            for (int i = 0; i < PST; i++) {
+                Slot &s = ctx->aslot[(size_t)(8 * t + i)];
+                if (!s.stream) CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+                if (!s.ev_h2d) CK(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+            }
+            bool first_claim = true;
+            for (int flip = 0;; flip = (flip + 1) % PST) {
+                int a_lo, a_hi;
+                {
+                    std::lock_guard<std::mutex> g(m);
+                    if (first_rc || tail <= head || taken_by_packers >= pack_budget) break;
+                    int grab = std::max(1, std::min<int>(packer_grab_max, (tail - head) / n_packers));
+                    // the threads pack at one pace: first claims of 1, 2, 3, 4 atoms take them out of step, so their copies
+                    // reach the link spread out instead of twelve at a time
+                    if (first_claim) { grab = std::min(grab, 1 + t % packer_grab_max); first_claim = false; }
+                    grab = std::min(grab, std::min(tail - head, pack_budget - taken_by_packers));
+                    a_hi = tail; a_lo = tail -= grab; taken_by_packers += grab; in_flight++;
+                    for (int i = a_lo; i < a_hi; i++) astate[(size_t)i] = 1;
+                }
+                const uint32_t u0 = atom_u[(size_t)a_lo], u1 = atom_u[(size_t)a_hi], nu = u1 - u0, nr = nu * rpu;
+                const uint64_t r0 = (uint64_t)u0 * rpu;
+                const uint64_t *off0 = rec_off + r0;
+                const uint64_t p0 = off0[0] & ~63ull;
+                const uint64_t p1 = a_hi == n_atoms ? B1 : (rec_off[(uint64_t)u1 * rpu] & ~63ull);   // (multiple of 32 from p0 unless it is the batch's end)
+                const uint64_t nb = p1 - p0;
+                const size_t n_words = 2 * (size_t)((nb + 31) / 32);
+                const size_t nl_words = ((size_t)nr + 31) / 32;
+                const uint32_t exc_cap = (uint32_t)std::min<uint64_t>(n_words / 64 + 4, 0x7FFFFFFFu);
+                // blob: codes | newline flags | exception list or dense mask | offsets
+                const size_t o_nl = align_up(n_words * 4, 8), o_x = o_nl + align_up(nl_words * 4 + 4, 8);
+                const size_t o_off = o_x + std::max<size_t>((size_t)exc_cap * 8, align_up(n_words * 2, 8));
+                const size_t blob = o_off + ((size_t)nr + 1) * 8;
+                Slot &s = ctx->aslot[(size_t)(8 * t + flip)];
+                if (s.busy) {   // the blob's previous copies have left the host
+                    const double w0 = now_ms();
+                    CK(cudaEventSynchronize(s.ev_h2d));
+                    wait_ms += now_ms() - w0;
+                    s.busy = false;
+                }
+                const double t0 = now_ms();
+                if (s.h_in.ensure(std::max(blob, (size_t)(packer_grab_max * atom_bases) / 2)) != cudaSuccess || s.in.ensure((size_t)exc_cap * 8 + 64) != cudaSuccess)
+                    return ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed", cudaGetLastError());
+                uint8_t *hin = s.h_in.as<uint8_t>();
+                const ChunkStats cs = chunk_stats(off0, nu, rpu);
+                uint32_t *h_codes = reinterpret_cast<uint32_t *>(hin);
+                uint32_t *h_nl = reinterpret_cast<uint32_t *>(hin + o_nl);
+                uint16_t *h_inv = reinterpret_cast<uint16_t *>(hin + o_x);
+                int64_t n_exc = -1;
+                if (sparse_wire) pack_records(bases, p0, nb, off0, nr, ctx->k, prefix_len, h_codes, nullptr, h_nl, bad32, &bad_mask);
+                else pack_records(bases, p0, nb, off0, nr, ctx->k, prefix_len, h_codes, h_inv, h_nl, bad32);
+                // records that end beyond p1 (the last < 64 bases of the claim's last unit are packed by the upper neighbour):
+                // their newline flags are looked at directly (src/filter_common.rs:217-229)
+                for (uint32_t q = nr; q-- > 0;) {
+                    const uint64_t len = off0[q + 1] - off0[q];
+                    const uint64_t e = off0[q] + ((prefix_len > 0 && len > prefix_len) ? prefix_len : len);
+                    if (off0[q + 1] <= p1) break;          // everything from here down lies inside [p0, p1)
+                    if (e <= p1 || len < (uint64_t)ctx->k) continue;
+                    if (bases[e - 1] == (uint8_t)'\n') h_nl[q / 32] |= 1u << (q % 32);
+                }
+                if (sparse_wire) {
+                    if (bad32.size() <= exc_cap) {
+                        n_exc = (int64_t)bad32.size();
+                        uint32_t *ex = reinterpret_cast<uint32_t *>(hin + o_x);
+                        for (size_t i = 0; i < bad32.size(); i++) { ex[2 * i] = (uint32_t)bad32[i]; ex[2 * i + 1] = bad_mask[i]; }
+                    } else {   // N-rich claim: the dense mask is smaller
+                        memset(h_inv, 0, n_words * 2);
+                        for (size_t i = 0; i < bad32.size(); i++) memcpy(h_inv + 2 * bad32[i], &bad_mask[i], 4);
+                    }
+                }
+                if (!cs.uniform) memcpy(hin + o_off, off0, ((size_t)nr + 1) * 8);
+                const double t1 = now_ms();
+                pack_ms += t1 - t0;
+                my_bases += nb;
+                // ---- copies to the claim's places in the arena
+                uint64_t moved = 0;
+                if (n_words) {
+                    CK(cudaMemcpyAsync(d_codes + (p0 - A0) / 16, h_codes, n_words * 4, cudaMemcpyHostToDevice, s.stream));
+                    moved += n_words * 4;
+                    uint16_t *inv_dst = d_inv + (p0 - A0) / 16;
+                    if (n_exc >= 0) {
+                        CK(cudaMemsetAsync(inv_dst, 0, n_words * 2, s.stream));
+                        if (n_exc) {
+                            CK(cudaMemcpyAsync(s.in.p, hin + o_x, (size_t)n_exc * 8, cudaMemcpyHostToDevice, s.stream));
+                            moved += (uint64_t)n_exc * 8;
+                            inv_scatter_kernel<<<grid_for(ctx, (uint64_t)n_exc, 128), 128, 0, s.stream>>>(
+                                reinterpret_cast<uint32_t *>(inv_dst), reinterpret_cast<const uint2 *>(s.in.p), (uint32_t)n_exc);
+                            ctx->launches += 1;
+                        }
+                    } else {
+                        CK(cudaMemcpyAsync(inv_dst, h_inv, n_words * 2, cudaMemcpyHostToDevice, s.stream));
+                        moved += n_words * 2;
+                    }
+                }
+                if (nl_words) {
+                    CK(cudaMemcpyAsync(d_nl + r0 / 32, h_nl, nl_words * 4, cudaMemcpyHostToDevice, s.stream));
+                    moved += nl_words * 4;
+                }
+                if (cs.uniform) {
+                    uniform_offsets_kernel<<<grid_for(ctx, (uint64_t)nr + 1, 256), 256, 0, s.stream>>>(d_off + r0, nr + 1, off0[0], cs.rec_len0);
+                    ctx->launches += 1;
+                    n_uniform++;
+                } else {
+                    CK(cudaMemcpyAsync(d_off + r0, hin + o_off, ((size_t)nr + 1) * 8, cudaMemcpyHostToDevice, s.stream));
+                    moved += ((uint64_t)nr + 1) * 8;
+                }
+                CK(cudaEventRecord(s.ev_h2d, s.stream));
+                CK(cudaGetLastError());
+                s.busy = true;
+                n_h2d += moved;
+                n_packed_claims++;
+                Range r;
+                bool go;
+                {
+                    std::lock_guard<std::mutex> g(m);
+                    for (int i = a_lo; i < a_hi; i++) { astate[(size_t)i] = 2; aev[(size_t)i] = s.ev_h2d; }
+                    claim_end[(size_t)a_lo] = a_hi; cstat[(size_t)a_lo] = cs.st;
+                    in_flight--;
+                    go = take_packed_range(false, r);
+                }
+                if (go) { const int rc = launch_range(r.seq, r.a_lo, r.a_hi, true, r.hs, r.waits); if (rc) return rc; }
+                t_last = now_ms() - t_call0;
+                ship_ms += t_last - (t1 - t_call0);
+                if (t_first == 0) t_first = t_last;
+            }
+            return DCN_OK;
+        };
+        const int rc = body();
+        if (rc) set_rc(rc);
+        packed_bases += my_bases;
+        std::lock_guard<std::mutex> g(m);
+        pack_busy_ms += pack_ms; pack_wait_ms += wait_ms;
+        if (trace_level >= 1)
+            fprintf(stderr, "[dcn packer %d] begin %.2f first copy %.2f last %.2f end %.2f ms; packing %.2f enqueueing %.2f waiting %.2f ms; %.1f MB\n",
+                    t, t_begin, t_first, t_last, now_ms() - t_call0, pack_ms, ship_ms, wait_ms, my_bases / 1e6);
+    };
+    std::vector<std::thread> packers;
+    for (int t = 0; t < n_packers; t++) {
+        try { packers.emplace_back(packer, t); } catch (const std::exception &) { break; }
+    }
+    if (packers.empty()) ascii_route = true;
+
+    // ---- the calling thread: the ASCII front
+    int rc = DCN_OK;
+    double main_wait_ms = 0;
+    {
+        int k_sub = 0, launched_front = 0, copied_front = 0;
+        BatchStats pend;
+        memset(&pend, 0, sizeof(pend));
+        auto launch_front = [&]() -> int {
+            unsigned seq;
+            { std::lock_guard<std::mutex> g(m); seq = launch_seq++; }
+            const int idx = (int)(seq % ArenaState::NL);
+            CK(cudaEventRecord(ar.ev_front[idx], ar.copy_stream));
+            std::vector<cudaEvent_t> waits{ar.ev_front[idx]};
+            const int r = launch_range(seq, launched_front, copied_front, false, pend, waits);
+            launched_front = copied_front;
+            memset(&pend, 0, sizeof(pend));
+            return r;
+        };
+        while (ascii_route && rc == DCN_OK) {
+            if (k_sub >= ascii_ahead) {   // no more than a few copies ahead of the link: the packed claims' copies queue on the same engine
+                const double w0 = now_ms();
+                const cudaError_t e = cudaEventSynchronize(ar.ev_sub[(k_sub - ascii_ahead) % 4]);
+                if (e != cudaSuccess) { rc = ctx->fail(DCN_ERR_CUDA, "cudaEventSynchronize(ev_sub)", e); break; }
+                main_wait_ms += now_ms() - w0;
+            }
+            int a_lo, a_hi;
+            {
+                std::lock_guard<std::mutex> g(m);
+                if (first_rc || head >= tail) break;
+                const bool packers_done = taken_by_packers >= pack_budget;
+                const int grab = packers_done ? std::min(8, tail - head) : std::max(1, std::min<int>(ascii_atoms, (tail - head) / 6));
+                a_lo = head;
+                a_hi = head = std::min<int>(tail, head + grab);
+            }
+            const uint32_t u0 = atom_u[(size_t)a_lo], u1 = atom_u[(size_t)a_hi], nu = u1 - u0, nr = nu * rpu;
+            const uint64_t r0 = (uint64_t)u0 * rpu;
+            const uint64_t x0 = a_lo == 0 ? A0 : rec_off[r0], x1 = rec_off[(uint64_t)u1 * rpu];
+            const ChunkStats cs = chunk_stats(rec_off + r0, nu, rpu);
+            auto enq = [&]() -> int {
+                if (x1 > x0) CK(cudaMemcpyAsync(d_ascii + (x0 - A0), bases + x0, (size_t)(x1 - x0), cudaMemcpyHostToDevice, ar.copy_stream));
+                n_h2d += x1 - x0;
+                if (cs.uniform) {
+                    uniform_offsets_kernel<<<grid_for(ctx, (uint64_t)nr + 1, 256), 256, 0, ar.copy_stream>>>(d_off + r0, nr + 1, rec_off[r0], cs.rec_len0);
+                    ctx->launches += 1;
+                    n_uniform++;
+                } else {
+                    CK(cudaMemcpyAsync(d_off + r0, rec_off + r0, ((size_t)nr + 1) * 8, cudaMemcpyHostToDevice, ar.copy_stream));
+                    n_h2d += ((uint64_t)nr + 1) * 8;
+                }
+                CK(cudaEventRecord(ar.ev_sub[k_sub % 4], ar.copy_stream));
+                return DCN_OK;
+            };
+            if ((rc = enq())) break;
+            k_sub++;
+            n_ascii_copies++;
+            pend.n_long += cs.st.n_long; pend.long_bases += cs.st.long_bases; pend.max_short = std::max(pend.max_short, cs.st.max_short);
+            copied_front = a_hi;
+            if (copied_front - launched_front >= launch_atoms_ascii || (copied_front - launched_front >= ascii_atoms && gpu_idle())) rc = launch_front();
+        }
+        if (rc == DCN_OK && copied_front > launched_front) rc = launch_front();
+    }
+    if (rc) set_rc(rc);
+    for (auto &t : packers) t.join();
+    {   // whatever the packers copied and nobody launched (their budget ran out before the fronts met, or an error stopped them)
+        Range r;
+        bool go;
+        { std::lock_guard<std::mutex> g(m); go = !first_rc && take_packed_range(true, r); }
+        while (go) {
+            const int r2 = launch_range(r.seq, r.a_lo, r.a_hi, true, r.hs, r.waits);
+            if (r2) { set_rc(r2); break; }
+            std::lock_guard<std::mutex> g(m);
+            go = take_packed_range(true, r);
+        }
+    }
+    for (int i = 0; i < ArenaState::NL; i++) {
+        std::lock_guard<std::mutex> lg(ar.launch_m[i]);
+        const int r2 = retire(ar.launch[i]);
+        if (r2) set_rc(r2);
+    }
+    rc = first_rc;
+    if (rc) {
+        cudaDeviceSynchronize();
+        for (int i = 0; i < ArenaState::NL; i++) ar.launch[i].busy = false;
+    }
+    for (auto &sl : ctx->aslot) sl.busy = false;   // every copy was waited for by a launch that has been retired
+    ctx->t_kernel = (float)kernel_ms_sum; ctx->t_d2h = (float)d2h_ms_sum;
+    ctx->bytes_h2d = n_h2d; ctx->bytes_d2h = n_d2h;
+    ctx->n_packed_chunks += n_packed_claims; ctx->n_ascii_chunks += n_ascii_copies; ctx->n_uniform_chunks += n_uniform;
+    if (ev_call) cudaEventDestroy(ev_call);
+    const double call_ms = now_ms() - t_call0;
+    if (trace_level >= 1)
+        fprintf(stderr, "[dcn host] arena: %d atoms, %d packers: %llu packed claims / %llu ascii copies, %llu + %llu launches; call %.2f ms; "
+                "front waited %.2f ms for the link; packers: packing %.2f ms, waiting for a blob %.2f ms (sums over threads); h2d %.1f MB\n",
+                n_atoms, n_packers, (unsigned long long)n_packed_claims.load(), (unsigned long long)n_ascii_copies.load(),
+                (unsigned long long)n_launch_p.load(), (unsigned long long)n_launch_a.load(), call_ms, main_wait_ms, pack_busy_ms, pack_wait_ms,
+                n_h2d.load() / 1e6);
+    if (packed_bases) {
+        ctx->t_pack = (float)call_ms;
+        if (pack_busy_ms > 0) ctx->pack_gbps = (double)packed_bases / 1e6 / pack_busy_ms * std::max(1, n_packers);
+    }
+    return rc;
+}
+
 static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec_off, uint32_t n_rec, int paired,
                            uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete,
                            uint8_t *keep, uint32_t *hits, uint32_t *total) {
@@ -843,6 +1372,16 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         else if (!pinned) { pack_share = 1.0; ascii_route = false; }
         else pack_share = total_bases >= 6 * chunk_bases ? 1.0 : 0.0;   // dynamic split; not worth the threads for a few chunks
         if (pack_share > 0) n_packers = pack_threads_of(ctx);
+    }
+
+    // ---- the two routes together: the arena form (kernels over whatever has arrived); the chunk form below serves the
+    // single-route cases (no packers, caller-packed input) and batches beyond the arena's size limit
+    static const bool arena_on = []() { const char *e = getenv("DCN_PIPELINE"); return !e || strcmp(e, "chunks") != 0; }();
+    static const uint64_t arena_max = []() { const char *e = getenv("DCN_ARENA_MAX_MB"); return (e ? strtoull(e, nullptr, 10) : 8192ull) << 20; }();
+    if (arena_on && n_packers > 0 && total_bases <= arena_max) {
+        const int rc = filter_pipeline_arena(ctx, bases, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr, deplete, keep, hits, total,
+                                             n_packers, ascii_route, pack_share, chunk_bases);
+        if (rc <= 0) return rc;   // (1: not handled)
     }
 
     // ---- plan: the batch is cut into unit-aligned ATOMS of 4 MB.  The ASCII route ships up to `atoms_per_chunk`
@@ -898,7 +1437,8 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         sparse_layout(c);
         return c;
     };
-    const int packer_grab_max = std::max<int>(1, (int)atoms_per_chunk / 2);
+    static const int env_grab = []() { const char *e = getenv("DCN_PACKER_GRAB"); return e ? std::max(1, atoi(e)) : 0; }();
+    const int packer_grab_max = env_grab ? env_grab : std::max<int>(1, (int)atoms_per_chunk / 2);
     const ChunkPlan big_ascii = layout_for(chunk_bases + 4096), big_packed = layout_for((uint64_t)packer_grab_max * atom_bases + 4096);
     const int pack_budget = (int)std::min<double>(n_atoms, pack_share * n_atoms + 0.5);   // atoms the packers may take
     n_packers = std::min(n_packers, pack_budget);
@@ -931,6 +1471,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         uint64_t h2d = 0, d2h = 0, n_packed = 0, n_ascii = 0, n_uniform = 0, packed_bases = 0;
         float t_h2d = 0, t_kernel = 0, t_d2h = 0;
         double wait_ms = 0, pack_ms = 0;   // waiting for a stage to come back; packing
+        double ship_ms = 0, t_begin = 0, t_first_ship = 0, t_last_ship = 0, t_end = 0;   // host-side trace (ms since the call began)
     };
     auto retire = [&](Slot &s, Acc &acc) -> int {  // wait for a stage and scatter its results (disjoint unit ranges per stage)
         if (!s.busy) return DCN_OK;
@@ -1080,7 +1621,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
     };
     // stages per packer thread: enough that a thread never waits for its own earlier atoms, whose copies queue behind
     // the ASCII chunks already handed to the copy engine (2 stages: the threads idled a quarter of the call)
-    constexpr int PST = 4;
+    static const int PST = []() { const char *e = getenv("DCN_PACKER_STAGES"); return e ? std::max(1, std::min(8, atoi(e))) : 4; }();
     if ((int)ctx->pslot.size() < PST * n_packers) ctx->pslot.resize((size_t)PST * n_packers);
 
     // A packer thread is a small pipeline of its own: claim atoms from the back of the batch (a few at a time while
@@ -1095,6 +1636,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         std::vector<uint32_t> bad_mask;
         static const bool sparse_wire = []() { const char *e = getenv("DCN_SPARSE_MASK"); return !e || atoi(e) != 0; }();
         auto body = [&]() -> int {
+            acc.t_begin = now_ms() - t_call0;
             CK(cudaSetDevice(ctx->device));
             for (int i = 0; i < PST; i++) {
                 Slot &s = ctx->pslot[(size_t)(PST * t + i)];
@@ -1155,10 +1697,15 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
                     // codes, non-ACGT bits and newline flags in one pass over the atom (dcn_host_pack.h)
                     pack_records(bases, c.a0, c.nb, off0, c.nr, ctx->k, prefix_len, h_codes, h_inv, h_nl, bad32);
                 }
-                acc.pack_ms += now_ms() - t0;
+                const double t1 = now_ms();
+                acc.pack_ms += t1 - t0;
                 acc.packed_bases += c.nb;
                 if ((r = ship(s, c, 2, cs, acc, false, n_exc))) return r;
+                acc.t_last_ship = now_ms() - t_call0;
+                acc.ship_ms += acc.t_last_ship - (t1 - t_call0);
+                if (acc.t_first_ship == 0) acc.t_first_ship = acc.t_last_ship;
             }
+            acc.t_end = now_ms() - t_call0;
             for (int i = 0; i < PST; i++) {
                 const int r = retire(ctx->pslot[(size_t)(PST * t + i)], acc);
                 if (r) return r;
@@ -1169,6 +1716,9 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         merge(acc, rc);
         std::lock_guard<std::mutex> g(m);
         pack_busy_ms += acc.pack_ms; pack_wait_ms += acc.wait_ms;
+        if (trace_level >= 1)
+            fprintf(stderr, "[dcn packer %d] begin %.2f first ship %.2f last ship %.2f claims done %.2f end %.2f ms; packing %.2f shipping %.2f waiting %.2f ms; %.1f MB\n",
+                    t, acc.t_begin, acc.t_first_ship, acc.t_last_ship, acc.t_end, now_ms() - t_call0, acc.pack_ms, acc.ship_ms, acc.wait_ms, acc.packed_bases / 1e6);
     };
     std::vector<std::thread> packers;
     for (int t = 0; t < n_packers; t++) {
@@ -1424,7 +1974,7 @@ static int tile_extract_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint6
     const int pb = 256;
     const int pg = (int)std::min<uint64_t>(((uint64_t)n_rec + pb - 1) / pb, (uint64_t)ctx->sm_count * 8);
     const int grid = (int)std::min<uint64_t>(n_bases / G31::BCAP + 1, (uint64_t)ctx->sm_count * (1024 / G31::NT));
-    const int wgrid = (int)std::min<uint64_t>((n_bases / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count);
+    const int wgrid = (int)std::min<uint64_t>((n_bases / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count * DCN_WCTAS);
     const uint64_t n_seg = (n_bases + DCN_WSEG - 1) / DCN_WSEG;
     const int sg = (int)std::max<uint64_t>(1, std::min<uint64_t>((n_seg + 7) / 8, (uint64_t)ctx->sm_count * 8));
     // ~0.095 picks per base for 150-base records; the warp kernel's warps take the temp arrays in blocks of DCN_XBLK

@@ -309,29 +309,49 @@ filter_fused_kernel(FilterParams P, const BatchStats *st, const uint32_t *__rest
 }
 
 // ------------------------------------------------------------------ warp-tile planner
-// One warp per 64 KB segment of the batch (units whose first base lies in the segment).  The greedy walk of
-// wplan_segment, 32 units at a time: the lanes load the offsets of the 32 units from the current tile start
-// (coalesced), one ballot says how many of them the tile takes.  Tiles are staged in shared memory and appended to
-// the list 64 at a time (one atomic per flush); the list order is irrelevant, tiles are claimed from a counter.
-// Long units (skipped here, cut into chunks by prep_long_kernel) are counted on the way: n_long, long_bases.
+// One warp per 64 KB segment of the batch (units whose first base lies in the segment), the greedy walk of
+// wplan_segment done 32 units at a time: the lanes load the offsets of 32 consecutive units (coalesced); every lane
+// works out the tile that would START at its unit (run of short units of this segment, then a binary search over
+// the lanes' end offsets for what fits 1536 bases from the lane's aligned origin); the warp then hops from tile
+// start to tile start through those counts (shuffles only) and the starting lanes write their tiles.  One round
+// trip to memory plans ~5 tiles, where the first version planned one: a small batch (a 16 MB chunk of the
+// host-pointer pipeline is 256 segments of 43 tiles) is bound by that latency, not by throughput.  The segment's
+// first unit is found by a 32-ary search (3-4 round trips instead of 16).  Tiles are staged in shared memory and
+// appended to the list 64 or more at a time (one atomic per flush); the list order is irrelevant, tiles are
+// claimed from a counter.  Long units (skipped here, cut into chunks by prep_long_warp_kernel) are counted on the
+// way: n_long, long_bases.
 __global__ void __launch_bounds__(256)
 wplan_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units, uint64_t base0, uint64_t n_rel,
              BatchStats *st, WTile *tiles, uint32_t tile_cap, uint32_t *promise_broken) {
-    __shared__ WTile buf[8][64];
+    __shared__ WTile buf[8][96];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t FULL = 0xFFFFFFFFu;
     const uint64_t n_seg = (n_rel + DCN_WSEG - 1) / DCN_WSEG;
     const uint64_t n_warps = (uint64_t)gridDim.x * 8u;
     const uint32_t maxu = wplan_max_units(rpu);
     const uint64_t HUGE = ~0ull >> 1;
     for (uint64_t seg = (uint64_t)blockIdx.x * 8u + warp; seg < n_seg; seg += n_warps) {
-        const uint64_t hi_pos = (seg + 1) * DCN_WSEG;
-        uint32_t u = wplan_first_unit(rec_off, base0, rpu, n_units, seg * DCN_WSEG);
+        const uint64_t lo_pos = seg * DCN_WSEG, hi_pos = lo_pos + DCN_WSEG;
+        // first unit with start >= lo_pos (wplan_first_unit), 32 probes per step
+        uint32_t u = 0;
+        {
+            uint32_t lo = 0, hi = n_units;
+            while (lo < hi) {
+                const uint32_t mid = lo + (uint32_t)(((uint64_t)(hi - lo) * (lane + 1u)) / 33u);   // lo <= mid < hi, non-decreasing in lane
+                const bool less = rec_off[(uint64_t)mid * rpu] - base0 < lo_pos;
+                const uint32_t c = (uint32_t)__popc(__ballot_sync(FULL, less));             // probes 0 .. c-1 lie before the segment
+                const uint32_t below = __shfl_sync(FULL, mid, (int)((c + 31u) & 31u)), above = __shfl_sync(FULL, mid, (int)(c & 31u));
+                if (c > 0u) lo = below + 1u;
+                if (c < 32u) hi = above;
+            }
+            u = lo;
+        }
         uint32_t nbuf = 0, n_long = 0;
-        unsigned long long long_bases = 0;
+        unsigned long long long_bases = 0;   // per lane; summed over the warp at the end
         auto flush = [&]() {
             uint32_t at = 0;
             if (lane == 0) at = atomicAdd(&st->n_wtiles, nbuf);
-            at = __shfl_sync(0xFFFFFFFFu, at, 0);
+            at = __shfl_sync(FULL, at, 0);
             for (uint32_t i = lane; i < nbuf; i += 32u) {
                 if (at + i < tile_cap) tiles[at + i] = buf[warp][i];
                 else st->overflow = 1;
@@ -342,24 +362,61 @@ wplan_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_unit
         while (u < n_units) {
             const uint64_t idx = (uint64_t)u + lane;
             const uint64_t s_l = idx <= n_units ? rec_off[idx * rpu] - base0 : HUGE;
-            const uint64_t e_l = idx + 1 <= n_units ? rec_off[(idx + 1) * rpu] - base0 : HUGE;
-            const uint64_t s0 = __shfl_sync(0xFFFFFFFFu, s_l, 0), e0 = __shfl_sync(0xFFFFFFFFu, e_l, 0);
+            uint64_t e_l = __shfl_down_sync(FULL, (unsigned long long)s_l, 1);
+            if (lane == 31u) e_l = idx + 1 <= n_units ? rec_off[(idx + 1) * rpu] - base0 : HUGE;
+            const uint64_t s0 = __shfl_sync(FULL, (unsigned long long)s_l, 0);
             if (s0 >= hi_pos) break;
-            if (e0 - s0 > DCN_MAX_SHORT) { n_long++; long_bases += e0 - s0; u++; continue; }
-            const uint64_t origin = s0 & ~15ull;
-            const bool fit = idx < n_units && s_l < hi_pos && e_l - s_l <= DCN_MAX_SHORT && e_l - origin <= (uint64_t)WG::TB && lane < maxu;
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, fit);          // bit 0 is set: a short unit always fits a tile of its own
-            const uint32_t cnt = m == 0xFFFFFFFFu ? 32u : (uint32_t)__ffs((int)~m) - 1u;
-            if (lane == 0) { WTile t; t.origin = origin; t.a = u; t.b = u + cnt; buf[warp][nbuf] = t; }
-            nbuf++;
-            u += cnt;
+            const bool inseg = idx < n_units && s_l < hi_pos;
+            const uint64_t len = e_l - s_l;
+            const bool is_long = inseg && len > DCN_MAX_SHORT;
+            const bool ok = inseg && !is_long;
+            const uint32_t okm = __ballot_sync(FULL, ok), longm = __ballot_sync(FULL, is_long), insegm = __ballot_sync(FULL, inseg);
+            // the tile that would start at this lane's unit: short units of the segment in a row (at most maxu) ...
+            const uint32_t nok = ~(okm >> lane);                                   // (bits beyond the window read as "not ok")
+            uint32_t run = nok ? (uint32_t)__ffs((int)nok) - 1u : 32u;
+            if (run > maxu) run = maxu;
+            // ... of which the first c end within 1536 bases of the tile's aligned origin (a short unit always fits alone)
+            const uint64_t origin = s_l & ~15ull, limit = origin + (uint64_t)WG::TB;
+            uint32_t c = ok ? 1u : 0u;
+#pragma unroll
+            for (uint32_t step = 16u; step >= 1u; step >>= 1) {
+                const uint32_t t = c + step;
+                const uint32_t from = lane + t - 1u;
+                const uint64_t ev = __shfl_sync(FULL, (unsigned long long)e_l, (int)(from & 31u));
+                if (ok && t <= run && from < 32u && ev <= limit) c = t;
+            }
+            // the count is final if the tile is full or the unit that ended it is in view; otherwise the walk restarts there
+            const uint32_t finalm = __ballot_sync(FULL, c == maxu || lane + c < 32u);
+            uint32_t p = 0, startm = 0, skipm = 0;
+            bool seg_done = false;
+            while (p < 32u) {
+                if (!((insegm >> p) & 1u)) { seg_done = true; break; }              // past the batch or the segment
+                if ((longm >> p) & 1u) { skipm |= 1u << p; p++; continue; }
+                if (!((finalm >> p) & 1u)) break;
+                startm |= 1u << p;
+                p += __shfl_sync(FULL, c, (int)p);
+            }
+            if ((skipm >> lane) & 1u) long_bases += len;
+            n_long += (uint32_t)__popc(skipm);
+            if ((startm >> lane) & 1u) {
+                WTile t;
+                t.origin = origin; t.a = u + lane; t.b = u + lane + c;
+                buf[warp][nbuf + (uint32_t)__popc(startm & ((1u << lane) - 1u))] = t;
+            }
+            nbuf += (uint32_t)__popc(startm);
+            u += p;                                                                  // p >= 1: lane 0's unit is in view and its count final
             __syncwarp();
-            if (nbuf == 64u) flush();
+            if (nbuf >= 64u) flush();
+            if (seg_done) break;
         }
         if (nbuf) flush();
-        if (lane == 0 && n_long) {
-            atomicAdd(&st->n_long, n_long); atomicAdd(&st->long_bases, long_bases);
-            if (promise_broken) *reinterpret_cast<volatile uint32_t *>(promise_broken) = 1u;   // pinned host word (dcn_filter_batch_device_hint)
+        if (n_long) {   // (warp-uniform)
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) long_bases += __shfl_xor_sync(FULL, long_bases, d);
+            if (lane == 0) {
+                atomicAdd(&st->n_long, n_long); atomicAdd(&st->long_bases, long_bases);
+                if (promise_broken) *reinterpret_cast<volatile uint32_t *>(promise_broken) = 1u;   // pinned host word (dcn_filter_batch_device_hint)
+            }
         }
     }
 }
@@ -407,6 +464,7 @@ __device__ __forceinline__ void add_summary(unsigned long long *counters, unsign
 #ifndef DCN_WARPS
 #define DCN_WARPS 32            // warps per CTA of filter_warp_kernel (one CTA per SM): 32 x 64 registers
 #endif
+#define DCN_WCTAS (32 / DCN_WARPS)   // CTAs per SM of the warp-tile kernels: 32 warps x 64 registers per SM either way
 
 // Per-warp pipeline state that is only touched between tiles lives in shared memory, not in registers: the
 // descriptors of the next two tiles (brought in by cp.async, so that no register waits for them).
@@ -512,7 +570,7 @@ struct WarpDevExec {
 // WITH_LONG: the batch holds long units (their chunks are listed behind the short tiles); a batch without any runs the
 // instantiation that does not carry that code (measured: 2 % on the headline config, registers and instruction cache).
 template <bool PACKED, bool WITH_LONG>
-__global__ void __launch_bounds__(DCN_WARPS * 32, 1)
+__global__ void __launch_bounds__(DCN_WARPS * 32, DCN_WCTAS)
 filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ tiles, uint32_t *ovf_list, uint32_t ovf_cap,
                    unsigned long long *counters, DedupView dd) {
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];
@@ -589,7 +647,7 @@ filter_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ til
 // B3 on warp tiles: the same skeleton, ASCII input, no long units (dcn_extract sends batches with a record above
 // DCN_MAX_SHORT bases through the generic kernels); records of more than a warp pass's picks are listed for
 // extract_tail_kernel.
-__global__ void __launch_bounds__(DCN_WARPS * 32, 1)
+__global__ void __launch_bounds__(DCN_WARPS * 32, DCN_WCTAS)
 extract_warp_kernel(FilterParams P, BatchStats *st, const WTile *__restrict__ tiles, uint32_t *ovf_list, uint32_t ovf_cap) {
     constexpr bool PACKED = false;
     extern __shared__ __align__(16) unsigned char dcn_smem_raw[];

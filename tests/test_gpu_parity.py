@@ -320,21 +320,25 @@ print("small atoms ok")
 """
 
 
-@pytest.mark.parametrize("n_every,sparse", [(500, "1"), (40000, "1"), (500, "0")],
-                         ids=["N-rich:dense-fallback", "N-rare:sparse-mask", "dense-wire"])
-def test_two_route_ingest_small_atoms(tmp_path, n_every, sparse):
+@pytest.mark.parametrize("n_every,sparse,extra", [(500, "1", {}), (40000, "1", {}), (500, "0", {}),
+                                                  (40000, "1", {"DCN_PIPELINE": "chunks"}),
+                                                  (500, "1", {"DCN_LAUNCH_ATOMS": "3", "DCN_LAUNCH_CAP_MB": "1", "DCN_PACKER_STAGES": "1"})],
+                         ids=["N-rich:dense-fallback", "N-rare:sparse-mask", "dense-wire", "chunk-pipeline", "arena:many-small-launches"])
+def test_two_route_ingest_small_atoms(tmp_path, n_every, sparse, extra):
     """The two-route ingest with 1 MB chunks (128 KB atoms; DCN_CHUNK_MB is read once per process, hence the
     subprocess): hundreds of atoms per call, every kind of record boundary inside them -- empty and sub-k records,
     newline-terminated ones, N runs, long-path units, prefix trimming -- on pageable buffers, all splits.  The packer
     threads ship the non-ACGT bits as a sparse exception list (an N every 40 000 bases: few blocks listed) and fall
     back to the dense mask when more than one 32-base block in 32 is listed (an N every 500 bases);
-    DCN_SPARSE_MASK=0 keeps the dense wire form of round 1."""
+    DCN_SPARSE_MASK=0 keeps the dense wire form of round 1.  The calls with packer threads run the arena form of the
+    pipeline (kernels over whatever contiguous range has arrived); DCN_PIPELINE=chunks runs the one-kernel-per-chunk form
+    that still serves the single-route cases, and tiny launch limits make the arena form launch hundreds of ranges."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "small_atoms.py"
     script.write_text(_SMALL_ATOMS)
-    env = dict(os.environ, DCN_CHUNK_MB="1", DCN_SPARSE_MASK=sparse)
+    env = dict(os.environ, DCN_CHUNK_MB="1", DCN_SPARSE_MASK=sparse, **extra)
     r = subprocess.run([sys.executable, str(script), root, str(n_every)], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "small atoms ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
