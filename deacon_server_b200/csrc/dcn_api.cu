@@ -402,11 +402,13 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
     const size_t smem = sizeof(TileSmem<G31>);
     const uint64_t tiles_lb = n_rel / G31::BCAP + 1;
     const int grid = (int)std::min<uint64_t>(tiles_lb, (uint64_t)ctx->sm_count * DCN_CTAS_PER_SM);
-    // Warp-tile grid: one CTA per SM for a big batch.  A small one (a chunk of the host-pointer pipeline) gets only as many
-    // CTAs as give every warp DCN_TILES_PER_WARP tiles: a warp holds claims on the next two or three tiles, so with two
-    // tiles per warp the "dynamic" schedule is a static, lopsided one, and the SMs a small kernel leaves alone run the
-    // kernels of the chunks on the other streams.
-    static const uint64_t tiles_per_warp = []() { const char *e = getenv("DCN_TILES_PER_WARP"); return e ? (uint64_t)std::max(0, atoi(e)) : 8ull; }();
+    // Warp-tile grid: one CTA per SM.  DCN_TILES_PER_WARP = n (A/B knob, off by default) gives a small batch only as many
+    // CTAs as leave every warp n tiles, so that kernels of different streams run side by side on disjoint SMs.  Measured
+    // (16.8 Mbp launches, tools/chunk_cost.py): one stream 150 us -> 193 us (n = 4) -> 298 us (n = 8); thirteen streams of
+    // the chunk pipeline: no gain beyond noise.  Small launches are slow for another reason -- all warps of an SM are in
+    // the same phase, so probe latency and ALU work do not overlap -- and the cure is fewer, larger launches
+    // (filter_pipeline_arena), not narrower ones.
+    static const uint64_t tiles_per_warp = []() { const char *e = getenv("DCN_TILES_PER_WARP"); return e ? (uint64_t)std::max(0, atoi(e)) : 0ull; }();
     int wgrid = (int)std::min<uint64_t>((n_rel / WG::TB + DCN_WARPS) / DCN_WARPS, (uint64_t)ctx->sm_count * DCN_WCTAS);
     if (tiles_per_warp) wgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)wgrid, (n_rel / WG::TB + 1 + DCN_WARPS * tiles_per_warp - 1) / (DCN_WARPS * tiles_per_warp)));
     const uint64_t n_seg = (n_rel + DCN_WSEG - 1) / DCN_WSEG;

@@ -192,27 +192,40 @@ DCN_HD void wslide_block(const uint32_t (&q)[15], uint32_t c0, uint32_t c1, uint
     for (int i = 1; i < 15; i++) oR[i] = umin32(key[i], key[14 + i]);
     oR[15] = key[29];
 
-    // canonical strand: #(T|G) > #(A|C) over the L bases of the window; T/G <=> bit 1 of the code
-    uint32_t cnt = popc32(c0 & 0xAAAAAAAAu) + popc32(c1 & 0xAAAAAAAAu) +
-                   popc32(c2 & (0xAAAAAAAAu & ((1u << (2 * ((WG::L - 32) & 15))) - 1u)));
-    constexpr int LW = (WG::L - 1) / 16, LS = 2 * ((WG::L - 1) % 16);
-    static_assert(LW == 2, "L = 45");
-    const uint32_t xw_lo = (c2 >> 1) & 0x55555555u, xw_hi = (c3 >> 1) & 0x55555555u;
-    const uint32_t xin = fshr(xw_lo, xw_hi, (uint32_t)LS) & ~3u;        // lane j = T/G flag of base L - 1 + j
-    const uint32_t xout = ((c0 >> 1) & 0x55555555u) << 2;               // lane j = flag of base j - 1
-    constexpr uint32_t THR = (uint32_t)(WG::L + 1) / 2;
+    // leftmost and rightmost smallest differ only where the window minimum is tied (~2e-4 of windows): the strand that
+    // chooses between them (below) is only worked out for a block that holds such a window
+    uint32_t l4[4], r4[4], tied = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        l4[g] = pack_low_bytes(oL[4 * g], oL[4 * g + 1], oL[4 * g + 2], oL[4 * g + 3]);
+        r4[g] = pack_low_bytes(oR[4 * g], oR[4 * g + 1], oR[4 * g + 2], oR[4 * g + 3]) ^ 0x1F1F1F1Fu;
+        tied |= l4[g] ^ r4[g];
+    }
+    if (tied) {
+        // canonical strand: #(T|G) > #(A|C) over the L bases of the window; T/G <=> bit 1 of the code
+        uint32_t cnt = popc32(c0 & 0xAAAAAAAAu) + popc32(c1 & 0xAAAAAAAAu) +
+                       popc32(c2 & (0xAAAAAAAAu & ((1u << (2 * ((WG::L - 32) & 15))) - 1u)));
+        constexpr int LW = (WG::L - 1) / 16, LS = 2 * ((WG::L - 1) % 16);
+        static_assert(LW == 2, "L = 45");
+        const uint32_t xw_lo = (c2 >> 1) & 0x55555555u, xw_hi = (c3 >> 1) & 0x55555555u;
+        const uint32_t xin = fshr(xw_lo, xw_hi, (uint32_t)LS) & ~3u;        // lane j = T/G flag of base L - 1 + j
+        const uint32_t xout = ((c0 >> 1) & 0x55555555u) << 2;               // lane j = flag of base j - 1
+        constexpr uint32_t THR = (uint32_t)(WG::L + 1) / 2;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t spi = (((xin >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
+            const uint32_t spo = (((xout >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
+            const uint32_t cnt4 = cnt * 0x01010101u + spi * 0x01010101u - spo * 0x01010101u;
+            cnt = cnt4 >> 24;
+            const uint32_t canon = ((cnt4 + (0x80u - THR) * 0x01010101u) >> 7) & 0x01010101u;
+            const uint32_t msk = canon * 0xFFu;
+            l4[g] = (l4[g] & msk) | (r4[g] & ~msk);
+        }
+    }
     uint32_t neq = 0, prev_hi = 0;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        const uint32_t spi = (((xin >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
-        const uint32_t spo = (((xout >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
-        const uint32_t cnt4 = cnt * 0x01010101u + spi * 0x01010101u - spo * 0x01010101u;
-        cnt = cnt4 >> 24;
-        const uint32_t canon = ((cnt4 + (0x80u - THR) * 0x01010101u) >> 7) & 0x01010101u;
-        const uint32_t msk = canon * 0xFFu;
-        const uint32_t l4 = pack_low_bytes(oL[4 * g], oL[4 * g + 1], oL[4 * g + 2], oL[4 * g + 3]);
-        const uint32_t r4 = pack_low_bytes(oR[4 * g], oR[4 * g + 1], oR[4 * g + 2], oR[4 * g + 3]) ^ 0x1F1F1F1Fu;
-        const uint32_t rel = (l4 & msk) | (r4 & ~msk);
+        const uint32_t rel = l4[g];
         rel4[g] = rel;
         const uint32_t before = (rel << 8) | (g == 0 ? (rel & 0xFFu) : prev_hi);
         const uint32_t xd = rel ^ before;
