@@ -592,6 +592,11 @@ def run_ours(args):
                                            limiter=("each rank's PCIe link (packing on: fewer bytes per base)" if (pack_threads or 0) > 0
                                                     else "host DRAM / PCIe root shared by the ranks (ASCII route only: a packed base costs 1.5 B of host DRAM traffic, a copied one 1.0 B)")),
                     "frac_of_ascii_ceiling": round(e2e_value / max(ingest["concurrent_sum_gbs"], 1e-9), 3),
+                    # every rank does the same work, so the rank with the smallest share of the host sets the time of the step
+                    "frac_of_slowest_rank_ceiling": round(e2e_value / max(world * ingest.get("concurrent_min_gbs", ingest["concurrent_gbs"]), 1e-9), 3),
+                    "pipeline": "arena (dcn_api.cu filter_pipeline_arena): copies land in one device arena, kernels run over whatever "
+                                "contiguous range of units has arrived" if (pack_threads is None or pack_threads > 0) and not os.environ.get("DCN_PIPELINE")
+                                else "chunks (one kernel chain per 32 MB copy)",
                     "api": "dcn_filter_batch (C ABI), ASCII records + u64 offsets in host memory; bytes as counted by the "
                            "library (dcn_last_transfer_bytes) for the last step: part of the batch crosses as ASCII, part is packed "
                            "by host threads inside the call (the split is dynamic), and the offsets of "

@@ -91,7 +91,7 @@ struct FilterInput {
 // cover any contiguous range of units that has arrived, however many copies brought it.
 struct ArenaState {
     DevBuf ascii, codes, inv, nl, off, out;
-    static const int NL = 16;
+    static const int NL = 8;
     Slot launch[NL];              // plan / longs / dedup / h_out / stream / events of one kernel launch
     std::mutex launch_m[NL];
     cudaStream_t copy_stream = nullptr;   // the ASCII route's copies, in order
@@ -1007,6 +1007,14 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
         const uint64_t r0 = (uint64_t)u_lo * rpu;
         const uint64_t base0 = rec_off[r0] & ~63ull, n_abs = rec_off[(uint64_t)u_hi * rpu];
         if (!out_pinned && s.h_out.ensure((size_t)nu * 9) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
+        if (hs.n_long) {
+            // long units: the distinct-hit set and the long-unit list of this slot at the size the largest range needs,
+            // once -- launches of varying size would otherwise grow them (cudaFree: a device-wide stall) call after call
+            const uint64_t cap_rel = std::max<uint64_t>(n_abs - base0, std::min<uint64_t>(nb_total, range_cap + (uint64_t)atom_bases));
+            if (s.dedup.ensure((size_t)std::max<uint64_t>(4096, cap_rel / 4) * 16) != cudaSuccess ||
+                s.longs.ensure((size_t)(cap_rel / DCN_MAX_SHORT + 64) * 4 + 64 + (size_t)(cap_rel / ChunkGeo<G31>::CSTRIDE + cap_rel / DCN_MAX_SHORT * rpu + 80) * sizeof(ChunkDesc)) != cudaSuccess)
+                return ctx->fail(DCN_ERR_NOMEM, "long-path scratch allocation failed", cudaGetLastError());
+        }
         for (cudaEvent_t e : waits) if (e) CK(cudaStreamWaitEvent(s.stream, e, 0));
         FilterInput in;
         if (packed) {

@@ -75,10 +75,16 @@ def h2d_probe(device, nbytes: int = 1 << 30, reps: int = 3) -> dict:
     conc = min(once() for _ in range(reps))      # everybody at once (the slowest repetition: the contended one)
     barrier()
     vec = torch.tensor([conc], dtype=torch.float64, device=device)
+    lo, hi = vec.clone(), vec.clone()
     if multi:
         dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     del h, d
-    return {"solo_gbs": round(solo, 2), "concurrent_gbs": round(conc, 2), "concurrent_sum_gbs": round(float(vec.item()), 2), "world": world}
+    # the ranks do not get equal shares of the host (measured on an 8-GPU box: 20 to 32 GB/s); with the same work per
+    # rank the slowest one sets the time, so world x min is the ceiling of an equal-shards step, sum only of a shared queue
+    return {"solo_gbs": round(solo, 2), "concurrent_gbs": round(conc, 2), "concurrent_sum_gbs": round(float(vec.item()), 2),
+            "concurrent_min_gbs": round(float(lo.item()), 2), "concurrent_max_gbs": round(float(hi.item()), 2), "world": world}
 
 
 def pack_threads_for_rank(local_world: int, probe: dict | None = None) -> int:
