@@ -174,7 +174,7 @@ static cudaError_t open_dedup_set(DevBuf &buf, uint64_t entries, cudaStream_t st
         buf.set_cleared = buf.cap;
         buf.set_epoch = 0;
     }
-    dd.slots = buf.as<unsigned __int128>(); dd.cap = entries; dd.overflow = overflow_flag; dd.epoch = ++buf.set_epoch;
+    dd.slots = buf.as<unsigned __int128>(); dd.cap = entries; dd.overflow = overflow_flag; dd.epoch = ++buf.set_epoch; dd.per16 = 0;
     return cudaSuccess;
 }
 
@@ -439,7 +439,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             CK(cudaStreamSynchronize(st));
         }
         DedupView dd;
-        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow; dd.epoch = 1;
+        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow; dd.epoch = 1; dd.per16 = 0;
         uint32_t *long_units = nullptr;
         ChunkDesc *desc = nullptr;
         if (hs.n_long) {
@@ -447,9 +447,15 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             // picks are ~0.13 per base, so 0.25 entries per base is at most half full; it grows x4 on
             // overflow (exactness is kept by retrying, never by dropping).  The set is cleared per call:
             // its size is what the long path pays up front (4 bytes per long base).
-            if (!dedup_cap) dedup_cap = std::max<uint64_t>(4096, hs.long_bases / 4);
+            // Warp tiles, batch mostly long units: per-unit regions of the set, laid out by position in the batch
+            // (DedupView::per16; 4 slots per 16 bases = the same 0.25 per base); a batch with few long units keeps the one
+            // small set (regions would reserve 4 bytes per base of the short units too).  DCN_DEDUP_LOCAL=0 forces the latter.
+            static const bool local_ok = []() { const char *e = getenv("DCN_DEDUP_LOCAL"); return !e || atoi(e) != 0; }();
+            const bool local = warp_impl && local_ok && hs.long_bases >= n_rel / 4;
+            if (!dedup_cap) dedup_cap = local ? 4 : std::max<uint64_t>(4096, hs.long_bases / 4);   // local: slots per 16 bases
             const uint32_t desc_cap = (uint32_t)(hs.long_bases / ChunkGeo<G31>::CSTRIDE + (uint64_t)hs.n_long * rpu + 16);
-            CK(open_dedup_set(dedup, dedup_cap, st, dd, &d_stats->overflow));
+            CK(open_dedup_set(dedup, local ? ((n_rel >> 4) + 2) * dedup_cap : dedup_cap, st, dd, &d_stats->overflow));
+            if (local) dd.per16 = (uint32_t)dedup_cap;
             CK(longs.ensure((size_t)hs.n_long * 4 + 64 + (size_t)desc_cap * sizeof(ChunkDesc)));
             long_units = longs.as<uint32_t>();
             desc = reinterpret_cast<ChunkDesc *>(longs.as<uint8_t>() + (((size_t)hs.n_long * 4 + 63) & ~(size_t)63));
@@ -1895,7 +1901,7 @@ static int lookup_device(dcn_ctx *ctx, const uint64_t *d_hashes, const uint64_t 
         CK(cudaMemcpyAsync(&hs, d_stats, sizeof(hs), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         DedupView dd;
-        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow; dd.epoch = 1;
+        dd.slots = nullptr; dd.cap = 0; dd.overflow = &d_stats->overflow; dd.epoch = 1; dd.per16 = 0;
         if (hs.n_long) {
             if (!dedup_cap) dedup_cap = std::max<uint64_t>(4096, hs.long_bases * 2);
             CK(open_dedup_set(ctx->dedup, dedup_cap, st, dd, &d_stats->overflow));

@@ -920,12 +920,27 @@ struct DedupView {
     uint64_t cap;         // entries (any size: the start slot is mulhi(mix, cap))
     uint32_t *overflow;   // set when an insert gives up
     uint32_t epoch;       // >= 1
+    // 0: one set for the whole launch (the slot of (hash, unit) is anywhere in it).  n > 0: every unit has a REGION of the
+    // set of its own, n slots per 16 bases of the unit, at the unit's place in the batch (dedup_region): the entries of a
+    // long read then sit in a few tens of KB that stay in L2 while its chunks are being processed, instead of costing one
+    // random DRAM request per hit
+    uint32_t per16;
 };
 
-DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
+// region of the set that belongs to the unit spanning bases [ub, ue) of the launch (relative to base0)
+DCN_HD void dedup_region(const DedupView &d, uint64_t ub, uint64_t ue, uint64_t &lo, uint32_t &sz) {
+    lo = (ub >> 4) * d.per16;
+    const uint64_t n = ((ue >> 4) - (ub >> 4)) * d.per16;
+    sz = n > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)n;
+}
+
+// reg_sz > 0: the unit's own region [reg_lo, reg_lo + reg_sz) of the set (linear probing wraps inside it)
+DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit, uint64_t reg_lo = 0, uint32_t reg_sz = 0) {
     const unsigned __int128 val = ((unsigned __int128)(((uint64_t)d.epoch << 32) | ((uint64_t)unit + 1)) << 64) | h;
-    uint64_t slot = mulhi64(h ^ ((uint64_t)unit * 0x9E3779B97F4A7C15ULL), d.cap);
-    for (uint32_t probes = 0; probes < 4096; probes++) {
+    const uint64_t lo = reg_sz ? reg_lo : 0, hi = reg_sz ? reg_lo + reg_sz : d.cap;
+    uint64_t slot = reg_sz ? reg_lo + mulhi64(h, (uint64_t)reg_sz) : mulhi64(h ^ ((uint64_t)unit * 0x9E3779B97F4A7C15ULL), d.cap);
+    const uint32_t max_probes = reg_sz && reg_sz < 4096u ? reg_sz : 4096u;
+    for (uint32_t probes = 0; probes < max_probes; probes++) {
 #ifdef __CUDA_ARCH__
         unsigned __int128 old = atomicCAS(&d.slots[slot], (unsigned __int128)0, val);
 #else
@@ -945,7 +960,7 @@ DCN_HD bool dedup_insert(const DedupView &d, uint64_t h, uint32_t unit) {
             if (old2 == val) return false;   // the same (hash, unit) got there first
             // somebody else's entry of this call took the slot meanwhile: occupied
         }
-        if (++slot == d.cap) slot = 0;
+        if (++slot == hi) slot = lo;
     }
     *d.overflow = 1;
     return false;

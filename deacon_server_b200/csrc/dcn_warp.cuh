@@ -290,7 +290,7 @@ DCN_HD uint32_t w_eff_len(const FilterParams &P, const WSrc &src, uint32_t r, ui
 // first one only carries the previous chunk's last pick for the consecutive-duplicate rule), no record table, every
 // window may emit (the pick list keeps positions only: 1600 fit), and the picks go through the global (hash, unit)
 // set `dd` and per-unit atomics instead of the per-unit count (filter_long_chunk is the CTA-tile form of the same).
-struct WLong { uint32_t unit, la, carry, nw; const DedupView *dd; };
+struct WLong { uint32_t unit, la, carry, nw; const DedupView *dd; uint64_t reg_lo; uint32_t reg_sz; };   // reg_*: the unit's region of the set (dedup_region), 0 = none
 
 // With EXTRACT (B3, get_minimizer_hashes_and_positions src/filter_common.rs:211-310; rpu = 1) nothing is probed: the
 // picks' hashes and record-relative positions go to a block of the temp arrays (ex.xalloc), per-record valid counts
@@ -489,8 +489,8 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
                 kA.k0 = kA.k1 = kA.k2 = kA.k3 = 0; kB = kA;
                 if (vA) { hA = wpick_hash(s, ppA); bA = table_bucket(hA, P.table.n_buckets); kA = load_bucket(P.table.slots, bA); }
                 if (vB) { hB = wpick_hash(s, ppB); bB = table_bucket(hB, P.table.n_buckets); kB = load_bucket(P.table.slots, bB); }
-                const bool fA = vA && table_contains_from(P.table, hA, bA, kA) && dedup_insert(*lg.dd, hA, lg.unit);
-                const bool fB = vB && table_contains_from(P.table, hB, bB, kB) && dedup_insert(*lg.dd, hB, lg.unit);
+                const bool fA = vA && table_contains_from(P.table, hA, bA, kA) && dedup_insert(*lg.dd, hA, lg.unit, lg.reg_lo, lg.reg_sz);
+                const bool fB = vB && table_contains_from(P.table, hB, bB, kB) && dedup_insert(*lg.dd, hB, lg.unit, lg.reg_lo, lg.reg_sz);
                 n_valid += (uint32_t)vA + (uint32_t)vB;
                 n_fresh += (uint32_t)fA + (uint32_t)fB;
             }
@@ -685,7 +685,7 @@ DCN_HD void warp_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterPara
         const uint64_t n_rel = P.n_bases - P.base0;
         src.words = PACKED ? ((n_rel + 15) >> 4) - (origin >> 4) : 0;
         WLong none;
-        none.unit = none.la = none.carry = none.nw = 0; none.dd = nullptr;
+        none.unit = none.la = none.carry = none.nw = 0; none.dd = nullptr; none.reg_lo = 0; none.reg_sz = 0;
         if (warp_run<PACKED, false, EXTRACT>(ex, T, s, P, src, origin, lo, hi, hi == tile.b, none)) {
             lo = hi;
         } else if (hi - lo == 1) {
@@ -705,6 +705,9 @@ DCN_HD void warp_long_tile(Ex &ex, const WarpTables &T, WarpSmem &s, const Filte
     const uint64_t origin = tile.origin & ~WTILE_LONG;
     WLong lg;
     lg.unit = tile.a / P.rpu; lg.la = tile.b & 15u; lg.carry = (tile.b >> 4) & 1u; lg.nw = tile.b >> 5; lg.dd = &dd;
+    lg.reg_lo = 0; lg.reg_sz = 0;
+    if (dd.per16)
+        dedup_region(dd, P.rec_off[(uint64_t)lg.unit * P.rpu] - P.base0, P.rec_off[(uint64_t)(lg.unit + 1) * P.rpu] - P.base0, lg.reg_lo, lg.reg_sz);
     WSrc src;
     src.stage = PACKED ? nullptr : s.stage;
     src.stage_bytes = (stage_bytes + 15u) & ~15u;

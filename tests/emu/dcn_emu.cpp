@@ -258,10 +258,14 @@ static int emu_filter_batch_t(const uint64_t *slots, uint64_t nb, int has_empty,
             }
         }
         uint64_t cap = std::max<uint64_t>(4096, long_bases / 4);
+        // the warp-tile path gives every long unit a region of the set of its own (enqueue_filter does so for batches that
+        // are mostly long units; here always, so that the mixed cases exercise it too)
+        const bool local = emu_impl != 1 && !dedup_cap_override;
+        if (local) cap = ((n_bases >> 4) + 2) * 4;
         if (dedup_cap_override) cap = dedup_cap_override;
         std::vector<unsigned __int128> slots(cap, 0);
         uint32_t overflow = 0;
-        DedupView dd{slots.data(), cap, &overflow, 7u};
+        DedupView dd{slots.data(), cap, &overflow, 7u, local ? 4u : 0u};
         // the set is never cleared between calls (epoch tags): run the whole long path twice over the same slots, the
         // first time under another epoch, so that the pass that counts finds every slot it wants taken by a stale entry
         for (uint32_t epoch = 6; epoch <= 7; epoch++) {
