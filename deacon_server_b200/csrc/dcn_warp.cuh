@@ -15,6 +15,8 @@
 // :84-112 (thresholds).  Same arithmetic as dcn_tile.cuh, another mapping of the work onto threads; the CTA-tile
 // code stays for what a warp tile cannot hold (units of more than PKCAP picks, long units, index builds).
 #pragma once
+#include <stddef.h>
+
 #include "dcn_tile.cuh"
 
 namespace dcn {
@@ -69,7 +71,7 @@ struct alignas(16) WarpSmem {
     uint16_t ufirst[WG::MAXR + 2];     // first pick index of each unit
     uint16_t ustartpos[WG::MAXR + 2];
     uint16_t lastpick[WG::NL];         // last window's pick of each lane (0xFFFF: that window is invalid)
-    uint32_t npicks, pad_;
+    uint32_t npicks, nhits;            // nhits: long chunks, entries of the compacted hit list
     unsigned long long mbar;           // transaction barrier of the bulk copy
 
     DCN_HD uint32_t *hx() { return reinterpret_cast<uint32_t *>(region); }
@@ -476,10 +478,23 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
                 }
             }
         });
-        // ---- P6 (long): probe, distinct hits through the global (hash, unit) set, per-unit atomics
+        // ---- P6 (long): probe every pick (two per lane in flight), then the hits alone through the (hash, unit) set.
+        // A set insert is two or three dependent round trips (compare-and-swap, again when the slot holds an entry of
+        // an earlier call); done inside the probe loop every iteration paid them as soon as one lane had a hit.  Now the
+        // probe loop only flags the hits, a ballot pass compacts them (~14 % of the picks of a read that shares a
+        // quarter of its minimizers with the index) and the inserts run over full lanes: 3 + 2 round trips per chunk
+        // instead of 9.
+        constexpr uint32_t HCAP = 2u * (uint32_t)(2 * (WG::NBW + 2));   // hit positions that fit brk | dead (free after the slide phase)
+        uint16_t *hl = reinterpret_cast<uint16_t *>(s.brk);
+#if defined(DCN_EMU_HCAP) && !defined(__CUDA_ARCH__)
+        const uint32_t hcap = (DCN_EMU_HCAP) < HCAP ? (DCN_EMU_HCAP) : HCAP;   // host emulation: a test shrinks the list to reach the leftover branch
+#else
+        const uint32_t hcap = HCAP;
+#endif
+        static_assert(offsetof(WarpSmem, dead) == offsetof(WarpSmem, brk) + sizeof(uint32_t) * (WG::NBW + 2), "brk | dead contiguous");
         ex.par([&](int l, Priv &) {
-            const uint16_t *pk_pos = s.pk_pos();
-            uint32_t n_valid = 0, n_fresh = 0;   // this lane's picks
+            uint16_t *pk_pos = s.pk_pos();
+            uint32_t n_valid = 0;   // this lane's picks
             for (uint32_t idx0 = (uint32_t)l; idx0 < npicks; idx0 += 2 * WG::NL) {
                 const uint32_t idxB = idx0 + WG::NL;
                 const uint32_t ppA = pk_pos[idx0], ppB = idxB < npicks ? pk_pos[idxB] : 0u;
@@ -489,12 +504,36 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
                 kA.k0 = kA.k1 = kA.k2 = kA.k3 = 0; kB = kA;
                 if (vA) { hA = wpick_hash(s, ppA); bA = table_bucket(hA, P.table.n_buckets); kA = load_bucket(P.table.slots, bA); }
                 if (vB) { hB = wpick_hash(s, ppB); bB = table_bucket(hB, P.table.n_buckets); kB = load_bucket(P.table.slots, bB); }
-                const bool fA = vA && table_contains_from(P.table, hA, bA, kA) && dedup_insert(*lg.dd, hA, lg.unit, lg.reg_lo, lg.reg_sz);
-                const bool fB = vB && table_contains_from(P.table, hB, bB, kB) && dedup_insert(*lg.dd, hB, lg.unit, lg.reg_lo, lg.reg_sz);
+                if (vA && table_contains_from(P.table, hA, bA, kA)) pk_pos[idx0] = (uint16_t)(ppA | 0x8000u);
+                if (vB && table_contains_from(P.table, hB, bB, kB)) pk_pos[idxB] = (uint16_t)(ppB | 0x8000u);
                 n_valid += (uint32_t)vA + (uint32_t)vB;
-                n_fresh += (uint32_t)fA + (uint32_t)fB;
             }
             s.ufirst[l] = (uint16_t)n_valid;      // (<= 47 per lane; the unit tables are free in a long chunk)
+        });
+        ex.par([&](int l, Priv &) {
+            uint16_t *pk_pos = s.pk_pos();
+            uint32_t nh = 0;
+            for (uint32_t base = 0; base < npicks; base += WG::NL) {
+                const uint32_t idx = base + (uint32_t)l;
+                const uint32_t pp = idx < npicks ? pk_pos[idx] : 0u;
+                const bool hit = (pp & 0x8000u) != 0;
+                const uint32_t m = ex.ballot(l, hit);
+                const uint32_t at = nh + popc32(m & ((1u << l) - 1u));
+                if (hit && at < hcap) { hl[at] = (uint16_t)(pp & 0x7FFFu); pk_pos[idx] = (uint16_t)(pp & 0x7FFFu); }   // (beyond the list: the flag stays)
+                nh += popc32(m);
+            }
+            if (l == 0) s.nhits = nh < hcap ? nh : hcap;
+        });
+        ex.par([&](int l, Priv &) {
+            const uint16_t *pk_pos = s.pk_pos();
+            const uint32_t nlist = s.nhits;
+            uint32_t n_fresh = 0;
+            for (uint32_t i = (uint32_t)l; i < nlist; i += WG::NL)
+                n_fresh += (uint32_t)dedup_insert(*lg.dd, wpick_hash(s, hl[i]), lg.unit, lg.reg_lo, lg.reg_sz);
+            for (uint32_t idx = (uint32_t)l; idx < npicks; idx += WG::NL) {   // a chunk with more than HCAP hits: the rest, lane by lane
+                const uint32_t pp = pk_pos[idx];
+                if (pp & 0x8000u) n_fresh += (uint32_t)dedup_insert(*lg.dd, wpick_hash(s, pp & 0x7FFFu), lg.unit, lg.reg_lo, lg.reg_sz);
+            }
             s.ustartpos[l] = (uint16_t)n_fresh;
         });
         ex.par([&](int l, Priv &) {

@@ -11,6 +11,9 @@
 #include <algorithm>
 #include <vector>
 
+static uint32_t emu_hcap = 0xFFFFFFFFu;   // test hook: capacity of the long path's compacted hit list (dcn_warp.cuh)
+#define DCN_EMU_HCAP emu_hcap
+
 #include "../../deacon_server_b200/csrc/dcn_plan.cuh"
 #include "../../deacon_server_b200/csrc/dcn_tile.cuh"
 #include "../../deacon_server_b200/csrc/dcn_warp.cuh"
@@ -121,6 +124,7 @@ struct WEmuGeo { static constexpr int NT = 32; };
 extern "C" {
 
 void emu_set_dedup_cap(uint64_t cap) { dedup_cap_override = cap; }
+void emu_set_hit_list_cap(uint32_t cap) { emu_hcap = cap ? cap : 0xFFFFFFFFu; }
 void emu_set_impl(int impl) { emu_impl = impl; }
 uint64_t emu_last_overflow_units() { return emu_ovf_units; }
 uint64_t emu_last_wtiles() { return emu_wtiles; }

@@ -106,6 +106,11 @@ def set_dedup_cap(cap):
     lib().emu_set_dedup_cap(C.c_uint64(cap))
 
 
+def set_hit_list_cap(cap):
+    """Long path of the warp-tile kernel: entries of the compacted hit list (0 = the real size)."""
+    lib().emu_set_hit_list_cap(C.c_uint32(cap))
+
+
 def generic_extract(bases, off, flavour=0, k=31, w=15, prefix=0, entropy_bitmap=None, cstride=256, cap=None):
     """-> (hashes, positions, out_off): the generic (k, w) extraction (B3), CSR per record."""
     L = lib()

@@ -81,6 +81,24 @@ def test_long_path_reports_dedup_overflow():
         E.set_dedup_cap(0)
 
 
+def test_long_path_hit_list_overflow_branch():
+    """Warp-tile long path: the hits of a chunk are compacted into a list before they go through the distinct-hit set;
+    a chunk with more hits than the list holds inserts the rest lane by lane.  A list of 5 entries sends most hits of
+    every chunk down that branch; results must not change."""
+    for case in CASES.make_long_cases()[:3]:
+        idx = _index_for(case)
+        bases, off = H.concat(case["records"])
+        want = O.filter_batch(idx, bases, off, paired=case["paired"], prefix_len=case["prefix"], abs_thr=case["abs"],
+                              rel_thr=case["rel"], deplete=case["deplete"])
+        E.set_hit_list_cap(5)
+        try:
+            rc, k, h, t = E.filter_batch(idx.keys(), bases, off, case["paired"], case["prefix"], case["abs"], case["rel"], case["deplete"])
+        finally:
+            E.set_hit_list_cap(0)
+        assert rc == 0
+        assert np.array_equal(t, want[2]) and np.array_equal(h, want[1]) and np.array_equal(k, want[0])
+
+
 def test_index_extraction_matches_oracle_set():
     g = H.random_genome(50_000, 41)
     recs = [g[:20_000].copy(), g[20_000:20_040].copy(), np.zeros(0, np.uint8), g[20_040:].copy(),
