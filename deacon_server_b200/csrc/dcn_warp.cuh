@@ -24,6 +24,9 @@ namespace dcn {
 #ifndef DCN_PICKS_IN_FLIGHT
 #define DCN_PICKS_IN_FLIGHT 2   // probes a lane has outstanding in P6
 #endif
+#ifndef DCN_LONG_PICKS_IN_FLIGHT
+#define DCN_LONG_PICKS_IN_FLIGHT 2   // the same in the probe loop of a long unit's chunk
+#endif
 
 struct WG {
     static constexpr int K = 31, W = 15, L = 45;
@@ -495,18 +498,27 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
         ex.par([&](int l, Priv &) {
             uint16_t *pk_pos = s.pk_pos();
             uint32_t n_valid = 0;   // this lane's picks
-            for (uint32_t idx0 = (uint32_t)l; idx0 < npicks; idx0 += 2 * WG::NL) {
-                const uint32_t idxB = idx0 + WG::NL;
-                const uint32_t ppA = pk_pos[idx0], ppB = idxB < npicks ? pk_pos[idxB] : 0u;
-                const bool vA = wpick_valid(s, ppA), vB = idxB < npicks && wpick_valid(s, ppB);
-                uint64_t hA = 0, hB = 0, bA = 0, bB = 0;
-                Bucket kA, kB;
-                kA.k0 = kA.k1 = kA.k2 = kA.k3 = 0; kB = kA;
-                if (vA) { hA = wpick_hash(s, ppA); bA = table_bucket(hA, P.table.n_buckets); kA = load_bucket(P.table.slots, bA); }
-                if (vB) { hB = wpick_hash(s, ppB); bB = table_bucket(hB, P.table.n_buckets); kB = load_bucket(P.table.slots, bB); }
-                if (vA && table_contains_from(P.table, hA, bA, kA)) pk_pos[idx0] = (uint16_t)(ppA | 0x8000u);
-                if (vB && table_contains_from(P.table, hB, bB, kB)) pk_pos[idxB] = (uint16_t)(ppB | 0x8000u);
-                n_valid += (uint32_t)vA + (uint32_t)vB;
+            constexpr int NF = DCN_LONG_PICKS_IN_FLIGHT;
+            for (uint32_t idx0 = (uint32_t)l; idx0 < npicks; idx0 += NF * WG::NL) {
+                uint32_t pp[NF];
+                bool v[NF];
+                uint64_t h[NF], bk[NF];
+                Bucket k[NF];
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
+                    pp[f] = idx < npicks ? pk_pos[idx] : 0u;
+                    v[f] = idx < npicks && wpick_valid(s, pp[f]);
+                    h[f] = 0; bk[f] = 0;
+                    k[f].k0 = k[f].k1 = k[f].k2 = k[f].k3 = 0;
+                    if (v[f]) { h[f] = wpick_hash(s, pp[f]); bk[f] = table_bucket(h[f], P.table.n_buckets); k[f] = load_bucket(P.table.slots, bk[f]); }
+                }
+#pragma unroll
+                for (int f = 0; f < NF; f++) {
+                    const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
+                    if (v[f] && table_contains_from(P.table, h[f], bk[f], k[f])) pk_pos[idx] = (uint16_t)(pp[f] | 0x8000u);
+                    n_valid += (uint32_t)v[f];
+                }
             }
             s.ufirst[l] = (uint16_t)n_valid;      // (<= 47 per lane; the unit tables are free in a long chunk)
         });
