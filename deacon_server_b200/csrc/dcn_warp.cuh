@@ -24,6 +24,9 @@ namespace dcn {
 #ifndef DCN_PICKS_IN_FLIGHT
 #define DCN_PICKS_IN_FLIGHT 2   // probes a lane has outstanding in P6
 #endif
+#ifndef DCN_PICKS_LAST_3
+#define DCN_PICKS_LAST_3 0      // A/B knob: one more pick per lane in the iteration that then finishes the tile's list (measured: slower)
+#endif
 #ifndef DCN_LONG_PICKS_IN_FLIGHT
 #define DCN_LONG_PICKS_IN_FLIGHT 2   // the same in the probe loop of a long unit's chunk
 #endif
@@ -264,6 +267,37 @@ DCN_HD uint64_t wpick_hash(const WarpSmem &s, uint32_t p) {
     const uint64_t fw = (((uint64_t)fshr(b, c, sh) << 32) | fshr(a, b, sh)) & ((1ULL << (2 * WG::K)) - 1ULL);
     const uint64_t rc = revcomp_2bit(fw, WG::K);
     return xxh3_u64(fw < rc ? fw : rc);
+}
+
+// NF picks of one lane (list entries idx0, idx0 + 32, ...): hash and request all of them, then test
+template <int NF, bool EXTRACT>
+DCN_HD void wprobe_picks(const FilterParams &P, WarpSmem &s, uint32_t idx0, uint32_t npicks) {
+    uint16_t *pk_pos = s.pk_pos();
+    uint64_t *pk_hash = s.pk_hash();
+    uint32_t pp[NF];
+    bool v[NF];
+    uint64_t h[NF], bk[NF];
+    Bucket k[NF];
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
+        pp[f] = idx < npicks ? pk_pos[idx] : 0u;
+        v[f] = idx < npicks && wpick_valid(s, pp[f]);
+        h[f] = 0; bk[f] = 0;
+        k[f].k0 = k[f].k1 = k[f].k2 = k[f].k3 = 0;
+        if (v[f]) {
+            h[f] = wpick_hash(s, pp[f]);
+            if (!EXTRACT) { bk[f] = table_bucket(h[f], P.table.n_buckets); k[f] = load_bucket(P.table.slots, bk[f]); }
+        }
+    }
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
+        if (v[f]) {
+            pk_hash[idx] = h[f];
+            pk_pos[idx] = (uint16_t)(pp[f] | 0x4000u | (!EXTRACT && table_contains_from(P.table, h[f], bk[f], k[f]) ? 0x8000u : 0u));
+        }
+    }
 }
 
 // ------------------------------------------------------------------ where a tile's bases come from
@@ -591,35 +625,24 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
     });
 
     // ---- P6: hash every pick and probe the table, DCN_PICKS_IN_FLIGHT picks per lane in flight: hash + request all
-    // of them, then test (the hashes take over rel4 / em).  pk_pos: position | valid << 14 | in-index << 15
+    // of them, then test (the hashes take over rel4 / em).  pk_pos: position | valid << 14 | in-index << 15.
+    // A tile of 2x150 pairs emits 141 +- 10 picks: at two per lane that is two full iterations and a third for a
+    // dozen lanes.  Measured (quick bench, Gbp/s): one per lane 298.2, two 296.0, three 268.6, four 252.5; two, and three
+    // in the iteration that then finishes the list (DCN_PICKS_LAST_3: two round trips per tile instead of three) 266.3;
+    // one, and two in the last 276.8.  Fewer round trips do not pay: a second copy of the probe body in the loop costs
+    // more in instruction fetch than a round trip costs in latency (the body is ~2800 instructions and 32 warps are in
+    // 32 different places of it), and more requests per warp at 74 % of the request ceiling only lengthen the queues.
     ex.par([&](int l, Priv &) {
-        uint16_t *pk_pos = s.pk_pos();
-        uint64_t *pk_hash = s.pk_hash();
         constexpr int NF = DCN_PICKS_IN_FLIGHT;
-        for (uint32_t idx0 = (uint32_t)l; idx0 < npicks; idx0 += NF * WG::NL) {
-            uint32_t pp[NF];
-            bool v[NF];
-            uint64_t h[NF], bk[NF];
-            Bucket k[NF];
-#pragma unroll
-            for (int f = 0; f < NF; f++) {
-                const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
-                pp[f] = idx < npicks ? pk_pos[idx] : 0u;
-                v[f] = idx < npicks && wpick_valid(s, pp[f]);
-                h[f] = 0; bk[f] = 0;
-                k[f].k0 = k[f].k1 = k[f].k2 = k[f].k3 = 0;
-                if (v[f]) {
-                    h[f] = wpick_hash(s, pp[f]);
-                    if (!EXTRACT) { bk[f] = table_bucket(h[f], P.table.n_buckets); k[f] = load_bucket(P.table.slots, bk[f]); }
-                }
-            }
-#pragma unroll
-            for (int f = 0; f < NF; f++) {
-                const uint32_t idx = idx0 + (uint32_t)f * WG::NL;
-                if (v[f]) {
-                    pk_hash[idx] = h[f];
-                    pk_pos[idx] = (uint16_t)(pp[f] | 0x4000u | (!EXTRACT && table_contains_from(P.table, h[f], bk[f], k[f]) ? 0x8000u : 0u));
-                }
+        uint32_t base = 0;
+        while (base < npicks) {
+            const uint32_t rem = npicks - base;
+            if (DCN_PICKS_LAST_3 && !EXTRACT && rem > (uint32_t)NF * WG::NL && rem <= (uint32_t)(NF + 1) * WG::NL) {
+                wprobe_picks<NF + 1, EXTRACT>(P, s, base + (uint32_t)l, npicks);
+                base += (uint32_t)(NF + 1) * WG::NL;
+            } else {
+                wprobe_picks<NF, EXTRACT>(P, s, base + (uint32_t)l, npicks);
+                base += (uint32_t)NF * WG::NL;
             }
         }
     });
