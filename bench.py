@@ -589,8 +589,11 @@ def run_ours(args):
                     # what the host can feed: pinned H2D GB/s of a rank alone and of all ranks at once (one ASCII base = one
                     # byte of it); packing on host threads is switched on while the ranks' own links are what binds
                     "ingest_ceiling": dict(ingest, ascii_route_gbp_per_s=ingest["concurrent_sum_gbs"],
-                                           limiter=("each rank's PCIe link (packing on: fewer bytes per base)" if (pack_threads or 0) > 0
-                                                    else "host DRAM / PCIe root shared by the ranks (ASCII route only: a packed base costs 1.5 B of host DRAM traffic, a copied one 1.0 B)")),
+                                           limiter=("the host the ranks share (DRAM / socket interconnect / PCIe root): the ranks' shares are unequal and the "
+                                                    "slowest sets the step time; ASCII route, two packer threads on the ranks well below the mean share "
+                                                    "(a packed base costs 1.5 B of host DRAM traffic, a copied one 1.0 B)"
+                                                    if ingest["concurrent_gbs"] < 0.8 * ingest["solo_gbs"] or (world > 1 and ingest.get("concurrent_min_gbs", 1e9) < 0.8 * ingest["solo_gbs"])
+                                                    else "each rank's own PCIe link and the host memory traffic of its packer threads (DESIGN.md 5)")),
                     "frac_of_ascii_ceiling": round(e2e_value / max(ingest["concurrent_sum_gbs"], 1e-9), 3),
                     # every rank does the same work, so the rank with the smallest share of the host sets the time of the step
                     "frac_of_slowest_rank_ceiling": round(e2e_value / max(world * ingest.get("concurrent_min_gbs", ingest["concurrent_gbs"]), 1e-9), 3),

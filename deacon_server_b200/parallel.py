@@ -95,11 +95,19 @@ def pack_threads_for_rank(local_world: int, probe: dict | None = None) -> int:
     costs when the ranks are already held back by the DRAM they share.  `probe` (h2d_probe) tells which: with every
     rank copying at once, a rank that still gets >= 80 % of its solo rate is link-bound -> pack with the CPUs this
     process may use, shared with the other ranks, minus four (caller, enqueueing thread, driver), at most 12;
-    otherwise 0 (ASCII route only: the copy engine needs no CPU).  Without a probe the round-1 rule applies
+    otherwise the ranks share a host that is the limit: 0 (ASCII route only: the copy engine needs no CPU), or 2 on a
+    rank whose share is well below the mean (the step waits for it).  Without a probe the round-1 rule applies
     (no packing from four ranks per host: measured host-DRAM-bound on the 8-GPU boxes of this pool)."""
     import os
     if probe is not None and probe.get("solo_gbs"):
         if probe["concurrent_gbs"] < 0.8 * probe["solo_gbs"]:
+            # Host-bound.  The ranks' shares are not equal (one 8-GPU box: four ranks at 20 GB/s, four at 35) and with the
+            # same work per rank the slow ones set the step time: two packers on a rank whose share is well below the mean
+            # shorten its step a little (measured with tools/ingest_sweep.py: 166-172 -> 177-180 Gbp/s; three: no better);
+            # on every rank they only add DRAM traffic (166 / 163 with two / three per rank).
+            mean = probe.get("concurrent_sum_gbs", 0.0) / max(1, probe.get("world", 1))
+            if probe["concurrent_gbs"] < 0.85 * mean:
+                return 2
             return 0
     elif local_world >= 4:
         return 0

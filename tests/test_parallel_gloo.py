@@ -116,4 +116,5 @@ def test_pack_threads_for_rank(monkeypatch):
     host_bound = {"solo_gbs": 54.0, "concurrent_gbs": 21.5, "concurrent_sum_gbs": 172.0, "world": 8}
     assert P.pack_threads_for_rank(4, link_bound) == 12
     assert P.pack_threads_for_rank(8, host_bound) == 0
+    assert P.pack_threads_for_rank(8, dict(host_bound, concurrent_gbs=17.0)) == 2       # a rank well below the mean share (21.5): the step waits for it
     assert P.pack_threads_for_rank(8, dict(host_bound, concurrent_gbs=50.0)) == 4      # 64 / 8 - 4

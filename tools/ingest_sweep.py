@@ -103,6 +103,14 @@ del bases
 
 probe = par.h2d_probe(dev)
 emit({"what": "h2d_probe", **probe})
+# every rank's share with all ranks copying (the ranks of one host do not get equal shares)
+shares = [probe["concurrent_gbs"]]
+if world > 1:
+    t = torch.tensor([probe["concurrent_gbs"]], dtype=torch.float64, device=dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t)
+    shares = [round(float(x.item()), 2) for x in parts]
+emit({"what": "h2d_share_per_rank", "gbs": shares})
 
 # ---- packing alone: t threads per rank run dcn_pack_ascii over slices of the batch, every rank at once
 lib = d.load()
@@ -135,7 +143,7 @@ def pack_rate(t, seconds=0.6):
     return sum(done) / (time.perf_counter() - t0) / 1e9
 
 
-for t in sorted({int(x) for x in args.threads.split(",") if int(x) > 0}):
+for t in sorted({int(x) for x in args.threads.split(",") if x.isdigit() and int(x) > 0}):
     r = pack_rate(t)
     emit({"what": "pack_only", "threads_per_rank": t, "sum_gbp_per_s": round(sum_over_ranks(r), 1), "rank0_gbp_per_s": round(r, 1)})
 
@@ -144,7 +152,19 @@ def e2e():
     gpu.filter_batch_ptr(hbases.data_ptr(), hoff.data_ptr(), NR, True, 0, 2, 0.01, True, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
 
 
-for t in [int(x) for x in args.threads.split(",")]:
+def threads_for(spec):
+    """'3' -> 3 on every rank; 'slow2' -> 2 on the ranks whose share of the host is below the mean, 0 on the others;
+    'eq' -> as many as lift the rank's share to the best rank's at ~8 GB/s per packer thread (at most 4)."""
+    mean = sum(shares) / len(shares)
+    if spec.startswith("slow"):
+        return int(spec[4:]) if shares[rank] < mean else 0
+    if spec == "eq":
+        return min(4, max(0, round((max(shares) - shares[rank]) / 8.0)))
+    return int(spec)
+
+
+for spec in args.threads.split(","):
+    t = threads_for(spec)
     gpu.host_pack_threads(t)
     gpu.host_pack_fraction(-1)
     e2e()
@@ -157,7 +177,7 @@ for t in [int(x) for x in args.threads.split(",")]:
     dt = max_over_ranks(time.perf_counter() - t0) / args.steps
     h2d = gpu.last_transfer_bytes()[0]
     assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu()) and torch.equal(ht, tot.cpu()), "host path != device path"
-    emit({"what": "e2e", "pack_threads_per_rank": t, "ms_per_step": round(dt * 1e3, 2), "sum_gbp_per_s": round(world * nb / dt / 1e9, 1),
+    emit({"what": "e2e", "pack_threads_per_rank": spec, "ms_per_step": round(dt * 1e3, 2), "sum_gbp_per_s": round(world * nb / dt / 1e9, 1),
           "h2d_mb_rank0": round(h2d / 1e6)})
     barrier()
 
