@@ -514,6 +514,29 @@ def run_ours(args):
     torch.cuda.synchronize()
     assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu()) and torch.equal(ht, tot.cpu()), \
         "caller-packed path and device-pointer path disagree"
+
+    # ---- ... and with the non-ACGT bits as the sparse list the library's own packers use (dcn_filter_batch_packed_sparse)
+    _, exc_np, _ = A.pack_records_sparse(hb[0].numpy(), hoff.numpy().view(np.uint64))
+    he = torch.from_numpy(np.ascontiguousarray(exc_np).view(np.int32).reshape(-1)).pin_memory() if len(exc_np) else None
+
+    def sparse_step():
+        gpu.filter_batch_packed_sparse_ptr(hc.data_ptr(), he.data_ptr() if he is not None else None, len(exc_np), None, hoff.data_ptr(),
+                                           NR, True, 0, 2, 0.01, True, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
+
+    hk.zero_()
+    sparse_step()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(p_steps):
+        sparse_step()
+    torch.cuda.synchronize()
+    svec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    s_h2d, s_d2h = gpu.last_transfer_bytes()
+    if world > 1:
+        dist.all_reduce(svec, op=dist.ReduceOp.MAX)
+    sparse_s = float(svec.item())
+    assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu()) and torch.equal(ht, tot.cpu()), \
+        "caller-packed (sparse) path and device-pointer path disagree"
     for i in range(1):
         e2e_step(e2e_steps - 1)   # leave the last e2e batch's result in the host buffers for the check below
 
@@ -609,6 +632,11 @@ def run_ours(args):
                                  "caller_buffer_bytes_per_step": int(codes_np.nbytes + inv_np.nbytes + (NR + 1) * 8),
                                  "api": "dcn_filter_batch_packed (C ABI): 2-bit codes + non-ACGT bits packed by the caller "
                                         "(packing time not included)"},
+            "e2e_packed_sparse_input": {"value": round(1e-9 * nb * p_steps * world / sparse_s, 3), "unit": "Gbp/s",
+                                        "h2d_bytes_per_step": int(s_h2d), "d2h_bytes_per_step": int(s_d2h), "steps": p_steps,
+                                        "caller_buffer_bytes_per_step": int(codes_np.nbytes + exc_np.nbytes + (NR + 1) * 8),
+                                        "api": "dcn_filter_batch_packed_sparse (C ABI): 2-bit codes + (block, mask) list of the non-ACGT "
+                                               "bases packed by the caller with dcn_pack_records_sparse (packing time not included)"},
             "gpu_launches": int(launches),
             # `bound` keeps the contract's vocabulary: the path is nominally HBM work.  What actually binds it is stated
             # next to it, each as a fraction measured by THIS run unless it is prefixed ncu_ (then it is read from the

@@ -38,6 +38,10 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p, C.c_uint32]),
     "dcn_filter_batch_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
                                           C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcn_filter_batch_packed_sparse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
+                                                C.c_uint32, C.c_uint32, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcn_pack_records_sparse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64,
+                                         C.c_void_p, C.c_void_p]),
     "dcn_newline_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint32, C.c_void_p]),
     "dcn_pack_records": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcn_host_pack_threads": (C.c_int, [C.c_void_p, C.c_int]),

@@ -244,6 +244,26 @@ class DeaconGpu:
                                                       prefix_length, abs_threshold, rel_threshold, int(deplete), keep_ptr,
                                                       hits_ptr, total_ptr))
 
+    def filter_batch_packed_sparse(self, codes, exc, nl_bits, rec_off, paired=False, prefix_length=0, abs_threshold=2,
+                                   rel_threshold=0.01, deplete=False):
+        """filter_batch for a batch in the sparse packed form (pack_records_sparse): exc = (block, mask) pairs, u32[n, 2]."""
+        rec_off = np.ascontiguousarray(rec_off, np.uint64)
+        exc = np.ascontiguousarray(exc, np.uint32).reshape(-1, 2)
+        n_rec = len(rec_off) - 1
+        nu = n_rec // 2 if paired else n_rec
+        keep, hits, total = np.zeros(max(nu, 1), np.uint8), np.zeros(max(nu, 1), np.uint32), np.zeros(max(nu, 1), np.uint32)
+        self._check(self._lib.dcn_filter_batch_packed_sparse(
+            self._ctx, codes.ctypes.data, exc.ctypes.data if len(exc) else None, len(exc),
+            nl_bits.ctypes.data if nl_bits is not None else None, rec_off.ctypes.data, n_rec, int(paired), prefix_length,
+            abs_threshold, rel_threshold, int(deplete), keep.ctypes.data, hits.ctypes.data, total.ctypes.data))
+        return keep[:nu], hits[:nu], total[:nu]
+
+    def filter_batch_packed_sparse_ptr(self, codes_ptr, exc_ptr, n_exc, nl_ptr, off_ptr, n_rec, paired, prefix_length,
+                                       abs_threshold, rel_threshold, deplete, keep_ptr, hits_ptr, total_ptr):
+        self._check(self._lib.dcn_filter_batch_packed_sparse(self._ctx, codes_ptr, exc_ptr, int(n_exc), nl_ptr, off_ptr, n_rec,
+                                                             int(paired), prefix_length, abs_threshold, rel_threshold,
+                                                             int(deplete), keep_ptr, hits_ptr, total_ptr))
+
     def host_pack_threads(self, n: int):
         """Host threads that pack chunks for filter_batch (0 = ship ASCII over PCIe)."""
         self._check(self._lib.dcn_host_pack_threads(self._ctx, int(n)))
@@ -568,3 +588,27 @@ def pack_records(bases: np.ndarray, rec_off: np.ndarray, k: int = 31, prefix_len
     if rc:
         raise DeaconCudaError(rc, "dcn_pack_records failed")
     return codes[:nw], inv[:nw], nl
+
+
+def pack_records_sparse(bases: np.ndarray, rec_off: np.ndarray, k: int = 31, prefix_length: int = 0):
+    """dcn_pack_records_sparse -> (codes u32[], exc u32[n, 2] = (32-base block, non-ACGT mask) ascending, nl_bits)."""
+    bases = np.ascontiguousarray(bases, np.uint8)
+    rec_off = np.ascontiguousarray(rec_off, np.uint64)
+    n = len(rec_off) - 1
+    nb = int(rec_off[-1]) if n else 0
+    nw = 2 * ((nb + 31) // 32)
+    codes = np.zeros(max(nw, 1), np.uint32)
+    nl = np.zeros(max(1, (n + 31) // 32), np.uint32)
+    bptr = bases.ctypes.data if len(bases) else codes.ctypes.data
+    cap = max(64, nw // 64)
+    while True:
+        exc = np.zeros((cap, 2), np.uint32)
+        n_exc = C.c_uint64()
+        rc = _lib.load().dcn_pack_records_sparse(bptr, rec_off.ctypes.data, n, k, prefix_length, codes.ctypes.data, exc.ctypes.data,
+                                                 cap, C.byref(n_exc), nl.ctypes.data)
+        if rc == -6 and n_exc.value > cap:   # DCN_ERR_OVERFLOW: the list is longer (N-rich input)
+            cap = int(n_exc.value)
+            continue
+        if rc:
+            raise DeaconCudaError(rc, "dcn_pack_records_sparse failed")
+        return codes[:nw], exc[:n_exc.value], nl

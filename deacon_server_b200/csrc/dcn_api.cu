@@ -796,6 +796,8 @@ struct HostSrc {   // caller's host buffers: ASCII, or already packed (dcn_filte
     const uint32_t *codes = nullptr;
     const uint16_t *inv = nullptr;
     const uint32_t *nl = nullptr;
+    const uint32_t *exc = nullptr;   // packed, sparse form (dcn_filter_batch_packed_sparse): (block, mask) pairs instead of `inv`
+    uint64_t n_exc = 0;
 };
 
 namespace {
@@ -1192,7 +1194,7 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
                             CK(cudaMemcpyAsync(s.in.p, hin + o_x, (size_t)n_exc * 8, cudaMemcpyHostToDevice, s.stream));
                             moved += (uint64_t)n_exc * 8;
                             inv_scatter_kernel<<<grid_for(ctx, (uint64_t)n_exc, 128), 128, 0, s.stream>>>(
-                                reinterpret_cast<uint32_t *>(inv_dst), reinterpret_cast<const uint2 *>(s.in.p), (uint32_t)n_exc);
+                                reinterpret_cast<uint32_t *>(inv_dst), reinterpret_cast<const uint2 *>(s.in.p), (uint32_t)n_exc, 0u);
                             ctx->launches += 1;
                         }
                     } else {
@@ -1525,7 +1527,8 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         // sized for the largest chunk the stage is likely to see, not for this one: growing a buffer later costs a
         // cudaFree / cudaFreeHost (a device-wide sync) in the middle of some call
         const ChunkPlan &big = route == 2 ? big_packed : big_ascii;
-        if (s.in.ensure(std::max(route ? std::max(c.in_packed, c.dev_sparse) + 8 : c.in_ascii, route ? std::max(big.in_packed, big.dev_sparse) + 8 : big.in_ascii)) != cudaSuccess ||
+        const size_t exc_room = route == 1 && src.exc ? 16 + (c.n_words / 2 + 1) * 8 : 0;   // caller's sparse list: at most one entry per 32-base block
+        if (s.in.ensure(std::max(route ? std::max(c.in_packed, c.dev_sparse) + 8 : c.in_ascii, route ? std::max(big.in_packed, big.dev_sparse) + 8 : big.in_ascii) + exc_room) != cudaSuccess ||
             s.out.ensure(std::max(c.out_bytes, big.out_bytes)) != cudaSuccess || s.h_out.ensure(std::max(c.out_bytes, big.out_bytes)) != cudaSuccess)
             return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
         uint8_t *din = s.in.as<uint8_t>();
@@ -1547,8 +1550,30 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
         if (route == 1) {   // slices of the caller's packed arrays, copied as they are
             const uint64_t r_first = (uint64_t)c.u0 * rpu;
             CK(cudaMemcpyAsync(din, src.codes + c.a0 / 16, c.n_words * 4, cudaMemcpyHostToDevice, s.stream));
-            CK(cudaMemcpyAsync(din + c.o_inv, src.inv + c.a0 / 16, c.n_words * 2, cudaMemcpyHostToDevice, s.stream));
-            acc.h2d += c.n_words * 6;
+            acc.h2d += c.n_words * 4;
+            if (src.exc) {
+                // sparse form: the listed blocks of this chunk (the list is ascending) are copied behind the blob and
+                // scattered into the cleared dense array; 0.25 B/bp cross PCIe instead of 0.375
+                const uint64_t blk0 = c.a0 / 32, blk1 = blk0 + c.n_words / 2;
+                auto first_at_least = [&](uint64_t b) {
+                    uint64_t lo = 0, hi = src.n_exc;
+                    while (lo < hi) { const uint64_t mid = lo + (hi - lo) / 2; if (src.exc[2 * mid] < b) lo = mid + 1; else hi = mid; }
+                    return lo;
+                };
+                const uint64_t e0 = first_at_least(blk0), e1 = first_at_least(blk1);
+                CK(cudaMemsetAsync(din + c.o_inv, 0, c.n_words * 2, s.stream));
+                if (e1 > e0) {
+                    const size_t o_exc = align_up(c.in_packed, 8);
+                    CK(cudaMemcpyAsync(din + o_exc, src.exc + 2 * e0, (size_t)(e1 - e0) * 8, cudaMemcpyHostToDevice, s.stream));
+                    acc.h2d += (e1 - e0) * 8;
+                    inv_scatter_kernel<<<grid_for(ctx, e1 - e0, 128), 128, 0, s.stream>>>(
+                        reinterpret_cast<uint32_t *>(din + c.o_inv), reinterpret_cast<const uint2 *>(din + o_exc), (uint32_t)(e1 - e0), (uint32_t)blk0);
+                    ctx->launches += 1;
+                }
+            } else {
+                CK(cudaMemcpyAsync(din + c.o_inv, src.inv + c.a0 / 16, c.n_words * 2, cudaMemcpyHostToDevice, s.stream));
+                acc.h2d += c.n_words * 2;
+            }
             CK(ship_offsets(din + c.o_off_p, off0));
             if (src.nl) {
                 const uint64_t w0 = r_first / 32, w1 = (r_first + c.nr + 31) / 32;
@@ -1571,7 +1596,7 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
             CK(cudaMemsetAsync(din + c.s_inv, 0, c.n_words * 2, s.stream));
             if (n_exc) {
                 inv_scatter_kernel<<<grid_for(ctx, (uint64_t)n_exc, 128), 128, 0, s.stream>>>(
-                    reinterpret_cast<uint32_t *>(din + c.s_inv), reinterpret_cast<const uint2 *>(din + c.s_exc), (uint32_t)n_exc);
+                    reinterpret_cast<uint32_t *>(din + c.s_inv), reinterpret_cast<const uint2 *>(din + c.s_exc), (uint32_t)n_exc, 0u);
                 ctx->launches += 1;
             }
             acc.n_packed++;
@@ -1833,6 +1858,32 @@ int dcn_filter_batch_packed(dcn_ctx *ctx, const uint32_t *codes, const uint16_t 
     HostSrc src;
     src.codes = codes; src.inv = inv; src.nl = nl_bits;
     return filter_pipeline(ctx, src, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr, deplete, keep, hits, total);
+}
+
+int dcn_filter_batch_packed_sparse(dcn_ctx *ctx, const uint32_t *codes, const uint32_t *exc, uint64_t n_exc, const uint32_t *nl_bits,
+                                   const uint64_t *rec_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
+                                   double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total) {
+    if (!ctx) return DCN_ERR_ARG;
+    if (!codes || (!exc && n_exc)) return ctx->fail(DCN_ERR_ARG, "null input pointer");
+    if (n_rec && rec_off && rec_off[0] != 0) return ctx->fail(DCN_ERR_ARG, "rec_off[0] must be 0");
+    for (uint64_t i = 1; i < n_exc; i++)
+        if (exc[2 * i] <= exc[2 * i - 2]) return ctx->fail(DCN_ERR_ARG, "the exception list must be in ascending block order");
+    static const uint32_t none[2] = {0xFFFFFFFFu, 0u};
+    HostSrc src;
+    src.codes = codes; src.exc = n_exc ? exc : none; src.n_exc = n_exc; src.nl = nl_bits;
+    return filter_pipeline(ctx, src, rec_off, n_rec, paired, prefix_len, abs_thr, rel_thr, deplete, keep, hits, total);
+}
+
+int dcn_pack_records_sparse(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
+                            uint32_t *codes, uint32_t *exc, uint64_t exc_cap, uint64_t *n_exc, uint32_t *nl_bits) {
+    if (!rec_off || !codes || !n_exc || !nl_bits || (!exc && exc_cap) || (!bases && n_rec && rec_off[n_rec] > 0)) return DCN_ERR_ARG;
+    std::vector<uint64_t> bad32;
+    std::vector<uint32_t> bad_mask;
+    pack_records(bases, 0, n_rec ? rec_off[n_rec] : 0, rec_off, n_rec, k, prefix_len, codes, nullptr, nl_bits, bad32, &bad_mask);
+    *n_exc = bad32.size();
+    if (bad32.size() > exc_cap) return DCN_ERR_OVERFLOW;
+    for (size_t i = 0; i < bad32.size(); i++) { exc[2 * i] = (uint32_t)bad32[i]; exc[2 * i + 1] = bad_mask[i]; }
+    return DCN_OK;
 }
 
 int dcn_newline_bits(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,

@@ -900,8 +900,10 @@ __global__ void uniform_offsets_kernel(uint64_t *__restrict__ off, uint32_t n, u
 // ------------------------------------------------------------------ sparse non-ACGT mask of the host-packed form
 // The packer threads ship (32-base block, 32-bit mask) pairs for the blocks that hold a non-ACGT byte; the dense bit
 // array the kernels read is a memset plus this.
-__global__ void inv_scatter_kernel(uint32_t *__restrict__ inv32, const uint2 *__restrict__ exc, uint32_t n) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) inv32[exc[i].x] = exc[i].y;
+// `base`: block index of inv32[0] (the packer threads list blocks relative to their chunk: 0; a caller's list counts from
+// the start of the batch)
+__global__ void inv_scatter_kernel(uint32_t *__restrict__ inv32, const uint2 *__restrict__ exc, uint32_t n, uint32_t base) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) inv32[exc[i].x - base] = exc[i].y;
 }
 
 // ------------------------------------------------------------------ summary counters (a13)

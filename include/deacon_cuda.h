@@ -114,6 +114,15 @@ int dcn_pack_ascii(const uint8_t *bases, uint64_t n_bases, uint32_t *codes, uint
 int dcn_filter_batch_packed(dcn_ctx *ctx, const uint32_t *codes, const uint16_t *inv, const uint32_t *nl_bits,
                             const uint64_t *rec_off, uint32_t n_rec, int paired, uint32_t prefix_len, uint32_t abs_thr,
                             double rel_thr, int deplete, uint8_t *keep, uint32_t *hits, uint32_t *total);
+/* The same with the non-ACGT bits as a sparse list instead of the dense `inv` array (what the library's own packer
+ * threads put on the wire): exc[2 i] = index of a 32-base block of the batch (base position / 32), exc[2 i + 1] = the
+ * 32 non-ACGT bits of that block; every block that holds a non-ACGT byte (or padding behind the last base) is listed,
+ * once, in ascending order (else DCN_ERR_ARG).  0.25 instead of 0.375 bytes per base cross PCIe; the dense array the
+ * kernels read is rebuilt on the device.  Replaces the same loop (src/filter_common.rs:238-258). */
+int dcn_filter_batch_packed_sparse(dcn_ctx *ctx, const uint32_t *codes, const uint32_t *exc, uint64_t n_exc,
+                                   const uint32_t *nl_bits, const uint64_t *rec_off, uint32_t n_rec, int paired,
+                                   uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *keep,
+                                   uint32_t *hits, uint32_t *total);
 /* bit r of nl_bits[(n_rec + 31) / 32] = record r (raw length >= k) ends its effective prefix in '\n'
  * (the one byte of the ASCII form the packed form cannot tell from other non-ACGT bytes; src/filter_common.rs:229). */
 int dcn_newline_bits(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
@@ -124,6 +133,10 @@ int dcn_newline_bits(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_r
  * codes / inv: 2 * ceil(rec_off[n_rec] / 32) entries each; nl_bits: ceil(n_rec / 32) words. */
 int dcn_pack_records(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
                      uint32_t *codes, uint16_t *inv, uint32_t *nl_bits);
+/* dcn_pack_records for dcn_filter_batch_packed_sparse: the non-ACGT bits as (block, mask) pairs in `exc` (2 * exc_cap
+ * words).  *n_exc = number of listed blocks; DCN_ERR_OVERFLOW (nothing written to exc) when exc_cap is smaller. */
+int dcn_pack_records_sparse(const uint8_t *bases, const uint64_t *rec_off, uint32_t n_rec, uint8_t k, uint32_t prefix_len,
+                            uint32_t *codes, uint32_t *exc, uint64_t exc_cap, uint64_t *n_exc, uint32_t *nl_bits);
 
 /* ---- B2: batch classify on pre-hashed records --------------------------------------------------
  * Replaces unpaired_should_keep / paired_should_keep (src/remote_filter.rs:230-301), i.e. the body of

@@ -103,6 +103,14 @@ def test_pack_records_matches_the_two_separate_passes():
         assert np.array_equal(nl, want_nl), (n_rec, prefix)
         if n_rec >= 700:
             assert int(np.unpackbits(nl.view(np.uint8)).sum()) > n_rec // 8
+        # the sparse form (dcn_pack_records_sparse): the same codes and flags, and a list that rebuilds the dense mask
+        codes_s, exc, nl_s = api.pack_records_sparse(b, off, 31, prefix)
+        assert np.array_equal(codes_s, want_c) and np.array_equal(nl_s, want_nl), (n_rec, prefix)
+        dense = np.zeros(len(want_i) // 2, np.uint32)
+        assert np.all(np.diff(exc[:, 0].astype(np.int64)) > 0)          # ascending, every block once
+        dense[exc[:, 0]] = exc[:, 1]
+        assert np.array_equal(dense.view(np.uint16), want_i), (n_rec, prefix)
+        assert np.all(exc[:, 1] != 0)                                   # only blocks that hold a non-ACGT base (or padding)
 
 
 def test_product_packer_matches_definition():

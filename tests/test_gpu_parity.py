@@ -343,6 +343,62 @@ def test_two_route_ingest_small_atoms(tmp_path, n_every, sparse, extra):
     assert r.returncode == 0 and "small atoms ok" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_caller_packed_sparse_form_matches_ascii(gpu):
+    """dcn_filter_batch_packed_sparse (2-bit codes + a sparse list of the 32-base blocks with a non-ACGT base, what a
+    parser that packs while it parses can emit) == dcn_filter_batch_packed (dense mask) == dcn_filter_batch (ASCII) on
+    ragged records with N runs, newline-terminated records, prefixes and pairs; 70 MB so that several pipeline chunks
+    split the exception list; an unsorted list is refused."""
+    from deacon_server_b200 import IndexHeader, DeaconCudaError, api as A
+    g = H.random_genome(300_000, 51)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    rng = np.random.default_rng(52)
+    n = 500_000
+    lens = rng.integers(60, 220, n).astype(np.uint64)
+    lens[rng.integers(0, n, 3000)] = rng.integers(0, 31, 3000).astype(np.uint64)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    assert total > (64 << 20)                                                         # three 32 MB chunks
+    start = rng.integers(0, len(g) - 300, total // 128 + 2)
+    bases = g[(start[:, None] + np.arange(128)[None, :])].reshape(-1)[:total].copy()
+    bases[rng.integers(0, total, total // 3000)] = ord("N")
+    run = int(rng.integers(0, total - 5000))
+    bases[run:run + 4000] = ord("N")                                                  # a long run: many consecutive listed blocks
+    nl = rng.integers(0, n, 5000); nl = nl[lens[nl] >= 31]
+    bases[(off[nl + 1] - 1).astype(np.int64)] = 10
+    gpu.host_pack_threads(0)
+    try:
+        for paired, prefix in ((False, 0), (True, 0), (False, 100)):
+            want = gpu.filter_batch(bases, off, paired=paired, prefix_length=prefix, deplete=paired)
+            ok = O.filter_batch(idx, bases, off, paired=paired, prefix_len=prefix, deplete=paired, threads=8)
+            for a, b in zip(want, ok):
+                assert np.array_equal(a, b)
+            codes, exc, nlb = A.pack_records_sparse(bases, off, 31, prefix)
+            assert 100 < len(exc) < total // 32 // 20
+            got = gpu.filter_batch_packed_sparse(codes, exc, nlb, off, paired=paired, prefix_length=prefix, deplete=paired)
+            for a, b in zip(got, want):
+                assert np.array_equal(a, b), (paired, prefix)
+            h2d, _ = gpu.last_transfer_bytes()
+            assert h2d < 0.27 * total + 8 * (n + 1) + 8 * len(exc) + 4096
+            codes_d, inv_d, nl_d = A.pack_records(bases, off, 31, prefix)
+            got_d = gpu.filter_batch_packed(codes_d, inv_d, nl_d, off, paired=paired, prefix_length=prefix, deplete=paired)
+            for a, b in zip(got_d, want):
+                assert np.array_equal(a, b), (paired, prefix)
+        with pytest.raises(DeaconCudaError):
+            gpu.filter_batch_packed_sparse(codes, exc[::-1].copy(), nlb, off)
+        # no exception at all: ACGT only, the batch ends on a block edge (no padding either)
+        reads = [g[i * 160:i * 160 + 160].copy() for i in range(1000)]
+        cb, co = H.concat(reads)
+        c2, e2, n2 = A.pack_records_sparse(cb, co, 31, 0)
+        assert len(e2) == 0
+        got = gpu.filter_batch_packed_sparse(c2, e2, n2, co)
+        for a, b in zip(got, gpu.filter_batch(cb, co)):
+            assert np.array_equal(a, b)
+    finally:
+        gpu.host_pack_threads(4)
+
+
 def test_device_pointer_api_matches_host_api(gpu):
     import torch
     from deacon_server_b200 import IndexHeader
