@@ -1368,12 +1368,18 @@ static int filter_pipeline(dcn_ctx *ctx, const HostSrc &src, const uint64_t *rec
     const uint32_t n_units = n_rec / rpu;
     if (n_units == 0) return DCN_OK;
 
-    static const uint64_t chunk_bases = []() {
+    static const uint64_t chunk_bases_env = []() {
         const char *e = getenv("DCN_CHUNK_MB");
         uint64_t mb = e ? strtoull(e, nullptr, 10) : 32;
         if (mb < 1) mb = 1;
         return mb << 20;
     }();
+    // Caller-packed input runs the chunk form (one route): its chunks are larger, because a kernel over 32 Mbp runs at half
+    // the rate of one over 128 Mbp (tools/chunk_cost.py) and at 0.25 - 0.375 B/bp the copy of a chunk is short anyway.
+    // Measured (bench.py, Gbp/s, dense mask / sparse list): 32 MB 119 / 137, 64 MB 131 / 144, 128 MB 128 / 172, 256 MB 122 / 161.
+    static const uint64_t packed_chunk_env = []() { const char *e = getenv("DCN_PACKED_CHUNK_MB"); return e ? std::max<uint64_t>(1, strtoull(e, nullptr, 10)) << 20 : 0ull; }();
+    const uint64_t chunk_bases = !prepacked || getenv("DCN_CHUNK_MB") ? chunk_bases_env
+                               : packed_chunk_env ? packed_chunk_env : (src.exc ? 128ull << 20 : 64ull << 20);
 
     // ---- routes
     int n_packers = 0;           // host threads packing atoms
