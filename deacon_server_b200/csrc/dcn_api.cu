@@ -1149,7 +1149,8 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
                     s.busy = false;
                 }
                 const double t0 = now_ms();
-                if (s.h_in.ensure(std::max(blob, (size_t)(packer_grab_max * atom_bases) / 2)) != cudaSuccess || s.in.ensure((size_t)exc_cap * 8 + 64) != cudaSuccess)
+                if (s.h_in.ensure(std::max(blob, (size_t)(packer_grab_max * atom_bases) / 2)) != cudaSuccess ||
+                    s.in.ensure(std::max(blob, (size_t)(packer_grab_max * atom_bases) / 2)) != cudaSuccess)
                     return ctx->fail(DCN_ERR_NOMEM, "pinned staging allocation failed", cudaGetLastError());
                 uint8_t *hin = s.h_in.as<uint8_t>();
                 const ChunkStats cs = chunk_stats(off0, nu, rpu);
@@ -1178,41 +1179,32 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
                         for (size_t i = 0; i < bad32.size(); i++) memcpy(h_inv + 2 * bad32[i], &bad_mask[i], 4);
                     }
                 }
-                if (!cs.uniform) memcpy(hin + o_off, off0, ((size_t)nr + 1) * 8);
+                // offsets (when they are shipped) right behind what the claim really uses of the blob: one copy carries it all
+                const size_t o_off_w = n_exc >= 0 ? align_up(o_x + (size_t)n_exc * 8, 8) : align_up(o_x + n_words * 2, 8);
+                if (!cs.uniform) memcpy(hin + o_off_w, off0, ((size_t)nr + 1) * 8);
+                const size_t wire = o_off_w + (cs.uniform ? 0 : ((size_t)nr + 1) * 8);
                 const double t1 = now_ms();
                 pack_ms += t1 - t0;
                 my_bases += nb;
-                // ---- copies to the claim's places in the arena
+                // ---- one copy into the stage's device buffer, one kernel to the claim's places in the arena
                 uint64_t moved = 0;
-                if (n_words) {
-                    CK(cudaMemcpyAsync(d_codes + (p0 - A0) / 16, h_codes, n_words * 4, cudaMemcpyHostToDevice, s.stream));
-                    moved += n_words * 4;
+                if (wire) {
+                    const uint8_t *dst = s.in.as<uint8_t>();
+                    CK(cudaMemcpyAsync(s.in.p, hin, wire, cudaMemcpyHostToDevice, s.stream));
+                    moved += wire;
                     uint16_t *inv_dst = d_inv + (p0 - A0) / 16;
-                    if (n_exc >= 0) {
-                        CK(cudaMemsetAsync(inv_dst, 0, n_words * 2, s.stream));
-                        if (n_exc) {
-                            CK(cudaMemcpyAsync(s.in.p, hin + o_x, (size_t)n_exc * 8, cudaMemcpyHostToDevice, s.stream));
-                            moved += (uint64_t)n_exc * 8;
-                            inv_scatter_kernel<<<grid_for(ctx, (uint64_t)n_exc, 128), 128, 0, s.stream>>>(
-                                reinterpret_cast<uint32_t *>(inv_dst), reinterpret_cast<const uint2 *>(s.in.p), (uint32_t)n_exc, 0u);
-                            ctx->launches += 1;
-                        }
-                    } else {
-                        CK(cudaMemcpyAsync(inv_dst, h_inv, n_words * 2, cudaMemcpyHostToDevice, s.stream));
-                        moved += n_words * 2;
-                    }
-                }
-                if (nl_words) {
-                    CK(cudaMemcpyAsync(d_nl + r0 / 32, h_nl, nl_words * 4, cudaMemcpyHostToDevice, s.stream));
-                    moved += nl_words * 4;
-                }
-                if (cs.uniform) {
-                    uniform_offsets_kernel<<<grid_for(ctx, (uint64_t)nr + 1, 256), 256, 0, s.stream>>>(d_off + r0, nr + 1, off0[0], cs.rec_len0);
+                    if (n_exc >= 0 && n_words) CK(cudaMemsetAsync(inv_dst, 0, n_words * 2, s.stream));
+                    ClaimUnpack cu;
+                    cu.codes = reinterpret_cast<const uint32_t *>(dst); cu.dst_codes = d_codes + (p0 - A0) / 16; cu.n_words = n_words;
+                    cu.nl = reinterpret_cast<const uint32_t *>(dst + o_nl); cu.dst_nl = d_nl + r0 / 32; cu.nl_words = (uint32_t)nl_words;
+                    cu.exc = reinterpret_cast<const uint2 *>(dst + o_x); cu.n_exc = n_exc;
+                    cu.inv = reinterpret_cast<const uint32_t *>(dst + o_x); cu.dst_inv32 = reinterpret_cast<uint32_t *>(inv_dst);
+                    cu.off = reinterpret_cast<const uint64_t *>(dst + o_off_w); cu.dst_off = d_off + r0;
+                    cu.n_off = cs.uniform ? 0u : nr + 1; cu.n_gen = cs.uniform ? nr + 1 : 0u;
+                    cu.off_first = off0[0]; cu.off_len = cs.rec_len0;
+                    claim_unpack_kernel<<<grid_for(ctx, std::max<uint64_t>(n_words / 4, (uint64_t)nr + 1), 256), 256, 0, s.stream>>>(cu);
                     ctx->launches += 1;
-                    n_uniform++;
-                } else {
-                    CK(cudaMemcpyAsync(d_off + r0, hin + o_off, ((size_t)nr + 1) * 8, cudaMemcpyHostToDevice, s.stream));
-                    moved += ((uint64_t)nr + 1) * 8;
+                    if (cs.uniform) n_uniform++;
                 }
                 CK(cudaEventRecord(s.ev_h2d, s.stream));
                 CK(cudaGetLastError());

@@ -906,6 +906,33 @@ __global__ void inv_scatter_kernel(uint32_t *__restrict__ inv32, const uint2 *__
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) inv32[exc[i].x - base] = exc[i].y;
 }
 
+// ------------------------------------------------------------------ arena form of the host pipeline: one claim's blob -> its places
+// A packer thread's claim crosses PCIe as ONE copy (codes | newline flags | exception list or dense mask | offsets) into a
+// staging buffer; this kernel moves the parts to the claim's places in the arena (device-to-device, a few microseconds)
+// -- three or four small copies per claim cost the copy engine more than their bytes (measured: 223 copies per call,
+// 12.5 ms of engine time for 575 MB).  The dense non-ACGT array was cleared by a memset enqueued before (sparse form).
+struct ClaimUnpack {
+    const uint32_t *codes; uint32_t *dst_codes; uint64_t n_words;
+    const uint32_t *nl; uint32_t *dst_nl; uint32_t nl_words;
+    const uint2 *exc; int64_t n_exc;            // sparse form: (block, mask) pairs; < 0: dense mask at `inv`
+    const uint32_t *inv; uint32_t *dst_inv32;
+    const uint64_t *off; uint64_t *dst_off; uint32_t n_off;   // offsets shipped (n_off entries), or generated:
+    uint64_t off_first, off_len; uint32_t n_gen;              // dst_off[i] = off_first + i * off_len, i < n_gen
+};
+__global__ void claim_unpack_kernel(ClaimUnpack u) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n4 = u.n_words / 4;   // (both sides are 16-byte aligned: claims start at 64-base cuts)
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(u.codes);
+    uint4 *d4 = reinterpret_cast<uint4 *>(u.dst_codes);
+    for (uint64_t i = tid; i < n4; i += nt) d4[i] = s4[i];
+    for (uint64_t i = 4 * n4 + tid; i < u.n_words; i += nt) u.dst_codes[i] = u.codes[i];
+    for (uint64_t i = tid; i < u.nl_words; i += nt) u.dst_nl[i] = u.nl[i];
+    if (u.n_exc >= 0) { for (uint64_t i = tid; i < (uint64_t)u.n_exc; i += nt) u.dst_inv32[u.exc[i].x] = u.exc[i].y; }
+    else { for (uint64_t i = tid; i < u.n_words / 2; i += nt) u.dst_inv32[i] = u.inv[i]; }
+    for (uint64_t i = tid; i < u.n_off; i += nt) u.dst_off[i] = u.off[i];
+    for (uint64_t i = tid; i < u.n_gen; i += nt) u.dst_off[i] = u.off_first + i * u.off_len;
+}
+
 // ------------------------------------------------------------------ summary counters (a13)
 // src/local_filter.rs:347-371 (single) / 488-525 (pair): seqs and bp in / kept / filtered.
 __global__ void stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu, uint32_t n_units,
