@@ -904,6 +904,7 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
         u0 = lo;
     }
     const int n_atoms = (int)atom_u.size() - 1;
+    if (n_atoms < 8) return 1;   // a handful of huge units (atoms hold at least 32): not handled, the chunk pipeline cuts finer
     const int pack_budget = (int)std::min<double>(n_atoms, pack_share * n_atoms + 0.5);
     n_packers = std::min(n_packers, pack_budget);
     if (n_packers <= 0) return 1;   // not handled: the caller falls back to the chunk pipeline
