@@ -288,6 +288,42 @@ def test_two_route_ingest_long_reads(gpu):
         gpu.host_pack_threads(4)
 
 
+def test_two_route_ingest_few_huge_units(gpu):
+    """A batch of a handful of chromosome-sized records (fewer than eight atoms of >= 32 units): the arena form declines
+    it and the chunk form, whose atoms hold single units, runs both routes."""
+    import torch
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(400_000, 61)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    rng = np.random.default_rng(62)
+    lens = np.full(12, 20_000_000, np.uint64)
+    lens[5] = 31_000_000
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    start = rng.integers(0, len(g) - 70_000, total // 65536 + 2)
+    bases = g[(start[:, None] + np.arange(65536)[None, :])].reshape(-1)[:total].copy()   # 64 kb stretches of the genome
+    rnd = rng.integers(0, 2, total // 1_000_000 + 1).astype(bool).repeat(1_000_000)[:total]
+    bases[rnd] = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, int(rnd.sum()))]
+    bases[rng.integers(0, total, 5000)] = ord("N")
+    hb = torch.from_numpy(bases).pin_memory()
+    ho = torch.from_numpy(off.view(np.int64)).pin_memory()
+    n = len(lens)
+    ok, oh, ot = O.filter_batch(idx, bases, off, paired=False, deplete=False, threads=8)
+    assert int(oh.min()) > 1000
+    try:
+        for threads in (6, 0):
+            gpu.host_pack_threads(threads)
+            k, h, t = (torch.zeros(n, dtype=torch.uint8).pin_memory(), torch.zeros(n, dtype=torch.int32).pin_memory(),
+                       torch.zeros(n, dtype=torch.int32).pin_memory())
+            gpu.filter_batch_ptr(hb.data_ptr(), ho.data_ptr(), n, False, 0, 2, 0.01, False, k.data_ptr(), h.data_ptr(), t.data_ptr())
+            assert np.array_equal(t.numpy().view(np.uint32), ot) and np.array_equal(h.numpy().view(np.uint32), oh)
+            assert np.array_equal(k.numpy(), ok)
+    finally:
+        gpu.host_pack_threads(4)
+
+
 _SMALL_ATOMS = r"""
 import sys, numpy as np
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests")
