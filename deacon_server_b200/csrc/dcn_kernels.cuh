@@ -798,22 +798,32 @@ extract_tiles_kernel(FilterParams P, const BatchStats *st, const uint32_t *__res
     }
 }
 
-// CSR compaction: one warp per record moves its valid picks from the tile block to out_off[r] ..
+// CSR compaction: a half warp per record moves its valid picks from the tile block to out_off[r] .. (a 150-base read has
+// ~14 picks: with a whole warp per record more than half of the lanes had nothing to move)
 __global__ void extract_compact_kernel(ExtractOut xo, const uint64_t *__restrict__ out_off, uint32_t n_rec,
                                        uint64_t *__restrict__ out_h, uint32_t *__restrict__ out_p) {
-    const uint32_t lane = threadIdx.x & 31u, warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rec; r += warps) {
-        const uint64_t rt = xo.rec_tmp[r], start = rt >> 16;
-        const uint32_t n = (uint32_t)(rt & 0xFFFFu);
-        uint64_t at = out_off[r];
-        for (uint32_t base = 0; base < n; base += 32u) {
-            const uint32_t i = base + lane;
+    const uint32_t lane = threadIdx.x & 31u, sub = lane & 15u, half = lane >> 4;
+    const uint32_t groups = (gridDim.x * blockDim.x) >> 4;
+    const uint32_t n_it = (n_rec + groups - 1) / groups;   // the same trip count for both halves of a warp (ballots below)
+    uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    for (uint32_t it = 0; it < n_it; it++, r += groups) {
+        uint64_t start = 0, at = 0;
+        uint32_t n = 0;
+        if (r < n_rec) {
+            const uint64_t rt = xo.rec_tmp[r];
+            start = rt >> 16; n = (uint32_t)(rt & 0xFFFFu);
+            at = out_off[r];
+        }
+        const uint32_t n_other = __shfl_xor_sync(0xFFFFFFFFu, n, 16);
+        const uint32_t n_max = n > n_other ? n : n_other;
+        for (uint32_t base = 0; base < n_max; base += 16u) {
+            const uint32_t i = base + sub;
             uint32_t pp = 0;
             if (i < n) pp = xo.tmp_p[start + i];
             const bool valid = (pp & 0x80000000u) != 0;
-            const uint32_t m = __ballot_sync(0xFFFFFFFFu, valid);
+            const uint32_t m = (__ballot_sync(0xFFFFFFFFu, valid) >> (16u * half)) & 0xFFFFu;
             if (valid) {
-                const uint64_t o = at + (uint64_t)__popc(m & ((1u << lane) - 1u));
+                const uint64_t o = at + (uint64_t)__popc(m & ((1u << sub) - 1u));
                 out_h[o] = xo.tmp_h[start + i];
                 if (out_p) out_p[o] = pp & 0x7FFFFFFFu;
             }
