@@ -100,7 +100,10 @@ def load():
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(make -C deacon_server_b200/csrc).  There is no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
+    old_variant = bool(os.environ.get("DCN_LIB")) and bool(os.environ.get("DCN_LIB_OLD"))   # kernel A/B against an older build only
     for name, (res, args) in SIGNATURES.items():
+        if old_variant and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
