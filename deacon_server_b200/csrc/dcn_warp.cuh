@@ -22,7 +22,7 @@
 namespace dcn {
 
 #ifndef DCN_PICKS_IN_FLIGHT
-#define DCN_PICKS_IN_FLIGHT 2   // probes a lane has outstanding in P6
+#define DCN_PICKS_IN_FLIGHT 1   // probes a lane has outstanding in P6 (measured: 1 -> 298.9, 2 -> 294.6, 3 -> 268.6, 4 -> 252.5 Gbp/s)
 #endif
 #ifndef DCN_PICKS_LAST_3
 #define DCN_PICKS_LAST_3 0      // A/B knob: one more pick per lane in the iteration that then finishes the tile's list (measured: slower)
@@ -627,7 +627,7 @@ DCN_HD bool warp_run(Ex &ex, const WarpTables &T, WarpSmem &s, const FilterParam
     // ---- P6: hash every pick and probe the table, DCN_PICKS_IN_FLIGHT picks per lane in flight: hash + request all
     // of them, then test (the hashes take over rel4 / em).  pk_pos: position | valid << 14 | in-index << 15.
     // A tile of 2x150 pairs emits 141 +- 10 picks: at two per lane that is two full iterations and a third for a
-    // dozen lanes.  Measured (quick bench, Gbp/s): one per lane 298.2, two 296.0, three 268.6, four 252.5; two, and three
+    // dozen lanes.  Measured (quick bench, Gbp/s): one per lane 298.9 (kept), two 294.6 - 296.0, three 268.6, four 252.5; two, and three
     // in the iteration that then finishes the list (DCN_PICKS_LAST_3: two round trips per tile instead of three) 266.3;
     // one, and two in the last 276.8.  Fewer round trips do not pay: a second copy of the probe body in the loop costs
     // more in instruction fetch than a round trip costs in latency (the body is ~2800 instructions and 32 warps are in
