@@ -56,7 +56,10 @@ hi = [i for i, r in enumerate(rows) if "Kernel Name" in r][0]
 h = rows[hi]
 kn, mv = h.index("Kernel Name"), h.index("Metric Value")
 tot = {}
-for r in rows[hi + 1:]:
+body = rows[hi + 1:]
+# the device-resident leg comes first; the end-to-end leg behind it launches the packed instantiation: stop there
+first_packed = next((i for i, r in enumerate(body) if len(r) > kn and "filter_warp_kernel<1" in r[kn].replace("(bool)", "")), len(body))
+for r in body[:first_packed]:
     if len(r) > mv:
         name = r[kn].split("(")[0].replace("void ", "").replace("dcn::", "")
         tot[name] = tot.get(name, 0) + float(r[mv].replace(",", ""))
