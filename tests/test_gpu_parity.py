@@ -435,6 +435,55 @@ def test_caller_packed_sparse_form_matches_ascii(gpu):
         gpu.host_pack_threads(4)
 
 
+@pytest.mark.parametrize("layout", ["edge-lengths", "empty-runs", "segment-straddle", "tiny-batch", "all-long", "tile-limits"])
+def test_warp_tile_planner_adversarial_layouts(gpu, layout):
+    """wplan_kernel plans ~5 tiles per memory round trip: every lane works out the tile that would start at its unit and
+    the warp hops through those counts.  Record layouts that sit on its limits -- units of exactly the longest short
+    length next to long ones, hundreds of empty records in a row (32 units / 64 records per tile), units straddling the
+    64 KB segment edges, a batch smaller than one segment, long units only, units that fill a tile to the byte -- must
+    give the oracle's result for every unit, single and paired."""
+    from deacon_server_b200 import IndexHeader
+    g = H.random_genome(300_000, 71)
+    idx = O.index_build([g], 31, 15, threads=8)
+    gpu.index_upload(idx.keys(), IndexHeader(2, 31, 15))
+    rng = np.random.default_rng(72)
+    if layout == "edge-lengths":
+        lens = rng.choice([1023, 1024, 1025, 1026, 31, 45, 44, 2048, 300], 6000)
+    elif layout == "empty-runs":
+        lens = rng.integers(100, 200, 20_000)
+        for s0 in rng.integers(0, 19_000, 30):
+            lens[s0:s0 + int(rng.integers(40, 700))] = 0
+        lens[rng.integers(0, 20_000, 2000)] = rng.integers(1, 31, 2000)
+    elif layout == "segment-straddle":
+        lens = np.full(9000, 4096 // 8, np.int64)            # 512-base units: starts on every 64 KB edge ...
+        lens[::7] = 65536 // 64 - 1                          # ... then drifting across them one base at a time
+        lens[3::11] = 1024
+    elif layout == "tiny-batch":
+        lens = rng.integers(0, 400, 37)
+    elif layout == "all-long":
+        lens = rng.integers(1025, 30_000, 400)
+    else:
+        lens = rng.choice([1536, 1521, 1520, 768, 760, 512, 384, 48, 47], 8000)   # > 1024 are long: tiles of exactly / almost 1536 bases
+    lens = np.asarray(lens, np.uint64)
+    if len(lens) % 2:
+        lens = lens[:-1]
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    start = rng.integers(0, len(g) - 3000, total // 2048 + 2)
+    bases = g[(start[:, None] + np.arange(2048)[None, :])].reshape(-1)[:total].copy()
+    bases[rng.integers(0, max(total, 1), total // 5000 + 1)] = ord("N")
+    gpu.host_pack_threads(0)
+    try:
+        for paired in (False, True):
+            got = gpu.filter_batch(bases, off, paired=paired, deplete=paired)
+            want = O.filter_batch(idx, bases, off, paired=paired, deplete=paired, threads=8)
+            for a, b, name in zip(got, want, ("keep", "hits", "total")):
+                assert np.array_equal(a, b), (layout, paired, name, int(np.flatnonzero(a != b)[0]))
+    finally:
+        gpu.host_pack_threads(4)
+
+
 def test_device_pointer_api_matches_host_api(gpu):
     import torch
     from deacon_server_b200 import IndexHeader
