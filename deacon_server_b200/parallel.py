@@ -87,20 +87,29 @@ def h2d_probe(device, nbytes: int = 1 << 30, reps: int = 3) -> dict:
             "concurrent_min_gbs": round(float(lo.item()), 2), "concurrent_max_gbs": round(float(hi.item()), 2), "world": world}
 
 
+HOST_BUSY_GBS = 150.0   # concurrent pinned H2D rate (sum over the ranks of a host) from which packer threads stop paying
+
+
 def pack_threads_for_rank(local_world: int, probe: dict | None = None) -> int:
     """Host packing threads for one rank of `local_world` on this box (dcn_host_pack_threads).
 
     Packing trades host work for PCIe bytes: a packed base costs ~1.5 B of host DRAM traffic (read, write, DMA read)
     and 0.25 B of the link, a copied one 1.0 B of each.  It pays while a rank's own link is what holds it back and
     costs when the ranks are already held back by the DRAM they share.  `probe` (h2d_probe) tells which: with every
-    rank copying at once, a rank that still gets >= 80 % of its solo rate is link-bound -> pack with the CPUs this
+    rank copying at once, a rank that still gets >= 80 % of its solo rate is link-bound and, while the ranks together move
+    less than HOST_BUSY_GBS, -> pack with the CPUs this
     process may use, shared with the other ranks, minus four (caller, enqueueing thread, driver), at most 12;
     otherwise the ranks share a host that is the limit: 0 (ASCII route only: the copy engine needs no CPU), or 2 on a
     rank whose share is well below the mean (the step waits for it).  Without a probe the round-1 rule applies
     (no packing from four ranks per host: measured host-DRAM-bound on the 8-GPU boxes of this pool)."""
     import os
     if probe is not None and probe.get("solo_gbs"):
-        if probe["concurrent_gbs"] < 0.8 * probe["solo_gbs"]:
+        # Packing pays while the DMA engines leave the host's memory system room: with all ranks copying at ~55 GB/s each, two
+        # ranks move 111 GB/s and 8 packers per rank lift e2e from 111 to 135 Gbp/s; four ranks move 217 GB/s and packers
+        # only take memory bandwidth away from the copies (183 -> 161 / 157 / 149 Gbp/s with 2 / 4 / 6 per rank: the cores
+        # of these hosts read memory at ~135 GB/s in total, tools/ingest_sweep.py).
+        host_busy = probe.get("concurrent_sum_gbs", 0.0) >= HOST_BUSY_GBS
+        if probe["concurrent_gbs"] < 0.8 * probe["solo_gbs"] or host_busy:
             # Host-bound.  The ranks' shares are not equal (one 8-GPU box: four ranks at 20 GB/s, four at 35) and with the
             # same work per rank the slow ones set the step time: two packers on a rank whose share is well below the mean
             # shorten its step a little (measured with tools/ingest_sweep.py: 166-172 -> 177-180 Gbp/s; three: no better);

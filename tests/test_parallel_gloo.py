@@ -112,9 +112,11 @@ def test_pack_threads_for_rank(monkeypatch):
     # with a probe the decision follows the measurement, not the rank count
     monkeypatch.setattr(os, "cpu_count", lambda: 64)
     monkeypatch.setattr(os, "sched_getaffinity", lambda pid: set(range(64)))
-    link_bound = {"solo_gbs": 54.0, "concurrent_gbs": 52.0, "concurrent_sum_gbs": 208.0, "world": 4}
+    link_bound = {"solo_gbs": 54.0, "concurrent_gbs": 52.0, "concurrent_sum_gbs": 104.0, "world": 2}
+    four_links = {"solo_gbs": 54.0, "concurrent_gbs": 52.0, "concurrent_sum_gbs": 208.0, "world": 4}
     host_bound = {"solo_gbs": 54.0, "concurrent_gbs": 21.5, "concurrent_sum_gbs": 172.0, "world": 8}
-    assert P.pack_threads_for_rank(4, link_bound) == 12
+    assert P.pack_threads_for_rank(2, link_bound) == 12
+    assert P.pack_threads_for_rank(4, four_links) == 0                                   # every link is full, and so is the host: packers would take memory bandwidth from the copies
     assert P.pack_threads_for_rank(8, host_bound) == 0
     assert P.pack_threads_for_rank(8, dict(host_bound, concurrent_gbs=17.0)) == 2       # a rank well below the mean share (21.5): the step waits for it
-    assert P.pack_threads_for_rank(8, dict(host_bound, concurrent_gbs=50.0)) == 4      # 64 / 8 - 4
+    assert P.pack_threads_for_rank(4, dict(link_bound, world=4)) == 12                   # four ranks on a host whose links are slow: 64 / 4 - 4
