@@ -231,9 +231,13 @@ def test_two_route_ingest_pinned_ragged(gpu):
             gpu.host_pack_fraction(fraction)
             for _ in range(2):                                                          # the second call reuses the packers' blobs
                 hk.zero_(); hh.zero_(); ht.zero_()
+                gpu.stats_reset()
                 gpu.filter_batch_ptr(hb.data_ptr(), ho.data_ptr(), n, True, 0, 2, 0.01, True, hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
                 assert np.array_equal(ht.numpy().view(np.uint32), ot) and np.array_equal(hh.numpy().view(np.uint32), oh)
                 assert np.array_equal(hk.numpy(), ok)
+                # the six summary counters are kept by the kernels, one share per launch of the pipeline, whatever its form
+                from deacon_server_b200 import parallel as P
+                assert gpu.stats() == P.counters_of(off, ok, True), (threads, fraction)
                 h2d, d2h = gpu.last_transfer_bytes()
                 assert d2h == 9 * np_units
                 if threads == 0:
