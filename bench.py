@@ -296,7 +296,8 @@ def extra_build(torch, dev, gpu, genome, coff, G):
     g2 = genome.clone()
     rs = np.random.default_rng(11)
     n_ins = int(G * 0.02 / 300)
-    pos = torch.from_numpy(rs.integers(0, G - 400, n_ins)).to(dev)
+    stride = G // n_ins   # one insert per stride: no two overlap, so the scatter below is deterministic (and the key counts reproducible)
+    pos = torch.from_numpy(np.arange(n_ins, dtype=np.int64) * stride + rs.integers(0, stride - 400, n_ins)).to(dev)
     ar = torch.arange(300, device=dev)
     kind = torch.from_numpy(rs.integers(0, 2, n_ins)).to(dev)
     homo = torch.tensor([65, 84], dtype=torch.uint8, device=dev)[kind][:, None].expand(n_ins, 300)

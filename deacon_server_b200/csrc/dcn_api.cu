@@ -2244,7 +2244,7 @@ static int index_extract_device(dcn_ctx *ctx, const uint8_t *d_bases, const uint
         CK(ctx->ib_alt.ensure(cap * sizeof(uint64_t)));
         CK(cudaMemsetAsync(ctx->ib_stats.p, 0, 64 + 16, st));
         const int pb = 256;
-        const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_rec + pb - 1) / pb, (uint64_t)ctx->sm_count * 8));
+        const int pg = (int)std::max<uint64_t>(1, std::min<uint64_t>(((uint64_t)n_rec * 32 + pb - 1) / pb, (uint64_t)ctx->sm_count * 8));   // a warp per record
         prep_index_chunks_kernel<G31><<<pg, pb, 0, st>>>(d_rec_off, n_rec, d_stats, reinterpret_cast<ChunkDesc *>(ctx->ib_desc.p), desc_cap);
         IndexParams P;
         P.bases = d_bases; P.base0 = 0; P.n_bases = n_bases; P.rec_off = d_rec_off; P.n_rec = n_rec;

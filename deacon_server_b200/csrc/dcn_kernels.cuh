@@ -168,16 +168,20 @@ __global__ void prep_long_warp_kernel(FilterParams P, BatchStats *st, uint32_t *
     }
 }
 
-// Index build: every record is cut into chunks.
+// Index build: every record is cut into chunks.  A warp per record, the lanes write its descriptors (a thread per record
+// wrote the 32 000 descriptors of a chromosome one after the other: 1.2 ms of the 50 ms build of a 24-contig reference).
 template <class G>
 __global__ void prep_index_chunks_kernel(const uint64_t *__restrict__ rec_off, uint32_t n_rec, BatchStats *st,
                                          ChunkDesc *desc, uint32_t desc_cap) {
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rec; r += gridDim.x * blockDim.x) {
+    const uint32_t lane = threadIdx.x & 31u, warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rec; r += warps) {
         uint64_t rl = rec_off[r + 1] - rec_off[r];
         uint32_t nc = chunks_of<G>(rl < (uint64_t)G::K ? 0 : rl);
-        if (!nc) continue;
-        uint32_t at = atomicAdd(&st->n_chunks, nc);
-        for (uint32_t c = 0; c < nc; c++)
+        if (!nc) continue;   // (warp-uniform)
+        uint32_t at = 0;
+        if (lane == 0) at = atomicAdd(&st->n_chunks, nc);
+        at = __shfl_sync(0xFFFFFFFFu, at, 0);
+        for (uint32_t c = lane; c < nc; c += 32u)
             if (at + c < desc_cap) desc[at + c] = ChunkDesc{r, c};
             else st->overflow = 1;
     }

@@ -330,44 +330,56 @@ DCN_HD void phase_slide(int t, TileSmem<G> &s, TilePriv<G> &pv) {
         oR[15] = key[29];
     }
 
-    // canonical strand: #(T|G) > #(A|C) over the L bases of the window (A.3 step 4).
-    // T/G <=> bit 1 of the 2-bit code.
-    const uint32_t c0 = pv.c0, c1 = s.codes[t + 1], c2 = s.codes[t + 2], c3 = s.codes[t + 3];
-    uint32_t cnt = 0;
-    {
-        // bases 0 .. L-1
-        cnt = popc32(c0 & 0xAAAAAAAAu) + popc32(c1 & 0xAAAAAAAAu);
-        constexpr int rem = G::L - 32;  // bases 32 .. L-1 live in c2 (and c3 if L > 48)
-        if (rem >= 16) {
-            cnt += popc32(c2 & 0xAAAAAAAAu);
-            constexpr int rem3 = rem - 16;
-            if (rem3 > 0) cnt += popc32(c3 & (rem3 >= 16 ? 0xAAAAAAAAu : (0xAAAAAAAAu & ((1u << (2 * (rem3 & 15))) - 1u))));
-        } else if (rem > 0) {
-            cnt += popc32(c2 & (0xAAAAAAAAu & ((1u << (2 * (rem & 15))) - 1u)));
+    // pick positions (low byte of the keys: the index 0..29), left and right flavour, four windows per word.  They differ
+    // only where the window minimum is tied (~2e-4 of windows): the strand that chooses between them (A.3 step 4) is only
+    // worked out for a thread that holds such a window
+    uint32_t l4[4], r4[4], tied = 0;
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        l4[g] = pack_low_bytes(oL[4 * g], oL[4 * g + 1], oL[4 * g + 2], oL[4 * g + 3]);
+        r4[g] = pack_low_bytes(oR[4 * g], oR[4 * g + 1], oR[4 * g + 2], oR[4 * g + 3]);
+        tied |= l4[g] ^ r4[g];
+    }
+    if (tied) {
+        // canonical strand: #(T|G) > #(A|C) over the L bases of the window.  T/G <=> bit 1 of the 2-bit code.
+        const uint32_t c0 = pv.c0, c1 = s.codes[t + 1], c2 = s.codes[t + 2], c3 = s.codes[t + 3];
+        uint32_t cnt = 0;
+        {
+            // bases 0 .. L-1
+            cnt = popc32(c0 & 0xAAAAAAAAu) + popc32(c1 & 0xAAAAAAAAu);
+            constexpr int rem = G::L - 32;  // bases 32 .. L-1 live in c2 (and c3 if L > 48)
+            if (rem >= 16) {
+                cnt += popc32(c2 & 0xAAAAAAAAu);
+                constexpr int rem3 = rem - 16;
+                if (rem3 > 0) cnt += popc32(c3 & (rem3 >= 16 ? 0xAAAAAAAAu : (0xAAAAAAAAu & ((1u << (2 * (rem3 & 15))) - 1u))));
+            } else if (rem > 0) {
+                cnt += popc32(c2 & (0xAAAAAAAAu & ((1u << (2 * (rem & 15))) - 1u)));
+            }
+        }
+        // The 16 windows of the thread, four at a time in byte lanes.  cnt(i) = cnt(0) + sum_{j<=i} (in(j) - out(j)),
+        // in(j) = T/G flag of base L-1+j, out(j) = flag of base j-1: the flags sit in the 2-bit lanes of the code
+        // words; a multiply spreads four of them into four bytes, a second multiply prefix-sums the bytes.
+        constexpr int LW = (G::L - 1) / 16, LS = 2 * ((G::L - 1) % 16);
+        const uint32_t xw_lo = ((LW == 0 ? c0 : LW == 1 ? c1 : c2) >> 1) & 0x55555555u;
+        const uint32_t xw_hi = ((LW == 0 ? c1 : LW == 1 ? c2 : c3) >> 1) & 0x55555555u;
+        const uint32_t xin = fshr(xw_lo, xw_hi, (uint32_t)LS) & ~3u;        // lane j = in(j); lane 0 belongs to cnt(0)
+        const uint32_t xout = ((c0 >> 1) & 0x55555555u) << 2;               // lane j = out(j); lane 0 = 0
+        constexpr uint32_t THR = (uint32_t)(G::L + 1) / 2;                  // canonical <=> cnt >= THR (L is odd)
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t spi = (((xin >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
+            const uint32_t spo = (((xout >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
+            const uint32_t cnt4 = cnt * 0x01010101u + spi * 0x01010101u - spo * 0x01010101u;   // cnt of windows 4g .. 4g+3
+            cnt = cnt4 >> 24;
+            const uint32_t canon = ((cnt4 + (0x80u - THR) * 0x01010101u) >> 7) & 0x01010101u;
+            const uint32_t msk = canon * 0xFFu;                                                  // 0xFF in the bytes of canonical windows
+            l4[g] = (l4[g] & msk) | (r4[g] & ~msk);                                              // A.3 step 4
         }
     }
-    // The 16 windows of the thread, four at a time in byte lanes.  cnt(i) = cnt(0) + sum_{j<=i} (in(j) - out(j)),
-    // in(j) = T/G flag of base L-1+j, out(j) = flag of base j-1: the flags sit in the 2-bit lanes of the code
-    // words; a multiply spreads four of them into four bytes, a second multiply prefix-sums the bytes.
-    constexpr int LW = (G::L - 1) / 16, LS = 2 * ((G::L - 1) % 16);
-    const uint32_t xw_lo = ((LW == 0 ? c0 : LW == 1 ? c1 : c2) >> 1) & 0x55555555u;
-    const uint32_t xw_hi = ((LW == 0 ? c1 : LW == 1 ? c2 : c3) >> 1) & 0x55555555u;
-    const uint32_t xin = fshr(xw_lo, xw_hi, (uint32_t)LS) & ~3u;        // lane j = in(j); lane 0 belongs to cnt(0)
-    const uint32_t xout = ((c0 >> 1) & 0x55555555u) << 2;               // lane j = out(j); lane 0 = 0
-    constexpr uint32_t THR = (uint32_t)(G::L + 1) / 2;                  // canonical <=> cnt >= THR (L is odd)
     uint32_t neq = 0, prev_hi = 0;
 #pragma unroll
     for (int g = 0; g < 4; g++) {
-        const uint32_t spi = (((xin >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
-        const uint32_t spo = (((xout >> (8 * g)) & 0xFFu) * 0x00041041u) & 0x01010101u;
-        const uint32_t cnt4 = cnt * 0x01010101u + spi * 0x01010101u - spo * 0x01010101u;   // cnt of windows 4g .. 4g+3
-        cnt = cnt4 >> 24;
-        const uint32_t canon = ((cnt4 + (0x80u - THR) * 0x01010101u) >> 7) & 0x01010101u;
-        const uint32_t msk = canon * 0xFFu;                                                  // 0xFF in the bytes of canonical windows
-        // pick positions (low byte of the keys: the index 0..29) of the four windows, left and right flavour
-        const uint32_t l4 = pack_low_bytes(oL[4 * g], oL[4 * g + 1], oL[4 * g + 2], oL[4 * g + 3]);
-        const uint32_t r4 = pack_low_bytes(oR[4 * g], oR[4 * g + 1], oR[4 * g + 2], oR[4 * g + 3]);
-        const uint32_t rel = (l4 & msk) | (r4 & ~msk);                                       // A.3 step 4
+        const uint32_t rel = l4[g];
         pv.rel4[g] = rel;
         // pick(i) != pick(i-1): compare every byte with the one before it (window 0 with itself)
         const uint32_t before = (rel << 8) | (g == 0 ? (rel & 0xFFu) : prev_hi);
