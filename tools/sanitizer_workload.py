@@ -26,4 +26,28 @@ k2, h2, t2 = gpu.filter_batch(bases, off)
 assert np.array_equal(k, k2) and np.array_equal(h, h2)
 keys = gpu.index_build(np.concatenate([g, g[:1000]]), np.array([0, len(g), len(g) + 1000], np.uint64), 31, 15, 0.0, False)
 assert np.array_equal(np.sort(keys), np.sort(O.index_build([g, g[:1000]], 31, 15).keys()))
+# the arena form of the host pipeline (DCN_CHUNK_MB=1 in the environment: 128 KB atoms, so a few MB are hundreds of
+# claims and dozens of launches), long units among the short ones, and the caller-packed sparse form
+if os.environ.get("DCN_CHUNK_MB") == "1":
+    from deacon_server_b200 import api as A
+    rng = np.random.default_rng(9)
+    n = 40_000
+    lens = rng.integers(0, 400, n).astype(np.uint64)
+    lens[::997] = 9_000
+    off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
+    total = int(off[-1])
+    start = rng.integers(0, len(g) - 300, total // 128 + 2)
+    bases = g[(start[:, None] + np.arange(128)[None, :])].reshape(-1)[:total].copy()
+    bases[rng.integers(0, total, total // 5000)] = ord("N")
+    want = O.filter_batch(idx, bases, off, paired=True, deplete=True, threads=4)
+    for threads in (0, 5):
+        gpu.host_pack_threads(threads)
+        got = gpu.filter_batch(bases, off, paired=True, deplete=True)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b), threads
+    gpu.host_pack_threads(0)
+    codes, exc, nl = A.pack_records_sparse(bases, off, 31, 0)
+    got = gpu.filter_batch_packed_sparse(codes, exc, nl, off, paired=True, deplete=True)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
 print("sanitizer workload ok")
