@@ -121,7 +121,7 @@ struct dcn_ctx {
     DevBuf keys_stage;
     DevBuf longs, dedup;   // long-path scratch of the device-pointer API
     // index build
-    DevBuf ib_bases, ib_off, ib_desc, ib_keys, ib_alt, ib_tmp, ib_entropy, ib_stats;
+    DevBuf ib_bases, ib_off, ib_desc, ib_keys, ib_alt, ib_tmp, ib_entropy, ib_stats, ib_runs;
     uint64_t ib_n = 0;     // the working key set: sorted unique keys of the last build / decode / union / diff (in ib_keys)
     uint8_t ws_k = 0, ws_w = 0;   // its header (src/index.rs:17-22)
     DevBuf ws_table, ws_flags;    // scratch table for set difference
@@ -587,7 +587,7 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
     ctx->table.release(); ctx->plan.release(); ctx->counters.release(); ctx->keys_stage.release();
     ctx->longs.release(); ctx->dedup.release();
     ctx->ib_bases.release(); ctx->ib_off.release(); ctx->ib_desc.release(); ctx->ib_keys.release();
-    ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->ib_entropy.release(); ctx->ib_stats.release();
+    ctx->ib_alt.release(); ctx->ib_tmp.release(); ctx->ib_entropy.release(); ctx->ib_stats.release(); ctx->ib_runs.release();
     ctx->gx_bases.release(); ctx->gx_off.release(); ctx->gx_rc.release(); ctx->gx_cc.release(); ctx->gx_tmp.release();
     ctx->gx_h.release(); ctx->gx_p.release(); ctx->gx_oo.release(); ctx->gx_entropy.release();
     ctx->ws_table.release(); ctx->ws_flags.release();
@@ -2181,6 +2181,7 @@ static int index_sort_unique(dcn_ctx *ctx, uint64_t n_picks, uint8_t k, uint8_t 
         if (make_resident) return dcn_index_upload_device(ctx, nullptr, 0, k, w, st);
         return DCN_OK;
     }
+    CK(ctx->ib_stats.ensure(128));   // (no-op after any build or decode: the buffer is allocated with slack)
     unsigned long long *d_count = reinterpret_cast<unsigned long long *>(ctx->ib_stats.as<uint8_t>() + 64);
     CK(ctx->ib_keys.ensure(n_picks * sizeof(uint64_t)));
     size_t tmp_sort = 0, tmp_sel = 0;
@@ -2188,7 +2189,25 @@ static int index_sort_unique(dcn_ctx *ctx, uint64_t n_picks, uint8_t k, uint8_t 
     CK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
     CK(cub::DeviceSelect::Unique(nullptr, tmp_sel, (const uint64_t *)nullptr, (uint64_t *)nullptr, (unsigned long long *)nullptr, (int64_t)n_picks, st));
     CK(ctx->ib_tmp.ensure(std::max(tmp_sort, tmp_sel)));
-    CK(cub::DeviceRadixSort::SortKeys(ctx->ib_tmp.p, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
+    // five radix passes over bits 24 .. 63, then the few runs of keys that share those bits are sorted in place
+    // (sort_prefix_runs_kernel); keys that are not hash-like (long runs) get the full eight passes
+    static const bool prefix_sort = []() { const char *e = getenv("DCN_PREFIX_SORT"); return !e || atoi(e) != 0; }();
+    bool full = !prefix_sort;
+    if (!full) {
+        uint32_t *d_flag = reinterpret_cast<uint32_t *>(ctx->ib_stats.as<uint8_t>() + 96), *d_nruns = d_flag + 1;
+        const uint32_t runs_cap = 1u << 20;
+        CK(ctx->ib_runs.ensure((size_t)runs_cap * 8));
+        CK(cudaMemsetAsync(d_flag, 0, 8, st));
+        CK(cub::DeviceRadixSort::SortKeys(ctx->ib_tmp.p, tmp_sort, db, (int64_t)n_picks, 24, 64, st));
+        find_prefix_runs_kernel<<<grid_for(ctx, n_picks, 256), 256, 0, st>>>(db.Current(), n_picks, ctx->ib_runs.as<uint64_t>(), runs_cap, d_nruns, d_flag);
+        sort_prefix_runs_kernel<<<grid_for(ctx, runs_cap, 128), 128, 0, st>>>(db.Current(), n_picks, ctx->ib_runs.as<uint64_t>(), d_nruns, runs_cap, d_flag);
+        uint32_t flag = 0;
+        CK(cudaMemcpyAsync(&flag, d_flag, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        ctx->launches += 7;
+        full = flag != 0;
+    }
+    if (full) CK(cub::DeviceRadixSort::SortKeys(ctx->ib_tmp.p, tmp_sort, db, (int64_t)n_picks, 0, 64, st));
     uint64_t *sorted = db.Current();
     uint64_t *uniq = db.Alternate();
     CK(cub::DeviceSelect::Unique(ctx->ib_tmp.p, tmp_sel, sorted, uniq, d_count, (int64_t)n_picks, st));

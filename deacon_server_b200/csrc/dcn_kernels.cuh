@@ -920,6 +920,54 @@ __global__ void inv_scatter_kernel(uint32_t *__restrict__ inv32, const uint2 *__
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) inv32[exc[i].x - base] = exc[i].y;
 }
 
+// ------------------------------------------------------------------ index build: finish a radix sort of the top 40 bits
+// The keys are XXH3 outputs: after a stable radix sort of bits 24 .. 63 (five 8-bit passes instead of eight) two keys are
+// out of order only if they share those 40 bits -- ~70 000 pairs among 4 x 10^8.  A thread that finds its key smaller
+// than the one before it (an inversion) and is the first such thread of its run of equal prefixes lists the run; a
+// second kernel sorts the listed runs in place, one thread each (insertion sort; runs of two or three distinct keys,
+// plus their duplicates).  Two kernels, because deciding who owns a run while somebody sorts it would be a race.  Runs of one repeated key -- a
+// minimizer of a repeat occurs thousands of times in the picks of a genome -- have no inversion and cost nothing.  A
+// run that reaches more than DCN_RUN_MAX keys from an inversion (keys that are not hashes: an .idx file may hold
+// anything) raises `too_long` and the caller sorts all 64 bits instead.
+static constexpr uint32_t DCN_RUN_MAX = 48;
+// pass 1 (reads only): the runs that need sorting, listed by their first key's index
+__global__ void find_prefix_runs_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint64_t *__restrict__ runs, uint32_t runs_cap,
+                                        uint32_t *n_runs, uint32_t *too_long) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t v = keys[i];
+        if (keys[i - 1] <= v) continue;                            // in order (the common case: one load pair per key)
+        const uint64_t p = v >> 24;
+        // back to the start of the run; another inversion on the way means an earlier thread lists the run
+        uint64_t s0 = i - 1;
+        bool mine = true;
+        while (s0 > 0 && i - s0 <= DCN_RUN_MAX && (keys[s0 - 1] >> 24) == p) {
+            if (keys[s0 - 1] > keys[s0]) { mine = false; break; }
+            s0--;
+        }
+        if (!mine) continue;
+        if (i - s0 > DCN_RUN_MAX) { *too_long = 1u; continue; }
+        const uint32_t at = atomicAdd(n_runs, 1u);
+        if (at < runs_cap) runs[at] = s0; else *too_long = 1u;
+    }
+}
+// pass 2: one thread per listed run sorts it in place (the runs are disjoint)
+__global__ void sort_prefix_runs_kernel(uint64_t *__restrict__ keys, uint64_t n, const uint64_t *__restrict__ runs, const uint32_t *n_runs,
+                                        uint32_t runs_cap, uint32_t *too_long) {
+    const uint32_t nr = *n_runs < runs_cap ? *n_runs : runs_cap;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < nr; r += gridDim.x * blockDim.x) {
+        const uint64_t s0 = runs[r], p = keys[s0] >> 24;
+        uint64_t e = s0 + 1;
+        while (e < n && e - s0 <= DCN_RUN_MAX && (keys[e] >> 24) == p) e++;
+        if (e - s0 > DCN_RUN_MAX) { *too_long = 1u; continue; }
+        for (uint64_t a = s0 + 1; a < e; a++) {
+            const uint64_t x = keys[a];
+            uint64_t b2 = a;
+            while (b2 > s0 && keys[b2 - 1] > x) { keys[b2] = keys[b2 - 1]; b2--; }
+            keys[b2] = x;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ arena form of the host pipeline: one claim's blob -> its places
 // A packer thread's claim crosses PCIe as ONE copy (codes | newline flags | exception list or dense mask | offsets) into a
 // staging buffer; this kernel moves the parts to the claim's places in the arena (device-to-device, a few microseconds)

@@ -890,6 +890,28 @@ def test_idx_decode_encode_matches_oracle_codec(gpu):
         gpu.idx_decode(O.idx_encode(_mixed_keys(4, 100), 31, 15)[:-3])
 
 
+def test_key_sort_prefix_runs_and_fallback(gpu):
+    """The working key set is sorted by five radix passes over bits 24..63 and a fix-up of the runs of keys that share
+    those bits (sort_prefix_runs_kernel); keys that are not hash-like make runs too long for it and get all eight passes.
+    Both must give sorted unique keys: hash-like keys with planted prefix collisions (runs of 2 .. 20, duplicates among
+    them), and sequential keys (one run of a million)."""
+    rng = np.random.default_rng(81)
+    base = rng.integers(0, 2**63, 300_000, dtype=np.uint64) * np.uint64(2)
+    planted = []
+    for p in base[:3000]:
+        m = int(rng.integers(2, 21))
+        low = rng.integers(0, 1 << 24, m, dtype=np.uint64)
+        planted.append((p & np.uint64(0xFFFFFFFFFF000000)) | low)
+        planted.append(planted[-1][: m // 2])                      # duplicates inside the run
+    hashy = np.concatenate([base] + planted)
+    for keys in (hashy, np.arange(5, 1_000_005, dtype=np.uint64), np.concatenate([hashy, np.arange(0, 100_000, dtype=np.uint64)])):
+        data = O.idx_encode(rng.permutation(keys), 31, 15)
+        hdr, n_file, n_set = gpu.idx_decode(data)
+        want = np.unique(keys)
+        assert n_file == len(keys) and n_set == len(want)
+        assert np.array_equal(gpu.working_keys(), want)
+
+
 def test_index_union_and_diff_match_set_algebra(gpu):
     """index::union (src/index.rs:563-664) and index::diff index - index (:421-537)."""
     a, b, c = _mixed_keys(11, 300_000), _mixed_keys(12, 200_000), _mixed_keys(13, 1000)
