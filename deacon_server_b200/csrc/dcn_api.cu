@@ -97,6 +97,7 @@ struct ArenaState {
     cudaStream_t copy_stream = nullptr;   // the ASCII route's copies, in order
     cudaEvent_t ev_sub[4] = {nullptr, nullptr, nullptr, nullptr};   // pacing of the ASCII copies
     cudaEvent_t ev_front[NL] = {};        // "ASCII copied up to here", one per launch slot
+    BatchStats *h_after = nullptr;        // pinned, NL entries: stats of a launch with long units (overflow flag of its distinct-hit set)
 };
 
 }  // namespace
@@ -358,7 +359,12 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
                           uint64_t base0, uint64_t n_bases_abs, const uint64_t *d_off, uint32_t n_rec, int paired,
                           uint32_t prefix_len, uint32_t abs_thr, double rel_thr, int deplete, uint8_t *d_keep,
                           uint32_t *d_hits, uint32_t *d_total, cudaStream_t st, const BatchStats *host_stats = nullptr,
-                          bool time_fused = true, bool promised_short = false) {   // false: no event pair around the fused kernel (the ring is not thread-safe)
+                          bool time_fused = true, bool promised_short = false,   // false: no event pair around the fused kernel (the ring is not thread-safe)
+                          BatchStats *async_after = nullptr, uint32_t dedup_grow = 1) {
+    // async_after (pinned host memory): a batch with long units is enqueued without waiting for it -- the batch's stats
+    // (with the overflow flag of the distinct-hit set) are copied there behind the kernels and the CALLER looks at them once
+    // the stream has got that far; on overflow it calls again with dedup_grow = 4 (and no async_after: that call retries
+    // by itself).  Without it the call waits for the long path and retries with a set four times the size.
     if (!ctx->table.p) return ctx->fail(DCN_ERR_NO_INDEX, "no index resident: call dcn_index_upload first");
     const uint32_t rpu = paired ? 2u : 1u;
     if (paired && (n_rec & 1u)) return ctx->fail(DCN_ERR_ARG, "paired batch needs an even record count");
@@ -452,7 +458,8 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
             // small set (regions would reserve 4 bytes per base of the short units too).  DCN_DEDUP_LOCAL=0 forces the latter.
             static const bool local_ok = []() { const char *e = getenv("DCN_DEDUP_LOCAL"); return !e || atoi(e) != 0; }();
             const bool local = warp_impl && local_ok && hs.long_bases >= n_rel / 4;
-            if (!dedup_cap) dedup_cap = local ? 4 : std::max<uint64_t>(4096, hs.long_bases / 4);   // local: slots per 16 bases
+            static const uint32_t shrink = []() { const char *e = getenv("DCN_DEDUP_SHRINK"); return e ? (uint32_t)std::max(1, atoi(e)) : 1u; }();   // tests: start too small
+            if (!dedup_cap) dedup_cap = (local ? std::max<uint64_t>(1, 4 / shrink) : std::max<uint64_t>(64, std::max<uint64_t>(4096, hs.long_bases / 4) / shrink)) * dedup_grow;   // local: slots per 16 bases
             const uint32_t desc_cap = (uint32_t)(hs.long_bases / ChunkGeo<G31>::CSTRIDE + (uint64_t)hs.n_long * rpu + 16);
             CK(open_dedup_set(dedup, local ? ((n_rel >> 4) + 2) * dedup_cap : dedup_cap, st, dd, &d_stats->overflow));
             if (local) dd.per16 = (uint32_t)dedup_cap;
@@ -493,6 +500,10 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         if (hs.n_long) {
             finalize_long_kernel<<<std::max(1, (int)std::min<uint32_t>((hs.n_long + 255) / 256, 1024)), 256, 0, st>>>(P, d_stats, long_units, warp_impl ? call_cnt : nullptr);
             ctx->launches += 1;
+            if (async_after && warp_impl) {
+                CK(cudaMemcpyAsync(async_after, d_stats, sizeof(BatchStats), cudaMemcpyDeviceToHost, st));
+                break;
+            }
             BatchStats after;
             CK(cudaMemcpyAsync(&after, d_stats, sizeof(after), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
@@ -504,7 +515,7 @@ static int enqueue_filter(dcn_ctx *ctx, DevBuf &plan, DevBuf &longs, DevBuf &ded
         }
         break;
     }
-    if (warp_impl) commit_counters_kernel<<<1, 32, 0, st>>>(call_cnt, ctx->counters.as<unsigned long long>());   // the warp-tile kernels counted on the way
+    if (warp_impl) commit_counters_kernel<<<1, 32, 0, st>>>(call_cnt, ctx->counters.as<unsigned long long>(), async_after ? d_stats : nullptr);   // the warp-tile kernels counted on the way
     else stats_kernel<<<pg, pb, 0, st>>>(d_off, rpu, n_units, d_keep, ctx->counters.as<unsigned long long>());
     ctx->launches += 1;
     CK(cudaGetLastError());
@@ -613,6 +624,7 @@ void dcn_ctx_destroy(dcn_ctx *ctx) {
             if (ar->ev_front[i]) cudaEventDestroy(ar->ev_front[i]);
         }
         for (int i = 0; i < 4; i++) if (ar->ev_sub[i]) cudaEventDestroy(ar->ev_sub[i]);
+        if (ar->h_after) cudaFreeHost(ar->h_after);
         if (ar->copy_stream) cudaStreamDestroy(ar->copy_stream);
         delete ar;
     }
@@ -919,6 +931,8 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
         ar.off.ensure(((size_t)n_rec + 1) * 8) != cudaSuccess || ar.out.ensure((size_t)n_units * 9 + 64) != cudaSuccess)
         return ctx->fail(DCN_ERR_NOMEM, "arena allocation failed", cudaGetLastError());
     if (!ar.copy_stream) {
+        CK(cudaMallocHost(reinterpret_cast<void **>(&ar.h_after), sizeof(BatchStats) * ArenaState::NL));
+        memset(ar.h_after, 0, sizeof(BatchStats) * ArenaState::NL);
         CK(cudaStreamCreateWithFlags(&ar.copy_stream, cudaStreamNonBlocking));
         for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&ar.ev_sub[i], cudaEventDisableTiming));
         for (int i = 0; i < ArenaState::NL; i++) {
@@ -981,9 +995,60 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
     double pack_busy_ms = 0, pack_wait_ms = 0;
     auto set_rc = [&](int rc) { std::lock_guard<std::mutex> g(m); if (rc && !first_rc) first_rc = rc; };
 
-    auto retire = [&](Slot &s) -> int {   // (the slot's mutex is held)
+    // what a launch slot is running: enough to enqueue it again (a launch whose distinct-hit set overflowed is repeated)
+    struct LInfo { int a_lo = 0, a_hi = 0; bool packed = false, has_long = false; BatchStats hs; };
+    LInfo linfo[ArenaState::NL];
+
+    // kernels + results of the launch in slot idx; `again`: the repeat after an overflow (larger set, waits for the long path itself)
+    auto enqueue_launch = [&](int idx, bool again) -> int {
+        Slot &s = ar.launch[idx];
+        const LInfo &L = linfo[idx];
+        const uint32_t u_lo = atom_u[(size_t)L.a_lo], u_hi = atom_u[(size_t)L.a_hi], nu = u_hi - u_lo, nr = nu * rpu;
+        const uint64_t r0 = (uint64_t)u_lo * rpu;
+        const uint64_t base0 = rec_off[r0] & ~63ull, n_abs = rec_off[(uint64_t)u_hi * rpu];
+        FilterInput in;
+        if (L.packed) {
+            in.codes = d_codes + (base0 - A0) / 16;
+            in.inv = d_inv + (base0 - A0) / 16;
+            in.nl = d_nl + r0 / 32;
+            in.nl_bit0 = (uint32_t)(r0 % 32);
+        } else {
+            in.bases = d_ascii + (base0 - A0);
+        }
+        CK(cudaEventRecord(s.ev_start, s.stream));
+        if (L.has_long && !again) ar.h_after[idx].overflow = 0;
+        const int rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, base0, n_abs, d_off + r0, nr, paired, prefix_len, abs_thr, rel_thr, deplete,
+                                      d_keep + u_lo, d_hits + u_lo, d_total + u_lo, s.stream, &L.hs, false, false,
+                                      L.has_long && !again ? &ar.h_after[idx] : nullptr, again ? 4u : 1u);
+        if (rc) return rc;
+        CK(cudaEventRecord(s.ev_kernel, s.stream));
+        if (out_pinned) {
+            CK(cudaMemcpyAsync(hits + u_lo, d_hits + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(total + u_lo, d_total + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(keep + u_lo, d_keep + u_lo, nu, cudaMemcpyDeviceToHost, s.stream));
+        } else {
+            uint8_t *o = s.h_out.as<uint8_t>();
+            CK(cudaMemcpyAsync(o, d_hits + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(o + (size_t)nu * 4, d_total + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(o + (size_t)nu * 8, d_keep + u_lo, nu, cudaMemcpyDeviceToHost, s.stream));
+        }
+        n_d2h += (uint64_t)nu * 9;
+        CK(cudaEventRecord(s.ev_done, s.stream));
+        s.busy = true; s.u0 = u_lo; s.u1 = u_hi; s.packed = L.packed;
+        return DCN_OK;
+    };
+
+    auto retire = [&](int idx) -> int {   // (the slot's mutex is held)
+        Slot &s = ar.launch[idx];
         if (!s.busy) return DCN_OK;
         CK(cudaEventSynchronize(s.ev_done));
+        if (linfo[idx].has_long && ar.h_after[idx].overflow) {
+            // the distinct-hit set of this launch was too small: nothing was committed; once more, four times the size
+            ar.h_after[idx].overflow = 0;
+            const int rc = enqueue_launch(idx, true);
+            if (rc) return rc;
+            CK(cudaEventSynchronize(s.ev_done));
+        }
         const uint32_t nu = s.u1 - s.u0;
         if (!out_pinned) {
             const uint8_t *o = s.h_out.as<uint8_t>();
@@ -1009,49 +1074,25 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
         const int idx = (int)(seq % ArenaState::NL);
         std::lock_guard<std::mutex> lg(ar.launch_m[idx]);
         Slot &s = ar.launch[idx];
-        int rc = retire(s);
+        int rc = retire(idx);
         if (rc) return rc;
-        const uint32_t u_lo = atom_u[(size_t)a_lo], u_hi = atom_u[(size_t)a_hi], nu = u_hi - u_lo, nr = nu * rpu;
+        const uint32_t u_lo = atom_u[(size_t)a_lo], u_hi = atom_u[(size_t)a_hi], nu = u_hi - u_lo;
         if (nu == 0) return DCN_OK;
-        const uint64_t r0 = (uint64_t)u_lo * rpu;
-        const uint64_t base0 = rec_off[r0] & ~63ull, n_abs = rec_off[(uint64_t)u_hi * rpu];
+        const uint64_t base0 = rec_off[(uint64_t)u_lo * rpu] & ~63ull, n_abs = rec_off[(uint64_t)u_hi * rpu];
         if (!out_pinned && s.h_out.ensure((size_t)nu * 9) != cudaSuccess) return ctx->fail(DCN_ERR_NOMEM, "staging allocation failed", cudaGetLastError());
         if (hs.n_long) {
             // long units: the distinct-hit set and the long-unit list of this slot at the size the largest range needs,
             // once -- launches of varying size would otherwise grow them (cudaFree: a device-wide stall) call after call
             const uint64_t cap_rel = std::max<uint64_t>(n_abs - base0, std::min<uint64_t>(nb_total, range_cap + (uint64_t)atom_bases));
-            if (s.dedup.ensure((size_t)std::max<uint64_t>(4096, cap_rel / 4) * 16) != cudaSuccess ||
+            if (s.dedup.ensure((size_t)std::max<uint64_t>(4096, cap_rel / 4 + 64) * 16) != cudaSuccess ||
                 s.longs.ensure((size_t)(cap_rel / DCN_MAX_SHORT + 64) * 4 + 64 + (size_t)(cap_rel / ChunkGeo<G31>::CSTRIDE + cap_rel / DCN_MAX_SHORT * rpu + 80) * sizeof(ChunkDesc)) != cudaSuccess)
                 return ctx->fail(DCN_ERR_NOMEM, "long-path scratch allocation failed", cudaGetLastError());
         }
         for (cudaEvent_t e : waits) if (e) CK(cudaStreamWaitEvent(s.stream, e, 0));
-        FilterInput in;
-        if (packed) {
-            in.codes = d_codes + (base0 - A0) / 16;
-            in.inv = d_inv + (base0 - A0) / 16;
-            in.nl = d_nl + r0 / 32;
-            in.nl_bit0 = (uint32_t)(r0 % 32);
-        } else {
-            in.bases = d_ascii + (base0 - A0);
-        }
-        CK(cudaEventRecord(s.ev_start, s.stream));
-        rc = enqueue_filter(ctx, s.plan, s.longs, s.dedup, in, base0, n_abs, d_off + r0, nr, paired, prefix_len, abs_thr, rel_thr, deplete,
-                            d_keep + u_lo, d_hits + u_lo, d_total + u_lo, s.stream, &hs, false);
+        LInfo &L = linfo[idx];
+        L.a_lo = a_lo; L.a_hi = a_hi; L.packed = packed; L.has_long = hs.n_long != 0; L.hs = hs;
+        rc = enqueue_launch(idx, false);
         if (rc) return rc;
-        CK(cudaEventRecord(s.ev_kernel, s.stream));
-        if (out_pinned) {
-            CK(cudaMemcpyAsync(hits + u_lo, d_hits + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(total + u_lo, d_total + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(keep + u_lo, d_keep + u_lo, nu, cudaMemcpyDeviceToHost, s.stream));
-        } else {
-            uint8_t *o = s.h_out.as<uint8_t>();
-            CK(cudaMemcpyAsync(o, d_hits + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(o + (size_t)nu * 4, d_total + u_lo, (size_t)nu * 4, cudaMemcpyDeviceToHost, s.stream));
-            CK(cudaMemcpyAsync(o + (size_t)nu * 8, d_keep + u_lo, nu, cudaMemcpyDeviceToHost, s.stream));
-        }
-        n_d2h += (uint64_t)nu * 9;
-        CK(cudaEventRecord(s.ev_done, s.stream));
-        s.busy = true; s.u0 = u_lo; s.u1 = u_hi; s.packed = packed;
         (packed ? n_launch_p : n_launch_a)++;
         if (trace_level >= 2)
             fprintf(stderr, "[dcn launch] %.2f ms: %s atoms %d..%d units %u..%u (%.1f MB)\n", now_ms() - t_call0, packed ? "packed" : "ascii", a_lo, a_hi,
@@ -1319,7 +1360,7 @@ static int filter_pipeline_arena(dcn_ctx *ctx, const uint8_t *bases, const uint6
     }
     for (int i = 0; i < ArenaState::NL; i++) {
         std::lock_guard<std::mutex> lg(ar.launch_m[i]);
-        const int r2 = retire(ar.launch[i]);
+        const int r2 = retire(i);
         if (r2) set_rc(r2);
     }
     rc = first_rc;

@@ -1023,7 +1023,10 @@ __global__ void stats_kernel(const uint64_t *__restrict__ rec_off, uint32_t rpu,
 }
 
 // one call's share of the summary counters -> the ctx's counters
-__global__ void commit_counters_kernel(const unsigned long long *__restrict__ call_cnt, unsigned long long *counters) {
+// `st` (optional): a launch whose distinct-hit set overflowed does not commit -- its caller repeats it with a larger set
+// (the launches of the arena pipeline find out when they are retired, not before the commit is enqueued)
+__global__ void commit_counters_kernel(const unsigned long long *__restrict__ call_cnt, unsigned long long *counters, const BatchStats *st) {
+    if (st && st->overflow) return;
     if (threadIdx.x < 6 && call_cnt[threadIdx.x]) atomicAdd(&counters[threadIdx.x], call_cnt[threadIdx.x]);
 }
 

@@ -353,17 +353,22 @@ for paired, prefix in ((False, 0), (True, 0), (False, 120)):
     want = O.filter_batch(idx, bases, off, paired=paired, prefix_len=prefix, deplete=paired, threads=8)
     for threads, fraction in ((0, -1.0), (5, -1.0), (3, 0.5), (5, 1.0)):
         gpu.host_pack_threads(threads); gpu.host_pack_fraction(fraction)
+        gpu.stats_reset()
         got = gpu.filter_batch(bases, off, paired=paired, prefix_length=prefix, deplete=paired)
         for a, b in zip(got, want):
             assert np.array_equal(a, b), (paired, prefix, threads, fraction)
+        from deacon_server_b200 import parallel as P
+        assert gpu.stats() == P.counters_of(off, want[0], paired), (paired, prefix, threads, fraction)
 print("small atoms ok")
 """
 
 
 @pytest.mark.parametrize("n_every,sparse,extra", [(500, "1", {}), (40000, "1", {}), (500, "0", {}),
                                                   (40000, "1", {"DCN_PIPELINE": "chunks"}),
-                                                  (500, "1", {"DCN_LAUNCH_ATOMS": "3", "DCN_LAUNCH_CAP_MB": "1", "DCN_PACKER_STAGES": "1"})],
-                         ids=["N-rich:dense-fallback", "N-rare:sparse-mask", "dense-wire", "chunk-pipeline", "arena:many-small-launches"])
+                                                  (500, "1", {"DCN_LAUNCH_ATOMS": "3", "DCN_LAUNCH_CAP_MB": "1", "DCN_PACKER_STAGES": "1"}),
+                                                  (40000, "1", {"DCN_DEDUP_SHRINK": "8"})],
+                         ids=["N-rich:dense-fallback", "N-rare:sparse-mask", "dense-wire", "chunk-pipeline", "arena:many-small-launches",
+                              "distinct-hit-set-overflow"])
 def test_two_route_ingest_small_atoms(tmp_path, n_every, sparse, extra):
     """The two-route ingest with 1 MB chunks (128 KB atoms; DCN_CHUNK_MB is read once per process, hence the
     subprocess): hundreds of atoms per call, every kind of record boundary inside them -- empty and sub-k records,
@@ -372,7 +377,10 @@ def test_two_route_ingest_small_atoms(tmp_path, n_every, sparse, extra):
     back to the dense mask when more than one 32-base block in 32 is listed (an N every 500 bases);
     DCN_SPARSE_MASK=0 keeps the dense wire form of round 1.  The calls with packer threads run the arena form of the
     pipeline (kernels over whatever contiguous range has arrived); DCN_PIPELINE=chunks runs the one-kernel-per-chunk form
-    that still serves the single-route cases, and tiny launch limits make the arena form launch hundreds of ranges."""
+    that still serves the single-route cases, and tiny launch limits make the arena form launch hundreds of ranges.
+    DCN_DEDUP_SHRINK starts the distinct-hit sets of the long units at an eighth of their size: every launch with a long
+    unit overflows and is repeated with a larger set (by the call itself in the chunk form, at retire time in the arena
+    form, where nothing may have been committed to the counters by the overflowed attempt)."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
