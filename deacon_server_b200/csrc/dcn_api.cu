@@ -787,14 +787,18 @@ static int pack_threads_of(dcn_ctx *ctx) {   // -> host threads available for pa
     return ctx->pack_threads;
 }
 
-// Host-pointer form (SURVEY.md 8f.1 "pinned double-buffered streams").  The batch is cut into unit-aligned atoms of
+// Host-pointer form (SURVEY.md 8f.1 "pinned double-buffered streams"), CHUNK form.  It serves the single-route cases
+// (no packer threads; caller-packed input, in 64 / 128 MB chunks) and what the arena form declines (a handful of huge
+// units, batches beyond DCN_ARENA_MAX_MB, DCN_PIPELINE=chunks); when both routes run, filter_pipeline_arena above takes
+// the call: same routes, same claims from the two ends, but kernels over whatever contiguous range has arrived instead
+// of one kernel chain per chunk.  The batch is cut into unit-aligned atoms of
 // 4 MB; a chunk (a run of atoms) goes through a pipeline stage with its own stream: copy in, kernels, results out
 // through a pinned blob, scattered into the caller's arrays when the stage is reused.  A chunk reaches the GPU by
 // one of two routes:
 //   ASCII   the bytes are copied as they are (1 B/bp over PCIe, no CPU work), the GPU converts them;
 //   packed  a host thread packs the chunk (2-bit codes + non-ACGT bits, plus record offsets and newline flags:
 //           what PackedSeqVec::from_ascii and the mask loop of src/filter_common.rs:238-258 compute) into one
-//           pinned blob and 0.43 B/bp cross PCIe.
+//           pinned blob and 0.25 B/bp cross PCIe (sparse non-ACGT list; 0.375 with the dense mask).
 // The copy engine and the host cores work at the same time (measured on the round-1 box: a pinned H2D stream keeps
 // 55 GB/s beside 12 packing threads doing 64 GB/s, tools/hybrid_probe.py), so with pinned caller buffers the two
 // routes share a batch dynamically.  The calling thread ships 32 MB ASCII chunks from the FRONT of the atom list
