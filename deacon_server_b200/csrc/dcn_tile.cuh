@@ -480,8 +480,22 @@ DCN_HD Bucket load_bucket(const uint64_t *slots, uint64_t b) {
     Bucket r;
     const uint64_t *p = slots + 4 * b;
 #ifdef __CUDA_ARCH__
+#if defined(DCN_L2_HINT) && DCN_L2_HINT == 64
+    asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.k0), "=l"(r.k1), "=l"(r.k2), "=l"(r.k3) : "l"(p));
+#elif defined(DCN_L2_HINT) && DCN_L2_HINT == 128
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.k0), "=l"(r.k1), "=l"(r.k2), "=l"(r.k3) : "l"(p));
+#elif defined(DCN_L2_HINT) && DCN_L2_HINT == 1
+    asm volatile("ld.global.cg.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.k0), "=l"(r.k1), "=l"(r.k2), "=l"(r.k3) : "l"(p));
+#elif defined(DCN_L2_HINT) && DCN_L2_HINT == 2
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(r.k0), "=l"(r.k1), "=l"(r.k2), "=l"(r.k3) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u64 {%0,%1,%2,%3}, [%4];"
                  : "=l"(r.k0), "=l"(r.k1), "=l"(r.k2), "=l"(r.k3) : "l"(p));
+#endif
 #else
     r.k0 = p[0]; r.k1 = p[1]; r.k2 = p[2]; r.k3 = p[3];
 #endif
