@@ -538,6 +538,36 @@ def run_ours(args):
     sparse_s = float(svec.item())
     assert torch.equal(hk, keep.cpu()) and torch.equal(hh, hits.cpu()) and torch.equal(ht, tot.cpu()), \
         "caller-packed (sparse) path and device-pointer path disagree"
+    # ---- the end-to-end leg once more with shards in proportion to each rank's share of the host (N > 1): does the rank with
+    # the smallest share (on an 8-GPU box: four ranks at 20 GB/s, four at 35) hold the others back?  Measured: no -- 176.9
+    # against 178.6 Gbp/s with equal shards: the host's aggregate rate is the limit, however the work is dealt out.
+    balanced = None
+    if world > 1:
+        sh = torch.tensor([ingest["concurrent_gbs"]], dtype=torch.float64, device=dev)
+        parts = [torch.empty_like(sh) for _ in range(world)]
+        dist.all_gather(parts, sh)
+        shares = [float(x.item()) for x in parts]
+        my_pairs = max(2, int(NP * shares[rank] / max(shares)) & ~1)
+
+        def balanced_step(i):
+            gpu.filter_batch_ptr(hb[i % n_host].data_ptr(), hoff.data_ptr(), 2 * my_pairs, True, 0, 2, 0.01, True,
+                                 hk.data_ptr(), hh.data_ptr(), ht.data_ptr())
+
+        balanced_step(0)
+        barrier()
+        b_steps = max(1, min(e2e_steps, 5))
+        t0 = time.perf_counter()
+        for i in range(b_steps):
+            balanced_step(i)
+        torch.cuda.synchronize()
+        bvec = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(bvec, op=dist.ReduceOp.MAX)
+        tot_pairs = torch.tensor([my_pairs], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot_pairs, op=dist.ReduceOp.SUM)
+        balanced = {"value": round(1e-9 * float(tot_pairs.item()) * 2 * READ_LEN * b_steps / float(bvec.item()), 3), "unit": "Gbp/s",
+                    "steps": b_steps, "pairs_per_step_per_rank": [int(NP * x / max(shares)) & ~1 for x in shares],
+                    "what": "dcn_filter_batch as in e2e, each rank's batch in proportion to its share of the host's concurrent H2D rate "
+                            "(reported beside e2e, never instead of it)"}
     for i in range(1):
         e2e_step(e2e_steps - 1)   # leave the last e2e batch's result in the host buffers for the check below
 
@@ -613,9 +643,10 @@ def run_ours(args):
                     # what the host can feed: pinned H2D GB/s of a rank alone and of all ranks at once (one ASCII base = one
                     # byte of it); packing on host threads is switched on while the ranks' own links are what binds
                     "ingest_ceiling": dict(ingest, ascii_route_gbp_per_s=ingest["concurrent_sum_gbs"],
-                                           limiter=("the host the ranks share (DRAM / socket interconnect / PCIe root): the ranks' shares are unequal and the "
-                                                    "slowest sets the step time; ASCII route, two packer threads on the ranks well below the mean share "
-                                                    "(a packed base costs 1.5 B of host DRAM traffic, a copied one 1.0 B)"
+                                           limiter=("the host the ranks share (DRAM / socket interconnect / PCIe root): its aggregate rate under the "
+                                                    "pipeline is ~0.8 of the copy-only probe's sum, with equal shards and with shards in proportion to the "
+                                                    "ranks' shares alike (e2e_balanced_shards); ASCII route, two packer threads on the ranks well below the "
+                                                    "mean share (a packed base costs 1.5 B of host DRAM traffic, a copied one 1.0 B)"
                                                     if ingest["concurrent_gbs"] < 0.8 * ingest["solo_gbs"] or (world > 1 and ingest.get("concurrent_min_gbs", 1e9) < 0.8 * ingest["solo_gbs"])
                                                     else "each rank's own PCIe link and the host memory traffic of its packer threads (DESIGN.md 5)")),
                     "frac_of_ascii_ceiling": round(e2e_value / max(ingest["concurrent_sum_gbs"], 1e-9), 3),
@@ -638,6 +669,7 @@ def run_ours(args):
                                         "caller_buffer_bytes_per_step": int(codes_np.nbytes + exc_np.nbytes + (NR + 1) * 8),
                                         "api": "dcn_filter_batch_packed_sparse (C ABI): 2-bit codes + (block, mask) list of the non-ACGT "
                                                "bases packed by the caller with dcn_pack_records_sparse (packing time not included)"},
+            **({"e2e_balanced_shards": balanced} if balanced else {}),
             "gpu_launches": int(launches),
             # `bound` keeps the contract's vocabulary: the path is nominally HBM work.  What actually binds it is stated
             # next to it, each as a fraction measured by THIS run unless it is prefixed ncu_ (then it is read from the
