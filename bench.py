@@ -650,7 +650,7 @@ def run_ours(args):
                                                     if ingest["concurrent_gbs"] < 0.8 * ingest["solo_gbs"] or (world > 1 and ingest.get("concurrent_min_gbs", 1e9) < 0.8 * ingest["solo_gbs"])
                                                     else "each rank's own PCIe link and the host memory traffic of its packer threads (DESIGN.md 5)")),
                     "frac_of_ascii_ceiling": round(e2e_value / max(ingest["concurrent_sum_gbs"], 1e-9), 3),
-                    # every rank does the same work, so the rank with the smallest share of the host sets the time of the step
+                    # e2e against world x the smallest share of the copy-only probe (> 1: the shares shift under the real pipeline)
                     "frac_of_slowest_rank_ceiling": round(e2e_value / max(world * ingest.get("concurrent_min_gbs", ingest["concurrent_gbs"]), 1e-9), 3),
                     "pipeline": "arena (dcn_api.cu filter_pipeline_arena): copies land in one device arena, kernels run over whatever "
                                 "contiguous range of units has arrived" if (pack_threads is None or pack_threads > 0) and not os.environ.get("DCN_PIPELINE")
