@@ -647,7 +647,7 @@ def run_ours(args):
                                                     "pipeline is ~0.8 of the copy-only probe's sum, with equal shards and with shards in proportion to the "
                                                     "ranks' shares alike (e2e_balanced_shards); ASCII route, two packer threads on the ranks well below the "
                                                     "mean share (a packed base costs 1.5 B of host DRAM traffic, a copied one 1.0 B)"
-                                                    if ingest["concurrent_gbs"] < 0.8 * ingest["solo_gbs"] or (world > 1 and ingest.get("concurrent_min_gbs", 1e9) < 0.8 * ingest["solo_gbs"])
+                                                    if ingest["concurrent_sum_gbs"] >= par.HOST_BUSY_GBS
                                                     else "each rank's own PCIe link and the host memory traffic of its packer threads (DESIGN.md 5)")),
                     "frac_of_ascii_ceiling": round(e2e_value / max(ingest["concurrent_sum_gbs"], 1e-9), 3),
                     # e2e against world x the smallest share of the copy-only probe (> 1: the shares shift under the real pipeline)

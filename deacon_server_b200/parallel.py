@@ -97,8 +97,8 @@ def pack_threads_for_rank(local_world: int, probe: dict | None = None) -> int:
     Packing trades host work for PCIe bytes: a packed base costs ~1.5 B of host DRAM traffic (read, write, DMA read)
     and 0.25 B of the link, a copied one 1.0 B of each.  It pays while a rank's own link is what holds it back and
     costs when the ranks are already held back by the DRAM they share.  `probe` (h2d_probe) tells which: with every
-    rank copying at once, a rank that still gets >= 80 % of its solo rate is link-bound and, while the ranks together move
-    less than HOST_BUSY_GBS, -> pack with the CPUs this
+    rank copying at once, while the ranks together move less than HOST_BUSY_GBS the host's memory system has room
+    -> pack with the CPUs this
     process may use, shared with the other ranks, minus four (caller, enqueueing thread, driver), at most 12;
     otherwise the ranks share a host that is the limit: 0 (ASCII route only: the copy engine needs no CPU), or 2 on a
     rank whose share is well below the mean (the step waits for it).  Without a probe the round-1 rule applies
@@ -109,8 +109,10 @@ def pack_threads_for_rank(local_world: int, probe: dict | None = None) -> int:
         # ranks move 111 GB/s and 8 packers per rank lift e2e from 111 to 135 Gbp/s; four ranks move 217 GB/s and packers
         # only take memory bandwidth away from the copies (183 -> 161 / 157 / 149 Gbp/s with 2 / 4 / 6 per rank: the cores
         # of these hosts read memory at ~135 GB/s in total, tools/ingest_sweep.py).
+        # Ranks that slow each other down while the host is NOT busy (two GPUs behind one PCIe root: 42 GB/s each, 85 in
+        # total) share a link, not the memory system: packing moves fewer bytes over that link, so they pack too.
         host_busy = probe.get("concurrent_sum_gbs", 0.0) >= HOST_BUSY_GBS
-        if probe["concurrent_gbs"] < 0.8 * probe["solo_gbs"] or host_busy:
+        if host_busy:
             # Host-bound.  The ranks' shares are not equal (one 8-GPU box: four ranks at 20 GB/s, four at 35) and with the
             # same work per rank the slow ones set the step time: two packers on a rank whose share is well below the mean
             # shorten its step a little (measured with tools/ingest_sweep.py: 166-172 -> 177-180 Gbp/s; three: no better);

@@ -120,3 +120,5 @@ def test_pack_threads_for_rank(monkeypatch):
     assert P.pack_threads_for_rank(8, host_bound) == 0
     assert P.pack_threads_for_rank(8, dict(host_bound, concurrent_gbs=17.0)) == 2       # a rank well below the mean share (21.5): the step waits for it
     assert P.pack_threads_for_rank(4, dict(link_bound, world=4)) == 12                   # four ranks on a host whose links are slow: 64 / 4 - 4
+    shared_root = {"solo_gbs": 55.0, "concurrent_gbs": 42.4, "concurrent_sum_gbs": 84.9, "world": 2}
+    assert P.pack_threads_for_rank(2, shared_root) == 12                                 # two ranks slow each other down over a shared link; the host's memory has room
